@@ -1,0 +1,140 @@
+/*
+ * demf_b200.h -- C ABI of libdemf_b200.so, the B200 (sm_100a) replacement for the
+ * native ops that haoy945/DeMF executes on its data-parallel hot path.
+ *
+ * The reference repository contains no native code: every entry point below
+ * replaces a pybind function of a pinned third-party extension
+ * (requirements.txt:2-4: mmcv_full==1.3.18, mmdet3d==0.18.1) that the reference
+ * reaches through
+ *     demf/modeling/heads/class_agnostic_vote_head.py:13   (build_sa_module, furthest_point_sample)
+ *     demf/modeling/heads/class_agnostic_vote_head.py:429  (furthest_point_sample call)
+ *     demf/modeling/heads/class_agnostic_vote_head.py:455  (vote aggregation SA module)
+ *     demf/modeling/layers/transformer.py:9,73-78          (MultiScaleDeformableAttention)
+ *     configs/demf/demf_votenet.py:48-62                   (PointNet2SASSG backbone)
+ * Each declaration names the upstream binding it stands in for.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; device pointers unless stated otherwise;
+ *   - all tensors dense, row-major ("contiguous"), float32 / int32 / int64;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - the library never allocates, never synchronises, never exits the process;
+ *   - return value: 0 = launched; >0 = cudaError_t of the failed launch;
+ *     <0 = argument check failed (DEMF_E_*); demf_last_error_string() explains;
+ *   - the caller owns every buffer; outputs marked "pre-zeroed" must be zero on
+ *     entry (the kernels accumulate into them with atomics).
+ *
+ * The CPU oracle (oracle/demf_oracle.c, test infrastructure only) exports
+ * host-pointer twins `demf_ref_*` with the same argument lists minus
+ * workspace/stream.
+ */
+#ifndef DEMF_B200_H_
+#define DEMF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEMF_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+enum {
+  DEMF_OK = 0,
+  DEMF_E_NULL = -1,        /* a required pointer is NULL */
+  DEMF_E_SIZE = -2,        /* a size is negative / zero where it must not be / overflows int32 indexing */
+  DEMF_E_UNSUPPORTED = -3, /* configuration outside what the kernels implement */
+  DEMF_E_WORKSPACE = -4    /* workspace required but not supplied */
+};
+
+/* Library version (DEMF_B200_VERSION of the build). */
+int demf_version(void);
+
+/* Human-readable description of the last non-zero return on this thread. */
+const char* demf_last_error_string(void);
+
+/* Number of kernels this library has launched in this process (all streams);
+ * used by bench.py for the "gpu_launches" claim. */
+uint64_t demf_launch_count(void);
+
+/* ---------------------------------------------------------------- FPS ---- */
+/* replaces mmdet3d furthest_point_sample_ext.furthest_point_sampling_wrapper
+ * (call sites: class_agnostic_vote_head.py:429-430; every SA module of
+ * configs/demf/demf_votenet.py:48-62).
+ *   xyz (B,N,3) f32 -> idx (B,m) i32.  idx[b,0] = 0; iterative D-FPS with the
+ * upstream block-tree tie rule (see oracle/demf_oracle.c: demf_ref_fps).
+ * `workspace` is only read when demf_fps_workspace_bytes() > 0. */
+size_t demf_fps_workspace_bytes(int B, int N, int m);
+int demf_fps(const float* xyz, int B, int N, int m, void* workspace, int32_t* idx, void* stream);
+
+/* ----------------------------------------------------------- ball query -- */
+/* replaces mmdet3d ball_query_ext.ball_query_wrapper (QueryAndGroup inside each
+ * PointSAModule; demf_votenet.py:52-53,155-162).
+ *   xyz (B,N,3), new_xyz (B,M,3) -> idx (B,M,nsample) i32. Every row is written
+ * (rows whose ball is empty are written as zeros, which is what upstream's
+ * pre-zeroed output holds). */
+int demf_ball_query(const float* xyz, const float* new_xyz, int B, int N, int M,
+                    float min_radius, float max_radius, int nsample, int32_t* idx, void* stream);
+
+/* ---------------------------------------------------- grouping / gather -- */
+/* replaces mmdet3d group_points_ext.forward / backward.
+ *   features (B,C,N), idx (B,M,ns) -> out (B,C,M,ns); bwd: grad_out (B,C,M,ns)
+ *   -> grad_features (B,C,N), pre-zeroed. */
+int demf_group_fwd(const float* features, const int32_t* idx, int B, int C, int N, int M, int ns,
+                   float* out, void* stream);
+int demf_group_bwd(const float* grad_out, const int32_t* idx, int B, int C, int N, int M, int ns,
+                   float* grad_features, void* stream);
+
+/* replaces mmdet3d gather_points_ext.gather_points_wrapper / _grad_wrapper.
+ *   features (B,C,N), idx (B,M) -> out (B,C,M); bwd -> grad_features (B,C,N), pre-zeroed. */
+int demf_gather_fwd(const float* features, const int32_t* idx, int B, int C, int N, int M,
+                    float* out, void* stream);
+int demf_gather_bwd(const float* grad_out, const int32_t* idx, int B, int C, int N, int M,
+                    float* grad_features, void* stream);
+
+/* Fused QueryAndGroup (ball query + group xyz + centre subtraction + radius
+ * normalisation + feature group + channel concat) = mmdet3d
+ * ops/group_points/group_points.py:QueryAndGroup.forward as one launch.
+ *   xyz (B,N,3), features (B,C,N) or NULL (C=0), new_xyz (B,M,3)
+ *   -> idx (B,M,ns) i32 and out (B, (use_xyz?3:0)+C, M, ns) f32
+ * The xyz rows come first on the channel axis (upstream torch.cat order). */
+int demf_query_and_group_fwd(const float* xyz, const float* features, const float* new_xyz,
+                             int B, int N, int M, int C, float min_radius, float max_radius, int ns,
+                             int use_xyz, int normalize_xyz, int32_t* idx, float* out, void* stream);
+
+/* --------------------------------------------- three_nn / interpolate ---- */
+/* replaces mmdet3d interpolate_ext.three_nn_wrapper.
+ *   unknown (B,n,3), known (B,m,3) -> dist2 (B,n,3) f32 (SQUARED distances, the
+ *   Python wrapper takes the square root exactly as upstream's does), idx (B,n,3) i32. */
+int demf_three_nn(const float* unknown, const float* known, int B, int n, int m,
+                  float* dist2, int32_t* idx, void* stream);
+
+/* replaces interpolate_ext.three_interpolate_wrapper / _grad_wrapper.
+ *   features (B,C,m), idx (B,n,3), weight (B,n,3) -> out (B,C,n);
+ *   bwd: grad_out (B,C,n) -> grad_features (B,C,m), pre-zeroed. */
+int demf_three_interpolate_fwd(const float* features, const int32_t* idx, const float* weight,
+                               int B, int C, int m, int n, float* out, void* stream);
+int demf_three_interpolate_bwd(const float* grad_out, const int32_t* idx, const float* weight,
+                               int B, int C, int n, int m, float* grad_features, void* stream);
+
+/* ------------------------------------ multi-scale deformable attention --- */
+/* replaces mmcv _ext.ms_deform_attn_forward / ms_deform_attn_backward
+ * (MultiScaleDeformableAttnFunction; reached from transformer.py:73-78).
+ *   value (B,S,H,D) f32; spatial_shapes (L,2) i64 [h,w]; level_start_index (L) i64;
+ *   sampling_loc (B,Q,H,L,P,2) f32 [x,y in 0..1]; attn_weight (B,Q,H,L,P) f32
+ *   -> out (B,Q,H*D) f32.
+ * spatial_shapes / level_start_index are DEVICE pointers (as in upstream).
+ * bwd: grad_out (B,Q,H*D) -> grad_value (B,S,H,D) pre-zeroed, grad_sampling_loc,
+ * grad_attn_weight (both fully written). */
+int demf_msda_fwd(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                  const float* sampling_loc, const float* attn_weight,
+                  int B, int S, int H, int D, int Q, int L, int P, float* out, void* stream);
+int demf_msda_bwd(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                  const float* sampling_loc, const float* attn_weight, const float* grad_out,
+                  int B, int S, int H, int D, int Q, int L, int P,
+                  float* grad_value, float* grad_sampling_loc, float* grad_attn_weight, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEMF_B200_H_ */
