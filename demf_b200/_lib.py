@@ -1,0 +1,75 @@
+"""ctypes binding of libdemf_b200.so (include/demf_b200.h).
+
+There is no CPU fallback and no alternative backend: if the library is missing or a launch
+fails, the caller gets an exception.
+"""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libdemf_b200.so")
+
+_c_int = ctypes.c_int
+_c_float = ctypes.c_float
+_ptr = ctypes.c_void_p
+
+# name -> argtypes ; every function returns int unless listed in _RESTYPES
+_SIGNATURES = {
+    "demf_version": [],
+    "demf_last_error_string": [],
+    "demf_launch_count": [],
+    "demf_fps_workspace_bytes": [_c_int, _c_int, _c_int],
+    "demf_fps": [_ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr],
+    "demf_ball_query": [_ptr, _ptr, _c_int, _c_int, _c_int, _c_float, _c_float, _c_int, _ptr, _ptr],
+    "demf_group_fwd": [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
+    "demf_group_bwd": [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
+    "demf_gather_fwd": [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
+    "demf_gather_bwd": [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
+    "demf_query_and_group_fwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float,
+                                 _c_int, _c_int, _c_int, _ptr, _ptr, _ptr],
+    "demf_three_nn": [_ptr, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr],
+    "demf_three_interpolate_fwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
+    "demf_three_interpolate_bwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
+    "demf_msda_fwd": [_ptr, _ptr, _ptr, _ptr, _ptr] + [_c_int] * 7 + [_ptr, _ptr],
+    "demf_msda_bwd": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr] + [_c_int] * 7 + [_ptr, _ptr, _ptr, _ptr],
+}
+_RESTYPES = {
+    "demf_last_error_string": ctypes.c_char_p,
+    "demf_launch_count": ctypes.c_uint64,
+    "demf_fps_workspace_bytes": ctypes.c_size_t,
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+class DemfLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library once; raises DemfLibraryError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DemfLibraryError(
+            f"{LIB_PATH} is missing: build it with `python -m demf_b200.build` "
+            "(there is no CPU or PyTorch fallback for the DeMF hot-path ops)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale: fail loudly
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, _c_int)
+    _lib = lib
+    return lib
+
+
+def check(rc, name):
+    if rc != 0:
+        msg = load().demf_last_error_string().decode("utf-8", "replace")
+        raise DemfLibraryError(f"{name} failed (code {rc}): {msg}")
+
+
+def launch_count():
+    return int(load().demf_launch_count())

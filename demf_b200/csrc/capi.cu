@@ -1,0 +1,40 @@
+// Library-wide C ABI pieces: version, error string, launch counter.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace demf {
+
+static thread_local char g_error[512] = "no error";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int after_launch(const char* kernel_name) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s (%s)", kernel_name, cudaGetErrorName(e), cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  return 0;
+}
+
+}  // namespace demf
+
+extern "C" {
+
+int demf_version(void) { return DEMF_B200_VERSION; }
+
+const char* demf_last_error_string(void) { return demf::g_error; }
+
+uint64_t demf_launch_count(void) { return demf::g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

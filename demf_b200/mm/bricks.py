@@ -1,0 +1,332 @@
+"""nn building blocks with the mmcv.cnn / mmcv.runner names the DeMF path instantiates.
+
+BaseModule, ConvModule (conv -> norm -> act with upstream's attribute names `conv`, `bn`,
+`activate`, so state-dict keys match released checkpoints), norm / conv
+builders, and the transformer bricks of mmcv.cnn.bricks.transformer 1.3.18 that
+configs/demf/demf_votenet.py:68-91 builds: MultiheadAttention, FFN, BaseTransformerLayer and
+mmdet's DetrTransformerDecoderLayer. Dense projections are plain library GEMMs (cuBLAS via
+torch); the sm_100a kernels live behind point_ops.py and ms_deform_attn.py.
+"""
+import copy
+import warnings
+
+import torch
+import torch.nn as nn
+
+from .config import ConfigDict
+from .registry import (ATTENTION, FEEDFORWARD_NETWORK, TRANSFORMER_LAYER, build_attention,
+                       build_feedforward_network)
+
+
+class BaseModule(nn.Module):
+    """mmcv.runner.BaseModule: carries init_cfg; init_weights() recurses into children."""
+
+    def __init__(self, init_cfg=None):
+        super().__init__()
+        self._is_init = False
+        self.init_cfg = copy.deepcopy(init_cfg)
+
+    @property
+    def is_init(self):
+        return self._is_init
+
+    def init_weights(self):
+        if self._is_init:
+            return
+        for m in self.children():
+            if hasattr(m, "init_weights"):
+                m.init_weights()
+        self._is_init = True
+
+
+class ModuleList(BaseModule, nn.ModuleList):
+    def __init__(self, modules=None, init_cfg=None):
+        BaseModule.__init__(self, init_cfg)
+        nn.ModuleList.__init__(self, modules)
+
+
+_NORMS = {
+    "BN": ("bn", nn.BatchNorm2d), "BN1d": ("bn", nn.BatchNorm1d), "BN2d": ("bn", nn.BatchNorm2d),
+    "BN3d": ("bn", nn.BatchNorm3d), "LN": ("ln", nn.LayerNorm), "GN": ("gn", nn.GroupNorm),
+}
+_CONVS = {"Conv1d": nn.Conv1d, "Conv2d": nn.Conv2d, "Conv": nn.Conv2d, None: nn.Conv2d}
+_ACTS = {"ReLU": nn.ReLU, "LeakyReLU": nn.LeakyReLU, "GELU": nn.GELU, "Sigmoid": nn.Sigmoid,
+         "Tanh": nn.Tanh}
+
+
+def build_norm_layer(cfg, num_features, postfix=""):
+    """-> (name, layer) like mmcv.cnn.build_norm_layer."""
+    cfg = dict(cfg)
+    layer_type = cfg.pop("type")
+    if layer_type not in _NORMS:
+        raise KeyError(f"Unrecognized norm type {layer_type}")
+    abbr, cls = _NORMS[layer_type]
+    requires_grad = cfg.pop("requires_grad", True)
+    cfg.setdefault("eps", 1e-5)
+    if layer_type == "GN":
+        layer = cls(num_channels=num_features, **cfg)
+    else:
+        layer = cls(num_features, **cfg)
+    for p in layer.parameters():
+        p.requires_grad = requires_grad
+    return abbr + str(postfix), layer
+
+
+def build_conv_layer(cfg, *args, **kwargs):
+    cfg = dict(type="Conv2d") if cfg is None else dict(cfg)
+    layer_type = cfg.pop("type")
+    if layer_type not in _CONVS:
+        raise KeyError(f"Unrecognized conv type {layer_type}")
+    return _CONVS[layer_type](*args, **kwargs, **cfg)
+
+
+def build_activation_layer(cfg):
+    cfg = dict(cfg)
+    return _ACTS[cfg.pop("type")](**cfg)
+
+
+def build_dropout(cfg):
+    if cfg is None:
+        return nn.Identity()
+    cfg = dict(cfg)
+    kind = cfg.pop("type", "Dropout")
+    if kind != "Dropout":
+        raise KeyError(f"Unrecognized dropout type {kind}")
+    return nn.Dropout(p=cfg.get("drop_prob", cfg.get("p", 0.5)))
+
+
+class ConvModule(nn.Module):
+    """conv -> norm -> activation. bias='auto' means "no bias when a norm follows"."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
+                 groups=1, bias="auto", conv_cfg=None, norm_cfg=None, act_cfg=dict(type="ReLU"),
+                 inplace=True, order=("conv", "norm", "act")):
+        super().__init__()
+        assert tuple(order) == ("conv", "norm", "act"), "only the default order is on the DeMF path"
+        self.with_norm = norm_cfg is not None
+        self.with_activation = act_cfg is not None
+        if bias == "auto":
+            bias = not self.with_norm
+        self.with_bias = bias
+        self.conv = build_conv_layer(conv_cfg, in_channels, out_channels, kernel_size, stride=stride,
+                                     padding=padding, dilation=dilation, groups=groups, bias=bias)
+        self.in_channels, self.out_channels = in_channels, out_channels
+        if self.with_norm:
+            self.norm_name, norm = build_norm_layer(norm_cfg, out_channels)
+            self.add_module(self.norm_name, norm)
+        else:
+            self.norm_name = None
+        if self.with_activation:
+            act_cfg = dict(act_cfg)
+            if act_cfg["type"] in ("ReLU", "LeakyReLU"):
+                act_cfg.setdefault("inplace", inplace)
+            self.activate = build_activation_layer(act_cfg)
+        self.init_weights()
+
+    @property
+    def norm(self):
+        return getattr(self, self.norm_name) if self.norm_name else None
+
+    def init_weights(self):
+        nn.init.kaiming_normal_(self.conv.weight, a=0, mode="fan_out", nonlinearity="relu")
+        if self.conv.bias is not None:
+            nn.init.constant_(self.conv.bias, 0)
+        if self.with_norm and getattr(self.norm, "weight", None) is not None:
+            nn.init.constant_(self.norm.weight, 1)
+            nn.init.constant_(self.norm.bias, 0)
+
+    def forward(self, x):
+        x = self.conv(x)
+        if self.with_norm:
+            x = self.norm(x)
+        if self.with_activation:
+            x = self.activate(x)
+        return x
+
+
+# ------------------------------------------------------------------------ transformer --
+@ATTENTION.register_module()
+class MultiheadAttention(BaseModule):
+    """mmcv MultiheadAttention: nn.MultiheadAttention + positional encodings + residual."""
+
+    def __init__(self, embed_dims, num_heads, attn_drop=0., proj_drop=0.,
+                 dropout_layer=dict(type="Dropout", drop_prob=0.), init_cfg=None, batch_first=False,
+                 **kwargs):
+        super().__init__(init_cfg)
+        dropout_layer = dict(dropout_layer) if dropout_layer else None
+        if "dropout" in kwargs:  # deprecated alias still used by configs/demf/demf_votenet.py:78
+            attn_drop = kwargs["dropout"]
+            dropout_layer["drop_prob"] = kwargs.pop("dropout")
+        self.embed_dims = embed_dims
+        self.num_heads = num_heads
+        self.batch_first = batch_first
+        self.attn = nn.MultiheadAttention(embed_dims, num_heads, attn_drop, **kwargs)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.dropout_layer = build_dropout(dropout_layer)
+
+    def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_pos=None,
+                attn_mask=None, key_padding_mask=None, **kwargs):
+        if key is None:
+            key = query
+        if value is None:
+            value = key
+        if identity is None:
+            identity = query
+        if key_pos is None and query_pos is not None and query_pos.shape == key.shape:
+            key_pos = query_pos
+        if query_pos is not None:
+            query = query + query_pos
+        if key_pos is not None:
+            key = key + key_pos
+        if self.batch_first:
+            query, key, value = (t.transpose(0, 1) for t in (query, key, value))
+        out = self.attn(query=query, key=key, value=value, attn_mask=attn_mask,
+                        key_padding_mask=key_padding_mask)[0]
+        if self.batch_first:
+            out = out.transpose(0, 1)
+        return identity + self.dropout_layer(self.proj_drop(out))
+
+
+@FEEDFORWARD_NETWORK.register_module()
+class FFN(BaseModule):
+    def __init__(self, embed_dims=256, feedforward_channels=1024, num_fcs=2,
+                 act_cfg=dict(type="ReLU", inplace=True), ffn_drop=0., dropout_layer=None,
+                 add_identity=True, init_cfg=None, **kwargs):
+        super().__init__(init_cfg)
+        assert num_fcs >= 2, f"num_fcs should be no less than 2. got {num_fcs}."
+        self.embed_dims = embed_dims
+        self.feedforward_channels = feedforward_channels
+        self.num_fcs = num_fcs
+        layers = []
+        in_channels = embed_dims
+        for _ in range(num_fcs - 1):
+            layers.append(nn.Sequential(nn.Linear(in_channels, feedforward_channels),
+                                        build_activation_layer(act_cfg), nn.Dropout(ffn_drop)))
+            in_channels = feedforward_channels
+        layers.append(nn.Linear(feedforward_channels, embed_dims))
+        layers.append(nn.Dropout(ffn_drop))
+        self.layers = nn.Sequential(*layers)
+        self.dropout_layer = build_dropout(dropout_layer) if dropout_layer else nn.Identity()
+        self.add_identity = add_identity
+
+    def forward(self, x, identity=None):
+        out = self.layers(x)
+        if not self.add_identity:
+            return self.dropout_layer(out)
+        if identity is None:
+            identity = x
+        return identity + self.dropout_layer(out)
+
+
+@TRANSFORMER_LAYER.register_module()
+class BaseTransformerLayer(BaseModule):
+    """Generic (self_attn | cross_attn | norm | ffn)* layer, post-norm unless order starts with norm."""
+
+    def __init__(self, attn_cfgs=None,
+                 ffn_cfgs=dict(type="FFN", embed_dims=256, feedforward_channels=1024, num_fcs=2,
+                               ffn_drop=0., act_cfg=dict(type="ReLU", inplace=True)),
+                 operation_order=None, norm_cfg=dict(type="LN"), init_cfg=None, batch_first=False,
+                 **kwargs):
+        ffn_cfgs = copy.deepcopy(dict(ffn_cfgs)) if isinstance(ffn_cfgs, dict) else copy.deepcopy(ffn_cfgs)
+        deprecated = dict(feedforward_channels="feedforward_channels", ffn_dropout="ffn_drop",
+                          ffn_num_fcs="num_fcs")
+        for ori, new in deprecated.items():
+            if ori in kwargs:
+                ffn_cfgs[new] = kwargs[ori]
+        super().__init__(init_cfg)
+        self.batch_first = batch_first
+        assert set(operation_order) & {"self_attn", "norm", "ffn", "cross_attn"} == set(operation_order)
+        num_attn = operation_order.count("self_attn") + operation_order.count("cross_attn")
+        if isinstance(attn_cfgs, dict):
+            attn_cfgs = [copy.deepcopy(attn_cfgs) for _ in range(num_attn)]
+        else:
+            assert num_attn == len(attn_cfgs), (
+                f"The length of attn_cfg {len(attn_cfgs)} is not consistent with the number of "
+                f"attention in operation_order {operation_order}.")
+        self.num_attn = num_attn
+        self.operation_order = tuple(operation_order)
+        self.norm_cfg = norm_cfg
+        self.pre_norm = operation_order[0] == "norm"
+        self.attentions = ModuleList()
+        index = 0
+        for name in operation_order:
+            if name in ("self_attn", "cross_attn"):
+                cfg = dict(attn_cfgs[index])
+                if "batch_first" in cfg:
+                    assert self.batch_first == cfg["batch_first"]
+                else:
+                    cfg["batch_first"] = self.batch_first
+                attention = build_attention(cfg)
+                attention.operation_name = name
+                self.attentions.append(attention)
+                index += 1
+        self.embed_dims = self.attentions[0].embed_dims
+        self.ffns = ModuleList()
+        num_ffns = operation_order.count("ffn")
+        if isinstance(ffn_cfgs, dict):
+            ffn_cfgs = [copy.deepcopy(ffn_cfgs) for _ in range(num_ffns)]
+        assert len(ffn_cfgs) == num_ffns
+        for i in range(num_ffns):
+            cfg = dict(ffn_cfgs[i])
+            if "embed_dims" not in cfg:
+                cfg["embed_dims"] = self.embed_dims
+            else:
+                assert cfg["embed_dims"] == self.embed_dims
+            cfg.setdefault("type", "FFN")
+            self.ffns.append(build_feedforward_network(cfg))
+        self.norms = ModuleList()
+        for _ in range(operation_order.count("norm")):
+            self.norms.append(build_norm_layer(norm_cfg, self.embed_dims)[1])
+
+    def forward(self, query, key=None, value=None, query_pos=None, key_pos=None, attn_masks=None,
+                query_key_padding_mask=None, key_padding_mask=None, **kwargs):
+        norm_index = attn_index = ffn_index = 0
+        identity = query
+        if attn_masks is None:
+            attn_masks = [None for _ in range(self.num_attn)]
+        elif isinstance(attn_masks, torch.Tensor):
+            attn_masks = [copy.deepcopy(attn_masks) for _ in range(self.num_attn)]
+            warnings.warn(f"Use same attn_mask in all attentions in {self.__class__.__name__} ")
+        else:
+            assert len(attn_masks) == self.num_attn
+        for layer in self.operation_order:
+            if layer == "self_attn":
+                temp_key = temp_value = query
+                query = self.attentions[attn_index](
+                    query, temp_key, temp_value, identity if self.pre_norm else None,
+                    query_pos=query_pos, key_pos=query_pos, attn_mask=attn_masks[attn_index],
+                    key_padding_mask=query_key_padding_mask, **kwargs)
+                attn_index += 1
+                identity = query
+            elif layer == "norm":
+                query = self.norms[norm_index](query)
+                norm_index += 1
+            elif layer == "cross_attn":
+                query = self.attentions[attn_index](
+                    query, key, value, identity if self.pre_norm else None, query_pos=query_pos,
+                    key_pos=key_pos, attn_mask=attn_masks[attn_index],
+                    key_padding_mask=key_padding_mask, **kwargs)
+                attn_index += 1
+                identity = query
+            elif layer == "ffn":
+                query = self.ffns[ffn_index](query, identity if self.pre_norm else None)
+                ffn_index += 1
+        return query
+
+
+@TRANSFORMER_LAYER.register_module()
+class DetrTransformerDecoderLayer(BaseTransformerLayer):
+    """mmdet DetrTransformerDecoderLayer: self_attn, norm, cross_attn, norm, ffn, norm."""
+
+    def __init__(self, attn_cfgs, feedforward_channels, ffn_dropout=0.0, operation_order=None,
+                 act_cfg=dict(type="ReLU", inplace=True), norm_cfg=dict(type="LN"), ffn_num_fcs=2,
+                 **kwargs):
+        super().__init__(attn_cfgs=attn_cfgs, feedforward_channels=feedforward_channels,
+                         ffn_dropout=ffn_dropout, operation_order=operation_order, act_cfg=act_cfg,
+                         norm_cfg=norm_cfg, ffn_num_fcs=ffn_num_fcs, **kwargs)
+        assert len(operation_order) == 6
+        assert set(operation_order) == {"self_attn", "norm", "cross_attn", "ffn"}
+
+
+def to_config_dict(cfg):
+    return cfg if isinstance(cfg, ConfigDict) or cfg is None else ConfigDict(cfg)

@@ -1,0 +1,339 @@
+"""PointNet++ ops with the mmdet3d.ops names and signatures, backed by libdemf_b200.so.
+
+Stands in for `from mmdet3d.ops import build_sa_module, furthest_point_sample`
+(reference: demf/modeling/heads/class_agnostic_vote_head.py:13) and the ops those modules use
+internally (mmdet3d 0.18.1 ops/{furthest_point_sample, ball_query, group_points,
+gather_points, interpolate}). Semantics follow upstream: float32 / int32 contiguous CUDA
+tensors, `assert`-style contiguity checks (no silent .contiguous()), index outputs
+non-differentiable. CUDA only -- there is deliberately no CPU implementation.
+"""
+import torch
+from torch.autograd import Function
+
+from .. import _lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "demf_b200 ops run on CUDA tensors only (no CPU fallback); got a "
+                f"{t.device} tensor")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class FurthestPointSampling(Function):
+    """xyz (B,N,3) f32 -> idx (B,m) i32, idx[:,0]=0 (upstream furthest_point_sample)."""
+
+    @staticmethod
+    def forward(ctx, points_xyz, num_points):
+        assert points_xyz.is_contiguous()
+        _need_cuda(points_xyz)
+        assert points_xyz.dtype == torch.float32 and points_xyz.dim() == 3 and points_xyz.size(2) == 3
+        B, N = points_xyz.shape[:2]
+        lib = _lib.load()
+        with torch.cuda.device_of(points_xyz):
+            idx = torch.empty(B, num_points, dtype=torch.int32, device=points_xyz.device)
+            ws_bytes = lib.demf_fps_workspace_bytes(B, N, num_points)
+            ws = (torch.empty(ws_bytes // 4, dtype=torch.float32, device=points_xyz.device)
+                  if ws_bytes else None)
+            _lib.check(lib.demf_fps(_p(points_xyz), B, N, num_points, _p(ws), _p(idx), _stream()),
+                       "demf_fps")
+        ctx.mark_non_differentiable(idx)
+        return idx
+
+    @staticmethod
+    def backward(ctx, grad=None):
+        return None, None
+
+
+furthest_point_sample = FurthestPointSampling.apply
+
+
+class BallQuery(Function):
+    """First `sample_num` points (index order) with d2==0 or min_r^2 <= d2 < max_r^2."""
+
+    @staticmethod
+    def forward(ctx, min_radius, max_radius, sample_num, xyz, center_xyz):
+        assert center_xyz.is_contiguous()
+        assert xyz.is_contiguous()
+        assert min_radius < max_radius
+        _need_cuda(xyz, center_xyz)
+        B, N, _ = xyz.shape
+        M = center_xyz.size(1)
+        with torch.cuda.device_of(xyz):
+            idx = torch.empty(B, M, sample_num, dtype=torch.int32, device=xyz.device)
+            _lib.check(_lib.load().demf_ball_query(_p(xyz), _p(center_xyz), B, N, M, min_radius,
+                                                   max_radius, sample_num, _p(idx), _stream()),
+                       "demf_ball_query")
+        ctx.mark_non_differentiable(idx)
+        return idx
+
+    @staticmethod
+    def backward(ctx, grad=None):
+        return None, None, None, None, None
+
+
+ball_query = BallQuery.apply
+
+
+class GroupingOperation(Function):
+    """features (B,C,N), indices (B,M,ns) -> (B,C,M,ns)."""
+
+    @staticmethod
+    def forward(ctx, features, indices):
+        assert features.is_contiguous()
+        assert indices.is_contiguous()
+        _need_cuda(features, indices)
+        B, C, N = features.shape
+        _, M, ns = indices.shape
+        with torch.cuda.device_of(features):
+            out = torch.empty(B, C, M, ns, dtype=features.dtype, device=features.device)
+            _lib.check(_lib.load().demf_group_fwd(_p(features), _p(indices), B, C, N, M, ns, _p(out),
+                                                  _stream()), "demf_group_fwd")
+        ctx.for_backwards = (indices, N)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        indices, N = ctx.for_backwards
+        B, C, M, ns = grad_out.shape
+        grad_out = grad_out.contiguous()
+        with torch.cuda.device_of(grad_out):
+            grad = torch.zeros(B, C, N, dtype=grad_out.dtype, device=grad_out.device)
+            _lib.check(_lib.load().demf_group_bwd(_p(grad_out), _p(indices), B, C, N, M, ns, _p(grad),
+                                                  _stream()), "demf_group_bwd")
+        return grad, None
+
+
+grouping_operation = GroupingOperation.apply
+
+
+class GatherPoints(Function):
+    """features (B,C,N), indices (B,M) -> (B,C,M)."""
+
+    @staticmethod
+    def forward(ctx, features, indices):
+        assert features.is_contiguous()
+        assert indices.is_contiguous()
+        _need_cuda(features, indices)
+        B, C, N = features.shape
+        M = indices.size(1)
+        with torch.cuda.device_of(features):
+            out = torch.empty(B, C, M, dtype=features.dtype, device=features.device)
+            _lib.check(_lib.load().demf_gather_fwd(_p(features), _p(indices), B, C, N, M, _p(out),
+                                                   _stream()), "demf_gather_fwd")
+        ctx.for_backwards = (indices, C, N)
+        ctx.mark_non_differentiable(indices)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        indices, C, N = ctx.for_backwards
+        B, M = indices.shape
+        grad_out = grad_out.contiguous()
+        with torch.cuda.device_of(grad_out):
+            grad = torch.zeros(B, C, N, dtype=grad_out.dtype, device=grad_out.device)
+            _lib.check(_lib.load().demf_gather_bwd(_p(grad_out), _p(indices), B, C, N, M, _p(grad),
+                                                   _stream()), "demf_gather_bwd")
+        return grad, None
+
+
+gather_points = GatherPoints.apply
+
+
+class ThreeNN(Function):
+    """target (B,n,3), source (B,m,3) -> (dist (B,n,3) = sqrt(d2), idx (B,n,3) i32)."""
+
+    @staticmethod
+    def forward(ctx, target, source):
+        assert target.is_contiguous()
+        assert source.is_contiguous()
+        _need_cuda(target, source)
+        B, n, _ = target.shape
+        m = source.size(1)
+        with torch.cuda.device_of(target):
+            dist2 = torch.empty(B, n, 3, dtype=torch.float32, device=target.device)
+            idx = torch.empty(B, n, 3, dtype=torch.int32, device=target.device)
+            _lib.check(_lib.load().demf_three_nn(_p(target), _p(source), B, n, m, _p(dist2), _p(idx),
+                                                 _stream()), "demf_three_nn")
+        ctx.mark_non_differentiable(idx)
+        return torch.sqrt(dist2), idx
+
+    @staticmethod
+    def backward(ctx, a=None, b=None):
+        return None, None
+
+
+three_nn = ThreeNN.apply
+
+
+class ThreeInterpolate(Function):
+    """features (B,C,m), indices (B,n,3), weight (B,n,3) -> (B,C,n)."""
+
+    @staticmethod
+    def forward(ctx, features, indices, weight):
+        assert features.is_contiguous()
+        assert indices.is_contiguous()
+        assert weight.is_contiguous()
+        _need_cuda(features, indices, weight)
+        B, C, m = features.shape
+        n = indices.size(1)
+        ctx.three_interpolate_for_backward = (indices, weight, m)
+        with torch.cuda.device_of(features):
+            out = torch.empty(B, C, n, dtype=features.dtype, device=features.device)
+            _lib.check(_lib.load().demf_three_interpolate_fwd(_p(features), _p(indices), _p(weight), B,
+                                                              C, m, n, _p(out), _stream()),
+                       "demf_three_interpolate_fwd")
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        indices, weight, m = ctx.three_interpolate_for_backward
+        B, C, n = grad_out.shape
+        grad_out = grad_out.contiguous()
+        with torch.cuda.device_of(grad_out):
+            grad = torch.zeros(B, C, m, dtype=grad_out.dtype, device=grad_out.device)
+            _lib.check(_lib.load().demf_three_interpolate_bwd(_p(grad_out), _p(indices), _p(weight), B,
+                                                              C, n, m, _p(grad), _stream()),
+                       "demf_three_interpolate_bwd")
+        return grad, None, None
+
+
+three_interpolate = ThreeInterpolate.apply
+
+
+class _FusedQueryAndGroup(Function):
+    """ball query + group + centre subtraction + radius normalisation + concat, one launch.
+
+    Returns (idx, grouped) with grouped = cat([ (xyz[idx]-centre)/r , features[idx] ], dim=1).
+    Backward reuses the grouping scatter: d/dfeatures, d/dxyz (vote aggregation needs it: the
+    grouped coordinates depend on the learned vote offsets) and d/dcentre.
+    """
+
+    @staticmethod
+    def forward(ctx, xyz, center_xyz, features, min_radius, max_radius, sample_num, use_xyz,
+                normalize_xyz):
+        assert xyz.is_contiguous()
+        assert center_xyz.is_contiguous()
+        assert features is None or features.is_contiguous()
+        _need_cuda(xyz, center_xyz, features)
+        B, N, _ = xyz.shape
+        M = center_xyz.size(1)
+        C = 0 if features is None else features.size(1)
+        Cx = 3 if use_xyz else 0
+        with torch.cuda.device_of(xyz):
+            idx = torch.empty(B, M, sample_num, dtype=torch.int32, device=xyz.device)
+            out = torch.empty(B, Cx + C, M, sample_num, dtype=torch.float32, device=xyz.device)
+            _lib.check(_lib.load().demf_query_and_group_fwd(
+                _p(xyz), _p(features), _p(center_xyz), B, N, M, C, min_radius, max_radius,
+                sample_num, int(use_xyz), int(normalize_xyz), _p(idx), _p(out), _stream()),
+                "demf_query_and_group_fwd")
+        ctx.saved = (idx, N, C, Cx, (1.0 / max_radius) if normalize_xyz else 1.0)
+        ctx.mark_non_differentiable(idx)
+        return idx, out
+
+    @staticmethod
+    def backward(ctx, _grad_idx, grad_out):
+        idx, N, C, Cx, scale = ctx.saved
+        need_xyz, need_center, need_feat = ctx.needs_input_grad[:3]
+        g_xyz = g_center = g_feat = None
+        if Cx and (need_xyz or need_center):
+            gx = grad_out[:, :Cx] * scale  # (B,3,M,ns)
+            if need_center:
+                g_center = -gx.sum(-1).transpose(1, 2).contiguous()
+            if need_xyz:
+                g_xyz = GroupingOperation.backward(_Ctx(idx, N), gx.contiguous())[0]
+                g_xyz = g_xyz.transpose(1, 2).contiguous()
+        if C and need_feat:
+            g_feat = GroupingOperation.backward(_Ctx(idx, N), grad_out[:, Cx:].contiguous())[0]
+        return g_xyz, g_center, g_feat, None, None, None, None, None
+
+
+class _Ctx:
+    def __init__(self, indices, N):
+        self.for_backwards = (indices, N)
+
+
+class QueryAndGroup(torch.nn.Module):
+    """mmdet3d.ops.QueryAndGroup (ops/group_points/group_points.py), same ctor and forward.
+
+    The common configuration (use_xyz, features given, no extra return values) runs as ONE
+    fused kernel; the rarely used options fall back to the individual ops (still CUDA).
+    """
+
+    def __init__(self, max_radius, sample_num, min_radius=0, use_xyz=True,
+                 return_grouped_xyz=False, normalize_xyz=False, uniform_sample=False,
+                 return_unique_cnt=False, return_grouped_idx=False):
+        super().__init__()
+        self.max_radius = max_radius
+        self.min_radius = min_radius
+        self.sample_num = sample_num
+        self.use_xyz = use_xyz
+        self.return_grouped_xyz = return_grouped_xyz
+        self.normalize_xyz = normalize_xyz
+        self.uniform_sample = uniform_sample
+        self.return_unique_cnt = return_unique_cnt
+        self.return_grouped_idx = return_grouped_idx
+        if self.return_unique_cnt:
+            assert self.uniform_sample, \
+                'uniform_sample should be True when returning the count of unique samples'
+        if self.max_radius is None:
+            raise NotImplementedError("kNN grouping (max_radius=None) is not on the DeMF path")
+        if self.uniform_sample:
+            raise NotImplementedError("uniform_sample is not on the DeMF path")
+
+    def forward(self, points_xyz, center_xyz, features=None):
+        fused_ok = not (self.uniform_sample or self.return_grouped_xyz or self.return_unique_cnt
+                        or self.return_grouped_idx) and (self.use_xyz or features is not None)
+        if fused_ok:
+            _, new_features = _FusedQueryAndGroup.apply(
+                points_xyz, center_xyz, features,
+                float(self.min_radius), float(self.max_radius), self.sample_num,
+                bool(self.use_xyz), bool(self.normalize_xyz))
+            return new_features
+        return self._forward_unfused(points_xyz, center_xyz, features)
+
+    def _forward_unfused(self, points_xyz, center_xyz, features):
+        idx = ball_query(self.min_radius, self.max_radius, self.sample_num, points_xyz, center_xyz)
+        xyz_trans = points_xyz.transpose(1, 2).contiguous()
+        grouped_xyz = grouping_operation(xyz_trans, idx)
+        grouped_xyz_diff = grouped_xyz - center_xyz.transpose(1, 2).unsqueeze(-1)
+        if self.normalize_xyz:
+            grouped_xyz_diff = grouped_xyz_diff / self.max_radius
+        if features is not None:
+            grouped_features = grouping_operation(features, idx)
+            new_features = (torch.cat([grouped_xyz_diff, grouped_features], dim=1)
+                            if self.use_xyz else grouped_features)
+        else:
+            assert self.use_xyz, 'Cannot have not features and not use xyz as a feature!'
+            new_features = grouped_xyz_diff
+        ret = [new_features]
+        if self.return_grouped_xyz:
+            ret.append(grouped_xyz)
+        if self.return_grouped_idx:
+            ret.append(idx)
+        return ret[0] if len(ret) == 1 else tuple(ret)
+
+
+class GroupAll(torch.nn.Module):
+    """mmdet3d.ops.GroupAll: one group holding every point (SA module with num_point=None)."""
+
+    def __init__(self, use_xyz=True):
+        super().__init__()
+        self.use_xyz = use_xyz
+
+    def forward(self, xyz, new_xyz, features=None):
+        grouped_xyz = xyz.transpose(1, 2).unsqueeze(2)
+        if features is not None:
+            grouped_features = features.unsqueeze(2)
+            return torch.cat([grouped_xyz, grouped_features], dim=1) if self.use_xyz \
+                else grouped_features
+        return grouped_xyz

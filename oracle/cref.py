@@ -33,8 +33,7 @@ def build(force=False):
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        build()  # no-op when libdemf_oracle.so is newer than demf_oracle.c
         _lib = ctypes.CDLL(_SO)
         _lib.demf_ref_num_threads.restype = ctypes.c_int
     return _lib

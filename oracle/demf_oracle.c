@@ -214,6 +214,9 @@ DEMF_API int demf_ref_query_and_group_fwd(const float* xyz, const float* feature
   const int Cx = use_xyz ? 3 : 0;
   const int Co = Cx + C;
   const long total = (long)B * M;
+  /* `grouped_xyz /= max_radius` runs on the GPU upstream, where ATen evaluates
+   * tensor / python_float as tensor * (1.0f / float) (BinaryDivTrueKernel.cu). */
+  const float inv_radius = 1.0f / max_radius;
 #pragma omp parallel for schedule(static)
   for (long bm = 0; bm < total; ++bm) {
     const int b = (int)(bm / M), m = (int)(bm % M);
@@ -225,7 +228,7 @@ DEMF_API int demf_ref_query_and_group_fwd(const float* xyz, const float* feature
       if (use_xyz) {
         for (int a = 0; a < 3; ++a) {
           float v = p[k * 3 + a] - c[a];
-          if (normalize_xyz) v = v / max_radius;
+          if (normalize_xyz) v = v * inv_radius;
           out[(((size_t)b * Co + a) * M + m) * ns + s] = v;
         }
       }

@@ -136,7 +136,7 @@ def test_query_and_group_matches_composition():
     idx, out = cref.query_and_group(pts, centres, feat, 0.0, 0.7, 8, True, True)
     assert torch.equal(idx, cref.ball_query(0.0, 0.7, 8, pts, centres))
     gx = cref.grouping_operation(pts.transpose(1, 2).contiguous(), idx)
-    gx = (gx - centres.transpose(1, 2)[..., None]) / 0.7
+    gx = (gx - centres.transpose(1, 2)[..., None]) * (torch.tensor(1.0) / torch.tensor(0.7))
     assert torch.equal(out[:, :3], gx)
     assert torch.equal(out[:, 3:], cref.grouping_operation(feat, idx))
 
