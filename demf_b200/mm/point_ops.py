@@ -44,8 +44,9 @@ class FurthestPointSampling(Function):
             ws_bytes = lib.demf_fps_workspace_bytes(B, N, num_points)
             ws = (torch.empty(ws_bytes // 4, dtype=torch.float32, device=points_xyz.device)
                   if ws_bytes else None)
-            _lib.check(lib.demf_fps(_p(points_xyz), B, N, num_points, _p(ws), _p(idx), _stream()),
-                       "demf_fps")
+            if idx.numel():
+                _lib.check(lib.demf_fps(_p(points_xyz), B, N, num_points, _p(ws), _p(idx),
+                                        _stream()), "demf_fps")
         ctx.mark_non_differentiable(idx)
         return idx
 
@@ -70,9 +71,10 @@ class BallQuery(Function):
         M = center_xyz.size(1)
         with torch.cuda.device_of(xyz):
             idx = torch.empty(B, M, sample_num, dtype=torch.int32, device=xyz.device)
-            _lib.check(_lib.load().demf_ball_query(_p(xyz), _p(center_xyz), B, N, M, min_radius,
-                                                   max_radius, sample_num, _p(idx), _stream()),
-                       "demf_ball_query")
+            if idx.numel():
+                _lib.check(_lib.load().demf_ball_query(_p(xyz), _p(center_xyz), B, N, M, min_radius,
+                                                       max_radius, sample_num, _p(idx), _stream()),
+                           "demf_ball_query")
         ctx.mark_non_differentiable(idx)
         return idx
 
@@ -96,8 +98,9 @@ class GroupingOperation(Function):
         _, M, ns = indices.shape
         with torch.cuda.device_of(features):
             out = torch.empty(B, C, M, ns, dtype=features.dtype, device=features.device)
-            _lib.check(_lib.load().demf_group_fwd(_p(features), _p(indices), B, C, N, M, ns, _p(out),
-                                                  _stream()), "demf_group_fwd")
+            if out.numel():
+                _lib.check(_lib.load().demf_group_fwd(_p(features), _p(indices), B, C, N, M, ns,
+                                                      _p(out), _stream()), "demf_group_fwd")
         ctx.for_backwards = (indices, N)
         return out
 
@@ -108,8 +111,9 @@ class GroupingOperation(Function):
         grad_out = grad_out.contiguous()
         with torch.cuda.device_of(grad_out):
             grad = torch.zeros(B, C, N, dtype=grad_out.dtype, device=grad_out.device)
-            _lib.check(_lib.load().demf_group_bwd(_p(grad_out), _p(indices), B, C, N, M, ns, _p(grad),
-                                                  _stream()), "demf_group_bwd")
+            if grad_out.numel():
+                _lib.check(_lib.load().demf_group_bwd(_p(grad_out), _p(indices), B, C, N, M, ns,
+                                                      _p(grad), _stream()), "demf_group_bwd")
         return grad, None
 
 
@@ -128,8 +132,9 @@ class GatherPoints(Function):
         M = indices.size(1)
         with torch.cuda.device_of(features):
             out = torch.empty(B, C, M, dtype=features.dtype, device=features.device)
-            _lib.check(_lib.load().demf_gather_fwd(_p(features), _p(indices), B, C, N, M, _p(out),
-                                                   _stream()), "demf_gather_fwd")
+            if out.numel():
+                _lib.check(_lib.load().demf_gather_fwd(_p(features), _p(indices), B, C, N, M, _p(out),
+                                                       _stream()), "demf_gather_fwd")
         ctx.for_backwards = (indices, C, N)
         ctx.mark_non_differentiable(indices)
         return out
@@ -141,8 +146,9 @@ class GatherPoints(Function):
         grad_out = grad_out.contiguous()
         with torch.cuda.device_of(grad_out):
             grad = torch.zeros(B, C, N, dtype=grad_out.dtype, device=grad_out.device)
-            _lib.check(_lib.load().demf_gather_bwd(_p(grad_out), _p(indices), B, C, N, M, _p(grad),
-                                                   _stream()), "demf_gather_bwd")
+            if grad_out.numel():
+                _lib.check(_lib.load().demf_gather_bwd(_p(grad_out), _p(indices), B, C, N, M,
+                                                       _p(grad), _stream()), "demf_gather_bwd")
         return grad, None
 
 
@@ -162,8 +168,9 @@ class ThreeNN(Function):
         with torch.cuda.device_of(target):
             dist2 = torch.empty(B, n, 3, dtype=torch.float32, device=target.device)
             idx = torch.empty(B, n, 3, dtype=torch.int32, device=target.device)
-            _lib.check(_lib.load().demf_three_nn(_p(target), _p(source), B, n, m, _p(dist2), _p(idx),
-                                                 _stream()), "demf_three_nn")
+            if idx.numel():
+                _lib.check(_lib.load().demf_three_nn(_p(target), _p(source), B, n, m, _p(dist2),
+                                                     _p(idx), _stream()), "demf_three_nn")
         ctx.mark_non_differentiable(idx)
         return torch.sqrt(dist2), idx
 
@@ -189,9 +196,10 @@ class ThreeInterpolate(Function):
         ctx.three_interpolate_for_backward = (indices, weight, m)
         with torch.cuda.device_of(features):
             out = torch.empty(B, C, n, dtype=features.dtype, device=features.device)
-            _lib.check(_lib.load().demf_three_interpolate_fwd(_p(features), _p(indices), _p(weight), B,
-                                                              C, m, n, _p(out), _stream()),
-                       "demf_three_interpolate_fwd")
+            if out.numel():
+                _lib.check(_lib.load().demf_three_interpolate_fwd(
+                    _p(features), _p(indices), _p(weight), B, C, m, n, _p(out), _stream()),
+                    "demf_three_interpolate_fwd")
         return out
 
     @staticmethod
@@ -201,9 +209,10 @@ class ThreeInterpolate(Function):
         grad_out = grad_out.contiguous()
         with torch.cuda.device_of(grad_out):
             grad = torch.zeros(B, C, m, dtype=grad_out.dtype, device=grad_out.device)
-            _lib.check(_lib.load().demf_three_interpolate_bwd(_p(grad_out), _p(indices), _p(weight), B,
-                                                              C, n, m, _p(grad), _stream()),
-                       "demf_three_interpolate_bwd")
+            if grad_out.numel():
+                _lib.check(_lib.load().demf_three_interpolate_bwd(
+                    _p(grad_out), _p(indices), _p(weight), B, C, n, m, _p(grad), _stream()),
+                    "demf_three_interpolate_bwd")
         return grad, None, None
 
 
@@ -232,10 +241,11 @@ class _FusedQueryAndGroup(Function):
         with torch.cuda.device_of(xyz):
             idx = torch.empty(B, M, sample_num, dtype=torch.int32, device=xyz.device)
             out = torch.empty(B, Cx + C, M, sample_num, dtype=torch.float32, device=xyz.device)
-            _lib.check(_lib.load().demf_query_and_group_fwd(
-                _p(xyz), _p(features), _p(center_xyz), B, N, M, C, min_radius, max_radius,
-                sample_num, int(use_xyz), int(normalize_xyz), _p(idx), _p(out), _stream()),
-                "demf_query_and_group_fwd")
+            if idx.numel():
+                _lib.check(_lib.load().demf_query_and_group_fwd(
+                    _p(xyz), _p(features), _p(center_xyz), B, N, M, C, min_radius, max_radius,
+                    sample_num, int(use_xyz), int(normalize_xyz), _p(idx), _p(out), _stream()),
+                    "demf_query_and_group_fwd")
         ctx.saved = (idx, N, C, Cx, (1.0 / max_radius) if normalize_xyz else 1.0)
         ctx.mark_non_differentiable(idx)
         return idx, out

@@ -179,6 +179,12 @@ def test_oracle_reproduces_golden_fixtures(golden):
         assert torch.equal(got, z["idx"])
     z = golden("group_c5")
     assert torch.equal(cref.grouping_operation(z["features"], z["idx"]), z["out"])
+    z = golden("gather_c5")
+    assert torch.equal(cref.gather_points(z["features"], z["idx"]), z["out"])
+    z = golden("query_and_group")
+    qidx, qout = cref.query_and_group(z["xyz"], z["new_xyz"], z["features"], 0.0, z["max_radius"], 8,
+                                      True, True)
+    assert torch.equal(qidx, z["idx"]) and torch.equal(qout, z["out"])
     z = golden("three_nn_interp")
     dist, idx = cref.three_nn(z["unknown"], z["known"])
     assert torch.equal(idx, z["idx"]) and torch.equal(dist, z["dist"])

@@ -1,0 +1,123 @@
+"""Per-kernel timings of libdemf_b200.so at the DeMF geometries (development tool, GPU only).
+
+    python tools/kbench.py [--B 8] [--reps 30] [--only msda,fps,...]
+
+CUDA events on the launching stream; an L2 flush (write of a 256 MB buffer) precedes every
+timed launch unless --hot. Prints one JSON line per kernel/config: median and min ms plus the
+algorithmic GB/s where one is defined.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from demf_b200 import _lib, synth  # noqa: E402
+from demf_b200.mm import point_ops as ops  # noqa: E402
+from demf_b200.mm.ms_deform_attn import MultiScaleDeformableAttnFunction as MSDA  # noqa: E402
+
+
+def timeit(fn, reps, flush):
+    dev = torch.device("cuda")
+    junk = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush else None
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        if junk is not None:
+            junk.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts), min(ts)
+
+
+def report(name, cfg, ms_med, ms_min, nbytes=None):
+    rec = dict(kernel=name, **cfg, ms_median=round(ms_med, 5), ms_min=round(ms_min, 5))
+    if nbytes:
+        rec["alg_MB"] = round(nbytes / 1e6, 3)
+        rec["GBps_median"] = round(nbytes / ms_med / 1e6, 1)
+        rec["GBps_best"] = round(nbytes / ms_min / 1e6, 1)
+    print(json.dumps(rec), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--B", type=int, default=8)
+    ap.add_argument("--reps", type=int, default=30)
+    ap.add_argument("--hot", action="store_true", help="no L2 flush between launches")
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    only = set(filter(None, args.only.split(",")))
+    want = lambda k: not only or k in only  # noqa: E731
+    dev = torch.device("cuda:0")
+    _lib.load()
+    B, flush = args.B, not args.hot
+    print(json.dumps(dict(device=torch.cuda.get_device_name(0), B=B, flush_l2=flush)), flush=True)
+
+    if want("msda"):
+        for name in ("S512", "REAL", "XL"):
+            for P in (4, 2):
+                Bm = B if name != "XL" else min(B, 4)
+                v, sh, lsi, loc, at = (t.to(dev) for t in synth.make_msda_inputs(B=Bm, name=name, P=P))
+                Q, H, D, L = 256, 8, 32, 4
+                nbytes = Bm * Q * H * L * P * (4 * D * 4 + 12) + Bm * Q * H * D * 4
+                med, mn = timeit(lambda: MSDA.apply(v, sh, lsi, loc, at, 64), args.reps, flush)
+                report("msda_fwd", dict(pyramid=name, P=P, B=Bm), med, mn, nbytes)
+                go = torch.randn(Bm, Q, H * D, device=dev)
+                gv = torch.zeros_like(v)
+                gl, ga = torch.empty_like(loc), torch.empty_like(at)
+                lib = _lib.load()
+                st = torch.cuda.current_stream().cuda_stream
+
+                def bwd():
+                    lib.demf_msda_bwd(v.data_ptr(), sh.data_ptr(), lsi.data_ptr(), loc.data_ptr(),
+                                      at.data_ptr(), go.data_ptr(), Bm, v.shape[1], H, D, Q, L, P,
+                                      gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), st)
+                med, mn = timeit(bwd, args.reps, flush)
+                report("msda_bwd", dict(pyramid=name, P=P, B=Bm), med, mn, 2 * nbytes)
+                del v, gv
+
+    pts = synth.make_points(B, 20000, seed=0, clustered=True)[..., :3].contiguous().to(dev)
+    geoms = [(20000, 2048, 0.2, 64, 1), (2048, 1024, 0.4, 32, 128), (1024, 512, 0.8, 16, 256),
+             (512, 256, 1.2, 16, 256), (1024, 256, 0.3, 16, 256)]
+    if want("fps"):
+        for N, m in ((20000, 2048), (2048, 1024), (1024, 512), (512, 256), (1024, 256)):
+            x = pts[:, :N].contiguous()
+            med, mn = timeit(lambda: ops.furthest_point_sample(x, m), max(5, args.reps // 3), False)
+            report("fps", dict(B=B, N=N, m=m, us_per_iter=round(med * 1e3 / (m - 1), 3)), med, mn)
+    if want("ball"):
+        for N, M, r, ns, C in geoms:
+            x = pts[:, :N].contiguous()
+            c = x[:, :M].contiguous()
+            med, mn = timeit(lambda: ops.ball_query(0.0, r, ns, x, c), args.reps, flush)
+            report("ball_query", dict(B=B, N=N, M=M, ns=ns), med, mn, B * (N * 12 + M * 12 + M * ns * 4))
+            f = torch.randn(B, C, N, device=dev)
+            qg = ops.QueryAndGroup(r, ns, use_xyz=True, normalize_xyz=True)
+            med, mn = timeit(lambda: qg(x, c, f), args.reps, flush)
+            report("query_and_group", dict(B=B, N=N, M=M, ns=ns, C=C), med, mn,
+                   B * (N * 12 + M * 12 + M * ns * 4 + C * N * 4 + (C + 3) * M * ns * 4))
+    if want("interp"):
+        for n, m in ((512, 256), (1024, 512)):
+            a, b = pts[:, :n].contiguous(), pts[:, 5000:5000 + m].contiguous()
+            med, mn = timeit(lambda: ops.three_nn(a, b), args.reps, flush)
+            report("three_nn", dict(B=B, n=n, m=m), med, mn)
+            dist, idx = ops.three_nn(a, b)
+            w = (1.0 / (dist + 1e-8))
+            w = (w / w.sum(2, keepdim=True)).contiguous()
+            f = torch.randn(B, 256, m, device=dev)
+            med, mn = timeit(lambda: ops.three_interpolate(f, idx, w), args.reps, flush)
+            report("three_interpolate", dict(B=B, n=n, m=m, C=256), med, mn,
+                   B * 256 * (n + m) * 4 + B * n * 24)
+    print(json.dumps(dict(launches=_lib.launch_count())))
+
+
+if __name__ == "__main__":
+    main()
