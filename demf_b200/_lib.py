@@ -30,6 +30,13 @@ _SIGNATURES = {
     "demf_three_nn": [_ptr, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr],
     "demf_three_interpolate_fwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
     "demf_three_interpolate_bwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
+    "demf_group_rows_width": [_c_int],
+    "demf_query_and_group_rows_fwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_float,
+                                      _c_float, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr],
+    "demf_group_rows_bwd": [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _ptr, _ptr,
+                            _ptr, _ptr],
+    "demf_three_interpolate_rows_fwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
+    "demf_three_interpolate_rows_bwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
     "demf_msda_fwd": [_ptr, _ptr, _ptr, _ptr, _ptr] + [_c_int] * 7 + [_ptr, _ptr],
     "demf_msda_bwd": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr] + [_c_int] * 7 + [_ptr, _ptr, _ptr, _ptr],
 }

@@ -330,3 +330,51 @@ class DetrTransformerDecoderLayer(BaseTransformerLayer):
 
 def to_config_dict(cfg):
     return cfg if isinstance(cfg, ConfigDict) or cfg is None else ConfigDict(cfg)
+
+
+# ------------------------------------------------------- kernel-size-1 convs on rows --
+def batch_norm_rows(bn, x):
+    """Apply a BatchNorm{1,2}d module to point-major rows x (R, C): identical statistics to
+    running the module on the (B,C,...) tensor those rows came from (BN reduces over every
+    axis but C), with the module's own buffers and momentum handling."""
+    if bn.momentum is None:
+        factor = 0.0
+    else:
+        factor = bn.momentum
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if bn.momentum is None:
+            factor = 1.0 / float(bn.num_batches_tracked)
+    use_batch_stats = bn.training or (bn.running_mean is None and bn.running_var is None)
+    return torch.nn.functional.batch_norm(
+        x, bn.running_mean if not bn.training or bn.track_running_stats else None,
+        bn.running_var if not bn.training or bn.track_running_stats else None,
+        bn.weight, bn.bias, use_batch_stats, factor, bn.eps)
+
+
+def permute_weight_columns(w, cols):
+    """w (Cout, Cin) -> (Cout, len(cols)); cols[j] = source column or -1 for a zero column."""
+    idx = torch.as_tensor([c if c >= 0 else w.size(1) for c in cols], device=w.device)
+    return torch.nn.functional.pad(w, (0, 1)).index_select(1, idx)
+
+
+def conv_module_rows(cm, x, cols=None):
+    """A kernel-size-1 ConvModule (Conv1d/Conv2d -> BN -> act) applied to rows x (R, Cin'): the
+    1x1 convolution IS a GEMM over rows (cuBLAS), so no im2col / NCHW round trip is needed.
+    `cols` permutes the weight's input columns to the row layout (point_ops.group_rows_columns)."""
+    w = cm.conv.weight.flatten(1)
+    if cols is not None:
+        w = permute_weight_columns(w, cols)
+    y = torch.nn.functional.linear(x, w, cm.conv.bias)
+    if cm.with_norm:
+        y = batch_norm_rows(cm.norm, y)
+    if cm.with_activation:
+        y = cm.activate(y)
+    return y
+
+
+def as_rows(features):
+    """(B,C,N) -> point-major (B,N,C) without a copy when the tensor already is a transposed
+    view of rows (which is what the modules of this package hand to each other)."""
+    rows = features.transpose(1, 2)
+    return rows if rows.is_contiguous() else rows.contiguous()

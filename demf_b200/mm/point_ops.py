@@ -347,3 +347,115 @@ class GroupAll(torch.nn.Module):
             return torch.cat([grouped_xyz, grouped_features], dim=1) if self.use_xyz \
                 else grouped_features
         return grouped_xyz
+
+
+# ----------------------------------------------------------------- point-major rows --
+def group_rows_width(C):
+    """Row width K of the grouped tensor for C feature channels: roundup(C,4)+4."""
+    return ((C + 3) // 4) * 4 + 4
+
+
+def group_rows_columns(C):
+    """Column index, for each of the K row slots, into upstream's [xyz(3), feat(C)] channel
+    order; -1 marks a zero-pad slot. Used to permute 1x1-conv weights to the row layout."""
+    Cp = ((C + 3) // 4) * 4
+    cols = [3 + c for c in range(C)] + [-1] * (Cp - C) + [0, 1, 2, -1]
+    return cols
+
+
+class QueryAndGroupRows(Function):
+    """Ball query + grouping as GEMM-ready rows (csrc/rows.cu), one launch.
+
+    xyz (B,N,3), center_xyz (B,M,3), feat_rows (B,N,C) or None ->
+      idx (B,M,ns) i32, rows (B,M,ns,K) with K = group_rows_width(C):
+      rows[b,m,s] = [feat_rows[b,idx] | 0.. | (xyz[idx]-centre)(/max_radius) | 0]
+    Same neighbour rows as upstream QueryAndGroup (use_xyz=True), xyz columns last.
+    """
+
+    @staticmethod
+    def forward(ctx, xyz, center_xyz, feat_rows, min_radius, max_radius, sample_num,
+                normalize_xyz):
+        assert xyz.is_contiguous()
+        assert center_xyz.is_contiguous()
+        assert feat_rows is None or feat_rows.is_contiguous()
+        _need_cuda(xyz, center_xyz, feat_rows)
+        B, N, _ = xyz.shape
+        M = center_xyz.size(1)
+        C = 0 if feat_rows is None else feat_rows.size(2)
+        K = group_rows_width(C)
+        with torch.cuda.device_of(xyz):
+            idx = torch.empty(B, M, sample_num, dtype=torch.int32, device=xyz.device)
+            out = torch.empty(B, M, sample_num, K, dtype=torch.float32, device=xyz.device)
+            if idx.numel():
+                _lib.check(_lib.load().demf_query_and_group_rows_fwd(
+                    _p(xyz), _p(feat_rows), _p(center_xyz), B, N, M, C, min_radius, max_radius,
+                    sample_num, int(normalize_xyz), 1, _p(idx), _p(out), _stream()),
+                    "demf_query_and_group_rows_fwd")
+        ctx.saved = (idx, N, C, (1.0 / max_radius) if normalize_xyz else 1.0)
+        ctx.mark_non_differentiable(idx)
+        return idx, out
+
+    @staticmethod
+    def backward(ctx, _grad_idx, grad_out):
+        idx, N, C, scale = ctx.saved
+        need_xyz, need_center, need_feat = ctx.needs_input_grad[:3]
+        B, M, ns, _ = grad_out.shape
+        grad_out = grad_out.contiguous()
+        dev = grad_out.device
+        with torch.cuda.device_of(grad_out):
+            g_feat = torch.zeros(B, N, C, dtype=torch.float32, device=dev) if (C and need_feat) else None
+            g_xyz = torch.zeros(B, N, 3, dtype=torch.float32, device=dev) if need_xyz else None
+            g_center = torch.empty(B, M, 3, dtype=torch.float32, device=dev) if need_center else None
+            if grad_out.numel() and (g_feat is not None or g_xyz is not None or g_center is not None):
+                _lib.check(_lib.load().demf_group_rows_bwd(
+                    _p(grad_out), _p(idx), B, N, M, C, ns, scale,
+                    _p(g_feat), _p(g_xyz), _p(g_center), _stream()), "demf_group_rows_bwd")
+        return g_xyz, g_center, g_feat, None, None, None, None
+
+
+def query_and_group_rows(xyz, center_xyz, feat_rows, min_radius, max_radius, sample_num,
+                         normalize_xyz):
+    return QueryAndGroupRows.apply(xyz, center_xyz, feat_rows, float(min_radius), float(max_radius),
+                                   int(sample_num), bool(normalize_xyz))
+
+
+class ThreeInterpolateRows(Function):
+    """feat_rows (B,m,C), indices (B,n,3), weight (B,n,3) -> (B,n,C); upstream's fma order."""
+
+    @staticmethod
+    def forward(ctx, feat_rows, indices, weight):
+        assert feat_rows.is_contiguous()
+        assert indices.is_contiguous()
+        assert weight.is_contiguous()
+        _need_cuda(feat_rows, indices, weight)
+        B, m, C = feat_rows.shape
+        n = indices.size(1)
+        ctx.saved = (indices, weight, m)
+        with torch.cuda.device_of(feat_rows):
+            out = torch.empty(B, n, C, dtype=feat_rows.dtype, device=feat_rows.device)
+            if out.numel():
+                _lib.check(_lib.load().demf_three_interpolate_rows_fwd(
+                    _p(feat_rows), _p(indices), _p(weight), B, C, m, n, _p(out), _stream()),
+                    "demf_three_interpolate_rows_fwd")
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        indices, weight, m = ctx.saved
+        B, n, C = grad_out.shape
+        grad_out = grad_out.contiguous()
+        with torch.cuda.device_of(grad_out):
+            grad = torch.zeros(B, m, C, dtype=grad_out.dtype, device=grad_out.device)
+            if grad_out.numel():
+                _lib.check(_lib.load().demf_three_interpolate_rows_bwd(
+                    _p(grad_out), _p(indices), _p(weight), B, C, n, m, _p(grad), _stream()),
+                    "demf_three_interpolate_rows_bwd")
+        return grad, None, None
+
+
+three_interpolate_rows = ThreeInterpolateRows.apply
+
+
+def gather_rows(rows, indices):
+    """rows (B,N,C), indices (B,M) i32 -> (B,M,C). Tiny (centre coordinates); torch.gather."""
+    return torch.gather(rows, 1, indices.long().unsqueeze(-1).expand(-1, -1, rows.size(-1)))

@@ -1,0 +1,430 @@
+"""PointNet++ modules with the mmdet3d names the DeMF configs instantiate.
+
+Stands in for mmdet3d 0.18.1 `ops/pointnet_modules/{point_sa_module,point_fp_module}.py`,
+`models/backbones/pointnet2_sa_ssg.py`, `models/model_utils/vote_module.py` and
+`models/dense_heads/base_conv_bbox_head.py` (reached from configs/demf/demf_votenet.py:48-62,
+142-162 and demf/modeling/heads/class_agnostic_vote_head.py:382-403). Constructor arguments,
+forward signatures, return shapes and parameter names (state-dict keys) are upstream's.
+
+What is different is the data layout INSIDE a module: activations are point-major rows
+(B,N,C) -- a neighbour is one contiguous row for the grouping kernel (csrc/rows.cu), and every
+kernel-size-1 convolution is a plain GEMM over rows -- and a module hands its features to the
+next one as a (B,C,N) *view* of those rows, so the upstream interface holds without a single
+layout copy between modules.
+"""
+import torch
+import torch.nn as nn
+
+from . import point_ops as P
+from .bricks import (BaseModule, ConvModule, as_rows, build_conv_layer, conv_module_rows)
+from .registry import BACKBONES, SA_MODULES
+
+
+# ------------------------------------------------------------------------- SA ---------
+class BasePointSAModule(nn.Module):
+    """mmdet3d BasePointSAModule: sample centres, group neighbours, shared MLP, pool."""
+
+    def __init__(self, num_point, radii, sample_nums, mlp_channels, fps_mod=['D-FPS'],
+                 fps_sample_range_list=[-1], dilated_group=False, use_xyz=True, pool_mod='max',
+                 normalize_xyz=False, grouper_return_grouped_xyz=False,
+                 grouper_return_grouped_idx=False):
+        super().__init__()
+        assert len(radii) == len(sample_nums) == len(mlp_channels)
+        assert pool_mod in ['max', 'avg']
+        assert isinstance(fps_mod, (list, tuple))
+        assert isinstance(fps_sample_range_list, (list, tuple))
+        assert len(fps_mod) == len(fps_sample_range_list)
+        if isinstance(mlp_channels, tuple):
+            mlp_channels = list(map(list, mlp_channels))
+        self.mlp_channels = mlp_channels
+        if isinstance(num_point, int):
+            self.num_point = [num_point]
+        elif isinstance(num_point, (list, tuple)):
+            self.num_point = list(num_point)
+        elif num_point is None:
+            self.num_point = None
+        else:
+            raise NotImplementedError('Error type of num_point!')
+        if list(fps_mod) != ['D-FPS'] or list(fps_sample_range_list) != [-1]:
+            raise NotImplementedError("only D-FPS over the whole cloud is on the DeMF path")
+        self.pool_mod = pool_mod
+        self.use_xyz = use_xyz
+        self.normalize_xyz = normalize_xyz
+        self.dilated_group = dilated_group
+        self.groupers = nn.ModuleList()
+        self.mlps = nn.ModuleList()
+        self.fps_mod_list = fps_mod
+        self.fps_sample_range_list = fps_sample_range_list
+        for i in range(len(radii)):
+            radius = radii[i]
+            sample_num = sample_nums[i]
+            if num_point is not None:
+                if dilated_group and i != 0:
+                    min_radius = radii[i - 1]
+                else:
+                    min_radius = 0
+                grouper = P.QueryAndGroup(
+                    radius, sample_num, min_radius=min_radius, use_xyz=use_xyz,
+                    normalize_xyz=normalize_xyz,
+                    return_grouped_xyz=grouper_return_grouped_xyz,
+                    return_grouped_idx=grouper_return_grouped_idx)
+            else:
+                grouper = P.GroupAll(use_xyz)
+            self.groupers.append(grouper)
+
+    def _sample_points(self, points_xyz, features, indices, target_xyz):
+        if indices is not None:
+            assert indices.shape[1] == self.num_point[0]
+            new_xyz = P.gather_rows(points_xyz, indices) if self.num_point is not None else None
+        elif target_xyz is not None:
+            new_xyz = target_xyz.contiguous()
+        else:
+            if self.num_point is not None:
+                indices = P.furthest_point_sample(points_xyz.contiguous(), self.num_point[0])
+                new_xyz = P.gather_rows(points_xyz, indices)
+            else:
+                new_xyz = None
+        return new_xyz, indices
+
+    def _pool_features(self, features):
+        """(B,C,M,ns) -> (B,C,M) (channel-major path)."""
+        if self.pool_mod == 'max':
+            return features.max(dim=-1)[0]
+        return features.mean(dim=-1)
+
+    def _rows_ok(self, grouper):
+        return (isinstance(grouper, P.QueryAndGroup) and grouper.use_xyz
+                and not (grouper.return_grouped_xyz or grouper.return_grouped_idx
+                         or grouper.uniform_sample))
+
+    def forward(self, points_xyz, features=None, indices=None, target_xyz=None):
+        """points_xyz (B,N,3), features (B,C,N) -> new_xyz (B,M,3), new_features (B,sum C_k,M),
+        indices (B,M)."""
+        new_xyz, indices = self._sample_points(points_xyz, features, indices, target_xyz)
+        points_xyz = points_xyz.contiguous()
+        out = []
+        for grouper, mlp in zip(self.groupers, self.mlps):
+            if self._rows_ok(grouper):
+                feat_rows = None if features is None else as_rows(features)
+                C = 0 if feat_rows is None else feat_rows.size(-1)
+                _, rows = P.query_and_group_rows(
+                    points_xyz, new_xyz.contiguous(), feat_rows, grouper.min_radius,
+                    grouper.max_radius, grouper.sample_num, grouper.normalize_xyz)
+                B, M, ns, K = rows.shape
+                x = rows.view(B * M * ns, K)
+                for j, layer in enumerate(mlp):
+                    x = conv_module_rows(layer, x, P.group_rows_columns(C) if j == 0 else None)
+                x = x.view(B, M, ns, -1)
+                x = x.max(dim=2)[0] if self.pool_mod == 'max' else x.mean(dim=2)
+                out.append(x)  # rows (B,M,C')
+            else:
+                grouped = grouper(points_xyz, new_xyz, features)
+                if isinstance(grouped, tuple):
+                    grouped = grouped[0]
+                out.append(self._pool_features(mlp(grouped)).transpose(1, 2))
+        rows = out[0] if len(out) == 1 else torch.cat(out, dim=-1)
+        return new_xyz, rows.transpose(1, 2), indices
+
+
+@SA_MODULES.register_module()
+class PointSAModuleMSG(BasePointSAModule):
+    def __init__(self, num_point, radii, sample_nums, mlp_channels, fps_mod=['D-FPS'],
+                 fps_sample_range_list=[-1], dilated_group=False, norm_cfg=dict(type='BN2d'),
+                 use_xyz=True, pool_mod='max', normalize_xyz=False, bias='auto'):
+        super().__init__(num_point=num_point, radii=radii, sample_nums=sample_nums,
+                         mlp_channels=mlp_channels, fps_mod=fps_mod,
+                         fps_sample_range_list=fps_sample_range_list, dilated_group=dilated_group,
+                         use_xyz=use_xyz, pool_mod=pool_mod, normalize_xyz=normalize_xyz)
+        for i in range(len(self.mlp_channels)):
+            mlp_channel = self.mlp_channels[i]
+            if use_xyz:
+                mlp_channel[0] += 3
+            mlp = nn.Sequential()
+            for j in range(len(mlp_channel) - 1):
+                mlp.add_module(
+                    f'layer{j}',
+                    ConvModule(mlp_channel[j], mlp_channel[j + 1], kernel_size=(1, 1),
+                               stride=(1, 1), conv_cfg=dict(type='Conv2d'), norm_cfg=norm_cfg,
+                               bias=bias))
+            self.mlps.append(mlp)
+
+
+@SA_MODULES.register_module()
+class PointSAModule(PointSAModuleMSG):
+    def __init__(self, mlp_channels, num_point=None, radius=None, num_sample=None,
+                 norm_cfg=dict(type='BN2d'), use_xyz=True, pool_mod='max', fps_mod=['D-FPS'],
+                 fps_sample_range_list=[-1], normalize_xyz=False):
+        super().__init__(mlp_channels=[list(mlp_channels)], num_point=num_point, radii=[radius],
+                         sample_nums=[num_sample], norm_cfg=norm_cfg, use_xyz=use_xyz,
+                         pool_mod=pool_mod, fps_mod=fps_mod,
+                         fps_sample_range_list=fps_sample_range_list, normalize_xyz=normalize_xyz)
+
+
+# ------------------------------------------------------------------------- FP ---------
+class PointFPModule(BaseModule):
+    """mmdet3d PointFPModule: 3-NN inverse-distance interpolation + skip concat + shared MLP."""
+
+    def __init__(self, mlp_channels, norm_cfg=dict(type='BN2d'), init_cfg=None):
+        super().__init__(init_cfg=init_cfg)
+        self.fp16_enabled = False
+        self.mlps = nn.Sequential()
+        for i in range(len(mlp_channels) - 1):
+            self.mlps.add_module(
+                f'layer{i}',
+                ConvModule(mlp_channels[i], mlp_channels[i + 1], kernel_size=(1, 1), stride=(1, 1),
+                           conv_cfg=dict(type='Conv2d'), norm_cfg=norm_cfg))
+
+    def forward(self, target, source, target_feats, source_feats):
+        """target (B,n,3), source (B,m,3), target_feats (B,C1,n), source_feats (B,C2,m)
+        -> (B,M,n)."""
+        src_rows = as_rows(source_feats)
+        if source is not None:
+            dist, idx = P.three_nn(target.contiguous(), source.contiguous())
+            dist_reciprocal = 1.0 / (dist + 1e-8)
+            norm = torch.sum(dist_reciprocal, dim=2, keepdim=True)
+            weight = dist_reciprocal / norm
+            if src_rows.size(-1) % 4 == 0:
+                interpolated = P.three_interpolate_rows(src_rows, idx, weight)
+            else:
+                interpolated = P.three_interpolate(source_feats.contiguous(), idx,
+                                                   weight).transpose(1, 2)
+        else:
+            interpolated = src_rows.expand(src_rows.size(0), target.size(1), src_rows.size(2))
+        if target_feats is not None:
+            x = torch.cat([interpolated, as_rows(target_feats)], dim=-1)
+        else:
+            x = interpolated
+        B, n, C = x.shape
+        x = x.reshape(B * n, C)
+        for layer in self.mlps:
+            x = conv_module_rows(layer, x)
+        return x.view(B, n, -1).transpose(1, 2)
+
+
+# ------------------------------------------------------------------- backbone ---------
+@BACKBONES.register_module()
+class PointNet2SASSG(BaseModule):
+    """PointNet++ single-scale-grouping backbone (configs/demf/demf_votenet.py:48-62)."""
+
+    def __init__(self, in_channels, num_points=(2048, 1024, 512, 256), radius=(0.2, 0.4, 0.8, 1.2),
+                 num_samples=(64, 32, 16, 16),
+                 sa_channels=((64, 64, 128), (128, 128, 256), (128, 128, 256), (128, 128, 256)),
+                 fp_channels=((256, 256), (256, 256)), norm_cfg=dict(type='BN2d'),
+                 sa_cfg=dict(type='PointSAModule', pool_mod='max', use_xyz=True,
+                             normalize_xyz=True),
+                 init_cfg=None):
+        super().__init__(init_cfg=init_cfg)
+        from .registry import build_sa_module
+        self.num_sa = len(sa_channels)
+        self.num_fp = len(fp_channels)
+        assert len(num_points) == len(radius) == len(num_samples) == len(sa_channels)
+        assert len(sa_channels) >= len(fp_channels)
+        self.SA_modules = nn.ModuleList()
+        sa_in_channel = in_channels - 3  # number of channels without xyz
+        skip_channel_list = [sa_in_channel]
+        for sa_index in range(self.num_sa):
+            cur_sa_mlps = list(sa_channels[sa_index])
+            cur_sa_mlps = [sa_in_channel] + cur_sa_mlps
+            sa_out_channel = cur_sa_mlps[-1]
+            self.SA_modules.append(
+                build_sa_module(num_point=num_points[sa_index], radius=radius[sa_index],
+                                num_sample=num_samples[sa_index], mlp_channels=cur_sa_mlps,
+                                norm_cfg=norm_cfg, cfg=sa_cfg))
+            skip_channel_list.append(sa_out_channel)
+            sa_in_channel = sa_out_channel
+        self.FP_modules = nn.ModuleList()
+        fp_source_channel = skip_channel_list.pop()
+        fp_target_channel = skip_channel_list.pop()
+        for fp_index in range(len(fp_channels)):
+            cur_fp_mlps = list(fp_channels[fp_index])
+            cur_fp_mlps = [fp_source_channel + fp_target_channel] + cur_fp_mlps
+            self.FP_modules.append(PointFPModule(mlp_channels=cur_fp_mlps))
+            if fp_index != len(fp_channels) - 1:
+                fp_source_channel = cur_fp_mlps[-1]
+                fp_target_channel = skip_channel_list.pop()
+
+    @staticmethod
+    def _split_point_feats(points):
+        xyz = points[..., 0:3].contiguous()
+        features = points[..., 3:].transpose(1, 2) if points.size(-1) > 3 else None
+        return xyz, features
+
+    def forward(self, points):
+        """points (B,N,3+C) -> dict of fp_xyz / fp_features / fp_indices / sa_*."""
+        xyz, features = self._split_point_feats(points)
+        batch, num_points = xyz.shape[:2]
+        indices = torch.arange(num_points, device=xyz.device).unsqueeze(0).repeat(batch, 1).long()
+        sa_xyz, sa_features, sa_indices = [xyz], [features], [indices]
+        for i in range(self.num_sa):
+            cur_xyz, cur_features, cur_indices = self.SA_modules[i](sa_xyz[i], sa_features[i])
+            sa_xyz.append(cur_xyz)
+            sa_features.append(cur_features)
+            sa_indices.append(torch.gather(sa_indices[-1], 1, cur_indices.long()))
+        fp_xyz, fp_features, fp_indices = [sa_xyz[-1]], [sa_features[-1]], [sa_indices[-1]]
+        for i in range(self.num_fp):
+            fp_features.append(self.FP_modules[i](sa_xyz[self.num_sa - i - 1],
+                                                  sa_xyz[self.num_sa - i],
+                                                  sa_features[self.num_sa - i - 1],
+                                                  fp_features[-1]))
+            fp_xyz.append(sa_xyz[self.num_sa - i - 1])
+            fp_indices.append(sa_indices[self.num_sa - i - 1])
+        return dict(fp_xyz=fp_xyz, fp_features=fp_features, fp_indices=fp_indices, sa_xyz=sa_xyz,
+                    sa_features=sa_features, sa_indices=sa_indices)
+
+
+# ---------------------------------------------------------------- vote module ---------
+class VoteModule(nn.Module):
+    """mmdet3d VoteModule: per-seed MLP -> (xyz offset, feature residual) -> votes."""
+
+    def __init__(self, in_channels, vote_per_seed=1, gt_per_seed=3, num_points=-1,
+                 conv_channels=(16, 16), conv_cfg=dict(type='Conv1d'), norm_cfg=dict(type='BN1d'),
+                 act_cfg=dict(type='ReLU'), norm_feats=True, with_res_feat=True,
+                 vote_xyz_range=None, vote_loss=None):
+        super().__init__()
+        from .registry import build_loss
+        self.in_channels = in_channels
+        self.vote_per_seed = vote_per_seed
+        self.gt_per_seed = gt_per_seed
+        self.num_points = num_points
+        self.norm_feats = norm_feats
+        self.with_res_feat = with_res_feat
+        assert vote_xyz_range is None or isinstance(vote_xyz_range, (list, tuple))
+        self.vote_xyz_range = vote_xyz_range
+        if vote_loss is not None:
+            self.vote_loss = build_loss(vote_loss)
+        prev_channels = in_channels
+        vote_conv_list = []
+        for k in range(len(conv_channels)):
+            vote_conv_list.append(
+                ConvModule(prev_channels, conv_channels[k], 1, padding=0, conv_cfg=conv_cfg,
+                           norm_cfg=norm_cfg, act_cfg=act_cfg, bias=True, inplace=True))
+            prev_channels = conv_channels[k]
+        self.vote_conv = nn.Sequential(*vote_conv_list)
+        if with_res_feat:
+            out_channel = (3 + in_channels) * self.vote_per_seed
+        else:
+            out_channel = 3 * self.vote_per_seed
+        self.conv_out = nn.Conv1d(prev_channels, out_channel, 1)
+
+    def forward(self, seed_points, seed_feats):
+        """seed_points (B,N,3), seed_feats (B,C,N) -> vote_points (B,N*vps,3),
+        vote_feats (B,C,N*vps), offset (B,3,N*vps)."""
+        if self.num_points != -1:
+            assert self.num_points < seed_points.shape[1], \
+                f'Number of vote points ({self.num_points}) should be smaller than seed ' \
+                f'points size ({seed_points.shape[1]})'
+            seed_points = seed_points[:, :self.num_points]
+            seed_feats = seed_feats[..., :self.num_points]
+        batch_size, feat_channels, num_seed = seed_feats.shape
+        num_vote = num_seed * self.vote_per_seed
+        seed_rows = as_rows(seed_feats)                       # (B,N,C)
+        x = seed_rows.reshape(batch_size * num_seed, feat_channels)
+        for layer in self.vote_conv:
+            x = conv_module_rows(layer, x)
+        votes = torch.nn.functional.linear(x, self.conv_out.weight.flatten(1), self.conv_out.bias)
+        votes = votes.view(batch_size, num_seed, self.vote_per_seed, -1)
+        offset = votes[:, :, :, 0:3]
+        if self.vote_xyz_range is not None:
+            limited = []
+            for axis in range(len(self.vote_xyz_range)):
+                limited.append(offset[..., axis].clamp(min=-self.vote_xyz_range[axis],
+                                                       max=self.vote_xyz_range[axis]))
+            offset = torch.stack(limited, -1)
+        vote_points = (seed_points.unsqueeze(2) + offset).contiguous()
+        vote_points = vote_points.view(batch_size, num_vote, 3)
+        offset = offset.reshape(batch_size, num_vote, 3).transpose(2, 1)
+        if self.with_res_feat:
+            res_feats = votes[:, :, :, 3:]
+            vote_rows = (seed_rows.unsqueeze(2) + res_feats).contiguous()
+            vote_rows = vote_rows.view(batch_size, num_vote, feat_channels)
+            if self.norm_feats:
+                features_norm = torch.norm(vote_rows, p=2, dim=2)
+                vote_rows = vote_rows.div(features_norm.unsqueeze(2))
+            vote_feats = vote_rows.transpose(2, 1)
+        else:
+            vote_feats = seed_feats
+        return vote_points, vote_feats, offset
+
+    def get_loss(self, seed_points, vote_points, seed_indices, vote_targets_mask, vote_targets):
+        """Chamfer-style vote loss: min over the gt_per_seed candidate votes, masked."""
+        batch_size, num_seed = seed_points.shape[:2]
+        seed_gt_votes_mask = torch.gather(vote_targets_mask, 1, seed_indices).float()
+        seed_indices_expand = seed_indices.unsqueeze(-1).repeat(1, 1, 3 * self.gt_per_seed)
+        seed_gt_votes = torch.gather(vote_targets, 1, seed_indices_expand)
+        seed_gt_votes = seed_gt_votes + seed_points.repeat(1, 1, self.gt_per_seed)
+        weight = seed_gt_votes_mask / (torch.sum(seed_gt_votes_mask) + 1e-6)
+        distance = self.vote_loss(
+            vote_points.view(batch_size * num_seed, -1, 3),
+            seed_gt_votes.view(batch_size * num_seed, -1, 3),
+            dst_weight=weight.view(batch_size * num_seed, 1))[1]
+        return torch.sum(torch.min(distance, dim=1)[0])
+
+
+# ------------------------------------------------------------- prediction head ---------
+class BaseConvBboxHead(BaseModule):
+    """mmdet3d BaseConvBboxHead: shared k=1 convs, then a classification and a regression conv."""
+
+    def __init__(self, in_channels=0, shared_conv_channels=(), cls_conv_channels=(),
+                 num_cls_out_channels=0, reg_conv_channels=(), num_reg_out_channels=0,
+                 conv_cfg=dict(type='Conv1d'), norm_cfg=dict(type='BN1d'),
+                 act_cfg=dict(type='ReLU'), bias='auto', init_cfg=None, *args, **kwargs):
+        super().__init__(init_cfg=init_cfg)
+        assert in_channels > 0
+        assert num_cls_out_channels > 0
+        assert num_reg_out_channels > 0
+        self.in_channels = in_channels
+        self.shared_conv_channels = shared_conv_channels
+        self.cls_conv_channels = cls_conv_channels
+        self.num_cls_out_channels = num_cls_out_channels
+        self.reg_conv_channels = reg_conv_channels
+        self.num_reg_out_channels = num_reg_out_channels
+        self.conv_cfg, self.norm_cfg, self.act_cfg, self.bias = conv_cfg, norm_cfg, act_cfg, bias
+        if len(self.shared_conv_channels) > 0:
+            self.shared_convs = self._add_conv_branch(self.in_channels, self.shared_conv_channels)
+            out_channels = self.shared_conv_channels[-1]
+        else:
+            out_channels = self.in_channels
+        prev_channel = out_channels
+        if len(self.cls_conv_channels) > 0:
+            self.cls_convs = self._add_conv_branch(prev_channel, self.cls_conv_channels)
+            prev_channel = self.cls_conv_channels[-1]
+        self.conv_cls = build_conv_layer(conv_cfg, in_channels=prev_channel,
+                                         out_channels=num_cls_out_channels, kernel_size=1)
+        prev_channel = out_channels
+        if len(self.reg_conv_channels) > 0:
+            self.reg_convs = self._add_conv_branch(prev_channel, self.reg_conv_channels)
+            prev_channel = self.reg_conv_channels[-1]
+        self.conv_reg = build_conv_layer(conv_cfg, in_channels=prev_channel,
+                                         out_channels=num_reg_out_channels, kernel_size=1)
+
+    def _add_conv_branch(self, in_channels, conv_channels):
+        conv_spec = [in_channels] + list(conv_channels)
+        conv_layers = nn.Sequential()
+        for i in range(len(conv_spec) - 1):
+            conv_layers.add_module(
+                f'layer{i}',
+                ConvModule(conv_spec[i], conv_spec[i + 1], kernel_size=1, padding=0,
+                           conv_cfg=self.conv_cfg, norm_cfg=self.norm_cfg, act_cfg=self.act_cfg,
+                           bias=self.bias, inplace=True))
+        return conv_layers
+
+    def forward(self, feats):
+        """feats (B,C,N) -> cls_score (B,num_cls,N), bbox_pred (B,num_reg,N)."""
+        rows = as_rows(feats)
+        B, N, C = rows.shape
+        x = rows.reshape(B * N, C)
+        if len(self.shared_conv_channels) > 0:
+            for layer in self.shared_convs:
+                x = conv_module_rows(layer, x)
+        x_cls = x_reg = x
+        if len(self.cls_conv_channels) > 0:
+            for layer in self.cls_convs:
+                x_cls = conv_module_rows(layer, x_cls)
+        cls_score = torch.nn.functional.linear(x_cls, self.conv_cls.weight.flatten(1),
+                                               self.conv_cls.bias)
+        if len(self.reg_conv_channels) > 0:
+            for layer in self.reg_convs:
+                x_reg = conv_module_rows(layer, x_reg)
+        bbox_pred = torch.nn.functional.linear(x_reg, self.conv_reg.weight.flatten(1),
+                                               self.conv_reg.bias)
+        return cls_score.view(B, N, -1).transpose(1, 2), bbox_pred.view(B, N, -1).transpose(1, 2)

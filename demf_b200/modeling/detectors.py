@@ -1,0 +1,171 @@
+"""DeMFVoteNet detector (reference: demf/modeling/detectors/demfnet.py:12-283).
+
+Point branch = PointNet2SASSG backbone + DeMFVoteHead; image branch (backbone, neck, deformable
+DETR encoder) is frozen in the reference and produces the 4-level feature pyramid the head
+samples. The image branch is outside this repository's scope (BASELINE
+configs feed synthetic pyramids); `img` may therefore be given directly as the list of
+(B,256,H_l,W_l) level features, which is what `extract_img_feat` returns upstream. When
+img_backbone / img_neck / img_encoder configs are present and their types are registered they are
+built and run exactly like the reference does; unregistered image modules are skipped with the
+pyramid passed through.
+"""
+import torch
+import torch.nn as nn
+
+from ..mm.bricks import BaseModule
+from ..mm.registry import BACKBONES, DETECTORS, HEADS, NECKS, build_backbone, build_head, build_neck
+
+
+def _registered(cfg, registry):
+    return cfg is not None and cfg.get('type') in registry
+
+
+@DETECTORS.register_module()
+class DeMFVoteNet(BaseModule):
+
+    def __init__(self, pts_backbone=None, pts_bbox_head=None, pts_neck=None, img_backbone=None,
+                 img_neck=None, img_encoder=None, freeze_img_branch=False, num_sampled_seed=None,
+                 train_cfg=None, test_cfg=None, pretrained=None, init_cfg=None, **kwargs):
+        super().__init__(init_cfg=init_cfg)
+        if pts_backbone is not None:
+            self.pts_backbone = build_backbone(pts_backbone)
+        if pts_neck is not None:
+            self.pts_neck = build_neck(pts_neck)
+        if pts_bbox_head is not None:
+            pts_bbox_head = dict(pts_bbox_head)
+            pts_bbox_head.update(train_cfg=train_cfg['pts'] if train_cfg is not None else None)
+            pts_bbox_head.update(test_cfg=test_cfg['pts'] if test_cfg is not None else None)
+            self.pts_bbox_head = build_head(pts_bbox_head)
+        # image branch: frozen feature extractor, out of scope here (see module docstring)
+        if _registered(img_backbone, BACKBONES):
+            self.img_backbone = build_backbone(img_backbone)
+        if _registered(img_neck, NECKS):
+            self.img_neck = build_neck(img_neck)
+        if _registered(img_encoder, HEADS):
+            self.img_encoder = build_head(img_encoder)
+        self.freeze_img_branch = freeze_img_branch
+        if freeze_img_branch:
+            self.freeze_img_branch_params()
+        self.num_sampled_seed = num_sampled_seed
+        self.train_cfg = train_cfg
+        self.test_cfg = test_cfg
+
+    # --- with_* properties of mmdet3d's ImVoteNet / Base3DDetector
+    @property
+    def with_img_backbone(self):
+        return getattr(self, 'img_backbone', None) is not None
+
+    @property
+    def with_img_neck(self):
+        return getattr(self, 'img_neck', None) is not None
+
+    @property
+    def with_img_encoder(self):
+        return getattr(self, 'img_encoder', None) is not None
+
+    @property
+    def with_pts_backbone(self):
+        return getattr(self, 'pts_backbone', None) is not None
+
+    @property
+    def with_pts_neck(self):
+        return getattr(self, 'pts_neck', None) is not None
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys,
+                              unexpected_keys, error_msgs):
+        """Stage-1 checkpoints keep the image encoder under img_bbox_head.transformer.*: remap
+        those keys to img_encoder.* and drop the rest of img_bbox_head (demfnet.py:85-101)."""
+        for key in list(state_dict):
+            if not key.startswith('img_bbox_head'):
+                continue
+            if 'encoder' in key or 'level_embeds' in key:
+                state_dict[key.replace('img_bbox_head.transformer', 'img_encoder')] = \
+                    state_dict.pop(key)
+            else:
+                state_dict.pop(key)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys,
+                                      unexpected_keys, error_msgs)
+
+    def _img_modules(self):
+        return [m for m in (getattr(self, n, None) for n in
+                            ('img_encoder', 'img_backbone', 'img_neck')) if m is not None]
+
+    def freeze_img_branch_params(self):
+        for m in self._img_modules():
+            for p in m.parameters():
+                p.requires_grad = False
+
+    def train(self, mode=True):
+        super().train(mode)
+        if self.freeze_img_branch:
+            for m in self._img_modules():
+                m.eval()
+        return self
+
+    @torch.no_grad()
+    def extract_img_feat(self, img, img_metas):
+        """img: (B,3,H,W) image batch when an image branch is built, else the list of pyramid
+        levels itself."""
+        if isinstance(img, (list, tuple)) and not self.with_img_backbone:
+            return list(img)
+        x = self.img_backbone(img)
+        if self.with_img_neck:
+            x = self.img_neck(x)
+        if self.with_img_encoder:
+            x = self.img_encoder(x, img_metas)
+        return x
+
+    def extract_pts_feat(self, pts):
+        x = self.pts_backbone(pts)
+        if self.with_pts_neck:
+            x = self.pts_neck(x)
+        return x['fp_xyz'][-1], x['fp_features'][-1], x['fp_indices'][-1]
+
+    @staticmethod
+    def _batch_input_shape(img, img_metas):
+        if isinstance(img, (list, tuple)):
+            return  # pyramid given directly: metas already carry batch_input_shape
+        shape = tuple(img[0].size()[-2:])
+        for meta in img_metas:
+            meta['batch_input_shape'] = shape
+
+    def _forward_head(self, points, img, img_metas, sample_mod):
+        self._batch_input_shape(img, img_metas)
+        img_features = self.extract_img_feat(img, img_metas)
+        points = torch.stack(list(points)) if not torch.is_tensor(points) else points
+        seeds_3d, seed_3d_features, seed_indices = self.extract_pts_feat(points)
+        feat_dict = dict(seed_points=seeds_3d, seed_features=seed_3d_features,
+                         seed_indices=seed_indices)
+        img_dict = dict(img_features=img_features, img_metas=img_metas)
+        return points, self.pts_bbox_head(feat_dict, sample_mod, img_dict)
+
+    def forward_train(self, points=None, img=None, img_metas=None, gt_bboxes_ignore=None,
+                      gt_bboxes_3d=None, gt_labels_3d=None, pts_semantic_mask=None,
+                      pts_instance_mask=None, **kwargs):
+        points, bbox_preds = self._forward_head(points, img, img_metas,
+                                                self.train_cfg['pts']['sample_mod'])
+        loss_inputs = (points, gt_bboxes_3d, gt_labels_3d, pts_semantic_mask, pts_instance_mask,
+                       img_metas)
+        return self.pts_bbox_head.loss(bbox_preds, *loss_inputs, gt_bboxes_ignore=gt_bboxes_ignore)
+
+    def forward_dummy(self, points=None, img=None, img_metas=None):
+        """Head outputs without post-processing: what the forward benchmark times."""
+        return self._forward_head(points, img, img_metas, self.test_cfg['pts']['sample_mod'])[1]
+
+    def simple_test(self, points=None, img_metas=None, img=None, bboxes_2d=None, rescale=False,
+                    **kwargs):
+        """Forward + box decoding of the ensemble layers (NMS is out of scope):
+        returns (boxes (B, len(ensemble)*Q, 7), objectness (B, .), semantic scores (B, ., C))."""
+        _, bbox_preds = self._forward_head(points, img, img_metas,
+                                           self.test_cfg['pts']['sample_mod'])
+        head = self.pts_bbox_head
+        obj, sem, box = [], [], []
+        for i in head.test_cfg['ensemble_layers']:
+            res = bbox_preds['decode_res_all'][i]
+            obj.append(torch.softmax(res['obj_scores'], dim=-1)[..., -1])
+            sem.append(torch.softmax(res['sem_scores'], dim=-1))
+            box.append(head.bbox_coder.decode(res))
+        return torch.cat(box, 1), torch.cat(obj, 1), torch.cat(sem, 1)
+
+    def forward(self, return_loss=True, **kwargs):
+        return self.forward_train(**kwargs) if return_loss else self.simple_test(**kwargs)

@@ -1,0 +1,351 @@
+"""DeMFVoteHead: VoteNet head whose proposals are refined by deformable attention over image
+features (reference: demf/modeling/heads/class_agnostic_vote_head.py:335-941).
+
+Same constructor arguments, forward signature, result-dict keys, parameter names and loss keys
+as the reference. What changed is how the work reaches the GPU:
+  * vote aggregation and the prediction convs run on point-major rows (mm/pointnet_modules.py);
+  * reference points for the whole batch come from one bmm (mm/geometry.py) instead of a Python
+    loop over scenes (reference :524-547);
+  * the image pyramid is laid out once as (B,S,C) -- the layout the MSDA kernel and the
+    value_proj GEMM both want -- and handed on as an (S,B,C) view (reference :570-591 builds a
+    (S,B,C) tensor that the attention module permutes back);
+  * targets are assigned for the whole batch with padded (B,G,*) tensors instead of per-scene,
+    per-box Python loops (reference :818-941).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..mm import geometry
+from ..mm import point_ops as P
+from ..mm.bricks import BaseModule
+from ..mm.pointnet_modules import BaseConvBboxHead, VoteModule
+from ..mm.registry import (HEADS, build_bbox_coder, build_loss, build_sa_module,
+                           build_transformer_layer)
+
+
+@HEADS.register_module()
+class DeMFVoteHead(BaseModule):
+
+    def __init__(self, num_classes, bbox_coder, train_cfg=None, test_cfg=None,
+                 vote_module_cfg=None, vote_aggregation_cfg=None, pred_layer_cfg=None,
+                 conv_cfg=dict(type='Conv1d'), norm_cfg=dict(type='BN1d'), objectness_loss=None,
+                 center_loss=None, dir_class_loss=None, dir_res_loss=None, size_class_loss=None,
+                 size_res_loss=None, semantic_loss=None, iou_loss=None, decoder=None,
+                 init_cfg=None):
+        super().__init__(init_cfg=init_cfg)
+        self.num_classes = num_classes
+        self.train_cfg = train_cfg
+        self.test_cfg = test_cfg
+        self.gt_per_seed = vote_module_cfg['gt_per_seed']
+        self.num_proposal = vote_aggregation_cfg['num_point']
+
+        self.objectness_loss = build_loss(objectness_loss)
+        self.center_loss = build_loss(center_loss)
+        self.dir_res_loss = build_loss(dir_res_loss)
+        self.dir_class_loss = build_loss(dir_class_loss)
+        self.size_res_loss = build_loss(size_res_loss)
+        if size_class_loss is not None:
+            self.size_class_loss = build_loss(size_class_loss)
+        if semantic_loss is not None:
+            self.semantic_loss = build_loss(semantic_loss)
+        self.iou_loss = build_loss(iou_loss) if iou_loss is not None else None
+
+        self.bbox_coder = build_bbox_coder(bbox_coder)
+        self.num_sizes = self.bbox_coder.num_sizes
+        self.num_dir_bins = self.bbox_coder.num_dir_bins
+
+        self.vote_module = VoteModule(**vote_module_cfg)
+        self.vote_aggregation = build_sa_module(vote_aggregation_cfg)
+        self.fp16_enabled = False
+
+        self.num_decoder_layers = decoder['num_layers']
+        self.num_fusion_layers = decoder['num_layers']
+        self.decoder = nn.ModuleList()
+        for _ in range(self.num_decoder_layers):
+            self.decoder.append(build_transformer_layer(decoder))
+
+        pred_layer_cfg = dict(pred_layer_cfg)
+        self.conv_pred_layers = pred_layer_cfg.pop('conv_pred_layers')
+        assert self.conv_pred_layers == self.num_decoder_layers + 1
+        self.conv_preds = []
+        for i in range(self.conv_pred_layers):
+            conv_pred = BaseConvBboxHead(**pred_layer_cfg,
+                                         num_cls_out_channels=self._get_cls_out_channels(),
+                                         num_reg_out_channels=self._get_reg_out_channels())
+            self.add_module('conv_pred' + str(i), conv_pred)
+            self.conv_preds.append(conv_pred)
+
+    def _get_cls_out_channels(self):
+        return self.num_classes + 2 if hasattr(self, 'semantic_loss') else 2
+
+    def _get_reg_out_channels(self):
+        return 6 + self.num_dir_bins * 2
+
+    def init_weights(self):
+        for layer in self.decoder:
+            layer.init_weights()
+        self._is_init = True
+
+    @staticmethod
+    def _extract_input(feat_dict):
+        if 'seed_points' in feat_dict and 'seed_features' in feat_dict \
+                and 'seed_indices' in feat_dict:
+            return feat_dict['seed_points'], feat_dict['seed_features'], feat_dict['seed_indices']
+        return feat_dict['fp_xyz'][-1], feat_dict['fp_features'][-1], feat_dict['fp_indices'][-1]
+
+    # ------------------------------------------------------------------ forward ---
+    def forward(self, feat_dict, sample_mod, img_dict):
+        assert sample_mod in ['vote', 'seed', 'random', 'spec']
+        seed_points, seed_features, seed_indices = self._extract_input(feat_dict)
+        img_features, img_metas = img_dict['img_features'], img_dict['img_metas']
+
+        vote_points, vote_features, vote_offset = self.vote_module(seed_points, seed_features)
+        results = dict(seed_points=seed_points, seed_indices=seed_indices, vote_points=vote_points,
+                       vote_features=vote_features, vote_offset=vote_offset)
+
+        if sample_mod == 'vote':
+            aggregation_inputs = dict(points_xyz=vote_points, features=vote_features)
+        elif sample_mod == 'seed':
+            sample_indices = P.furthest_point_sample(seed_points.contiguous(), self.num_proposal)
+            aggregation_inputs = dict(points_xyz=vote_points, features=vote_features,
+                                      indices=sample_indices)
+        elif sample_mod == 'random':
+            batch_size, num_seed = seed_points.shape[:2]
+            sample_indices = torch.randint(0, num_seed, (batch_size, self.num_proposal),
+                                           dtype=torch.int32, device=seed_points.device)
+            aggregation_inputs = dict(points_xyz=vote_points, features=vote_features,
+                                      indices=sample_indices)
+        else:  # 'spec'
+            aggregation_inputs = dict(points_xyz=seed_points, features=seed_features,
+                                      target_xyz=vote_points)
+
+        aggregated_points, features, aggregated_indices = self.vote_aggregation(
+            **aggregation_inputs)
+        results['aggregated_points'] = aggregated_points
+        results['aggregated_indices'] = aggregated_indices
+        results['decode_res_all'] = self.transformer_decoder(features, aggregated_points,
+                                                             img_features, img_metas)
+        return results
+
+    def transformer_decoder(self, features, aggregated_points, img_features, img_metas):
+        """features (B,C,Q) -> list of num_layers+1 prediction dicts (reference :468-512)."""
+        decode_res_all = []
+        cls_predictions, reg_predictions = self.conv_preds[0](features)
+        decode_res = self.bbox_coder.split_pred(cls_predictions, reg_predictions, aggregated_points)
+        decode_res_all.append(decode_res)
+
+        feat_flatten, mask_flatten, reference_points, spatial_shapes, level_start_index, \
+            valid_ratios = self.prepare_decoder_inputs(aggregated_points, img_features, img_metas)
+
+        query = features.permute(2, 0, 1)
+        for i in range(self.num_decoder_layers):
+            query_pos = torch.cat([decode_res['center'], decode_res['size']], dim=-1).detach()
+            query = self.decoder[i](
+                query=query, key=None, value=feat_flatten, query_pos=query_pos,
+                key_padding_mask=mask_flatten, reference_points=reference_points,
+                spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                valid_ratios=valid_ratios)
+            cls_predictions, reg_predictions = self.conv_preds[i + 1](query.permute(1, 2, 0))
+            decode_res = self.bbox_coder.split_pred(cls_predictions, reg_predictions,
+                                                    aggregated_points)
+            decode_res_all.append(decode_res)
+        return decode_res_all
+
+    @staticmethod
+    def get_valid_ratio(mask):
+        _, H, W = mask.shape
+        valid_H = torch.sum(~mask[:, :, 0], 1)
+        valid_W = torch.sum(~mask[:, 0, :], 1)
+        return torch.stack([valid_W.float() / W, valid_H.float() / H], -1)
+
+    def get_reference_points(self, seeds_3d_batch, img_metas):
+        """(B,Q,3) proposals -> (B,Q,2) normalised image coordinates, clamped to [0,1].
+        Whole batch in one bmm; the per-scene matrices are folded on the host (geometry.py)."""
+        mats, affs = geometry.fold_projection(img_metas)
+        dev = seeds_3d_batch.device
+        return geometry.project_batched(seeds_3d_batch, mats.to(dev, non_blocking=True),
+                                        affs.to(dev, non_blocking=True))
+
+    def prepare_decoder_inputs(self, seeds_3d, mlvl_feats, img_metas):
+        """-> feat_flatten (S,B,C) [view of a (B,S,C) buffer], mask_flatten (B,S) bool or None,
+        reference_points (B,Q,2), spatial_shapes (L,2) i64, level_start_index (L) i64,
+        valid_ratios (B,L,2). Reference :549-594."""
+        reference_points = self.get_reference_points(seeds_3d, img_metas)
+        dev = mlvl_feats[0].device
+        batch_size, channels = mlvl_feats[0].shape[:2]
+        shapes = [tuple(f.shape[-2:]) for f in mlvl_feats]
+        starts = np.concatenate([[0], np.cumsum([h * w for h, w in shapes])])
+        num_value = int(starts[-1])
+
+        pyramid = mlvl_feats[0].new_empty(batch_size, num_value, channels)
+        for lvl, feat in enumerate(mlvl_feats):
+            pyramid[:, starts[lvl]:starts[lvl + 1]].copy_(feat.flatten(2).transpose(1, 2))
+        feat_flatten = pyramid.permute(1, 0, 2)
+
+        input_img_h, input_img_w = img_metas[0]['batch_input_shape']
+        padded = any(tuple(m['img_shape'][:2]) != (input_img_h, input_img_w) for m in img_metas)
+        if padded:
+            img_masks = mlvl_feats[0].new_ones((batch_size, input_img_h, input_img_w))
+            for img_id in range(batch_size):
+                img_h, img_w = img_metas[img_id]['img_shape'][:2]
+                img_masks[img_id, :img_h, :img_w] = 0
+            mlvl_masks = [F.interpolate(img_masks[None], size=s).to(torch.bool).squeeze(0)
+                          for s in shapes]
+            mask_flatten = torch.cat([m.flatten(1) for m in mlvl_masks], 1)
+            valid_ratios = torch.stack([self.get_valid_ratio(m) for m in mlvl_masks], 1)
+        else:  # nothing is padding: no mask to apply, every valid ratio is exactly 1
+            mask_flatten = None
+            valid_ratios = reference_points.new_ones(batch_size, len(shapes), 2)
+
+        spatial_shapes = torch.as_tensor(shapes, dtype=torch.long).to(dev, non_blocking=True)
+        level_start_index = torch.as_tensor(starts[:-1], dtype=torch.long).to(dev, non_blocking=True)
+        return (feat_flatten, mask_flatten, reference_points, spatial_shapes, level_start_index,
+                valid_ratios)
+
+    # --------------------------------------------------------------------- loss ---
+    def loss(self, bbox_preds, *args, **kwargs):
+        """Average of _loss over the num_fusion_layers+1 prediction stages (reference :596-620).
+        Targets do not depend on the stage, so they are assigned once."""
+        bbox_preds = dict(bbox_preds)
+        decode_res_all = bbox_preds.pop('decode_res_all')
+        common = {k: bbox_preds[k] for k in ('seed_points', 'seed_indices', 'aggregated_points',
+                                             'vote_points')}
+        targets = self.get_targets(args[0], args[1], args[2], bbox_preds=common)
+        assert self.num_fusion_layers + 1 == len(decode_res_all)
+        losses = dict()
+        for decode_res in decode_res_all:
+            stage = self._loss(dict(common, **decode_res), *args, targets=targets, **kwargs)
+            for k, v in stage.items():
+                losses[k] = losses.get(k, 0) + v / (self.num_fusion_layers + 1)
+        return losses
+
+    def _loss(self, bbox_preds, points, gt_bboxes_3d, gt_labels_3d, pts_semantic_mask=None,
+              pts_instance_mask=None, img_metas=None, gt_bboxes_ignore=None, ret_target=False,
+              targets=None):
+        if targets is None:
+            targets = self.get_targets(points, gt_bboxes_3d, gt_labels_3d, pts_semantic_mask,
+                                       pts_instance_mask, bbox_preds)
+        (vote_targets, vote_target_masks, dir_class_targets, dir_res_targets, mask_targets,
+         objectness_targets, objectness_weights, box_loss_weights, distance_targets, dir_targets,
+         size_targets, center_targets) = targets
+
+        vote_loss = self.vote_module.get_loss(bbox_preds['seed_points'], bbox_preds['vote_points'],
+                                              bbox_preds['seed_indices'], vote_target_masks,
+                                              vote_targets)
+        objectness_loss = self.objectness_loss(bbox_preds['obj_scores'].transpose(2, 1),
+                                               objectness_targets, weight=objectness_weights)
+        w3 = box_loss_weights.unsqueeze(-1).expand(-1, -1, 3)
+        size_reg_loss = self.size_res_loss(bbox_preds['size'], size_targets, weight=w3)
+        center_loss = self.center_loss(bbox_preds['center'], center_targets, weight=w3)
+        dir_class_loss = self.dir_class_loss(bbox_preds['dir_class'].transpose(2, 1),
+                                             dir_class_targets, weight=box_loss_weights)
+        dir_res_norm = torch.gather(bbox_preds['dir_res_norm'], 2,
+                                    dir_class_targets.unsqueeze(-1)).squeeze(-1)
+        dir_res_loss = self.dir_res_loss(dir_res_norm, dir_res_targets, weight=box_loss_weights)
+        losses = dict(vote_loss=vote_loss, objectness_loss=objectness_loss,
+                      dir_class_loss=dir_class_loss, dir_res_loss=dir_res_loss,
+                      size_res_loss=size_reg_loss, center_loss=center_loss)
+        if hasattr(self, 'semantic_loss'):
+            losses['semantic_loss'] = self.semantic_loss(bbox_preds['sem_scores'].transpose(2, 1),
+                                                         mask_targets, weight=box_loss_weights)
+        if self.iou_loss:
+            corners_pred = self.bbox_coder.decode_corners(bbox_preds['center'], bbox_preds['size'])
+            corners_target = self.bbox_coder.decode_corners(center_targets, size_targets)
+            losses['iou_loss'] = self.iou_loss(corners_pred, corners_target,
+                                               weight=box_loss_weights)
+        if ret_target:
+            losses['targets'] = targets
+        return losses
+
+    # ------------------------------------------------------------------ targets ---
+    def get_targets(self, points, gt_bboxes_3d, gt_labels_3d, pts_semantic_mask=None,
+                    pts_instance_mask=None, bbox_preds=None):
+        """Batched target assignment (reference :756-941 loops scenes and boxes in Python).
+        Scenes are padded to G boxes; an empty scene gets one all-zero box, as upstream."""
+        if not self.bbox_coder.with_rot:
+            raise NotImplementedError("only the with_rot (SUN RGB-D) target path is implemented")
+        points = torch.stack(list(points)) if not torch.is_tensor(points) else points
+        dev = points.device
+        B = points.shape[0]
+        boxes, labels = [], []
+        for b in range(B):
+            t = gt_bboxes_3d[b].tensor.to(dev)
+            lab = gt_labels_3d[b].to(dev)
+            if lab.numel() == 0:
+                t = t.new_zeros(1, 7)
+                lab = lab.new_zeros(1)
+            boxes.append(t)
+            labels.append(lab.long())
+        G = max(t.shape[0] for t in boxes)
+        box = points.new_zeros(B, G, 7)
+        label = torch.zeros(B, G, dtype=torch.long, device=dev)
+        valid = torch.zeros(B, G, dtype=torch.bool, device=dev)
+        for b in range(B):
+            g = boxes[b].shape[0]
+            box[b, :g] = boxes[b]
+            label[b, :g] = labels[b]
+            valid[b, :g] = True
+
+        centre = box[..., :3].clone()
+        centre[..., 2] = centre[..., 2] + box[..., 5] * 0.5      # gravity centre
+        size = box[..., 3:6]
+        yaw = box[..., 6]
+
+        # ---- vote targets: slot0 = first containing box, slot1 = second (else first),
+        #      slot2 = last of >=3 (else first); reference :834-858
+        inside = geometry.points_in_boxes_batch(points[..., :3], box).bool() & valid[:, None, :]
+        rank = inside.cumsum(-1)
+        count = rank[..., -1]
+        gidx = torch.arange(G, device=dev)
+        first = (inside & (rank == 1)).float().argmax(-1)
+        second = (inside & (rank == 2)).float().argmax(-1)
+        last = torch.where(inside, gidx.expand_as(inside), gidx.new_full((), -1)).amax(-1).clamp(min=0)
+        second = torch.where(count >= 2, second, first)
+        third = torch.where(count >= 3, last, first)
+        xyz = points[..., :3]
+        slots = []
+        for sel in (first, second, third):
+            c = torch.gather(centre, 1, sel.unsqueeze(-1).expand(-1, -1, 3))
+            slots.append(c - xyz)
+        vote_target_masks = (count > 0).long()
+        vote_targets = torch.cat(slots, -1) * vote_target_masks.unsqueeze(-1).float()
+
+        # ---- proposal -> nearest GT centre (chamfer l2, reference :868-873)
+        agg = bbox_preds['aggregated_points']
+        d2 = ((agg[:, :, None, :] - centre[:, None, :, :]) ** 2).sum(-1)
+        d2 = d2.masked_fill(~valid[:, None, :], float('inf'))
+        distance1, assignment = d2.min(-1)
+        euclidean_distance1 = torch.sqrt(distance1 + 1e-6)
+        pos_thr, neg_thr = self.train_cfg['pos_distance_thr'], self.train_cfg['neg_distance_thr']
+        objectness_masks = ((euclidean_distance1 < pos_thr) | (euclidean_distance1 > neg_thr)).float()
+
+        def take(t):
+            idx = assignment if t.dim() == 2 else assignment.unsqueeze(-1).expand(-1, -1, t.shape[-1])
+            return torch.gather(t, 1, idx)
+
+        dir_class, dir_res = self.bbox_coder.angle2class(yaw)
+        center_targets = take(centre)
+        size_targets = take(size)
+        dir_class_targets = take(dir_class)
+        dir_res_targets = take(dir_res) / (np.pi / self.num_dir_bins)
+        dir_targets = take(yaw)
+        mask_targets = take(label)
+
+        # ---- inside-the-box test in the box frame (reference :899-935)
+        canonical = agg - center_targets
+        cosa, sina = torch.cos(dir_targets), torch.sin(dir_targets)
+        cx = canonical[..., 0] * cosa - canonical[..., 1] * sina   # rotation_3d_in_axis(-yaw, 2)
+        cy = canonical[..., 0] * sina + canonical[..., 1] * cosa
+        local = torch.stack([cx, cy, canonical[..., 2]], -1)
+        half = size_targets / 2.0
+        distance_targets = torch.cat([half - local, half + local], dim=-1)
+        inside_mask = (distance_targets >= 0.).all(dim=-1)
+        objectness_targets = ((euclidean_distance1 < pos_thr) & inside_mask).long()
+
+        objectness_weights = objectness_masks / (torch.sum(objectness_masks) + 1e-6)
+        box_loss_weights = objectness_targets.float() / (torch.sum(objectness_targets).float() + 1e-6)
+        return (vote_targets, vote_target_masks, dir_class_targets, dir_res_targets, mask_targets,
+                objectness_targets, objectness_weights, box_loss_weights, distance_targets,
+                dir_targets, size_targets, center_targets)

@@ -117,6 +117,36 @@ int demf_three_interpolate_fwd(const float* features, const int32_t* idx, const 
 int demf_three_interpolate_bwd(const float* grad_out, const int32_t* idx, const float* weight,
                                int B, int C, int n, int m, float* grad_features, void* stream);
 
+/* ------------------------------------------- point-major ("rows") layout -- */
+/* The layout the B200 backbone runs on: features are kept point-major, (B,N,C), so that a
+ * neighbour is ONE contiguous row. These entry points replace the same upstream bindings as
+ * demf_query_and_group_fwd / demf_group_bwd / demf_three_interpolate_* (mmdet3d
+ * ball_query_ext + group_points_ext + interpolate_ext, reached from PointSAModule /
+ * PointFPModule of configs/demf/demf_votenet.py:48-62,155-162) for a caller that keeps
+ * activations as GEMM-ready rows.
+ *
+ * Row width K = demf_group_rows_width(C) = roundup(C,4) + 4 floats:
+ *   out[b,m,s,:] = [ feat[b,idx,0:C] | 0-pad to a multiple of 4 | (xyz[idx]-centre)(/r) | 0 ]
+ * query != 0: run the ball query (idx is an OUTPUT, same rows as demf_ball_query);
+ * query == 0: idx is an INPUT. */
+int demf_group_rows_width(int C);
+int demf_query_and_group_rows_fwd(const float* xyz, const float* feat_rows, const float* new_xyz,
+                                  int B, int N, int M, int C, float min_radius, float max_radius,
+                                  int ns, int normalize_xyz, int query, int32_t* idx, float* out,
+                                  void* stream);
+/* grad_out (B,M,ns,K) -> grad_feat_rows (B,N,C) pre-zeroed (may be NULL when C == 0),
+ * grad_xyz (B,N,3) pre-zeroed or NULL, grad_centre (B,M,3) fully written or NULL.
+ * xyz_scale = 1/max_radius when normalize_xyz was set, else 1. */
+int demf_group_rows_bwd(const float* grad_out, const int32_t* idx, int B, int N, int M, int C, int ns,
+                        float xyz_scale, float* grad_feat_rows, float* grad_xyz, float* grad_centre,
+                        void* stream);
+/* feat_rows (B,m,C), idx (B,n,3), weight (B,n,3) -> out (B,n,C); C % 4 == 0.
+ * bwd: grad_out (B,n,C) -> grad_feat_rows (B,m,C) pre-zeroed. */
+int demf_three_interpolate_rows_fwd(const float* feat_rows, const int32_t* idx, const float* weight,
+                                    int B, int C, int m, int n, float* out, void* stream);
+int demf_three_interpolate_rows_bwd(const float* grad_out, const int32_t* idx, const float* weight,
+                                    int B, int C, int n, int m, float* grad_feat_rows, void* stream);
+
 /* ------------------------------------ multi-scale deformable attention --- */
 /* replaces mmcv _ext.ms_deform_attn_forward / ms_deform_attn_backward
  * (MultiScaleDeformableAttnFunction; reached from transformer.py:73-78).
