@@ -23,6 +23,30 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class _KernelTimer:
+    """Optional CUDA-event bracket around each forward sampling-kernel launch (bench.py's
+    roofline figure is measured with it, live, on the launch stream)."""
+
+    def __init__(self):
+        self.enabled = False
+        self.pairs = []
+
+    def enable(self):
+        self.enabled, self.pairs = True, []
+
+    def disable(self):
+        self.enabled = False
+
+    def drain(self):
+        torch.cuda.synchronize()
+        out = [a.elapsed_time(b) for a, b in self.pairs]
+        self.pairs = []
+        return out
+
+
+KERNEL_TIMER = _KernelTimer()
+
+
 class MultiScaleDeformableAttnFunction(Function):
 
     @staticmethod
@@ -48,10 +72,16 @@ class MultiScaleDeformableAttnFunction(Function):
         ctx.im2col_step = im2col_step
         with torch.cuda.device_of(value):
             out = torch.empty(B, Q, H * D, dtype=value.dtype, device=value.device)
+            if KERNEL_TIMER.enabled:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             _lib.check(_lib.load().demf_msda_fwd(
                 value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), sampling_locations.data_ptr(),
                 attention_weights.data_ptr(), B, S, H, D, Q, L, P, out.data_ptr(), _stream()),
                 "demf_msda_fwd")
+            if KERNEL_TIMER.enabled:
+                ev[1].record()
+                KERNEL_TIMER.pairs.append(ev)
         ctx.save_for_backward(value, shapes, lsi, sampling_locations, attention_weights)
         return out
 

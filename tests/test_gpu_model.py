@@ -1,0 +1,171 @@
+"""GPU parity of the point-major ("rows") kernels and of the whole DeMF(VoteNet) forward /
+training step against the CPU oracle backend (oracle/cpu_backend.py), through the C ABI."""
+import pytest
+import torch
+
+import demf_b200  # noqa: F401
+from demf_b200 import _lib, engine, synth
+from demf_b200.mm import point_ops as ops
+from oracle import cpu_backend
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    _lib.load()
+    engine.set_gemm_precision("fp32")
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("B,N,M,C,r,ns,norm", [
+    (2, 20000, 2048, 1, 0.2, 64, True),    # SA1
+    (2, 2048, 1024, 128, 0.4, 32, True),   # SA2
+    (2, 1024, 512, 256, 0.8, 16, True),    # SA3
+    (3, 512, 256, 256, 1.2, 16, True),     # SA4
+    (2, 1024, 256, 256, 0.3, 16, True),    # vote aggregation
+    (1, 300, 37, 5, 0.5, 8, False),        # C % 4 != 0, ragged M
+    (1, 100, 10, 0, 0.3, 4, True),         # xyz only
+])
+def test_query_and_group_rows_matches_oracle(dev, B, N, M, C, r, ns, norm):
+    xyz = synth.make_points(B, N, seed=N + M, clustered=(N >= 1024))[..., :3].contiguous()
+    centres = xyz[:, torch.randperm(N, generator=torch.Generator().manual_seed(1))[:M]].contiguous()
+    feats = torch.randn(B, N, C, generator=torch.Generator().manual_seed(2)) if C else None
+    ridx, rrows = cpu_backend._query_and_group_rows(xyz, centres, feats, 0.0, r, ns, norm)
+    idx, rows = ops.query_and_group_rows(xyz.to(dev), centres.to(dev),
+                                         None if feats is None else feats.to(dev), 0.0, r, ns, norm)
+    assert torch.equal(idx.cpu(), ridx)
+    assert torch.equal(rows.cpu(), rrows), (rows.cpu() - rrows).abs().max()
+
+
+def test_query_and_group_rows_backward(dev):
+    B, N, M, C, ns = 2, 600, 64, 8, 16
+    g = torch.Generator().manual_seed(0)
+    xyz = synth.make_points(B, N, seed=9)[..., :3].contiguous()
+    centres = (xyz[:, :M] + 0.01).contiguous()
+    feats = torch.randn(B, N, C, generator=g)
+    go = torch.randn(B, M, ns, ops.group_rows_width(C), generator=g)
+    cpu_in = [t.clone().requires_grad_(True) for t in (xyz, centres, feats)]
+    _, rr = cpu_backend._query_and_group_rows(*cpu_in, 0.0, 0.6, ns, True)
+    rr.backward(go)
+    gpu_in = [t.to(dev).requires_grad_(True) for t in (xyz, centres, feats)]
+    _, gr = ops.query_and_group_rows(*gpu_in, 0.0, 0.6, ns, True)
+    gr.backward(go.to(dev))
+    for a, b in zip(gpu_in, cpu_in):
+        torch.testing.assert_close(a.grad.cpu(), b.grad, atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("B,n,m,C", [(2, 512, 256, 256), (2, 1024, 512, 256), (1, 33, 7, 8)])
+def test_three_interpolate_rows(dev, B, n, m, C):
+    g = torch.Generator().manual_seed(n)
+    tgt = synth.make_points(B, n, seed=1)[..., :3].contiguous()
+    src = synth.make_points(B, m, seed=2)[..., :3].contiguous()
+    feats = torch.randn(B, m, C, generator=g)
+    dist, idx = ops.three_nn(tgt.to(dev), src.to(dev))
+    w = 1.0 / (dist + 1e-8)
+    w = (w / w.sum(2, keepdim=True)).contiguous()
+    f_gpu = feats.to(dev).requires_grad_(True)
+    out = ops.three_interpolate_rows(f_gpu, idx, w)
+    f_cpu = feats.clone().requires_grad_(True)
+    ref = cpu_backend._three_interpolate_rows(f_cpu, idx.cpu(), w.cpu())
+    torch.testing.assert_close(out.cpu(), ref, atol=1e-5, rtol=1e-5)
+    go = torch.randn(B, n, C, generator=g)
+    out.backward(go.to(dev))
+    ref.backward(go)
+    torch.testing.assert_close(f_gpu.grad.cpu(), f_cpu.grad, atol=1e-4, rtol=1e-4)
+
+
+def _frac_close(a, b, atol):
+    return ((a - b).abs() <= atol).float().mean().item()
+
+
+def test_backbone_forward_matches_cpu_oracle(dev):
+    """Eval-mode PointNet2SASSG on 20k-point clouds: every index tensor bit-exact (FPS and ball
+    query only ever see input coordinates), features within 1e-4 of the CPU port (fp32 GEMMs,
+    different summation order in cuBLAS vs MKL)."""
+    torch.manual_seed(0)
+    model = engine.build_demf_votenet(num_points=4).eval()
+    for m in model.modules():  # non-trivial BN statistics
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.5, 1.5)
+    pts = synth.make_points(2, 20000, seed=4, clustered=True)
+    with cpu_backend.oracle_ops(), torch.no_grad():
+        ref = model.pts_backbone(pts)
+    gm = model.to(dev)
+    with torch.no_grad():
+        got = gm.pts_backbone(pts.to(dev))
+    for k in ("sa_indices", "fp_indices"):
+        for a, b in zip(got[k], ref[k]):
+            assert torch.equal(a.cpu(), b)
+    for a, b in zip(got["sa_xyz"], ref["sa_xyz"]):
+        assert torch.equal(a.cpu(), b)
+    for a, b in zip(got["sa_features"][1:] + got["fp_features"], ref["sa_features"][1:] + ref["fp_features"]):
+        torch.testing.assert_close(a.cpu(), b, atol=1e-4, rtol=1e-4)
+    model.cpu()
+
+
+def test_full_forward_matches_cpu_oracle(dev):
+    torch.manual_seed(1)
+    model = engine.build_demf_votenet(num_points=4).eval()
+    # give the offset/attention projections non-zero weights so that MSDA sampling is exercised
+    attn = model.pts_bbox_head.decoder[0].layer.attentions[1]
+    torch.nn.init.normal_(attn.sampling_offsets.weight, std=0.02)
+    torch.nn.init.normal_(attn.attention_weights.weight, std=0.05)
+    batch = engine.synthetic_batch(2, 20000, "S512", seed=6, with_gt=False)
+    with cpu_backend.oracle_ops(), torch.no_grad():
+        ref = model.forward_dummy(points=batch["points"], img=batch["img"], img_metas=batch["img_metas"])
+    gm = model.to(dev)
+    with torch.no_grad():
+        got = gm.forward_dummy(points=batch["points"].to(dev), img=[l.to(dev) for l in batch["img"]],
+                               img_metas=batch["img_metas"])
+    assert torch.equal(got["seed_indices"].cpu(), ref["seed_indices"])
+    assert torch.equal(got["aggregated_indices"].cpu(), ref["aggregated_indices"])
+    torch.testing.assert_close(got["vote_points"].cpu(), ref["vote_points"], atol=1e-4, rtol=1e-4)
+    # ball membership of a vote within 1e-6 of the radius may flip between the two GEMM
+    # implementations; require agreement on (almost) all proposals
+    for a, b in zip(got["decode_res_all"], ref["decode_res_all"]):
+        for k in ("center", "size", "obj_scores", "sem_scores", "dir_class"):
+            assert _frac_close(a[k].cpu(), b[k], 1e-3) > 0.995, k
+    model.cpu()
+
+
+def test_training_step_gradients_match_cpu_oracle(dev):
+    """One forward_train + backward at batch 2: losses and the flat gradient agree with the CPU
+    port (dropout off, BN in train mode on identical batches)."""
+    torch.manual_seed(2)
+    model = engine.build_demf_votenet(num_points=4).train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = 0.0
+    batch = engine.synthetic_batch(2, 20000, "S512", seed=8)
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    with cpu_backend.oracle_ops():
+        ref_losses = model.forward_train(**batch)
+        sum(ref_losses.values()).backward()
+    ref_grads = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    model.zero_grad(set_to_none=True)
+    model.load_state_dict(state)
+    gm = model.to(dev)
+    gbatch = engine.synthetic_batch(2, 20000, "S512", seed=8, device=dev)
+    losses = gm.forward_train(**gbatch)
+    sum(losses.values()).backward()
+    for k in ref_losses:
+        assert abs(losses[k].item() - ref_losses[k].item()) <= 2e-3 * max(1.0, abs(ref_losses[k].item())), k
+    num = den = 0.0
+    for n, p in gm.named_parameters():
+        if n in ref_grads:
+            num += (p.grad.cpu() - ref_grads[n]).pow(2).sum().item()
+            den += ref_grads[n].pow(2).sum().item()
+    assert den > 0 and (num / den) ** 0.5 < 2e-2, (num / den) ** 0.5
+    model.cpu()
+
+
+def test_ops_refuse_cpu_tensors():
+    with pytest.raises(RuntimeError):
+        ops.furthest_point_sample(torch.zeros(1, 8, 3), 2)
+    with pytest.raises(RuntimeError):
+        ops.query_and_group_rows(torch.zeros(1, 8, 3), torch.zeros(1, 2, 3), None, 0.0, 1.0, 4, True)
