@@ -155,22 +155,29 @@ class GatherPoints(Function):
 gather_points = GatherPoints.apply
 
 
+def three_nn_squared(target, source):
+    """Raw kernel result: SQUARED distances (B,n,3) f32 and indices (B,n,3) i32."""
+    assert target.is_contiguous()
+    assert source.is_contiguous()
+    _need_cuda(target, source)
+    B, n, _ = target.shape
+    m = source.size(1)
+    with torch.cuda.device_of(target):
+        dist2 = torch.empty(B, n, 3, dtype=torch.float32, device=target.device)
+        idx = torch.empty(B, n, 3, dtype=torch.int32, device=target.device)
+        if idx.numel():
+            _lib.check(_lib.load().demf_three_nn(_p(target), _p(source), B, n, m, _p(dist2),
+                                                 _p(idx), _stream()), "demf_three_nn")
+    return dist2, idx
+
+
 class ThreeNN(Function):
-    """target (B,n,3), source (B,m,3) -> (dist (B,n,3) = sqrt(d2), idx (B,n,3) i32)."""
+    """target (B,n,3), source (B,m,3) -> (dist (B,n,3) = sqrt(d2), idx (B,n,3) i32).
+    The square root is torch.sqrt on the device, as in the upstream wrapper."""
 
     @staticmethod
     def forward(ctx, target, source):
-        assert target.is_contiguous()
-        assert source.is_contiguous()
-        _need_cuda(target, source)
-        B, n, _ = target.shape
-        m = source.size(1)
-        with torch.cuda.device_of(target):
-            dist2 = torch.empty(B, n, 3, dtype=torch.float32, device=target.device)
-            idx = torch.empty(B, n, 3, dtype=torch.int32, device=target.device)
-            if idx.numel():
-                _lib.check(_lib.load().demf_three_nn(_p(target), _p(source), B, n, m, _p(dist2),
-                                                     _p(idx), _stream()), "demf_three_nn")
+        dist2, idx = three_nn_squared(target, source)
         ctx.mark_non_differentiable(idx)
         return torch.sqrt(dist2), idx
 

@@ -133,6 +133,12 @@ def query_and_group(xyz, new_xyz, features, min_radius, max_radius, ns, use_xyz=
 
 def three_nn(unknown, known):
     """Returns (dist, idx) with dist = sqrt(dist2), exactly like the upstream wrapper."""
+    dist2, idx = three_nn_squared(unknown, known)
+    return torch.sqrt(dist2), idx
+
+
+def three_nn_squared(unknown, known):
+    """The kernel's own outputs: squared distances and indices."""
     unknown, known = _f32(unknown), _f32(known)
     B, n, _ = unknown.shape
     m = known.shape[1]
@@ -140,7 +146,7 @@ def three_nn(unknown, known):
     idx = torch.empty(B, n, 3, dtype=torch.int32)
     _check(lib().demf_ref_three_nn(_p(unknown), _p(known), B, n, m, _p(dist2), _p(idx)),
            "three_nn")
-    return torch.sqrt(dist2), idx
+    return dist2, idx
 
 
 def three_interpolate(features, idx, weight):

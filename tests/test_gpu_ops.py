@@ -201,7 +201,10 @@ def test_three_nn_interpolate_golden(dev, golden):
     z = golden("three_nn_interp")
     dist, idx = ops.three_nn(z["unknown"].to(dev), z["known"].to(dev))
     assert torch.equal(idx.cpu(), z["idx"])
-    assert torch.equal(dist.cpu(), z["dist"])
+    d2, _ = ops.three_nn_squared(z["unknown"].to(dev), z["known"].to(dev))
+    assert torch.equal(d2.cpu(), cref.three_nn_squared(z["unknown"], z["known"])[0])
+    # the wrapper's sqrt is torch.sqrt on the device (as upstream): 1 ulp from the host's
+    torch.testing.assert_close(dist.cpu(), z["dist"], rtol=2.4e-7, atol=0)
     f = z["features"].to(dev).requires_grad_()
     out = ops.three_interpolate(f, z["idx"].to(dev), z["weight"].to(dev))
     assert torch.equal(out.detach().cpu(), z["out"])
@@ -218,7 +221,9 @@ def test_three_nn_matches_oracle(dev, n, m):
     dist, idx = ops.three_nn(a.to(dev), b.to(dev))
     rdist, ridx = cref.three_nn(a, b)
     assert torch.equal(idx.cpu(), ridx)
-    assert torch.equal(dist.cpu(), rdist)
+    d2, _ = ops.three_nn_squared(a.to(dev), b.to(dev))
+    assert torch.equal(d2.cpu(), cref.three_nn_squared(a, b)[0])   # kernel output: bit-exact
+    torch.testing.assert_close(dist.cpu(), rdist, rtol=2.4e-7, atol=0)  # device sqrt: <= 1 ulp
 
 
 def test_three_interpolate_fp_module_sizes(dev):
