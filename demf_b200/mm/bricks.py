@@ -358,10 +358,63 @@ def permute_weight_columns(w, cols):
     return torch.nn.functional.pad(w, (0, 1)).index_select(1, idx)
 
 
+def _fold_conv_bn(cm, cols):
+    """(W', b') with  act(bn(conv(x))) == act(x @ W'^T + b')  for a ConvModule in eval mode:
+    W' = W * gamma / sqrt(var + eps) (rows), b' = beta + (bias - mean) * gamma / sqrt(var + eps)."""
+    w = cm.conv.weight.flatten(1)
+    if cols is not None:
+        w = permute_weight_columns(w, cols)
+    b = cm.conv.bias
+    if cm.with_norm:
+        bn = cm.norm
+        scale = torch.rsqrt(bn.running_var + bn.eps)
+        if bn.weight is not None:
+            scale = scale * bn.weight
+        w = w * scale.unsqueeze(1)
+        shift = -bn.running_mean * scale if b is None else (b - bn.running_mean) * scale
+        b = shift if bn.bias is None else shift + bn.bias
+    elif b is None:
+        b = w.new_zeros(w.size(0))
+    return w.contiguous(), b.contiguous()
+
+
+def _folded_cached(cm, cols):
+    tensors = [cm.conv.weight, cm.conv.bias]
+    if cm.with_norm:
+        bn = cm.norm
+        tensors += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+    key = (tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors),
+           None if cols is None else tuple(cols))
+    cache = cm.__dict__.get("_rows_fold")
+    if cache is None or cache[0] != key:
+        cache = (key,) + _fold_conv_bn(cm, cols)
+        cm.__dict__["_rows_fold"] = cache
+    return cache[1], cache[2]
+
+
+def _foldable(cm):
+    if cm.with_norm:
+        bn = cm.norm
+        if bn.training or not bn.track_running_stats or not isinstance(
+                bn, nn.modules.batchnorm._BatchNorm):
+            return False
+    return (not cm.with_activation) or type(cm.activate) is nn.ReLU
+
+
 def conv_module_rows(cm, x, cols=None):
     """A kernel-size-1 ConvModule (Conv1d/Conv2d -> BN -> act) applied to rows x (R, Cin'): the
-    1x1 convolution IS a GEMM over rows (cuBLAS), so no im2col / NCHW round trip is needed.
-    `cols` permutes the weight's input columns to the row layout (point_ops.group_rows_columns)."""
+    1x1 convolution IS a GEMM over rows, so no im2col / NCHW round trip is needed.
+    `cols` permutes the weight's input columns to the row layout (point_ops.group_rows_columns).
+
+    Inference (BN in eval mode, no autograd): BN is folded into the weights once and the layer
+    is ONE library GEMM with a bias+ReLU epilogue -- the activation tensor is written exactly
+    once and never re-read by a normalisation or clamp pass.
+    Training: GEMM, then batch-statistics BN (F.batch_norm on rows), then the activation."""
+    if not torch.is_grad_enabled() and _foldable(cm):
+        w, b = _folded_cached(cm, cols)
+        if cm.with_activation:
+            return torch._addmm_activation(b, x, w.t())
+        return torch.addmm(b, x, w.t())
     w = cm.conv.weight.flatten(1)
     if cols is not None:
         w = permute_weight_columns(w, cols)

@@ -43,6 +43,14 @@ class _KernelTimer:
         self.pairs = []
         return out
 
+    def read_last(self):
+        """Elapsed ms of the most recent pair (re-recorded by every replay of a captured graph);
+        the caller synchronises first."""
+        if not self.pairs:
+            return None
+        a, b = self.pairs[-1]
+        return a.elapsed_time(b)
+
 
 KERNEL_TIMER = _KernelTimer()
 
@@ -73,7 +81,9 @@ class MultiScaleDeformableAttnFunction(Function):
         with torch.cuda.device_of(value):
             out = torch.empty(B, Q, H * D, dtype=value.dtype, device=value.device)
             if KERNEL_TIMER.enabled:
-                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ext = dict(external=True) if torch.cuda.is_current_stream_capturing() else {}
+                ev = (torch.cuda.Event(enable_timing=True, **ext),
+                      torch.cuda.Event(enable_timing=True, **ext))
                 ev[0].record()
             _lib.check(_lib.load().demf_msda_fwd(
                 value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), sampling_locations.data_ptr(),

@@ -75,7 +75,10 @@ class BasePointSAModule(nn.Module):
     def _sample_points(self, points_xyz, features, indices, target_xyz):
         if indices is not None:
             assert indices.shape[1] == self.num_point[0]
-            new_xyz = P.gather_rows(points_xyz, indices) if self.num_point is not None else None
+            if target_xyz is not None:  # centres already gathered by the caller (sampling chain)
+                new_xyz = target_xyz
+            else:
+                new_xyz = P.gather_rows(points_xyz, indices) if self.num_point is not None else None
         elif target_xyz is not None:
             new_xyz = target_xyz.contiguous()
         else:
@@ -115,7 +118,10 @@ class BasePointSAModule(nn.Module):
                 for j, layer in enumerate(mlp):
                     x = conv_module_rows(layer, x, P.group_rows_columns(C) if j == 0 else None)
                 x = x.view(B, M, ns, -1)
-                x = x.max(dim=2)[0] if self.pool_mod == 'max' else x.mean(dim=2)
+                if self.pool_mod == 'max':  # amax: no index tensor when nothing back-propagates
+                    x = x.max(dim=2)[0] if torch.is_grad_enabled() else x.amax(dim=2)
+                else:
+                    x = x.mean(dim=2)
                 out.append(x)  # rows (B,M,C')
             else:
                 grouped = grouper(points_xyz, new_xyz, features)
@@ -249,14 +255,67 @@ class PointNet2SASSG(BaseModule):
         features = points[..., 3:].transpose(1, 2) if points.size(-1) > 3 else None
         return xyz, features
 
+    # Furthest point sampling only ever sees coordinates: level i+1 samples the centres level i
+    # picked, never its features. The whole sampling chain (2048 -> 1024 -> 512 -> 256, plus the
+    # head's 1024 -> 256 proposal sampling when asked for) is therefore issued up front on a
+    # side stream, and the grouping / MLP work of level i on the main stream overlaps the serial
+    # FPS iterations of levels > i. Each level publishes an event the main stream waits on.
+    prefetch_seed_fps = None   # set by the detector: (fp level whose xyz are the seeds, m)
+
+    def _side_stream(self, device):
+        streams = self.__dict__.setdefault("_streams", {})
+        if device not in streams:
+            streams[device] = torch.cuda.Stream(device=device)
+        return streams[device]
+
+    def _sampling_chain(self, xyz):
+        """-> per-level (indices (B,M) i32, new_xyz (B,M,3), ready event), seed fps or None."""
+        overlap = xyz.is_cuda
+        levels, seed_fps = [], None
+        if overlap:
+            main = torch.cuda.current_stream(xyz.device)
+            side = self._side_stream(xyz.device)
+            side.wait_stream(main)
+            ctx = torch.cuda.stream(side)
+        else:
+            import contextlib
+            ctx = contextlib.nullcontext()
+        with ctx:
+            cur = xyz
+            for i, sa in enumerate(self.SA_modules):
+                idx = P.furthest_point_sample(cur, sa.num_point[0])
+                new_xyz = P.gather_rows(cur, idx).contiguous()
+                ev = None
+                if overlap:
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                levels.append((idx, new_xyz, ev))
+                cur = new_xyz
+                if self.prefetch_seed_fps is not None and self.prefetch_seed_fps[0] == i + 1:
+                    seed_fps = (P.furthest_point_sample(cur, self.prefetch_seed_fps[1]),
+                                torch.cuda.Event() if overlap else None)
+                    if overlap:
+                        seed_fps[1].record(side)
+        return levels, seed_fps
+
     def forward(self, points):
         """points (B,N,3+C) -> dict of fp_xyz / fp_features / fp_indices / sa_*."""
         xyz, features = self._split_point_feats(points)
         batch, num_points = xyz.shape[:2]
+        chained = all(getattr(sa, "num_point", None) is not None and len(sa.num_point) == 1
+                      for sa in self.SA_modules)
+        levels, seed_fps = self._sampling_chain(xyz) if chained else (None, None)
         indices = torch.arange(num_points, device=xyz.device).unsqueeze(0).repeat(batch, 1).long()
         sa_xyz, sa_features, sa_indices = [xyz], [features], [indices]
         for i in range(self.num_sa):
-            cur_xyz, cur_features, cur_indices = self.SA_modules[i](sa_xyz[i], sa_features[i])
+            if levels is not None:
+                idx, new_xyz, ev = levels[i]
+                if ev is not None:
+                    torch.cuda.current_stream(xyz.device).wait_event(ev)
+                cur_xyz, cur_features, cur_indices = self.SA_modules[i](
+                    sa_xyz[i], sa_features[i], indices=idx, target_xyz=new_xyz)
+            else:
+                cur_xyz, cur_features, cur_indices = self.SA_modules[i](sa_xyz[i], sa_features[i])
             sa_xyz.append(cur_xyz)
             sa_features.append(cur_features)
             sa_indices.append(torch.gather(sa_indices[-1], 1, cur_indices.long()))
@@ -268,8 +327,13 @@ class PointNet2SASSG(BaseModule):
                                                   fp_features[-1]))
             fp_xyz.append(sa_xyz[self.num_sa - i - 1])
             fp_indices.append(sa_indices[self.num_sa - i - 1])
-        return dict(fp_xyz=fp_xyz, fp_features=fp_features, fp_indices=fp_indices, sa_xyz=sa_xyz,
-                    sa_features=sa_features, sa_indices=sa_indices)
+        ret = dict(fp_xyz=fp_xyz, fp_features=fp_features, fp_indices=fp_indices, sa_xyz=sa_xyz,
+                   sa_features=sa_features, sa_indices=sa_indices)
+        if seed_fps is not None:
+            if seed_fps[1] is not None:
+                torch.cuda.current_stream(xyz.device).wait_event(seed_fps[1])
+            ret['seed_fps_indices'] = seed_fps[0]
+        return ret
 
 
 # ---------------------------------------------------------------- vote module ---------

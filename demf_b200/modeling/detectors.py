@@ -49,6 +49,11 @@ class DeMFVoteNet(BaseModule):
         self.num_sampled_seed = num_sampled_seed
         self.train_cfg = train_cfg
         self.test_cfg = test_cfg
+        # the head's proposal FPS (sample_mod='seed') runs on the seed coordinates = xyz of SA
+        # level num_sa - num_fp: let the backbone's sampling chain issue it early
+        bb, head = getattr(self, 'pts_backbone', None), getattr(self, 'pts_bbox_head', None)
+        if bb is not None and head is not None and hasattr(bb, 'num_fp'):
+            self._seed_fps_level = (bb.num_sa - bb.num_fp, head.num_proposal)
 
     # --- with_* properties of mmdet3d's ImVoteNet / Base3DDetector
     @property
@@ -115,8 +120,11 @@ class DeMFVoteNet(BaseModule):
             x = self.img_encoder(x, img_metas)
         return x
 
-    def extract_pts_feat(self, pts):
+    def extract_pts_feat(self, pts, sample_mod=None):
+        prefetch = sample_mod == 'seed' and hasattr(self, '_seed_fps_level')
+        self.pts_backbone.prefetch_seed_fps = self._seed_fps_level if prefetch else None
         x = self.pts_backbone(pts)
+        self._seed_fps_indices = x.get('seed_fps_indices') if isinstance(x, dict) else None
         if self.with_pts_neck:
             x = self.pts_neck(x)
         return x['fp_xyz'][-1], x['fp_features'][-1], x['fp_indices'][-1]
@@ -129,14 +137,18 @@ class DeMFVoteNet(BaseModule):
         for meta in img_metas:
             meta['batch_input_shape'] = shape
 
-    def _forward_head(self, points, img, img_metas, sample_mod):
+    def _forward_head(self, points, img, img_metas, sample_mod, projection=None):
         self._batch_input_shape(img, img_metas)
         img_features = self.extract_img_feat(img, img_metas)
         points = torch.stack(list(points)) if not torch.is_tensor(points) else points
-        seeds_3d, seed_3d_features, seed_indices = self.extract_pts_feat(points)
+        seeds_3d, seed_3d_features, seed_indices = self.extract_pts_feat(points, sample_mod)
         feat_dict = dict(seed_points=seeds_3d, seed_features=seed_3d_features,
                          seed_indices=seed_indices)
+        if self._seed_fps_indices is not None:
+            feat_dict['seed_sample_indices'] = self._seed_fps_indices
         img_dict = dict(img_features=img_features, img_metas=img_metas)
+        if projection is not None:
+            img_dict['projection'] = projection
         return points, self.pts_bbox_head(feat_dict, sample_mod, img_dict)
 
     def forward_train(self, points=None, img=None, img_metas=None, gt_bboxes_ignore=None,
@@ -153,11 +165,11 @@ class DeMFVoteNet(BaseModule):
         return self._forward_head(points, img, img_metas, self.test_cfg['pts']['sample_mod'])[1]
 
     def simple_test(self, points=None, img_metas=None, img=None, bboxes_2d=None, rescale=False,
-                    **kwargs):
+                    projection=None, **kwargs):
         """Forward + box decoding of the ensemble layers (NMS is out of scope):
         returns (boxes (B, len(ensemble)*Q, 7), objectness (B, .), semantic scores (B, ., C))."""
         _, bbox_preds = self._forward_head(points, img, img_metas,
-                                           self.test_cfg['pts']['sample_mod'])
+                                           self.test_cfg['pts']['sample_mod'], projection)
         head = self.pts_bbox_head
         obj, sem, box = [], [], []
         for i in head.test_cfg['ensemble_layers']:

@@ -108,7 +108,12 @@ class DeMFVoteHead(BaseModule):
         if sample_mod == 'vote':
             aggregation_inputs = dict(points_xyz=vote_points, features=vote_features)
         elif sample_mod == 'seed':
-            sample_indices = P.furthest_point_sample(seed_points.contiguous(), self.num_proposal)
+            # FPS on the seeds (reference :429-430); the backbone's sampling chain may already
+            # have run it on its side stream (same input, same kernel)
+            sample_indices = feat_dict.get('seed_sample_indices')
+            if sample_indices is None:
+                sample_indices = P.furthest_point_sample(seed_points.contiguous(),
+                                                         self.num_proposal)
             aggregation_inputs = dict(points_xyz=vote_points, features=vote_features,
                                       indices=sample_indices)
         elif sample_mod == 'random':
@@ -125,11 +130,13 @@ class DeMFVoteHead(BaseModule):
             **aggregation_inputs)
         results['aggregated_points'] = aggregated_points
         results['aggregated_indices'] = aggregated_indices
-        results['decode_res_all'] = self.transformer_decoder(features, aggregated_points,
-                                                             img_features, img_metas)
+        results['decode_res_all'] = self.transformer_decoder(
+            features, aggregated_points, img_features, img_metas,
+            projection=img_dict.get('projection'))
         return results
 
-    def transformer_decoder(self, features, aggregated_points, img_features, img_metas):
+    def transformer_decoder(self, features, aggregated_points, img_features, img_metas,
+                            projection=None):
         """features (B,C,Q) -> list of num_layers+1 prediction dicts (reference :468-512)."""
         decode_res_all = []
         cls_predictions, reg_predictions = self.conv_preds[0](features)
@@ -137,7 +144,8 @@ class DeMFVoteHead(BaseModule):
         decode_res_all.append(decode_res)
 
         feat_flatten, mask_flatten, reference_points, spatial_shapes, level_start_index, \
-            valid_ratios = self.prepare_decoder_inputs(aggregated_points, img_features, img_metas)
+            valid_ratios = self.prepare_decoder_inputs(aggregated_points, img_features, img_metas,
+                                                       projection=projection)
 
         query = features.permute(2, 0, 1)
         for i in range(self.num_decoder_layers):
@@ -160,19 +168,33 @@ class DeMFVoteHead(BaseModule):
         valid_W = torch.sum(~mask[:, 0, :], 1)
         return torch.stack([valid_W.float() / W, valid_H.float() / H], -1)
 
-    def get_reference_points(self, seeds_3d_batch, img_metas):
+    def get_reference_points(self, seeds_3d_batch, img_metas, projection=None):
         """(B,Q,3) proposals -> (B,Q,2) normalised image coordinates, clamped to [0,1].
-        Whole batch in one bmm; the per-scene matrices are folded on the host (geometry.py)."""
-        mats, affs = geometry.fold_projection(img_metas)
-        dev = seeds_3d_batch.device
-        return geometry.project_batched(seeds_3d_batch, mats.to(dev, non_blocking=True),
-                                        affs.to(dev, non_blocking=True))
+        Whole batch in one bmm; the per-scene matrices are folded on the host (geometry.py).
+        `projection` = (mats (B,3,4), affs (B,4)) already on the device (CUDA-graph replay keeps
+        them in static buffers, engine.GraphedForward)."""
+        if projection is None:
+            mats, affs = geometry.fold_projection(img_metas)
+            dev = seeds_3d_batch.device
+            projection = (mats.to(dev, non_blocking=True), affs.to(dev, non_blocking=True))
+        return geometry.project_batched(seeds_3d_batch, *projection)
 
-    def prepare_decoder_inputs(self, seeds_3d, mlvl_feats, img_metas):
+    _level_cache = {}
+
+    @classmethod
+    def _level_tensors(cls, shapes, starts, dev):
+        key = (tuple(shapes), str(dev))
+        if key not in cls._level_cache:
+            cls._level_cache[key] = (
+                torch.as_tensor(shapes, dtype=torch.long).to(dev),
+                torch.as_tensor(starts[:-1], dtype=torch.long).to(dev))
+        return cls._level_cache[key]
+
+    def prepare_decoder_inputs(self, seeds_3d, mlvl_feats, img_metas, projection=None):
         """-> feat_flatten (S,B,C) [view of a (B,S,C) buffer], mask_flatten (B,S) bool or None,
         reference_points (B,Q,2), spatial_shapes (L,2) i64, level_start_index (L) i64,
         valid_ratios (B,L,2). Reference :549-594."""
-        reference_points = self.get_reference_points(seeds_3d, img_metas)
+        reference_points = self.get_reference_points(seeds_3d, img_metas, projection)
         dev = mlvl_feats[0].device
         batch_size, channels = mlvl_feats[0].shape[:2]
         shapes = [tuple(f.shape[-2:]) for f in mlvl_feats]
@@ -199,8 +221,7 @@ class DeMFVoteHead(BaseModule):
             mask_flatten = None
             valid_ratios = reference_points.new_ones(batch_size, len(shapes), 2)
 
-        spatial_shapes = torch.as_tensor(shapes, dtype=torch.long).to(dev, non_blocking=True)
-        level_start_index = torch.as_tensor(starts[:-1], dtype=torch.long).to(dev, non_blocking=True)
+        spatial_shapes, level_start_index = self._level_tensors(shapes, starts, dev)
         return (feat_flatten, mask_flatten, reference_points, spatial_shapes, level_start_index,
                 valid_ratios)
 
