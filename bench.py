@@ -41,6 +41,7 @@ PYRAMID = "S512"
 P_POINTS = 4
 ROTATE = 4  # resident input sets, rotated so that a step never finds its inputs in L2
 CPU_SAMPLE_SCENES = 2
+LANES = 4   # forward graphs in flight (engine.ForwardPipeline)
 
 
 def workload_config(n_gpus):
@@ -238,12 +239,13 @@ def main():
         forward(sets[i % ROTATE])
     torch.cuda.synchronize()
 
-    # one CUDA graph per resident input set (shared memory pool): a step = one graph launch
-    graphs = []
-    for b in sets:
-        graphs.append(engine.GraphedForward(model, b, pool=graphs[0].pool if graphs else None))
+    # one captured forward per resident input set, alternating between LANES streams: a step =
+    # one graph launch, and consecutive (independent) batches overlap on the device
+    pipe = engine.ForwardPipeline(model, sets, lanes=LANES)
+    graphs = pipe.slots
     for i in range(args.warmup):
-        graphs[i % ROTATE].replay()
+        pipe.submit()
+    pipe.join()
     torch.cuda.synchronize()
     lp0 = _lib.launch_count()
     forward(sets[0])
@@ -255,7 +257,8 @@ def main():
     barrier()
     start.record()
     for i in range(args.steps):
-        graphs[i % ROTATE].replay()
+        pipe.submit()
+    pipe.join()
     end.record()
     barrier()
     launches = launches_per_step * args.steps
@@ -263,10 +266,19 @@ def main():
     ms_per_step = ms_total / args.steps
     value = BATCH_PER_GPU * n_gpus * args.steps / (ms_total * 1e-3)
 
+    # ---- same, one forward at a time (latency of a single batch)
+    barrier()
+    start.record()
+    for i in range(args.steps):
+        graphs[i % ROTATE].replay()
+    end.record()
+    barrier()
+    serial_ms = max_over_ranks(start.elapsed_time(end)) / args.steps
+
     # ---- the MSDA sampling kernel, timed in situ: the same graphs replayed with CUDA events
     #      (external event-record nodes captured around the kernel launch), one read per replay
     msda_mod.KERNEL_TIMER.enable()
-    timed_graph = engine.GraphedForward(model, sets[0], pool=graphs[0].pool)
+    timed_graph = engine.GraphedForward(model, sets[0])
     msda_mod.KERNEL_TIMER.disable()
     msda_ms = []
     for i in range(args.steps):
@@ -283,20 +295,22 @@ def main():
     h2d = sum(t.numel() * 4 for t in [host[0]["points"]] + host[0]["img"]) + (12 + 4) * 4 * BATCH_PER_GPU
     d2h = sum(t.numel() * 4 for t in host_out)
 
-    def e2e_step(i):
-        hb = host[i % ROTATE]
-        g = graphs[i % ROTATE]
-        outs = g(hb["points"], hb["img"], hb["img_metas"])   # public API: load + replay
-        for dst, src in zip(host_out, outs):
-            dst.copy_(src, non_blocking=True)
+    host_outs = [[torch.empty(tuple(t.shape), dtype=torch.float32).pin_memory()
+                  for t in graphs[0].outputs] for _ in range(ROTATE)]
 
-    for i in range(3):
+    def e2e_step(i):
+        hb = host[i % ROTATE]   # public API: pinned host batch in, pinned host results out
+        pipe.submit(hb["points"], hb["img"], hb["img_metas"], outputs_to=host_outs[i % ROTATE])
+
+    for i in range(ROTATE):
         e2e_step(i)
+    pipe.join()
     barrier()
     t0 = time.perf_counter()
     start.record()
     for i in range(args.steps):
         e2e_step(i)
+    pipe.join()
     end.record()
     barrier()
     wall = time.perf_counter() - t0
@@ -318,24 +332,39 @@ def main():
     if not args.no_train:
         torch.manual_seed(99)
         tmodel = engine.build_demf_votenet(num_points=P_POINTS).to(dev).train()
-        trainer = engine.Trainer(tmodel)
+        trainer = engine.Trainer(tmodel, capturable=True)
         tsets = [engine.synthetic_batch(TRAIN_BATCH_PER_GPU, NUM_POINTS, PYRAMID,
                                         seed=777 + rank * 100 + i, device=dev) for i in range(ROTATE)]
+        for ts in tsets:   # fixed-shape ground truth, resident
+            ts["gt_bboxes_3d"], ts["gt_labels_3d"] = engine.pad_gt(ts["gt_bboxes_3d"],
+                                                                   ts["gt_labels_3d"], 16, dev)
         tsteps = max(5, args.steps // 3)
         for i in range(3):
             trainer.step(tsets[i % ROTATE])
         barrier()
         start.record()
         for i in range(tsteps):
-            loss, _ = trainer.step(tsets[i % ROTATE])
+            trainer.step(tsets[i % ROTATE])
+        end.record()
+        barrier()
+        eager_tms = max_over_ranks(start.elapsed_time(end)) / tsteps
+        gstep = engine.GraphedTrainStep(trainer, tsets[0], max_gt=16)
+        for i in range(3):
+            gstep(tsets[i % ROTATE])
+        barrier()
+        start.record()
+        for i in range(tsteps):
+            loss, _ = gstep(tsets[i % ROTATE])
         end.record()
         barrier()
         tms = max_over_ranks(start.elapsed_time(end))
-        train = {"workload": "forward+backward+grad all-reduce+clip+AdamW (BASELINE.json configs[3])",
+        train = {"workload": "forward+backward+grad all-reduce+clip+AdamW (BASELINE.json configs[3]), "
+                             "whole step as one CUDA graph, inputs copied device-to-device per step",
                  "batch_per_gpu": TRAIN_BATCH_PER_GPU, "steps": tsteps,
-                 "ms_per_step": tms / tsteps,
+                 "ms_per_step": tms / tsteps, "eager_ms_per_step": eager_tms,
                  "scenes_per_s": TRAIN_BATCH_PER_GPU * n_gpus * tsteps / (tms * 1e-3),
                  "loss": float(loss)}
+        del gstep
         del trainer, tmodel, tsets
 
     if rank != 0:
@@ -382,9 +411,9 @@ def main():
                 "wall_ms_per_step": 1e3 * wall / args.steps},
         "gpu_launches": int(launches),
         "gpu_launches_per_step": launches / args.steps,
-        "execution": "one CUDA graph launch per step (whole forward captured, FPS chain on a "
-                     "parallel branch)",
-        "eager_ms_per_step": eager_ms,
+        "execution": f"one CUDA graph launch per step (whole forward captured, FPS chain on a "
+                     f"parallel branch); {LANES} independent batches in flight on {LANES} streams",
+        "single_batch_latency_ms": serial_ms, "eager_ms_per_step": eager_ms,
         "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu, "train_step": train,
     }
     print(json.dumps(line), flush=True)

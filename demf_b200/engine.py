@@ -134,41 +134,71 @@ class FlatGradients:
         return norm
 
 
-def build_optimizer(model, cfg=None):
+def build_optimizer(model, cfg=None, capturable=False):
     """AdamW with mmcv's paramwise `custom_keys` (lr_mult / decay_mult by parameter-name
-    substring; configs/demf/demf_votenet.py:16-24)."""
+    substring; configs/demf/demf_votenet.py:16-24). Parameters that end up with the same
+    (lr, weight_decay) share one group, and the update is the fused multi-tensor kernel: one
+    launch per group instead of ~10 small launches per parameter."""
     if cfg is None:
         cfg = Config.fromfile(CONFIG).optimizer.to_dict()
     cfg = dict(cfg)
     assert cfg.pop("type") == "AdamW"
     custom = (cfg.pop("paramwise_cfg", None) or {}).get("custom_keys", {})
     base_lr, base_wd = cfg["lr"], cfg.get("weight_decay", 0.0)
-    groups = []
+    groups = {}
     for name, p in model.named_parameters():
         if not p.requires_grad:
             continue
-        group = dict(params=[p], lr=base_lr, weight_decay=base_wd)
+        lr, wd = base_lr, base_wd
         for key in sorted(custom, key=len, reverse=True):
             if key in name:
-                group["lr"] = base_lr * custom[key].get("lr_mult", 1.0)
-                group["weight_decay"] = base_wd * custom[key].get("decay_mult", 1.0)
+                lr = base_lr * custom[key].get("lr_mult", 1.0)
+                wd = base_wd * custom[key].get("decay_mult", 1.0)
                 break
-        groups.append(group)
-    return torch.optim.AdamW(groups, **cfg, foreach=True)
+        groups.setdefault((lr, wd), dict(params=[], names=[], lr=lr, weight_decay=wd))
+        groups[(lr, wd)]["params"].append(p)
+        groups[(lr, wd)]["names"].append(name)
+    on_cuda = all(p.is_cuda for g in groups.values() for p in g["params"])
+    extra = dict(fused=True, capturable=capturable) if on_cuda else dict(foreach=False)
+    return torch.optim.AdamW(list(groups.values()), **cfg, **extra)
+
+
+def pad_gt(gt_bboxes_3d, gt_labels_3d, max_gt=None, device=None):
+    """Lists of per-scene boxes / labels -> fixed-shape (B,G,7) f32 and (B,G) i64 (label -1 =
+    padding). An empty scene gets one all-zero box with label 0, as upstream
+    (class_agnostic_vote_head.py:766-775). Fixed shapes are what a captured training step needs."""
+    tensors = [b.tensor if hasattr(b, "tensor") else b for b in gt_bboxes_3d]
+    G = max([t.shape[0] for t in tensors] + [1])
+    if max_gt is not None:
+        assert G <= max_gt, f"{G} boxes in a scene > max_gt={max_gt}"
+        G = max_gt
+    B = len(tensors)
+    box = torch.zeros(B, G, 7)
+    label = torch.full((B, G), -1, dtype=torch.long)
+    for b, (t, lab) in enumerate(zip(tensors, gt_labels_3d)):
+        g = t.shape[0]
+        if g == 0:
+            label[b, 0] = 0
+            continue
+        box[b, :g] = t.cpu()
+        label[b, :g] = lab.cpu().long()
+    if device is not None:
+        box, label = box.to(device), label.to(device)
+    return box, label
 
 
 class Trainer:
     """forward_train -> sum of losses -> backward into the flat buffer -> one all-reduce ->
     clip (max_norm 10, schedule_3x.py:6) -> AdamW."""
 
-    def __init__(self, model, grad_clip=10.0, group=None):
+    def __init__(self, model, grad_clip=10.0, group=None, capturable=False):
         self.model = model
         self.flat = FlatGradients(model.parameters())
-        self.optimizer = build_optimizer(model)
+        self.optimizer = build_optimizer(model, capturable=capturable)
         self.grad_clip = grad_clip
         self.group = group
 
-    def step(self, batch):
+    def step(self, batch, sync_collective=False):
         self.flat.zero()
         losses = self.model.forward_train(**batch)
         total = sum(losses.values())
@@ -180,6 +210,102 @@ class Trainer:
             self.flat.clip_norm_(self.grad_clip)
         self.optimizer.step()
         return total.detach(), losses
+
+
+class GraphedTrainStep:
+    """One whole training step -- forward, loss, backward, gradient all-reduce, clip, AdamW -- as
+    ONE CUDA-graph launch for a fixed batch shape.
+
+    An eager step is ~1 500 kernel launches for ~10 ms of device work and is bound by the host;
+    captured, a step is the input copies plus one cudaGraphLaunch. Ground truth is padded to
+    `max_gt` boxes per scene (pad_gt) so that every shape is static; the NCCL all-reduce of the
+    flat gradient buffer is captured with the rest. The warm-up steps needed before capture are
+    undone (parameters, BN buffers and optimizer state are restored), so step 1 of the graph is
+    step 1 of training.
+    """
+
+    def __init__(self, trainer, example, max_gt=16, warmup=3):
+        import copy
+        from .mm import geometry
+        model = trainer.model
+        assert model.training
+        dev = example["points"].device
+        self.trainer = trainer
+        self.max_gt = max_gt
+        self._fold = geometry.fold_projection
+        self.points = example["points"].clone()
+        self.levels = [lv.clone() for lv in example["img"]]
+        self.metas = example["img_metas"]
+        mats, affs = geometry.fold_projection(self.metas)
+        self._mats_host, self._affs_host = mats.pin_memory(), affs.pin_memory()
+        self.mats, self.affs = mats.to(dev), affs.to(dev)
+        box, label = pad_gt(example["gt_bboxes_3d"], example["gt_labels_3d"], max_gt)
+        self._box_host, self._label_host = box.pin_memory(), label.pin_memory()
+        self.box, self.label = box.to(dev), label.to(dev)
+
+        snapshot = copy.deepcopy(model.state_dict())
+        self.stream = torch.cuda.Stream(device=dev)
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.stream):
+            for _ in range(warmup):
+                self._eager()
+        torch.cuda.current_stream(dev).wait_stream(self.stream)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self.loss, self.losses = self._eager()
+        # undo the warm-up / capture-time updates in place (captured pointers stay valid)
+        with torch.no_grad():
+            model.load_state_dict(snapshot)
+            for state in trainer.optimizer.state.values():
+                for v in state.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+        torch.cuda.synchronize(dev)
+
+    def _eager(self):
+        t = self.trainer
+        t.flat.zero()
+        losses = t.model.forward_train(points=self.points, img=self.levels, img_metas=self.metas,
+                                       gt_bboxes_3d=self.box, gt_labels_3d=self.label,
+                                       projection=(self.mats, self.affs))
+        total = sum(losses.values())
+        total.backward()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(t.group) > 1:
+            t.flat.buffer.div_(dist.get_world_size(t.group))
+            dist.all_reduce(t.flat.buffer, op=dist.ReduceOp.SUM, group=t.group)
+        if t.grad_clip:
+            t.flat.clip_norm_(t.grad_clip)
+        t.optimizer.step()
+        return total.detach(), {k: v.detach() for k, v in losses.items()}
+
+    def load(self, batch):
+        self.points.copy_(batch["points"], non_blocking=True)
+        for dst, src in zip(self.levels, batch["img"]):
+            dst.copy_(src, non_blocking=True)
+        mats, affs = self._fold(batch["img_metas"])
+        self._mats_host.copy_(mats)
+        self._affs_host.copy_(affs)
+        self.mats.copy_(self._mats_host, non_blocking=True)
+        self.affs.copy_(self._affs_host, non_blocking=True)
+        box, label = batch["gt_bboxes_3d"], batch["gt_labels_3d"]
+        if not torch.is_tensor(box):
+            box, label = pad_gt(box, label, self.max_gt)
+        if box.is_cuda:
+            self.box.copy_(box, non_blocking=True)
+            self.label.copy_(label, non_blocking=True)
+        else:
+            self._box_host.copy_(box)
+            self._label_host.copy_(label)
+            self.box.copy_(self._box_host, non_blocking=True)
+            self.label.copy_(self._label_host, non_blocking=True)
+
+    def __call__(self, batch=None):
+        """Run one step (on the current stream) and return the static (total loss, loss dict)."""
+        if batch is not None:
+            self.load(batch)
+        self.graph.replay()
+        return self.loss, self.losses
 
 
 # ----------------------------------------------------------------------- inference ---
@@ -196,7 +322,7 @@ class GraphedForward:
     affs (B,4)) that `geometry.fold_projection(img_metas)` computes on the host per batch.
     """
 
-    def __init__(self, model, example, pool=None, warmup=3):
+    def __init__(self, model, example, pool=None, warmup=3, stream=None):
         assert not model.training, "GraphedForward captures the eval-mode forward"
         dev = example["points"].device
         assert dev.type == "cuda"
@@ -212,15 +338,18 @@ class GraphedForward:
         self.mats = mats.to(dev)
         self.affs = affs.to(dev)
         self._fold = geometry.fold_projection
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side), torch.no_grad():
+        # warm up and capture on the stream this graph will be replayed on: library workspaces
+        # (cuBLAS/cuBLASLt) are per stream, so graphs captured on different streams can be in
+        # flight at the same time (ForwardPipeline) without sharing one
+        self.stream = stream if stream is not None else torch.cuda.Stream(device=dev)
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.stream), torch.no_grad():
             for _ in range(warmup):
                 self._eager()
-        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.current_stream(dev).wait_stream(self.stream)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self.graph, pool=pool):
+        with torch.no_grad(), torch.cuda.graph(self.graph, pool=pool, stream=self.stream):
             self.outputs = self._eager()
         self.pool = self.graph.pool()
 
@@ -247,3 +376,60 @@ class GraphedForward:
     def __call__(self, points, levels, img_metas=None):
         self.load(points, levels, img_metas)
         return self.replay()
+
+
+class ForwardPipeline:
+    """`lanes` forward graphs in flight at once, each on its own stream with its own static
+    buffers and memory pool.
+
+    One forward is a dependency chain (FPS -> group -> MLP -> ... -> decoder) in which the
+    furthest-point sampling kernels are latency-bound and occupy a fraction of each SM: a single
+    forward cannot fill a B200. Batches are independent, so consecutive batches alternate
+    between lanes: while batch i runs its GEMMs, batch i+1 runs its sampling chain and its H2D
+    copies. `submit` returns the lane's static output tensors; they are valid after
+    `lane_done(slot).synchronize()` (or any later stream sync) and until that lane is submitted to
+    again.
+    """
+
+    def __init__(self, model, examples, lanes=2):
+        if isinstance(examples, dict):
+            examples = [examples] * lanes
+        dev = examples[0]["points"].device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(lanes)]
+        self.slots = []          # one captured forward (own static buffers) per example
+        pools = [None] * lanes   # slots of one lane never overlap in time: they share a pool
+        for j, ex in enumerate(examples):
+            lane = j % lanes
+            g = GraphedForward(model, ex, pool=pools[lane], stream=self.streams[lane])
+            pools[lane] = g.pool
+            self.slots.append(g)
+        self._events = [torch.cuda.Event() for _ in self.slots]
+        self._next = 0
+
+    def submit(self, points=None, levels=None, img_metas=None, outputs_to=None):
+        """Enqueue one batch on the next slot (slots alternate between lanes). With
+        points/levels given they are first copied into the slot's static buffers on its lane's
+        stream (H2D when they are pinned host tensors); `outputs_to` = pinned host tensors that
+        receive the results (D2H on the lane). Returns (slot index, static output tensors)."""
+        k = self._next
+        self._next = (k + 1) % len(self.slots)
+        slot = self.slots[k]
+        slot.stream.wait_stream(torch.cuda.current_stream(slot.device))
+        with torch.cuda.stream(slot.stream):
+            if points is not None:
+                slot.load(points, levels, img_metas)
+            outs = slot.replay()
+            if outputs_to is not None:
+                for dst, src in zip(outputs_to, outs):
+                    dst.copy_(src, non_blocking=True)
+            self._events[k].record(slot.stream)
+        return k, outs
+
+    def lane_done(self, k):
+        return self._events[k]
+
+    def join(self):
+        """Make the current stream wait for everything submitted so far."""
+        cur = torch.cuda.current_stream(self.slots[0].device)
+        for stream in self.streams:
+            cur.wait_stream(stream)

@@ -352,9 +352,16 @@ def batch_norm_rows(bn, x):
         bn.weight, bn.bias, use_batch_stats, factor, bn.eps)
 
 
+_column_index_cache = {}
+
+
 def permute_weight_columns(w, cols):
     """w (Cout, Cin) -> (Cout, len(cols)); cols[j] = source column or -1 for a zero column."""
-    idx = torch.as_tensor([c if c >= 0 else w.size(1) for c in cols], device=w.device)
+    key = (tuple(cols), w.size(1), str(w.device))
+    idx = _column_index_cache.get(key)
+    if idx is None:  # built once per layout and device: no host->device copy in the step
+        idx = torch.as_tensor([c if c >= 0 else w.size(1) for c in cols]).to(w.device)
+        _column_index_cache[key] = idx
     return torch.nn.functional.pad(w, (0, 1)).index_select(1, idx)
 
 

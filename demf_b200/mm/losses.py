@@ -39,13 +39,21 @@ class CrossEntropyLoss(nn.Module):
         self.reduction = reduction
         self.loss_weight = loss_weight
         self.class_weight = class_weight
+        self._class_weight_cache = {}
+
+    def _class_weight(self, like):
+        if self.class_weight is None:
+            return None
+        key = (str(like.device), like.dtype)
+        if key not in self._class_weight_cache:  # once per device: no H2D copy in the step
+            self._class_weight_cache[key] = like.new_tensor(self.class_weight)
+        return self._class_weight_cache[key]
 
     def forward(self, cls_score, label, weight=None, avg_factor=None, reduction_override=None,
                 **kwargs):
         assert reduction_override in (None, 'none', 'mean', 'sum')
         reduction = reduction_override if reduction_override else self.reduction
-        class_weight = (cls_score.new_tensor(self.class_weight)
-                        if self.class_weight is not None else None)
+        class_weight = self._class_weight(cls_score)
         loss = F.cross_entropy(cls_score, label, weight=class_weight, reduction='none')
         if weight is not None:
             weight = weight.float()
@@ -78,7 +86,7 @@ def axis_aligned_iou_aligned(b1, b2, eps=1e-6):
     rb = torch.min(b1[..., 3:], b2[..., 3:])
     wh = (rb - lt).clamp(min=0)
     overlap = wh[..., 0] * wh[..., 1] * wh[..., 2]
-    union = torch.max(area1 + area2 - overlap, overlap.new_tensor([eps]))
+    union = (area1 + area2 - overlap).clamp(min=eps)
     return overlap / union
 
 

@@ -261,6 +261,7 @@ class PointNet2SASSG(BaseModule):
     # side stream, and the grouping / MLP work of level i on the main stream overlaps the serial
     # FPS iterations of levels > i. Each level publishes an event the main stream waits on.
     prefetch_seed_fps = None   # set by the detector: (fp level whose xyz are the seeds, m)
+    overlap_sampling = True    # False: run the sampling chain on the current stream
 
     def _side_stream(self, device):
         streams = self.__dict__.setdefault("_streams", {})
@@ -270,7 +271,7 @@ class PointNet2SASSG(BaseModule):
 
     def _sampling_chain(self, xyz):
         """-> per-level (indices (B,M) i32, new_xyz (B,M,3), ready event), seed fps or None."""
-        overlap = xyz.is_cuda
+        overlap = xyz.is_cuda and self.overlap_sampling
         levels, seed_fps = [], None
         if overlap:
             main = torch.cuda.current_stream(xyz.device)

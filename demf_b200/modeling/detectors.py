@@ -153,9 +153,9 @@ class DeMFVoteNet(BaseModule):
 
     def forward_train(self, points=None, img=None, img_metas=None, gt_bboxes_ignore=None,
                       gt_bboxes_3d=None, gt_labels_3d=None, pts_semantic_mask=None,
-                      pts_instance_mask=None, **kwargs):
+                      pts_instance_mask=None, projection=None, **kwargs):
         points, bbox_preds = self._forward_head(points, img, img_metas,
-                                                self.train_cfg['pts']['sample_mod'])
+                                                self.train_cfg['pts']['sample_mod'], projection)
         loss_inputs = (points, gt_bboxes_3d, gt_labels_3d, pts_semantic_mask, pts_instance_mask,
                        img_metas)
         return self.pts_bbox_head.loss(bbox_preds, *loss_inputs, gt_bboxes_ignore=gt_bboxes_ignore)

@@ -290,24 +290,31 @@ class DeMFVoteHead(BaseModule):
         points = torch.stack(list(points)) if not torch.is_tensor(points) else points
         dev = points.device
         B = points.shape[0]
-        boxes, labels = [], []
-        for b in range(B):
-            t = gt_bboxes_3d[b].tensor.to(dev)
-            lab = gt_labels_3d[b].to(dev)
-            if lab.numel() == 0:
-                t = t.new_zeros(1, 7)
-                lab = lab.new_zeros(1)
-            boxes.append(t)
-            labels.append(lab.long())
-        G = max(t.shape[0] for t in boxes)
-        box = points.new_zeros(B, G, 7)
-        label = torch.zeros(B, G, dtype=torch.long, device=dev)
-        valid = torch.zeros(B, G, dtype=torch.bool, device=dev)
-        for b in range(B):
-            g = boxes[b].shape[0]
-            box[b, :g] = boxes[b]
-            label[b, :g] = labels[b]
-            valid[b, :g] = True
+        if torch.is_tensor(gt_bboxes_3d):
+            # already padded (engine.pad_gt): (B,G,7) boxes, (B,G) labels with -1 = padding
+            box = gt_bboxes_3d.to(dev)
+            valid = gt_labels_3d.to(dev) >= 0
+            label = gt_labels_3d.to(dev).clamp(min=0)
+            G = box.shape[1]
+        else:
+            boxes, labels = [], []
+            for b in range(B):
+                t = gt_bboxes_3d[b].tensor.to(dev)
+                lab = gt_labels_3d[b].to(dev)
+                if lab.numel() == 0:
+                    t = t.new_zeros(1, 7)
+                    lab = lab.new_zeros(1)
+                boxes.append(t)
+                labels.append(lab.long())
+            G = max(t.shape[0] for t in boxes)
+            box = points.new_zeros(B, G, 7)
+            label = torch.zeros(B, G, dtype=torch.long, device=dev)
+            valid = torch.zeros(B, G, dtype=torch.bool, device=dev)
+            for b in range(B):
+                g = boxes[b].shape[0]
+                box[b, :g] = boxes[b]
+                label[b, :g] = labels[b]
+                valid[b, :g] = True
 
         centre = box[..., :3].clone()
         centre[..., 2] = centre[..., 2] + box[..., 5] * 0.5      # gravity centre
@@ -317,14 +324,16 @@ class DeMFVoteHead(BaseModule):
         # ---- vote targets: slot0 = first containing box, slot1 = second (else first),
         #      slot2 = last of >=3 (else first); reference :834-858
         inside = geometry.points_in_boxes_batch(points[..., :3], box).bool() & valid[:, None, :]
-        rank = inside.cumsum(-1)
-        count = rank[..., -1]
-        gidx = torch.arange(G, device=dev)
-        first = (inside & (rank == 1)).float().argmax(-1)
-        second = (inside & (rank == 2)).float().argmax(-1)
-        last = torch.where(inside, gidx.expand_as(inside), gidx.new_full((), -1)).amax(-1).clamp(min=0)
-        second = torch.where(count >= 2, second, first)
-        third = torch.where(count >= 3, last, first)
+        count = inside.sum(-1, dtype=torch.int32)
+        gidx = torch.arange(G, device=dev, dtype=torch.int32)
+        big = gidx.new_full((), G)
+        first = torch.where(inside, gidx, big).amin(-1)                      # lowest box index
+        after_first = inside & (gidx > first.unsqueeze(-1))
+        second = torch.where(after_first, gidx, big).amin(-1)                # next one
+        last = torch.where(inside, gidx, gidx.new_full((), -1)).amax(-1)     # highest
+        first = first.clamp(max=G - 1).long()
+        second = torch.where(count >= 2, second.long(), first)
+        third = torch.where(count >= 3, last.long(), first)
         xyz = points[..., :3]
         slots = []
         for sel in (first, second, third):

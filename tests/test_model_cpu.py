@@ -227,8 +227,28 @@ def test_batched_targets_match_per_scene_reference(model):
 def test_adamw_param_groups_follow_custom_keys(model):
     opt = engine.build_optimizer(model)
     lrs = {}
-    names = [n for n, p in model.named_parameters() if p.requires_grad]
-    for name, group in zip(names, opt.param_groups):
-        lrs[name] = group["lr"]
-    assert math.isclose(lrs["pts_bbox_head.decoder.0.layer.attentions.1.value_proj.weight"], 0.008 * 0.05)
-    assert math.isclose(lrs["pts_backbone.SA_modules.0.mlps.0.layer0.conv.weight"], 0.008)
+    for group in opt.param_groups:
+        for name in group["names"]:
+            lrs[name] = (group["lr"], group["weight_decay"])
+    assert len(opt.param_groups) == 2      # base group + the `decoder` group (lr_mult 0.05)
+    lr, wd = lrs["pts_bbox_head.decoder.0.layer.attentions.1.value_proj.weight"]
+    assert math.isclose(lr, 0.008 * 0.05) and math.isclose(wd, 0.01)
+    assert math.isclose(lrs["pts_backbone.SA_modules.0.mlps.0.layer0.conv.weight"][0], 0.008)
+    n = sum(len(g["params"]) for g in opt.param_groups)
+    assert n == sum(1 for p in model.parameters() if p.requires_grad)
+
+
+def test_padded_gt_gives_the_same_targets(model):
+    head = model.pts_bbox_head
+    B = 3
+    pts = synth.make_points(B, 2500, seed=2, clustered=True)
+    boxes, labels = engine.synthetic_gt(B, seed=2)
+    boxes[2] = boxes[2].new_box(torch.zeros(0, 7))
+    labels[2] = labels[2].new_zeros(0)
+    agg = torch.randn(B, 256, 3, generator=torch.Generator().manual_seed(1))
+    a = head.get_targets(pts, boxes, labels, bbox_preds=dict(aggregated_points=agg))
+    box, lab = engine.pad_gt(boxes, labels, max_gt=16)
+    assert tuple(box.shape) == (B, 16, 7) and (lab[2] >= 0).sum() == 1
+    b = head.get_targets(pts, box, lab, bbox_preds=dict(aggregated_points=agg))
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
