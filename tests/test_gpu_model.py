@@ -217,7 +217,7 @@ def test_graphed_train_step_equals_eager(dev):
         _no_dropout(model)
         trainer = engine.Trainer(model, capturable=True)
         step = engine.GraphedTrainStep(trainer, batches[0], max_gt=16) if graphed else None
-        losses = []
+        losses, grad1 = [], None
         for i in range(3):
             batch = batches[i % 2]
             if graphed:
@@ -226,12 +226,15 @@ def test_graphed_train_step_equals_eager(dev):
                 box, lab = engine.pad_gt(batch["gt_bboxes_3d"], batch["gt_labels_3d"], 16, dev)
                 total, _ = trainer.step(dict(batch, gt_bboxes_3d=box, gt_labels_3d=lab))
             losses.append(total.item())
-        results.append((losses, torch.cat([p.detach().flatten() for p in model.parameters()]).clone()))
-    (l0, p0), (l1, p1) = results
-    # step 1 sees identical weights: same loss. Later steps are only statistically equal: the
-    # backward accumulates with float atomics (as upstream's does) and AdamW's first updates are
-    # +-lr*sign(g), so a rounding-level difference in a near-zero gradient moves that weight by 2*lr.
+            if i == 0:
+                grad1 = trainer.flat.buffer.clone()   # clipped gradient of step 1
+        results.append((losses, grad1))
+    (l0, g0), (l1, g1) = results
+    # Step 1 sees identical weights: same loss and -- up to the order of the float atomics in the
+    # backward kernels (as upstream's) -- the same clipped gradient. Later steps are only
+    # statistically equal: AdamW's first updates are +-lr*sign(g), so a rounding-level difference
+    # in a near-zero gradient moves that weight by 2*lr.
     assert abs(l0[0] - l1[0]) <= 1e-4 * abs(l0[0]), (l0, l1)
-    assert abs(l0[1] - l1[1]) <= 3e-2 * abs(l0[1]), (l0, l1)
-    assert ((p0 - p1).abs() <= 1e-3).float().mean().item() > 0.97
+    assert ((g0 - g1).norm() / g0.norm()).item() <= 1e-3
+    assert abs(l0[1] - l1[1]) <= 5e-2 * abs(l0[1]), (l0, l1)
     assert l0[0] != l0[2]
