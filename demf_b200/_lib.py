@@ -37,6 +37,12 @@ _SIGNATURES = {
                             _ptr, _ptr],
     "demf_three_interpolate_rows_fwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
     "demf_three_interpolate_rows_bwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
+    "demf_sa_pack_floats": [_c_int, _c_int],
+    "demf_sa_pack_weights": [_ptr, _c_int, _c_int, _ptr, _ptr],
+    "demf_sa_fused_supported": [_c_int] * 5,
+    "demf_sa_fused_fwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, _c_int,
+                          _c_int, _c_int, _ptr, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr],
+    "demf_sa_fused_error": [],
     "demf_msda_fwd": [_ptr, _ptr, _ptr, _ptr, _ptr] + [_c_int] * 7 + [_ptr, _ptr],
     "demf_msda_bwd": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr] + [_c_int] * 7 + [_ptr, _ptr, _ptr, _ptr],
 }
@@ -44,6 +50,7 @@ _RESTYPES = {
     "demf_last_error_string": ctypes.c_char_p,
     "demf_launch_count": ctypes.c_uint64,
     "demf_fps_workspace_bytes": ctypes.c_size_t,
+    "demf_sa_pack_floats": ctypes.c_long,
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -1,0 +1,622 @@
+// One launch per set-abstraction level in inference: ball query -> grouping -> 3-layer shared MLP
+// (BN folded, bias + ReLU) -> max over the neighbourhood. Nothing but the (B,M,C3) result leaves
+// the SM: the grouped tensor (a5) and the three activation tensors (a6) of SURVEY.md section 8 --
+// ~275 MB per scene upstream -- live in shared memory and TMEM only.
+//
+// Replaces, for `PointSAModule.forward` in eval mode (mmdet3d ops/pointnet_modules/point_sa_module.py,
+// reached from configs/demf/demf_votenet.py:48-62,155-162): ball_query_kernel + 2x group_points_kernel
+// + transpose/sub/div/cat + 3x (cuDNN 1x1 conv + BN + ReLU) + max_pool2d.
+//
+// CTA = G centres of one scene (G*ns = 128*tiles grouped rows), 18 warps:
+//   warp 0      : tcgen05.mma issuer (one lane)          D[tmem] += A[smem] * W[smem]^T, kind::tf32
+//   warp 1      : weight producer (one lane)             1-D bulk copies of host-packed, pre-swizzled
+//                                                         weight chunks from L2 into a ring
+//   warps 2..17 : workers                                ball query (cloud staged through smem,
+//                                                         ballot/popc compaction = "first ns hits in
+//                                                         index order"), neighbour-row gather into
+//                                                         the swizzled A operand, TMEM epilogues
+// Per 128-row tile:  gather A0 (128 x K0)  ->  MMA layer 0 -> epilogue (bias, ReLU, tf32 round) writes
+// act1 over A0 -> MMA layer 1 -> epilogue -> act2 -> MMA layer 2 -> epilogue: column max over the ns
+// rows of each centre (register butterfly across the 32 TMEM lanes a warp owns), bias, ReLU, store.
+//
+// Arithmetic: TF32 products (operands rounded to nearest, ties away: cvt.rna), fp32 accumulation --
+// the same class as the cuDNN/cuBLAS TF32 convolutions PyTorch >= 1.7 runs for the reference on
+// Ampere and later. Indices are exact (the ball query is the fp32 fma-ordered one of ball_query.cu).
+//
+// Roofline: tensor pipe / L2 (weights re-streamed per tile). HBM bytes per scene = N*12 + N*C*4 +
+// M*12 + M*C3*4 (+ weights once).
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace demf {
+namespace {
+
+using namespace umma;
+
+constexpr int kWorkerWarps = 16;
+constexpr int kWorkers = kWorkerWarps * 32;  // 512
+constexpr int kThreads = kWorkers + 64;      // + issuer warp + producer warp
+constexpr int kTileRows = 128;
+constexpr int kChunkBytes = kTileRows * 128;  // one 32-float K chunk of a 128-row operand
+constexpr int kCloudTile = 2048;              // cloud points per ball-query tile (24 KB)
+constexpr int kMaxSlots = 8;
+
+__device__ int g_sa_error = 0;  // sticky: first protocol time-out (never expected)
+
+struct SaParams {
+  const float* xyz;
+  const float* feat;
+  const float* new_xyz;
+  const float* wpack;
+  const float* bias;
+  float* out;
+  int32_t* idx;
+  int N, M, C, ns, G, tiles, K0;
+  int c[3];
+  int query, normalize_xyz;
+  float min_r2, max_r2, inv_radius;
+  int slots, slot_bytes, resident, act_bytes;
+  int tmem_cols, acc_col[3];
+};
+
+struct SmemLayout {
+  int ring, rows, centres, bias, part, bars, total;
+};
+
+__host__ __device__ inline SmemLayout smem_layout(const SaParams& p) {
+  SmemLayout L;
+  L.ring = p.act_bytes;
+  L.rows = L.ring + p.slots * p.slot_bytes;
+  L.centres = L.rows + p.G * p.ns * 4;
+  L.bias = L.centres + p.G * 16;
+  L.part = L.bias + (p.c[0] + p.c[1] + p.c[2]) * 4;
+  L.bars = (L.part + (p.ns == 64 ? 2 * p.c[2] * 4 : 0) + 15) & ~15;
+  L.total = L.bars + (2 * kMaxSlots + 2) * 8 + 16 + 1024;  // + alignment slack
+  return L;
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory"); }
+
+__device__ __forceinline__ bool worker_sync_and(bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.u32 q, %1, 0;\n\t"
+      "bar.red.and.pred p, 1, %2, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r)
+      : "r"((uint32_t)pred), "n"(kWorkers)
+      : "memory");
+  return r != 0;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Bounded wait that also gives up as soon as any thread of the CTA has flagged a failure.
+__device__ __forceinline__ bool wait_or_fail(uint32_t bar, uint32_t parity, volatile int* failed, int code) {
+  if (mbar_try_wait(bar, parity)) return true;
+  unsigned long long t0 = 0;
+  for (uint32_t spin = 1;; ++spin) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if ((spin & 255u) == 0) {
+      if (*failed) return false;
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 400ull * 1000 * 1000) {  // 0.4 s: a protocol bug, not a slow kernel
+        *failed = code;
+        atomicCAS(&g_sa_error, 0, code);
+        return false;
+      }
+    }
+  }
+}
+
+// 32 -> 1 (FULL) or 32 -> 2 (half warps) column maxima held across the lanes of a warp.
+// After the call: FULL: v[0] = max over the 32 lanes of column `lane`;
+//                 half: v[0], v[1] = max over the 16 lanes of this half of columns 2*(lane&15)+{0,1}.
+template <bool FULL>
+__device__ __forceinline__ void lane_max_transpose(float (&v)[32], unsigned lane) {
+  if (FULL) {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float send = up ? v[i] : v[i + 16];
+      const float keep = up ? v[i + 16] : v[i];
+      v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+    }
+  }
+  constexpr int n0 = FULL ? 16 : 32;
+#pragma unroll
+  for (int n = n0, o = 8; o >= 1; n >>= 1, o >>= 1) {
+    const bool up = lane & o;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? v[i] : v[i + n / 2];
+      const float keep = up ? v[i + n / 2] : v[i];
+      v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, o));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned chunks: align the carve-up by hand
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const SmemLayout L = smem_layout(p);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const unsigned lane = tid & 31u;
+  const int b = blockIdx.y;
+  const int m_base = blockIdx.x * p.G;
+  const int cpt = kTileRows / p.ns;  // centres per tile
+  const int ntiles = min(p.tiles, (min(p.G, p.M - m_base) + cpt - 1) / cpt);
+
+  unsigned char* act = smem;
+  unsigned char* ring = smem + L.ring;
+  int32_t* rows = reinterpret_cast<int32_t*>(smem + L.rows);
+  float4* centres = reinterpret_cast<float4*>(smem + L.centres);
+  float* bias_s = reinterpret_cast<float*>(smem + L.bias);
+  float* part = reinterpret_cast<float*>(smem + L.part);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSlots + 2);
+  volatile int* failed = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  const uint32_t wfull0 = smem_u32(&bars[0]), wempty0 = smem_u32(&bars[kMaxSlots]);
+  const uint32_t op_ready = smem_u32(&bars[2 * kMaxSlots]), acc_full = smem_u32(&bars[2 * kMaxSlots + 1]);
+  const uint32_t act_u32 = smem_u32(act), ring_u32 = smem_u32(ring);
+
+  if (tid == 0) {
+    *failed = 0;
+    for (int s = 0; s < kMaxSlots; ++s) {
+      mbar_init(wfull0 + 8 * s, 1);
+      mbar_init(wempty0 + 8 * s, 1);
+    }
+    mbar_init(op_ready, kWorkerWarps);
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  }
+  for (int i = tid; i < p.c[0] + p.c[1] + p.c[2]; i += kThreads) bias_s[i] = __ldg(p.bias + i);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const int nch0 = (p.K0 + 31) >> 5;
+
+  if (warp == 0) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      uint32_t opp = 0, slot = 0, wph = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        for (int l = 0; l < 3; ++l) {
+          if (!wait_or_fail(op_ready, opp, failed, 1)) break;
+          opp ^= 1;
+          tc_fence_after_sync();
+          const int nch = l == 0 ? nch0 : (p.c[l - 1] >> 5);
+          const uint32_t idesc = instr_desc_tf32(kTileRows, p.c[l]);
+          const uint32_t d = tmem + p.acc_col[l];
+          for (int ch = 0; ch < nch; ++ch) {
+            if (!p.resident || t == 0) {
+              if (!wait_or_fail(wfull0 + 8 * slot, wph, failed, 2)) break;
+            }
+            const int ksteps = l == 0 ? (min(32, p.K0 - 32 * ch) >> 3) : 4;
+            const uint32_t a = act_u32 + ch * kChunkBytes, w = ring_u32 + slot * p.slot_bytes;
+            for (int k = 0; k < ksteps; ++k)
+              mma_tf32(d, smem_desc_sw128(a + 32 * k), smem_desc_sw128(w + 32 * k), idesc, (ch | k) != 0);
+            if (!p.resident) mma_commit(wempty0 + 8 * slot);
+            if (++slot == (uint32_t)p.slots) {
+              slot = 0;
+              wph ^= 1;
+            }
+          }
+          mma_commit(acc_full);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================= weight producer ============================
+    if (lane == 0) {
+      uint32_t slot = 0, ph = 0;
+      const int passes = p.resident ? min(ntiles, 1) : ntiles;
+      for (int t = 0; t < passes; ++t) {
+        const float* src = p.wpack;
+        for (int l = 0; l < 3; ++l) {
+          const int nch = l == 0 ? nch0 : (p.c[l - 1] >> 5);
+          const uint32_t bytes = p.c[l] * 128;
+          for (int ch = 0; ch < nch; ++ch) {
+            if (!p.resident) {
+              if (!wait_or_fail(wempty0 + 8 * slot, ph ^ 1, failed, 3)) break;
+            }
+            mbar_expect_tx(wfull0 + 8 * slot, bytes);
+            bulk_g2s(ring_u32 + slot * p.slot_bytes, src, bytes, wfull0 + 8 * slot);
+            src += bytes >> 2;
+            if (++slot == (uint32_t)p.slots) {
+              slot = 0;
+              ph ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ================================= workers ================================
+    const int wt = tid - 64;
+    const int ww = wt >> 5;
+    const float* cloud = p.xyz + (long)b * p.N * 3;
+    const int ns = p.ns;
+
+    // ---- phase Q: neighbour index rows of the G centres into shared memory
+    {
+      const int m = m_base + ww;
+      const bool active = ww < p.G && m < p.M;
+      float cx = 0.f, cy = 0.f, cz = 0.f;
+      if (active) {
+        const float* c = p.new_xyz + ((long)b * p.M + m) * 3;
+        cx = __ldg(c + 0);
+        cy = __ldg(c + 1);
+        cz = __ldg(c + 2);
+      }
+      if (ww < p.G && lane == 0) centres[ww] = make_float4(cx, cy, cz, 0.f);
+      int32_t* row = rows + ww * ns;  // only dereferenced when ww < G
+      if (p.query) {
+        float* tile = reinterpret_cast<float*>(act);  // the A0 region is free until the first gather
+        int cnt = 0, first = 0;
+        bool done = !active;
+        for (int base = 0; base < p.N; base += kCloudTile) {
+          const int npts = min(kCloudTile, p.N - base);
+          worker_sync();
+          for (int i = wt; i < npts * 3; i += kWorkers) tile[i] = __ldg(cloud + (long)base * 3 + i);
+          worker_sync();
+          if (!done) {
+            for (int j = 0; j < npts; j += 32) {
+              const int q = j + lane;
+              bool hit = false;
+              if (q < npts) {
+                const float d2 = sqdist(cx, cy, cz, tile[q * 3 + 0], tile[q * 3 + 1], tile[q * 3 + 2]);
+                hit = (d2 == 0.f) || (d2 >= p.min_r2 && d2 < p.max_r2);
+              }
+              const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+              if (ballot) {
+                if (cnt == 0) first = base + j + (__ffs(ballot) - 1);
+                const int pos = cnt + __popc(ballot & ((1u << lane) - 1u));
+                if (hit && pos < ns) row[pos] = base + q;
+                cnt += __popc(ballot);
+                if (cnt >= ns) {
+                  done = true;
+                  break;
+                }
+              }
+            }
+          }
+          if (worker_sync_and(done)) break;
+        }
+        if (ww < p.G) {
+          if (cnt > ns) cnt = ns;
+          __syncwarp();
+          for (int l = cnt + lane; l < ns; l += 32) row[l] = first;  // inactive / empty ball: 0
+          __syncwarp();
+          if (active && p.idx) {
+            int32_t* grow = p.idx + ((long)b * p.M + m) * ns;
+            for (int l = lane; l < ns; l += 32) grow[l] = row[l];
+          }
+        }
+      } else if (ww < p.G) {
+        const int32_t* grow = p.idx + ((long)b * p.M + (active ? m : 0)) * ns;
+        for (int l = lane; l < ns; l += 32) row[l] = active ? __ldg(grow + l) : 0;
+      }
+      worker_sync();  // rows + centres visible; cloud tile (aliasing A0) no longer read
+    }
+
+    // ---- phase M: per 128-row tile
+    const int S4 = p.K0 >> 2;       // 16-byte slots per A0 row
+    const int C4 = (p.C + 3) >> 2;  // feature slots; slot C4 = xyz; beyond = zero
+    const bool vec = (p.C & 3) == 0;
+    const float* fb = p.feat ? p.feat + (long)b * p.N * p.C : nullptr;
+    const float scale = p.normalize_xyz ? p.inv_radius : 1.f;
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int cg = ww >> 2;  // column group
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int r_epi = q * 32 + lane;
+    uint32_t accp = 0;
+    bool ok = true;
+
+    for (int t = 0; t < ntiles && ok; ++t) {
+      // gather the 128 grouped rows of this tile as the swizzled A0 operand
+      const int32_t* trow = rows + t * kTileRows;  // rows of centre g are contiguous: g*ns
+#pragma unroll 4
+      for (int e = wt; e < kTileRows * S4; e += kWorkers) {
+        const int r = e / S4;
+        const int j = e - r * S4;
+        const int k = trow[r];
+        float4 v;
+        if (j < C4) {
+          if (vec) {
+            v = __ldg(reinterpret_cast<const float4*>(fb + (long)k * p.C) + j);
+          } else {
+            const float* f = fb + (long)k * p.C + j * 4;
+            const int left = p.C - j * 4;
+            v.x = __ldg(f);
+            v.y = left > 1 ? __ldg(f + 1) : 0.f;
+            v.z = left > 2 ? __ldg(f + 2) : 0.f;
+            v.w = left > 3 ? __ldg(f + 3) : 0.f;
+          }
+        } else if (j == C4) {
+          const float4 c = centres[t * cpt + r / ns];
+          const float* pt = cloud + (long)k * 3;
+          v.x = __fsub_rn(__ldg(pt + 0), c.x);
+          v.y = __fsub_rn(__ldg(pt + 1), c.y);
+          v.z = __fsub_rn(__ldg(pt + 2), c.z);
+          if (p.normalize_xyz) {
+            v.x = __fmul_rn(v.x, scale);
+            v.y = __fmul_rn(v.y, scale);
+            v.z = __fmul_rn(v.z, scale);
+          }
+          v.w = 0.f;
+        } else {
+          v = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        v.x = tf32_rna(v.x);
+        v.y = tf32_rna(v.y);
+        v.z = tf32_rna(v.z);
+        v.w = tf32_rna(v.w);
+        *reinterpret_cast<float4*>(act + (j >> 3) * kChunkBytes + sw128_offset(r, j & 7)) = v;
+      }
+      fence_proxy_async();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(op_ready);
+
+      // layers 0 and 1: accumulator -> bias, ReLU, tf32 -> next layer's A operand
+      for (int l = 0; l < 2 && ok; ++l) {
+        ok = wait_or_fail(acc_full, accp, failed, 4);
+        accp ^= 1;
+        tc_fence_after_sync();
+        const float* bl = bias_s + (l == 0 ? 0 : p.c[0]);
+        for (int blk = cg; blk < (p.c[l] >> 5); blk += 4) {
+          uint32_t u[32];
+          tmem_ld32(tmem + lane_base + p.acc_col[l] + blk * 32, u);
+          tmem_ld_wait();
+          unsigned char* dst = act + blk * kChunkBytes;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 v;
+            v.x = tf32_rna(fmaxf(__uint_as_float(u[4 * j + 0]) + bl[blk * 32 + 4 * j + 0], 0.f));
+            v.y = tf32_rna(fmaxf(__uint_as_float(u[4 * j + 1]) + bl[blk * 32 + 4 * j + 1], 0.f));
+            v.z = tf32_rna(fmaxf(__uint_as_float(u[4 * j + 2]) + bl[blk * 32 + 4 * j + 2], 0.f));
+            v.w = tf32_rna(fmaxf(__uint_as_float(u[4 * j + 3]) + bl[blk * 32 + 4 * j + 3], 0.f));
+            *reinterpret_cast<float4*>(dst + sw128_offset(r_epi, j)) = v;
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(op_ready);
+      }
+      if (!ok) break;
+
+      // layer 2: max over the ns rows of each centre, then bias + ReLU (both commute with max)
+      ok = wait_or_fail(acc_full, accp, failed, 5);
+      accp ^= 1;
+      tc_fence_after_sync();
+      const float* b2 = bias_s + p.c[0] + p.c[1];
+      const int c3 = p.c[2];
+      const int m_tile = m_base + t * cpt;
+      float keep[2] = {0.f, 0.f};
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int blk = cg + 4 * it;
+        if (blk >= (c3 >> 5)) break;
+        uint32_t u[32];
+        tmem_ld32(tmem + lane_base + p.acc_col[2] + blk * 32, u);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]);
+        if (ns == 16) {
+          lane_max_transpose<false>(v, lane);
+          const int m = m_tile + q * 2 + (lane >> 4);
+          if (m < p.M) {
+            const int col = blk * 32 + 2 * (lane & 15);
+            float2 o;
+            o.x = fmaxf(v[0] + b2[col], 0.f);
+            o.y = fmaxf(v[1] + b2[col + 1], 0.f);
+            *reinterpret_cast<float2*>(p.out + ((long)b * p.M + m) * c3 + col) = o;
+          }
+        } else {
+          lane_max_transpose<true>(v, lane);
+          const int col = blk * 32 + lane;
+          if (ns == 32) {
+            const int m = m_tile + q;
+            if (m < p.M) p.out[((long)b * p.M + m) * c3 + col] = fmaxf(v[0] + b2[col], 0.f);
+          } else {  // ns == 64: a centre spans two lane quarters -> combine through smem
+            if (q & 1) {
+              part[(q >> 1) * c3 + col] = v[0];
+            } else {
+              keep[it] = v[0];
+            }
+          }
+        }
+      }
+      if (ns == 64) {
+        worker_sync();
+        if (!(q & 1)) {
+          const int m = m_tile + (q >> 1);
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const int blk = cg + 4 * it;
+            if (blk >= (c3 >> 5)) break;
+            const int col = blk * 32 + lane;
+            const float mx = fmaxf(keep[it], part[(q >> 1) * c3 + col]);
+            if (m < p.M) p.out[((long)b * p.M + m) * c3 + col] = fmaxf(mx + b2[col], 0.f);
+          }
+        }
+      }
+      tc_fence_before_sync();
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_free(tmem, p.tmem_cols);
+  }
+}
+
+// (Cout, Cin) row-major fp32 -> ceil(Cin/32) chunks of Cout x 32 floats in the swizzled K-major
+// operand image the kernel bulk-copies, zero padded, rounded to TF32 (nearest, ties away).
+__global__ void sa_pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int chunks,
+                                       float* __restrict__ packed) {
+  const long total = (long)chunks * Cout * 32;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(e / ((long)Cout * 32));
+    const int rem = (int)(e - (long)c * Cout * 32);
+    const int n = rem >> 5, kk = rem & 31;
+    const int k = c * 32 + kk;
+    const float v = k < Cin ? tf32_rna(__ldg(w + (long)n * Cin + k)) : 0.f;
+    const long byte = (long)c * Cout * 128 + sw128_offset(n, kk >> 2) + (kk & 3) * 4;
+    packed[byte >> 2] = v;
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+}  // namespace demf
+
+using namespace demf;
+
+extern "C" {
+
+long demf_sa_pack_floats(int Cout, int Cin) { return (long)((Cin + 31) / 32) * Cout * 32; }
+
+int demf_sa_pack_weights(const float* w, int Cout, int Cin, float* packed, void* stream) {
+  DEMF_REQUIRE_PTR(w);
+  DEMF_REQUIRE_PTR(packed);
+  DEMF_REQUIRE(Cout > 0 && Cout % 8 == 0 && Cin > 0, DEMF_E_SIZE);
+  DEMF_REQUIRE(aligned16(packed), DEMF_E_UNSUPPORTED);
+  const int chunks = (Cin + 31) / 32;
+  const long total = (long)chunks * Cout * 32;
+  const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+  sa_pack_weights_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, Cout, Cin, chunks, packed);
+  return after_launch("sa_pack_weights_kernel");
+}
+
+int demf_sa_fused_supported(int C, int ns, int c1, int c2, int c3) {
+  if (!(ns == 16 || ns == 32 || ns == 64)) return 0;
+  if (C < 0 || C > 512) return 0;
+  const int cs[3] = {c1, c2, c3};
+  for (int c : cs)
+    if (c < 32 || c > 256 || c % 32 != 0) return 0;
+  return 1;
+}
+
+int demf_sa_fused_error(void) {
+  int e = 0;
+  cudaMemcpyFromSymbol(&e, g_sa_error, sizeof(int));
+  return e;
+}
+
+int demf_sa_fused_fwd(const float* xyz, const float* feat_rows, const float* new_xyz, int B, int N, int M,
+                      int C, float min_radius, float max_radius, int ns, int normalize_xyz, int query,
+                      const float* wpack, const float* bias, int c1, int c2, int c3, int32_t* idx,
+                      float* out, void* stream) {
+  DEMF_REQUIRE_PTR(xyz);
+  DEMF_REQUIRE_PTR(new_xyz);
+  DEMF_REQUIRE_PTR(wpack);
+  DEMF_REQUIRE_PTR(bias);
+  DEMF_REQUIRE_PTR(out);
+  if (C > 0) DEMF_REQUIRE_PTR(feat_rows);
+  if (!query) DEMF_REQUIRE_PTR(idx);
+  DEMF_REQUIRE(B >= 0 && N > 0 && M >= 0, DEMF_E_SIZE);
+  DEMF_REQUIRE(B <= 65535, DEMF_E_SIZE);
+  DEMF_REQUIRE(demf_sa_fused_supported(C, ns, c1, c2, c3), DEMF_E_UNSUPPORTED);
+  DEMF_REQUIRE(aligned16(wpack) && aligned16(out) && (C % 4 != 0 || aligned16(feat_rows)), DEMF_E_UNSUPPORTED);
+  if (B == 0 || M == 0) return 0;
+
+  SaParams p{};
+  p.xyz = xyz;
+  p.feat = C > 0 ? feat_rows : nullptr;
+  p.new_xyz = new_xyz;
+  p.wpack = wpack;
+  p.bias = bias;
+  p.out = out;
+  p.idx = idx;
+  p.N = N;
+  p.M = M;
+  p.C = C;
+  p.ns = ns;
+  p.K0 = ((((C + 3) / 4) * 4 + 4) + 7) / 8 * 8;
+  p.c[0] = c1;
+  p.c[1] = c2;
+  p.c[2] = c3;
+  p.query = query;
+  p.normalize_xyz = normalize_xyz;
+  p.min_r2 = min_radius * min_radius;
+  p.max_r2 = max_radius * max_radius;
+  p.inv_radius = 1.0f / max_radius;
+
+  // tiles per CTA: up to 16 centres (one per worker warp in the ball-query phase), but keep at
+  // least ~2 CTAs per SM in the grid so the tail wave stays small
+  const int cpt = kTileRows / ns;
+  int tiles = 16 / cpt;
+  while (tiles > 1 && (long)B * ((M + tiles * cpt - 1) / (tiles * cpt)) < 2L * kNumSMs) tiles >>= 1;
+  p.tiles = tiles;
+  p.G = tiles * cpt;
+
+  const int nch0 = (p.K0 + 31) / 32, nch1 = c1 / 32, nch2 = c2 / 32;
+  const int cmax = c1 > c2 ? (c1 > c3 ? c1 : c3) : (c2 > c3 ? c2 : c3);
+  const int amax = nch0 > nch1 ? (nch0 > nch2 ? nch0 : nch2) : (nch1 > nch2 ? nch1 : nch2);
+  p.act_bytes = amax * kChunkBytes;
+  if (query && p.act_bytes < kCloudTile * 12) p.act_bytes = ((kCloudTile * 12 + 1023) / 1024) * 1024;
+  p.slot_bytes = cmax * 128;
+  const int total_chunks = nch0 + nch1 + nch2;
+  // accumulators: [0,c1) [c1,c1+c2) then layer 2 after them if it fits in 512 columns, else at 0
+  p.acc_col[0] = 0;
+  p.acc_col[1] = c1;
+  p.acc_col[2] = (c1 + c2 + c3 <= 512) ? c1 + c2 : 0;
+  int cols = p.acc_col[2] + c3 > c1 + c2 ? p.acc_col[2] + c3 : c1 + c2;
+  p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+
+  const int budget = 227 * 1024;
+  p.slots = 0;
+  for (int s = kMaxSlots; s >= 2; --s) {
+    p.slots = s;
+    if (smem_layout(p).total <= budget) break;
+    p.slots = 0;
+  }
+  DEMF_REQUIRE(p.slots >= 2, DEMF_E_UNSUPPORTED);
+  p.resident = total_chunks <= p.slots;
+  if (p.resident) p.slots = total_chunks;
+  const SmemLayout L = smem_layout(p);
+
+  static int configured_smem = 0;
+  if (L.total > configured_smem) {
+    cudaError_t e = cudaFuncSetAttribute(sa_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L.total);
+    if (e != cudaSuccess) {
+      set_error("demf_sa_fused_fwd: cannot reserve %d bytes of shared memory: %s", L.total,
+                cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    configured_smem = L.total;
+  }
+  dim3 grid((M + p.G - 1) / p.G, B);
+  sa_fused_fwd_kernel<<<grid, kThreads, L.total, as_stream(stream)>>>(p);
+  return after_launch("sa_fused_fwd_kernel");
+}
+
+}  // extern "C"

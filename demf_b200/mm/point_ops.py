@@ -466,3 +466,60 @@ three_interpolate_rows = ThreeInterpolateRows.apply
 def gather_rows(rows, indices):
     """rows (B,N,C), indices (B,M) i32 -> (B,M,C). Tiny (centre coordinates); torch.gather."""
     return torch.gather(rows, 1, indices.long().unsqueeze(-1).expand(-1, -1, rows.size(-1)))
+
+
+# ------------------------------------------------- fused set abstraction (inference) --
+def sa_fused_supported(C, sample_num, widths):
+    """True when csrc/sa_fused.cu covers this (feature channels, nsample, 3 MLP widths)."""
+    return len(widths) == 3 and bool(_lib.load().demf_sa_fused_supported(
+        int(C), int(sample_num), int(widths[0]), int(widths[1]), int(widths[2])))
+
+
+def sa_pack_mlp(weights, biases):
+    """Three BN-folded (Cout,Cin) weights (first one with its columns in row order,
+    group_rows_columns) + biases -> (wpack, bias, widths) for `sa_fused`: each matrix in the
+    swizzled K-major chunk image the kernel bulk-copies into shared memory, TF32-rounded."""
+    assert len(weights) == 3 and len(biases) == 3
+    _need_cuda(*weights)
+    lib = _lib.load()
+    dev = weights[0].device
+    sizes = [int(lib.demf_sa_pack_floats(w.size(0), w.size(1))) for w in weights]
+    with torch.cuda.device_of(weights[0]):
+        wpack = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        off = 0
+        for w, n in zip(weights, sizes):
+            w = w.detach().float().contiguous()
+            _lib.check(lib.demf_sa_pack_weights(_p(w), w.size(0), w.size(1),
+                                                wpack.data_ptr() + 4 * off, _stream()),
+                       "demf_sa_pack_weights")
+            off += n
+    bias = torch.cat([b.detach().float().flatten() for b in biases]).contiguous()
+    return wpack, bias, tuple(int(w.size(0)) for w in weights)
+
+
+def sa_fused(xyz, center_xyz, feat_rows, min_radius, max_radius, sample_num, normalize_xyz, wpack,
+             bias, widths, idx=None, return_idx=False):
+    """Ball query + grouping + 3-layer MLP (bias, ReLU) + max over the neighbourhood in one launch
+    (csrc/sa_fused.cu): xyz (B,N,3), center_xyz (B,M,3), feat_rows (B,N,C) or None -> (B,M,c3)
+    rows. `idx` (B,M,ns) i32 given: grouping uses it instead of running the ball query.
+    Inference only (no autograd)."""
+    assert xyz.is_contiguous() and center_xyz.is_contiguous()
+    assert feat_rows is None or feat_rows.is_contiguous()
+    _need_cuda(xyz, center_xyz, feat_rows, wpack, bias)
+    B, N, _ = xyz.shape
+    M = center_xyz.size(1)
+    C = 0 if feat_rows is None else feat_rows.size(2)
+    query = idx is None
+    with torch.cuda.device_of(xyz):
+        out = torch.empty(B, M, widths[2], dtype=torch.float32, device=xyz.device)
+        if query and return_idx:
+            idx = torch.empty(B, M, sample_num, dtype=torch.int32, device=xyz.device)
+        elif not query:
+            assert idx.is_contiguous() and idx.dtype == torch.int32
+        if out.numel():
+            _lib.check(_lib.load().demf_sa_fused_fwd(
+                _p(xyz), _p(feat_rows), _p(center_xyz), B, N, M, C, float(min_radius),
+                float(max_radius), int(sample_num), int(bool(normalize_xyz)), int(query), _p(wpack),
+                _p(bias), widths[0], widths[1], widths[2], _p(idx), _p(out), _stream()),
+                "demf_sa_fused_fwd")
+    return (out, idx) if return_idx else out

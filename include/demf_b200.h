@@ -147,6 +147,30 @@ int demf_three_interpolate_rows_fwd(const float* feat_rows, const int32_t* idx, 
 int demf_three_interpolate_rows_bwd(const float* grad_out, const int32_t* idx, const float* weight,
                                     int B, int C, int n, int m, float* grad_feat_rows, void* stream);
 
+/* ------------------------- fused set abstraction (inference), tcgen05 --- */
+/* replaces, for one PointSAModule forward in eval mode (mmdet3d
+ * ops/pointnet_modules/point_sa_module.py; configs/demf/demf_votenet.py:48-62,155-162;
+ * call site class_agnostic_vote_head.py:455): ball_query_wrapper + 2x group_points_wrapper
+ * + the three Conv2d(1x1)+BN2d+ReLU layers + max_pool2d, in ONE launch.
+ *   xyz (B,N,3), feat_rows (B,N,C) point-major or NULL when C == 0, new_xyz (B,M,3)
+ *   -> out (B,M,c3) point-major = max over the ns neighbours of relu(W3 relu(W2 relu(W1 g + b1) + b2) + b3),
+ *   g = [feat | 0-pad to 4 | (xyz[idx]-centre)(/r) | 0]  (the row of demf_query_and_group_rows_fwd).
+ * wpack: the three BN-folded weight matrices (c1 x K, c2 x c1, c3 x c2; K = demf_group_rows_width(C),
+ * columns in row order), each packed by demf_sa_pack_weights and concatenated; bias: c1+c2+c3 floats.
+ * query != 0: the ball query runs in the kernel; idx (B,M,ns) is an optional OUTPUT (may be NULL);
+ * query == 0: idx is an INPUT. TF32 tensor-core products, fp32 accumulation; indices exact.
+ * Supported: ns in {16,32,64}; c1,c2,c3 multiples of 32 in [32,256] (demf_sa_fused_supported).
+ * demf_sa_fused_error(): synchronising debug read of the kernel's protocol-time-out flag (0 = none). */
+long demf_sa_pack_floats(int Cout, int Cin);
+int demf_sa_pack_weights(const float* w /* (Cout,Cin) device */, int Cout, int Cin, float* packed,
+                         void* stream);
+int demf_sa_fused_supported(int C, int ns, int c1, int c2, int c3);
+int demf_sa_fused_fwd(const float* xyz, const float* feat_rows, const float* new_xyz, int B, int N, int M,
+                      int C, float min_radius, float max_radius, int ns, int normalize_xyz, int query,
+                      const float* wpack, const float* bias, int c1, int c2, int c3, int32_t* idx,
+                      float* out, void* stream);
+int demf_sa_fused_error(void);
+
 /* ------------------------------------ multi-scale deformable attention --- */
 /* replaces mmcv _ext.ms_deform_attn_forward / ms_deform_attn_backward
  * (MultiScaleDeformableAttnFunction; reached from transformer.py:73-78).

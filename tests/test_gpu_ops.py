@@ -345,3 +345,54 @@ def test_empty_batches_are_noops(dev):
     assert d.shape == (1, 0, 3) and i.shape == (1, 0, 3)
     assert np.prod(ops.grouping_operation(torch.zeros(1, 0, 5, device=dev),
                                           torch.zeros(1, 2, 2, dtype=torch.int32, device=dev)).shape) == 0
+
+
+# ------------------------------------------- fused set abstraction (tcgen05, inference) --
+def _sa_case(B, N, M, C, ns, radius, widths, seed, clustered=True):
+    from oracle import sa_module
+    g = torch.Generator().manual_seed(seed)
+    xyz = _xyz(B, N, seed=seed, clustered=clustered)
+    centres = torch.gather(xyz, 1, cref.furthest_point_sample(xyz, M).long()[..., None].expand(-1, -1, 3)).contiguous()
+    feats = torch.randn(B, C, N, generator=g) if C else None
+    cin = [C + 3] + list(widths[:-1])
+    weights = [torch.randn(co, ci, generator=g) * (1.5 / ci ** 0.5) for co, ci in zip(widths, cin)]
+    biases = [torch.randn(co, generator=g) * 0.2 for co in widths]
+    return sa_module, xyz, centres, feats, weights, biases
+
+
+@pytest.mark.parametrize("B,N,M,C,ns,radius,widths", [
+    (2, 20000, 2048, 1, 64, 0.2, (64, 64, 128)),      # SA1 (configs/demf/demf_votenet.py:51-55)
+    (2, 2048, 1024, 128, 32, 0.4, (128, 128, 256)),   # SA2
+    (2, 1024, 512, 256, 16, 0.8, (128, 128, 256)),    # SA3
+    (2, 512, 256, 256, 16, 1.2, (128, 128, 256)),     # SA4
+    (2, 1024, 256, 256, 16, 0.3, (256, 256, 256)),    # vote aggregation (:155-162)
+    (1, 777, 101, 0, 16, 0.5, (32, 64, 96)),          # no features, ragged M, odd widths
+    (3, 300, 37, 8, 32, 0.6, (64, 32, 224)),
+    (1, 5000, 50, 12, 64, 0.35, (32, 32, 32)),
+])
+def test_sa_fused_matches_oracle(dev, B, N, M, C, ns, radius, widths):
+    sa_module, xyz, centres, feats, weights, biases = _sa_case(B, N, M, C, ns, radius, widths, seed=N + M)
+    assert ops.sa_fused_supported(C, ns, widths)
+    # device side: weights to the row layout, packed
+    cols = ops.group_rows_columns(C)
+    from demf_b200.mm.bricks import permute_weight_columns
+    w0 = permute_weight_columns(weights[0].to(dev), cols)
+    wpack, bias, wd = ops.sa_pack_mlp([w0, weights[1].to(dev), weights[2].to(dev)], [b.to(dev) for b in biases])
+    feat_rows = None if feats is None else feats.transpose(1, 2).contiguous().to(dev)
+    out, idx = ops.sa_fused(xyz.to(dev), centres.to(dev), feat_rows, 0.0, radius, ns, True, wpack, bias, wd,
+                            return_idx=True)
+    torch.cuda.synchronize()
+    assert _lib.load().demf_sa_fused_error() == 0
+    ref_idx, ref_tf32 = sa_module.sa_forward(xyz, centres, feats, 0.0, radius, ns, True, weights, biases, tf32=True)
+    _, ref_fp32 = sa_module.sa_forward(xyz, centres, feats, 0.0, radius, ns, True, weights, biases, tf32=False)
+    assert torch.equal(idx.cpu(), ref_idx)                       # neighbour rows: bit-exact
+    got = out.cpu().transpose(1, 2)
+    scale = ref_fp32.abs().max().item()
+    # same arithmetic class (TF32 operands, wide accumulation): only accumulation order differs
+    assert (got - ref_tf32).abs().max().item() <= 1e-3 * scale
+    # against IEEE fp32 layers: the TF32 rounding of three chained layers
+    assert (got - ref_fp32).abs().max().item() <= 1e-2 * scale
+    # given indices (query=0) reproduce the same result bit for bit
+    out2 = ops.sa_fused(xyz.to(dev), centres.to(dev), feat_rows, 0.0, radius, ns, True, wpack, bias, wd,
+                        idx=idx)
+    assert torch.equal(out2, out)
