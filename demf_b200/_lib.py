@@ -32,7 +32,11 @@ _SIGNATURES = {
     "demf_three_interpolate_bwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
     "demf_group_rows_width": [_c_int],
     "demf_query_and_group_rows_fwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_float,
-                                      _c_float, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr],
+                                      _c_float, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr],
+    "demf_ball_grid_workspace_bytes": [_c_int, _c_int],
+    "demf_ball_grid_build": [_ptr, _c_int, _c_int, _c_float, _ptr, _ptr],
+    "demf_ball_query_grid": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_float, _c_float, _c_int, _ptr,
+                             _ptr],
     "demf_group_rows_bwd": [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _ptr, _ptr,
                             _ptr, _ptr],
     "demf_three_interpolate_rows_fwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
@@ -41,8 +45,9 @@ _SIGNATURES = {
     "demf_sa_pack_weights": [_ptr, _c_int, _c_int, _ptr, _ptr],
     "demf_sa_fused_supported": [_c_int] * 5,
     "demf_sa_fused_fwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, _c_int,
-                          _c_int, _c_int, _ptr, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr],
+                          _c_int, _c_int, _ptr, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr],
     "demf_sa_fused_error": [],
+    "demf_sa_fused_set_profile": [_ptr],
     "demf_msda_fwd": [_ptr, _ptr, _ptr, _ptr, _ptr] + [_c_int] * 7 + [_ptr, _ptr],
     "demf_msda_bwd": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr] + [_c_int] * 7 + [_ptr, _ptr, _ptr, _ptr],
 }
@@ -51,6 +56,7 @@ _RESTYPES = {
     "demf_launch_count": ctypes.c_uint64,
     "demf_fps_workspace_bytes": ctypes.c_size_t,
     "demf_sa_pack_floats": ctypes.c_long,
+    "demf_ball_grid_workspace_bytes": ctypes.c_size_t,
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -12,6 +12,7 @@
 //
 // Roofline: HBM. Algorithmic bytes per scene = N*12 (cloud) + M*12 + M*ns*4 (idx) +
 // M*ns*C*4 (row gather, L2-resident source) + M*ns*K*4 (rows written).
+#include "ball_grid.cuh"
 #include "common.cuh"
 
 namespace demf {
@@ -32,7 +33,7 @@ template <bool kQuery>
 __global__ void __launch_bounds__(kThreads) group_rows_fwd_kernel(
     const float* __restrict__ xyz, const float* __restrict__ feat, const float* __restrict__ new_xyz,
     int N, int M, int C, float min_r2, float max_r2, float inv_radius, int ns, int normalize_xyz,
-    int32_t* __restrict__ idx, float* __restrict__ out) {
+    const void* __restrict__ grid, int32_t* __restrict__ idx, float* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);
   int32_t* rows = reinterpret_cast<int32_t*>(smem_raw + (kQuery ? kTile * 3 * 4 : 0));
@@ -54,7 +55,14 @@ __global__ void __launch_bounds__(kThreads) group_rows_fwd_kernel(
   int32_t* row = rows + warp * ns;
   int32_t* grow = idx + ((long)b * M + (active ? m : 0)) * ns;
 
-  if (kQuery) {
+  if (kQuery && grid != nullptr) {
+    // exact grid query (ball_grid.cuh): only the 3x3x3 cell neighbourhood of the centre is tested
+    if (!active) return;
+    int* scratch = reinterpret_cast<int*>(tile) + warp * (kGridCap + kGridHist);
+    const BallGridView g = ball_grid_view(grid, b, N);
+    ball_query_warp(g, cloud, N, cx, cy, cz, min_r2, max_r2, ns, row, scratch, scratch + kGridCap, lane);
+    for (int l = lane; l < ns; l += 32) grow[l] = row[l];
+  } else if (kQuery) {
     int cnt = 0, first = 0;
     bool done = !active;
     for (int base = 0; base < N; base += kTile) {
@@ -261,8 +269,8 @@ int demf_group_rows_width(int C) { return ((C + 3) / 4) * 4 + 4; }
 
 int demf_query_and_group_rows_fwd(const float* xyz, const float* feat_rows, const float* new_xyz,
                                   int B, int N, int M, int C, float min_radius, float max_radius,
-                                  int ns, int normalize_xyz, int query, int32_t* idx, float* out,
-                                  void* stream) {
+                                  int ns, int normalize_xyz, int query, const void* grid, int32_t* idx,
+                                  float* out, void* stream) {
   DEMF_REQUIRE_PTR(xyz);
   DEMF_REQUIRE_PTR(new_xyz);
   DEMF_REQUIRE_PTR(idx);
@@ -276,19 +284,20 @@ int demf_query_and_group_rows_fwd(const float* xyz, const float* feat_rows, cons
   DEMF_REQUIRE(smem <= 200 * 1024, DEMF_E_UNSUPPORTED);
   const float min_r2 = min_radius * min_radius, max_r2 = max_radius * max_radius;
   const float inv_radius = 1.0f / max_radius;
-  dim3 grid((M + kWarps - 1) / kWarps, B);
+  dim3 grid_dim((M + kWarps - 1) / kWarps, B);
   cudaStream_t st = as_stream(stream);
   if (query) {
     auto k = group_rows_fwd_kernel<true>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, kThreads, smem, st>>>(xyz, feat_rows, new_xyz, N, M, C, min_r2, max_r2, inv_radius, ns,
-                                    normalize_xyz, idx, out);
+    static_assert(kWarps * (kGridCap + kGridHist) * 4 <= kTile * 3 * 4, "grid scratch fits the cloud tile");
+    k<<<grid_dim, kThreads, smem, st>>>(xyz, feat_rows, new_xyz, N, M, C, min_r2, max_r2, inv_radius, ns,
+                                        normalize_xyz, ns <= kGridCap ? grid : nullptr, idx, out);
     return after_launch("query_group_rows_fwd_kernel");
   }
   auto k = group_rows_fwd_kernel<false>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k<<<grid, kThreads, smem, st>>>(xyz, feat_rows, new_xyz, N, M, C, min_r2, max_r2, inv_radius, ns,
-                                  normalize_xyz, idx, out);
+  k<<<grid_dim, kThreads, smem, st>>>(xyz, feat_rows, new_xyz, N, M, C, min_r2, max_r2, inv_radius, ns,
+                                      normalize_xyz, nullptr, idx, out);
   return after_launch("group_rows_fwd_kernel");
 }
 

@@ -7,24 +7,31 @@
 // reached from configs/demf/demf_votenet.py:48-62,155-162): ball_query_kernel + 2x group_points_kernel
 // + transpose/sub/div/cat + 3x (cuDNN 1x1 conv + BN + ReLU) + max_pool2d.
 //
-// CTA = G centres of one scene (G*ns = 128*tiles grouped rows), 18 warps:
+// CTA = G <= 16 centres of one scene (G*ns = 128*tiles grouped rows), 18 warps:
 //   warp 0      : tcgen05.mma issuer (one lane)          D[tmem] += A[smem] * W[smem]^T, kind::tf32
 //   warp 1      : weight producer (one lane)             1-D bulk copies of host-packed, pre-swizzled
-//                                                         weight chunks from L2 into a ring
-//   warps 2..17 : workers                                ball query (cloud staged through smem,
-//                                                         ballot/popc compaction = "first ns hits in
-//                                                         index order"), neighbour-row gather into
-//                                                         the swizzled A operand, TMEM epilogues
-// Per 128-row tile:  gather A0 (128 x K0)  ->  MMA layer 0 -> epilogue (bias, ReLU, tf32 round) writes
-// act1 over A0 -> MMA layer 1 -> epilogue -> act2 -> MMA layer 2 -> epilogue: column max over the ns
-// rows of each centre (register butterfly across the 32 TMEM lanes a warp owns), bias, ReLU, store.
+//                                                         weight chunks from L2 into a ring (or once,
+//                                                         when all three matrices fit: "resident")
+//   warps 2..17 : workers                                ball query (uniform-grid neighbourhood, or the
+//                                                         cloud staged through smem), neighbour-row
+//                                                         gather into the swizzled A operand, TMEM
+//                                                         epilogues
+// The workers form 1, 2 or 4 LANES; a lane owns a 128-row tile at a time with its own operand
+// region, TMEM columns and mbarrier pair, so that while one lane runs an epilogue or a gather the
+// tensor pipe works on another lane's tile (the phases of one tile are strictly dependent and
+// each costs a few hundred ns of latency). Per tile and lane:
+//   gather A0 (128 x K0, in passes of `cpp` 32-column chunks when K0 is wide) -> MMA layer 0 ->
+//   epilogue (bias, ReLU, tf32 round) writes act1 over A0 -> MMA layer 1 -> epilogue -> act2 ->
+//   MMA layer 2 -> epilogue: column max over the ns rows of each centre (register butterfly across
+//   the 32 TMEM lanes a warp owns), bias, ReLU, store.
 //
 // Arithmetic: TF32 products (operands rounded to nearest, ties away: cvt.rna), fp32 accumulation --
 // the same class as the cuDNN/cuBLAS TF32 convolutions PyTorch >= 1.7 runs for the reference on
 // Ampere and later. Indices are exact (the ball query is the fp32 fma-ordered one of ball_query.cu).
 //
-// Roofline: tensor pipe / L2 (weights re-streamed per tile). HBM bytes per scene = N*12 + N*C*4 +
-// M*12 + M*C3*4 (+ weights once).
+// Roofline: tensor pipe / L2 (weights re-streamed per tile unless resident). HBM bytes per scene =
+// N*12 + N*C*4 + M*12 + M*C3*4 (+ weights once).
+#include "ball_grid.cuh"
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -40,8 +47,10 @@ constexpr int kTileRows = 128;
 constexpr int kChunkBytes = kTileRows * 128;  // one 32-float K chunk of a 128-row operand
 constexpr int kCloudTile = 2048;              // cloud points per ball-query tile (24 KB)
 constexpr int kMaxSlots = 8;
+constexpr int kMaxLanes = 4;
 
 __device__ int g_sa_error = 0;  // sticky: first protocol time-out (never expected)
+long long* g_sa_prof = nullptr;  // host copy of the debug stamp buffer pointer (demf_sa_fused_set_profile)
 
 struct SaParams {
   const float* xyz;
@@ -51,12 +60,15 @@ struct SaParams {
   const float* bias;
   float* out;
   int32_t* idx;
+  const void* grid;  // ball_grid workspace of this cloud, or NULL: scan the whole cloud
+  long long* prof;   // debug: clock64 stamps of the first worker thread of CTA (0,0), or NULL
   int N, M, C, ns, G, tiles, K0;
   int c[3];
   int query, normalize_xyz;
   float min_r2, max_r2, inv_radius;
-  int slots, slot_bytes, resident, act_bytes;
-  int tmem_cols, acc_col[3];
+  int lanes, cpp, npass, lane_act_bytes;  // tile pipelines; A0 chunks per layer-0 pass; passes
+  int slots, slot_bytes, resident;
+  int tmem_cols, lane_cols, acc_col[3];
 };
 
 struct SmemLayout {
@@ -65,13 +77,13 @@ struct SmemLayout {
 
 __host__ __device__ inline SmemLayout smem_layout(const SaParams& p) {
   SmemLayout L;
-  L.ring = p.act_bytes;
+  L.ring = p.lanes * p.lane_act_bytes;
   L.rows = L.ring + p.slots * p.slot_bytes;
   L.centres = L.rows + p.G * p.ns * 4;
   L.bias = L.centres + p.G * 16;
   L.part = L.bias + (p.c[0] + p.c[1] + p.c[2]) * 4;
-  L.bars = (L.part + (p.ns == 64 ? 2 * p.c[2] * 4 : 0) + 15) & ~15;
-  L.total = L.bars + (2 * kMaxSlots + 2) * 8 + 16 + 1024;  // + alignment slack
+  L.bars = (L.part + (p.ns == 64 ? p.lanes * 2 * p.c[2] * 4 : 0) + 15) & ~15;
+  L.total = L.bars + (2 * kMaxSlots + 2 * kMaxLanes) * 8 + 16 + 1024;  // + alignment slack
   return L;
 }
 
@@ -81,7 +93,13 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(u);
 }
 
-__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory"); }
+__device__ __forceinline__ float4 tf32_rna4(float4 v) {
+  return make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+}
+
+__device__ __forceinline__ void named_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
 __device__ __forceinline__ bool worker_sync_and(bool pred) {
   uint32_t r;
@@ -147,6 +165,20 @@ __device__ __forceinline__ void lane_max_transpose(float (&v)[32], unsigned lane
   }
 }
 
+// The (layer, first chunk, chunk count) of MMA group g of a tile: groups 0..npass-1 are the passes of
+// layer 0, then layers 1 and 2.
+__device__ __forceinline__ void group_span(const SaParams& p, int nch0, int g, int& layer, int& ch0, int& nch) {
+  if (g < p.npass) {
+    layer = 0;
+    ch0 = g * p.cpp;
+    nch = min(p.cpp, nch0 - ch0);
+  } else {
+    layer = g - p.npass + 1;
+    ch0 = 0;
+    nch = p.c[layer - 1] >> 5;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParams p) {
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned chunks: align the carve-up by hand
@@ -160,19 +192,20 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
   const int m_base = blockIdx.x * p.G;
   const int cpt = kTileRows / p.ns;  // centres per tile
   const int ntiles = min(p.tiles, (min(p.G, p.M - m_base) + cpt - 1) / cpt);
+  const int nrounds = (ntiles + p.lanes - 1) / p.lanes;
+  const int ngroups = p.npass + 2;
 
-  unsigned char* act = smem;
   unsigned char* ring = smem + L.ring;
   int32_t* rows = reinterpret_cast<int32_t*>(smem + L.rows);
   float4* centres = reinterpret_cast<float4*>(smem + L.centres);
   float* bias_s = reinterpret_cast<float*>(smem + L.bias);
-  float* part = reinterpret_cast<float*>(smem + L.part);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSlots + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSlots + 2 * kMaxLanes);
   volatile int* failed = reinterpret_cast<volatile int*>(tmem_slot + 1);
   const uint32_t wfull0 = smem_u32(&bars[0]), wempty0 = smem_u32(&bars[kMaxSlots]);
-  const uint32_t op_ready = smem_u32(&bars[2 * kMaxSlots]), acc_full = smem_u32(&bars[2 * kMaxSlots + 1]);
-  const uint32_t act_u32 = smem_u32(act), ring_u32 = smem_u32(ring);
+  const uint32_t op_ready0 = smem_u32(&bars[2 * kMaxSlots]), acc_full0 = smem_u32(&bars[2 * kMaxSlots + kMaxLanes]);
+  const uint32_t act_u32 = smem_u32(smem), ring_u32 = smem_u32(ring);
+  const int wpl = kWorkerWarps / p.lanes;  // worker warps per lane
 
   if (tid == 0) {
     *failed = 0;
@@ -180,8 +213,10 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
       mbar_init(wfull0 + 8 * s, 1);
       mbar_init(wempty0 + 8 * s, 1);
     }
-    mbar_init(op_ready, kWorkerWarps);
-    mbar_init(acc_full, 1);
+    for (int l = 0; l < kMaxLanes; ++l) {
+      mbar_init(op_ready0 + 8 * l, wpl);
+      mbar_init(acc_full0 + 8 * l, 1);
+    }
     mbar_fence_init();
   }
   if (warp == 0) {
@@ -198,53 +233,81 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
   if (warp == 0) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
-      uint32_t opp = 0, slot = 0, wph = 0;
-      for (int t = 0; t < ntiles; ++t) {
-        for (int l = 0; l < 3; ++l) {
-          if (!wait_or_fail(op_ready, opp, failed, 1)) break;
-          opp ^= 1;
-          tc_fence_after_sync();
-          const int nch = l == 0 ? nch0 : (p.c[l - 1] >> 5);
-          const uint32_t idesc = instr_desc_tf32(kTileRows, p.c[l]);
-          const uint32_t d = tmem + p.acc_col[l];
-          for (int ch = 0; ch < nch; ++ch) {
-            if (!p.resident || t == 0) {
-              if (!wait_or_fail(wfull0 + 8 * slot, wph, failed, 2)) break;
+      uint32_t opp = 0, slot = 0, wph = 0;  // opp: one parity bit per lane
+      for (int r = 0; r < nrounds; ++r) {
+        for (int g = 0; g < ngroups; ++g) {
+          int layer, ch0, nch;
+          group_span(p, nch0, g, layer, ch0, nch);
+          const uint32_t idesc = instr_desc_tf32(kTileRows, p.c[layer]);
+          int cid = layer == 0 ? ch0 : (layer == 1 ? nch0 : nch0 + (p.c[0] >> 5));  // resident slot
+          for (int ln = 0; ln < p.lanes; ++ln) {
+            if (r * p.lanes + ln >= ntiles) break;
+            if (!wait_or_fail(op_ready0 + 8 * ln, (opp >> ln) & 1u, failed, 1)) break;
+            opp ^= 1u << ln;
+            tc_fence_after_sync();
+            const uint32_t d = tmem + ln * p.lane_cols + p.acc_col[layer];
+            const uint32_t a0 = act_u32 + ln * p.lane_act_bytes;
+            for (int ch = 0; ch < nch; ++ch) {
+              const uint32_t s = p.resident ? (uint32_t)(cid + ch) : slot;
+              if (!wait_or_fail(wfull0 + 8 * s, p.resident ? 0u : wph, failed, 2)) break;
+              const int ksteps = layer == 0 ? (min(32, p.K0 - 32 * (ch0 + ch)) >> 3) : 4;
+              const uint32_t a = a0 + ch * kChunkBytes, w = ring_u32 + s * p.slot_bytes;
+              for (int k = 0; k < ksteps; ++k)
+                mma_tf32(d, smem_desc_sw128(a + 32 * k), smem_desc_sw128(w + 32 * k), idesc,
+                         (ch0 | ch | k) != 0);
+              if (!p.resident) {
+                mma_commit(wempty0 + 8 * slot);
+                if (++slot == (uint32_t)p.slots) {
+                  slot = 0;
+                  wph ^= 1;
+                }
+              }
             }
-            const int ksteps = l == 0 ? (min(32, p.K0 - 32 * ch) >> 3) : 4;
-            const uint32_t a = act_u32 + ch * kChunkBytes, w = ring_u32 + slot * p.slot_bytes;
-            for (int k = 0; k < ksteps; ++k)
-              mma_tf32(d, smem_desc_sw128(a + 32 * k), smem_desc_sw128(w + 32 * k), idesc, (ch | k) != 0);
-            if (!p.resident) mma_commit(wempty0 + 8 * slot);
-            if (++slot == (uint32_t)p.slots) {
-              slot = 0;
-              wph ^= 1;
-            }
+            mma_commit(acc_full0 + 8 * ln);
           }
-          mma_commit(acc_full);
         }
       }
     }
   } else if (warp == 1) {
     // ============================= weight producer ============================
     if (lane == 0) {
-      uint32_t slot = 0, ph = 0;
-      const int passes = p.resident ? min(ntiles, 1) : ntiles;
-      for (int t = 0; t < passes; ++t) {
+      if (p.resident) {
         const float* src = p.wpack;
+        int s = 0;
         for (int l = 0; l < 3; ++l) {
           const int nch = l == 0 ? nch0 : (p.c[l - 1] >> 5);
           const uint32_t bytes = p.c[l] * 128;
-          for (int ch = 0; ch < nch; ++ch) {
-            if (!p.resident) {
-              if (!wait_or_fail(wempty0 + 8 * slot, ph ^ 1, failed, 3)) break;
-            }
-            mbar_expect_tx(wfull0 + 8 * slot, bytes);
-            bulk_g2s(ring_u32 + slot * p.slot_bytes, src, bytes, wfull0 + 8 * slot);
+          for (int ch = 0; ch < nch; ++ch, ++s) {
+            mbar_expect_tx(wfull0 + 8 * s, bytes);
+            bulk_g2s(ring_u32 + s * p.slot_bytes, src, bytes, wfull0 + 8 * s);
             src += bytes >> 2;
-            if (++slot == (uint32_t)p.slots) {
-              slot = 0;
-              ph ^= 1;
+          }
+        }
+      } else {
+        uint32_t slot = 0, ph = 0;
+        bool ok = true;
+        for (int r = 0; r < nrounds && ok; ++r) {
+          for (int g = 0; g < ngroups && ok; ++g) {
+            int layer, ch0, nch;
+            group_span(p, nch0, g, layer, ch0, nch);
+            const uint32_t bytes = p.c[layer] * 128;
+            // chunk offsets in wpack: layer 0 at 0, layer 1 after nch0 chunks of c0 rows, ...
+            const float* base = p.wpack;
+            if (layer >= 1) base += (size_t)nch0 * p.c[0] * 32;
+            if (layer >= 2) base += (size_t)(p.c[0] >> 5) * p.c[1] * 32;
+            for (int ln = 0; ln < p.lanes && ok; ++ln) {
+              if (r * p.lanes + ln >= ntiles) break;
+              for (int ch = 0; ch < nch; ++ch) {
+                ok = wait_or_fail(wempty0 + 8 * slot, ph ^ 1, failed, 3);
+                if (!ok) break;
+                mbar_expect_tx(wfull0 + 8 * slot, bytes);
+                bulk_g2s(ring_u32 + slot * p.slot_bytes, base + (size_t)(ch0 + ch) * (bytes >> 2), bytes,
+                         wfull0 + 8 * slot);
+                if (++slot == (uint32_t)p.slots) {
+                  slot = 0;
+                  ph ^= 1;
+                }
+              }
             }
           }
         }
@@ -254,10 +317,17 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
     // ================================= workers ================================
     const int wt = tid - 64;
     const int ww = wt >> 5;
+    int nstamp = 0;
+    const bool prof = p.prof != nullptr && wt == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+#define SA_STAMP()                                             \
+  do {                                                         \
+    if (prof && nstamp < 62) p.prof[1 + nstamp++] = clock64(); \
+  } while (0)
+    SA_STAMP();
     const float* cloud = p.xyz + (long)b * p.N * 3;
     const int ns = p.ns;
 
-    // ---- phase Q: neighbour index rows of the G centres into shared memory
+    // ---- phase Q: neighbour index rows of the G centres into shared memory (all 16 warps)
     {
       const int m = m_base + ww;
       const bool active = ww < p.G && m < p.M;
@@ -270,15 +340,31 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
       }
       if (ww < p.G && lane == 0) centres[ww] = make_float4(cx, cy, cz, 0.f);
       int32_t* row = rows + ww * ns;  // only dereferenced when ww < G
-      if (p.query) {
-        float* tile = reinterpret_cast<float*>(act);  // the A0 region is free until the first gather
+      if (p.query && p.grid) {
+        // exact grid query: each warp tests only the 3x3x3 cell neighbourhood of its centre
+        if (ww < p.G) {
+          int* scratch = reinterpret_cast<int*>(smem) + ww * (kGridCap + kGridHist);  // A0 regions are free
+          if (active) {
+            const BallGridView g = ball_grid_view(p.grid, b, p.N);
+            ball_query_warp(g, cloud, p.N, cx, cy, cz, p.min_r2, p.max_r2, ns, row, scratch,
+                            scratch + kGridCap, lane);
+            if (p.idx) {
+              int32_t* grow = p.idx + ((long)b * p.M + m) * ns;
+              for (int l = lane; l < ns; l += 32) grow[l] = row[l];
+            }
+          } else {
+            for (int l = lane; l < ns; l += 32) row[l] = 0;
+          }
+        }
+      } else if (p.query) {
+        float* tile = reinterpret_cast<float*>(smem);  // the A0 regions are free until the first gather
         int cnt = 0, first = 0;
         bool done = !active;
         for (int base = 0; base < p.N; base += kCloudTile) {
           const int npts = min(kCloudTile, p.N - base);
-          worker_sync();
+          named_sync(1, kWorkers);
           for (int i = wt; i < npts * 3; i += kWorkers) tile[i] = __ldg(cloud + (long)base * 3 + i);
-          worker_sync();
+          named_sync(1, kWorkers);
           if (!done) {
             for (int j = 0; j < npts; j += 32) {
               const int q = j + lane;
@@ -316,75 +402,111 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
         const int32_t* grow = p.idx + ((long)b * p.M + (active ? m : 0)) * ns;
         for (int l = lane; l < ns; l += 32) row[l] = active ? __ldg(grow + l) : 0;
       }
-      worker_sync();  // rows + centres visible; cloud tile (aliasing A0) no longer read
+      named_sync(1, kWorkers);  // rows + centres visible; query scratch (aliasing A0) no longer used
     }
+    SA_STAMP();
 
-    // ---- phase M: per 128-row tile
+    // ---- phase M: this warp's lane works through tiles ln, ln + lanes, ...
+    const int ln = ww / wpl;         // lane (tile pipeline) of this warp
+    const int wl = ww - ln * wpl;    // warp within the lane
+    const int lt = wl * 32 + lane;   // thread within the lane
+    const int lthreads = wpl * 32;
+    const int ncg = wpl >> 2;        // column groups per TMEM lane quarter
+    const int q = warp & 3;          // TMEM lane quarter this warp may read
+    const int cg = wl >> 2;
+    const uint32_t lane_base = ((uint32_t)(q * 32) << 16) + ln * p.lane_cols;
+    const int r_epi = q * 32 + lane;
+    unsigned char* act = smem + ln * p.lane_act_bytes;
+    float* part = reinterpret_cast<float*>(smem + L.part) + ln * 2 * p.c[2];
+    const uint32_t op_ready = op_ready0 + 8 * ln, acc_full = acc_full0 + 8 * ln;
+    const int C4 = (p.C + 3) >> 2;  // feature slots per row; slot C4 = xyz; beyond = zero
     const int S4 = p.K0 >> 2;       // 16-byte slots per A0 row
-    const int C4 = (p.C + 3) >> 2;  // feature slots; slot C4 = xyz; beyond = zero
     const bool vec = (p.C & 3) == 0;
     const float* fb = p.feat ? p.feat + (long)b * p.N * p.C : nullptr;
     const float scale = p.normalize_xyz ? p.inv_radius : 1.f;
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int cg = ww >> 2;  // column group
-    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const int r_epi = q * 32 + lane;
     uint32_t accp = 0;
     bool ok = true;
 
-    for (int t = 0; t < ntiles && ok; ++t) {
-      // gather the 128 grouped rows of this tile as the swizzled A0 operand
+    for (int t = ln; t < ntiles && ok; t += p.lanes) {
       const int32_t* trow = rows + t * kTileRows;  // rows of centre g are contiguous: g*ns
-#pragma unroll 4
-      for (int e = wt; e < kTileRows * S4; e += kWorkers) {
-        const int r = e / S4;
-        const int j = e - r * S4;
-        const int k = trow[r];
-        float4 v;
-        if (j < C4) {
-          if (vec) {
-            v = __ldg(reinterpret_cast<const float4*>(fb + (long)k * p.C) + j);
-          } else {
-            const float* f = fb + (long)k * p.C + j * 4;
-            const int left = p.C - j * 4;
-            v.x = __ldg(f);
-            v.y = left > 1 ? __ldg(f + 1) : 0.f;
-            v.z = left > 2 ? __ldg(f + 2) : 0.f;
-            v.w = left > 3 ? __ldg(f + 3) : 0.f;
+      // ---- layer 0: gather the 128 grouped rows (one pass = `cpp` chunks = 8*cpp slots per row)
+      for (int pass = 0; pass < p.npass && ok; ++pass) {
+        const int s_lo = pass * p.cpp * 8, s_hi = min(S4, s_lo + p.cpp * 8);
+        // (a) feature slots: batches of independent 16-byte loads, then the swizzled stores
+        const int f_hi = min(s_hi, C4);
+        if (vec && f_hi > s_lo) {
+          const int w = f_hi - s_lo, total = kTileRows * w;
+          const int w_shift = (w & (w - 1)) == 0 ? 31 - __clz(w) : -1;
+          constexpr int U = 4;
+          for (int e0 = lt; e0 < total; e0 += lthreads * U) {
+            float4 v[U];
+            int off[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int e = e0 + u * lthreads;
+              off[u] = -1;
+              if (e < total) {
+                const int r = w_shift >= 0 ? (e >> w_shift) : (e / w);
+                const int j = s_lo + (e - r * w);
+                v[u] = __ldg(reinterpret_cast<const float4*>(fb + (long)trow[r] * p.C) + j);
+                off[u] = ((j - s_lo) >> 3) * kChunkBytes + sw128_offset(r, j & 7);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              if (off[u] >= 0) *reinterpret_cast<float4*>(act + off[u]) = tf32_rna4(v[u]);
           }
-        } else if (j == C4) {
-          const float4 c = centres[t * cpt + r / ns];
-          const float* pt = cloud + (long)k * 3;
-          v.x = __fsub_rn(__ldg(pt + 0), c.x);
-          v.y = __fsub_rn(__ldg(pt + 1), c.y);
-          v.z = __fsub_rn(__ldg(pt + 2), c.z);
-          if (p.normalize_xyz) {
-            v.x = __fmul_rn(v.x, scale);
-            v.y = __fmul_rn(v.y, scale);
-            v.z = __fmul_rn(v.z, scale);
-          }
-          v.w = 0.f;
-        } else {
-          v = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        v.x = tf32_rna(v.x);
-        v.y = tf32_rna(v.y);
-        v.z = tf32_rna(v.z);
-        v.w = tf32_rna(v.w);
-        *reinterpret_cast<float4*>(act + (j >> 3) * kChunkBytes + sw128_offset(r, j & 7)) = v;
+        // (b) the remaining slots of the pass: unaligned features, the xyz slot, zero padding
+        const int t_lo = vec ? max(s_lo, C4) : s_lo;
+        if (s_hi > t_lo) {
+          const int w = s_hi - t_lo;
+          for (int e = lt; e < kTileRows * w; e += lthreads) {
+            const int r = e / w;
+            const int j = t_lo + (e - r * w);
+            const int k = trow[r];
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < C4) {
+              const float* f = fb + (long)k * p.C + j * 4;
+              const int left = p.C - j * 4;
+              v.x = __ldg(f);
+              v.y = left > 1 ? __ldg(f + 1) : 0.f;
+              v.z = left > 2 ? __ldg(f + 2) : 0.f;
+              v.w = left > 3 ? __ldg(f + 3) : 0.f;
+            } else if (j == C4) {
+              const float4 c = centres[t * cpt + r / ns];
+              const float* pt = cloud + (long)k * 3;
+              v.x = __fsub_rn(__ldg(pt + 0), c.x);
+              v.y = __fsub_rn(__ldg(pt + 1), c.y);
+              v.z = __fsub_rn(__ldg(pt + 2), c.z);
+              if (p.normalize_xyz) {
+                v.x = __fmul_rn(v.x, scale);
+                v.y = __fmul_rn(v.y, scale);
+                v.z = __fmul_rn(v.z, scale);
+              }
+            }
+            *reinterpret_cast<float4*>(act + ((j - s_lo) >> 3) * kChunkBytes + sw128_offset(r, j & 7)) = tf32_rna4(v);
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(op_ready);
+        SA_STAMP();
+        if (pass + 1 < p.npass) {  // the next pass overwrites the region: its MMAs must be done
+          ok = wait_or_fail(acc_full, accp, failed, 6);
+          accp ^= 1;
+        }
       }
-      fence_proxy_async();
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(op_ready);
 
-      // layers 0 and 1: accumulator -> bias, ReLU, tf32 -> next layer's A operand
+      // ---- layers 0 and 1: accumulator -> bias, ReLU, tf32 -> next layer's A operand
       for (int l = 0; l < 2 && ok; ++l) {
         ok = wait_or_fail(acc_full, accp, failed, 4);
         accp ^= 1;
         tc_fence_after_sync();
+        SA_STAMP();
         const float* bl = bias_s + (l == 0 ? 0 : p.c[0]);
-        for (int blk = cg; blk < (p.c[l] >> 5); blk += 4) {
+        for (int blk = cg; blk < (p.c[l] >> 5); blk += ncg) {
           uint32_t u[32];
           tmem_ld32(tmem + lane_base + p.acc_col[l] + blk * 32, u);
           tmem_ld_wait();
@@ -403,20 +525,22 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(op_ready);
+        SA_STAMP();
       }
       if (!ok) break;
 
-      // layer 2: max over the ns rows of each centre, then bias + ReLU (both commute with max)
+      // ---- layer 2: max over the ns rows of each centre, then bias + ReLU (both commute with max)
       ok = wait_or_fail(acc_full, accp, failed, 5);
       accp ^= 1;
       tc_fence_after_sync();
+      SA_STAMP();
       const float* b2 = bias_s + p.c[0] + p.c[1];
       const int c3 = p.c[2];
       const int m_tile = m_base + t * cpt;
-      float keep[2] = {0.f, 0.f};
+      float keep[8];
 #pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        const int blk = cg + 4 * it;
+      for (int it = 0; it < 8; ++it) {
+        const int blk = cg + ncg * it;
         if (blk >= (c3 >> 5)) break;
         uint32_t u[32];
         tmem_ld32(tmem + lane_base + p.acc_col[2] + blk * 32, u);
@@ -450,12 +574,12 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
         }
       }
       if (ns == 64) {
-        worker_sync();
+        named_sync(2 + ln, lthreads);
         if (!(q & 1)) {
           const int m = m_tile + (q >> 1);
 #pragma unroll
-          for (int it = 0; it < 2; ++it) {
-            const int blk = cg + 4 * it;
+          for (int it = 0; it < 8; ++it) {
+            const int blk = cg + ncg * it;
             if (blk >= (c3 >> 5)) break;
             const int col = blk * 32 + lane;
             const float mx = fmaxf(keep[it], part[(q >> 1) * c3 + col]);
@@ -464,7 +588,9 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
         }
       }
       tc_fence_before_sync();
+      SA_STAMP();
     }
+    if (prof) p.prof[0] = nstamp;
   }
 
   // ---- teardown
@@ -493,6 +619,68 @@ __global__ void sa_pack_weights_kernel(const float* __restrict__ w, int Cout, in
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Pick lanes / passes / ring depth for one level. Returns false when nothing fits.
+bool configure(SaParams& p, int B) {
+  const int c1 = p.c[0], c2 = p.c[1], c3 = p.c[2];
+  const int cpt = kTileRows / p.ns;
+  const int nch0 = (p.K0 + 31) / 32, nch1 = c1 / 32, nch2 = c2 / 32;
+  const int total_chunks = nch0 + nch1 + nch2;
+  const int cmax = c1 > c2 ? (c1 > c3 ? c1 : c3) : (c2 > c3 ? c2 : c3);
+  const int act_chunks = nch1 > nch2 ? nch1 : nch2;
+  const int budget = 227 * 1024;
+  p.slot_bytes = cmax * 128;
+  const int max_tiles = 16 / cpt > 0 ? 16 / cpt : 1;  // <= 16 centres per CTA (one per warp in phase Q)
+  const int scratch = p.query ? kCloudTile * 12 : 0;  // phase Q borrows the operand regions
+
+  for (int lanes = kMaxLanes; lanes >= 1; lanes >>= 1) {
+    if (lanes > max_tiles) continue;
+    const int lane_cols = 512 / lanes;
+    if (c1 + c2 > lane_cols || c3 > lane_cols) continue;
+    // layer-0 passes of `cpp` chunks: fewer passes first; a pass shorter than the activation
+    // region would not shrink the lane's operand region any further
+    const int cpp_min = nch0 < act_chunks ? nch0 : act_chunks;
+    for (int cpp = nch0; cpp >= cpp_min; --cpp) {
+      p.lanes = lanes;
+      p.cpp = cpp;
+      p.npass = (nch0 + cpp - 1) / cpp;
+      int region = (cpp > act_chunks ? cpp : act_chunks) * kChunkBytes;
+      while (lanes * region < scratch) region += kChunkBytes;
+      p.lane_act_bytes = region;
+      p.tiles = max_tiles;
+      p.G = max_tiles * cpt;
+      // resident weights if they fit, else the deepest ring (>= 2 slots) that does
+      p.resident = 1;
+      p.slots = total_chunks;
+      if (total_chunks > kMaxSlots || smem_layout(p).total > budget) {
+        p.resident = 0;
+        p.slots = 0;
+        for (int sl = kMaxSlots; sl >= 2; --sl) {
+          p.slots = sl;
+          if (smem_layout(p).total <= budget) break;
+          p.slots = 0;
+        }
+      }
+      if (p.slots == 0) continue;
+      p.lane_cols = lane_cols;
+      p.acc_col[0] = 0;
+      p.acc_col[1] = c1;
+      p.acc_col[2] = (c1 + c2 + c3 <= lane_cols) ? c1 + c2 : 0;
+      const int top = p.acc_col[2] + c3 > c1 + c2 ? p.acc_col[2] + c3 : c1 + c2;
+      const int used = (lanes - 1) * lane_cols + top;
+      p.tmem_cols = used <= 32 ? 32 : used <= 64 ? 64 : used <= 128 ? 128 : used <= 256 ? 256 : 512;
+      // fewer tiles per CTA when the grid would not fill the GPU (but keep every lane busy)
+      int tiles = max_tiles;
+      while (tiles > 1 && tiles / 2 >= lanes &&
+             (long)B * ((p.M + tiles * cpt - 1) / (tiles * cpt)) < kNumSMs)
+        tiles >>= 1;
+      p.tiles = tiles;
+      p.G = tiles * cpt;
+      return true;
+    }
+  }
+  return false;
+}
 
 }  // namespace
 }  // namespace demf
@@ -524,6 +712,12 @@ int demf_sa_fused_supported(int C, int ns, int c1, int c2, int c3) {
   return 1;
 }
 
+/* debug: device buffer of 64 int64 that receives [count, clock64 stamps...] of one worker thread */
+int demf_sa_fused_set_profile(long long* device_buffer) {
+  g_sa_prof = device_buffer;
+  return 0;
+}
+
 int demf_sa_fused_error(void) {
   int e = 0;
   cudaMemcpyFromSymbol(&e, g_sa_error, sizeof(int));
@@ -532,8 +726,8 @@ int demf_sa_fused_error(void) {
 
 int demf_sa_fused_fwd(const float* xyz, const float* feat_rows, const float* new_xyz, int B, int N, int M,
                       int C, float min_radius, float max_radius, int ns, int normalize_xyz, int query,
-                      const float* wpack, const float* bias, int c1, int c2, int c3, int32_t* idx,
-                      float* out, void* stream) {
+                      const float* wpack, const float* bias, int c1, int c2, int c3, const void* grid,
+                      int32_t* idx, float* out, void* stream) {
   DEMF_REQUIRE_PTR(xyz);
   DEMF_REQUIRE_PTR(new_xyz);
   DEMF_REQUIRE_PTR(wpack);
@@ -568,39 +762,20 @@ int demf_sa_fused_fwd(const float* xyz, const float* feat_rows, const float* new
   p.min_r2 = min_radius * min_radius;
   p.max_r2 = max_radius * max_radius;
   p.inv_radius = 1.0f / max_radius;
-
-  // tiles per CTA: up to 16 centres (one per worker warp in the ball-query phase), but keep at
-  // least ~2 CTAs per SM in the grid so the tail wave stays small
-  const int cpt = kTileRows / ns;
-  int tiles = 16 / cpt;
-  while (tiles > 1 && (long)B * ((M + tiles * cpt - 1) / (tiles * cpt)) < 2L * kNumSMs) tiles >>= 1;
-  p.tiles = tiles;
-  p.G = tiles * cpt;
-
-  const int nch0 = (p.K0 + 31) / 32, nch1 = c1 / 32, nch2 = c2 / 32;
-  const int cmax = c1 > c2 ? (c1 > c3 ? c1 : c3) : (c2 > c3 ? c2 : c3);
-  const int amax = nch0 > nch1 ? (nch0 > nch2 ? nch0 : nch2) : (nch1 > nch2 ? nch1 : nch2);
-  p.act_bytes = amax * kChunkBytes;
-  if (query && p.act_bytes < kCloudTile * 12) p.act_bytes = ((kCloudTile * 12 + 1023) / 1024) * 1024;
-  p.slot_bytes = cmax * 128;
-  const int total_chunks = nch0 + nch1 + nch2;
-  // accumulators: [0,c1) [c1,c1+c2) then layer 2 after them if it fits in 512 columns, else at 0
-  p.acc_col[0] = 0;
-  p.acc_col[1] = c1;
-  p.acc_col[2] = (c1 + c2 + c3 <= 512) ? c1 + c2 : 0;
-  int cols = p.acc_col[2] + c3 > c1 + c2 ? p.acc_col[2] + c3 : c1 + c2;
-  p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
-
-  const int budget = 227 * 1024;
-  p.slots = 0;
-  for (int s = kMaxSlots; s >= 2; --s) {
-    p.slots = s;
-    if (smem_layout(p).total <= budget) break;
-    p.slots = 0;
+  p.prof = g_sa_prof;
+  p.grid = (query && ns <= kGridCap) ? grid : nullptr;
+  // With a grid and an index buffer from the caller, the neighbour search runs as its own launch:
+  // it is a latency-bound index chase that wants 64 warps per SM, while this kernel -- one CTA per
+  // SM because of its operand regions -- could only give it 16.
+  if (p.grid && idx) {
+    const int rc = launch_ball_query_grid(xyz, new_xyz, grid, B, N, M, min_radius, max_radius, ns, idx,
+                                          as_stream(stream));
+    if (rc != 0) return rc;
+    p.grid = nullptr;
+    p.query = query = 0;
   }
-  DEMF_REQUIRE(p.slots >= 2, DEMF_E_UNSUPPORTED);
-  p.resident = total_chunks <= p.slots;
-  if (p.resident) p.slots = total_chunks;
+  static_assert(kWorkerWarps * (kGridCap + kGridHist) * 4 <= kCloudTile * 12, "grid scratch fits the tile");
+  DEMF_REQUIRE(configure(p, B), DEMF_E_UNSUPPORTED);
   const SmemLayout L = smem_layout(p);
 
   static int configured_smem = 0;
@@ -614,8 +789,8 @@ int demf_sa_fused_fwd(const float* xyz, const float* feat_rows, const float* new
     }
     configured_smem = L.total;
   }
-  dim3 grid((M + p.G - 1) / p.G, B);
-  sa_fused_fwd_kernel<<<grid, kThreads, L.total, as_stream(stream)>>>(p);
+  dim3 grid_dim((M + p.G - 1) / p.G, B);
+  sa_fused_fwd_kernel<<<grid_dim, kThreads, L.total, as_stream(stream)>>>(p);
   return after_launch("sa_fused_fwd_kernel");
 }
 

@@ -42,11 +42,15 @@ def build_demf_votenet(num_points=4, cfg_options=None, init=True):
 def set_gemm_precision(mode):
     """Arithmetic of the dense projections (library GEMMs): 'fp32' = IEEE fp32 FMA,
     'tf32' = fp32 storage with TF32 tensor-core products (what the reference's PyTorch 1.8
-    does by default on Ampere and later). The sampling / index kernels are always fp32."""
+    does by default on Ampere and later). The sampling / index kernels are always fp32.
+    The fused set-abstraction kernel (csrc/sa_fused.cu) computes TF32 products, so it is part of
+    the 'tf32' mode only; 'fp32' runs the levels layer by layer with IEEE fp32 library GEMMs."""
     assert mode in ("fp32", "tf32")
     on = mode == "tf32"
     torch.backends.cuda.matmul.allow_tf32 = on
     torch.backends.cudnn.allow_tf32 = on
+    from .mm.pointnet_modules import BasePointSAModule
+    BasePointSAModule.fused_eval = on
 
 
 # ----------------------------------------------------------------------------- data ---

@@ -381,7 +381,7 @@ class QueryAndGroupRows(Function):
 
     @staticmethod
     def forward(ctx, xyz, center_xyz, feat_rows, min_radius, max_radius, sample_num,
-                normalize_xyz):
+                normalize_xyz, grid=None):
         assert xyz.is_contiguous()
         assert center_xyz.is_contiguous()
         assert feat_rows is None or feat_rows.is_contiguous()
@@ -396,7 +396,7 @@ class QueryAndGroupRows(Function):
             if idx.numel():
                 _lib.check(_lib.load().demf_query_and_group_rows_fwd(
                     _p(xyz), _p(feat_rows), _p(center_xyz), B, N, M, C, min_radius, max_radius,
-                    sample_num, int(normalize_xyz), 1, _p(idx), _p(out), _stream()),
+                    sample_num, int(normalize_xyz), 1, _p(grid), _p(idx), _p(out), _stream()),
                     "demf_query_and_group_rows_fwd")
         ctx.saved = (idx, N, C, (1.0 / max_radius) if normalize_xyz else 1.0)
         ctx.mark_non_differentiable(idx)
@@ -417,13 +417,46 @@ class QueryAndGroupRows(Function):
                 _lib.check(_lib.load().demf_group_rows_bwd(
                     _p(grad_out), _p(idx), B, N, M, C, ns, scale,
                     _p(g_feat), _p(g_xyz), _p(g_center), _stream()), "demf_group_rows_bwd")
-        return g_xyz, g_center, g_feat, None, None, None, None
+        return g_xyz, g_center, g_feat, None, None, None, None, None
 
 
 def query_and_group_rows(xyz, center_xyz, feat_rows, min_radius, max_radius, sample_num,
-                         normalize_xyz):
+                         normalize_xyz, grid=None):
+    """`grid` = ball_grid(xyz, r >= max_radius): same rows, but each centre only tests its 3x3x3
+    cell neighbourhood instead of the whole cloud."""
     return QueryAndGroupRows.apply(xyz, center_xyz, feat_rows, float(min_radius), float(max_radius),
-                                   int(sample_num), bool(normalize_xyz))
+                                   int(sample_num), bool(normalize_xyz), grid)
+
+
+def ball_grid(xyz, radius):
+    """Bin xyz (B,N,3) into a uniform grid with cell edge >= radius (csrc/ball_grid.cu): the opaque
+    workspace tensor accepted as `grid=` by ball_query_grid / query_and_group_rows / sa_fused for
+    queries on the SAME xyz with max_radius <= radius."""
+    assert xyz.is_contiguous()
+    _need_cuda(xyz)
+    B, N, _ = xyz.shape
+    lib = _lib.load()
+    with torch.cuda.device_of(xyz):
+        ws = torch.empty(int(lib.demf_ball_grid_workspace_bytes(B, N)), dtype=torch.uint8,
+                         device=xyz.device)
+        _lib.check(lib.demf_ball_grid_build(_p(xyz), B, N, float(radius), _p(ws), _stream()),
+                   "demf_ball_grid_build")
+    return ws
+
+
+def ball_query_grid(min_radius, max_radius, sample_num, xyz, center_xyz, grid):
+    """ball_query through a ball_grid workspace: bit-identical (B,M,ns) int32 rows."""
+    assert xyz.is_contiguous() and center_xyz.is_contiguous()
+    _need_cuda(xyz, center_xyz, grid)
+    B, N, _ = xyz.shape
+    M = center_xyz.size(1)
+    with torch.cuda.device_of(xyz):
+        idx = torch.zeros(B, M, sample_num, dtype=torch.int32, device=xyz.device)
+        if idx.numel():
+            _lib.check(_lib.load().demf_ball_query_grid(
+                _p(xyz), _p(center_xyz), _p(grid), B, N, M, float(min_radius), float(max_radius),
+                int(sample_num), _p(idx), _stream()), "demf_ball_query_grid")
+    return idx
 
 
 class ThreeInterpolateRows(Function):
@@ -498,7 +531,7 @@ def sa_pack_mlp(weights, biases):
 
 
 def sa_fused(xyz, center_xyz, feat_rows, min_radius, max_radius, sample_num, normalize_xyz, wpack,
-             bias, widths, idx=None, return_idx=False):
+             bias, widths, idx=None, return_idx=False, grid=None):
     """Ball query + grouping + 3-layer MLP (bias, ReLU) + max over the neighbourhood in one launch
     (csrc/sa_fused.cu): xyz (B,N,3), center_xyz (B,M,3), feat_rows (B,N,C) or None -> (B,M,c3)
     rows. `idx` (B,M,ns) i32 given: grouping uses it instead of running the ball query.
@@ -512,7 +545,7 @@ def sa_fused(xyz, center_xyz, feat_rows, min_radius, max_radius, sample_num, nor
     query = idx is None
     with torch.cuda.device_of(xyz):
         out = torch.empty(B, M, widths[2], dtype=torch.float32, device=xyz.device)
-        if query and return_idx:
+        if query and (return_idx or grid is not None):
             idx = torch.empty(B, M, sample_num, dtype=torch.int32, device=xyz.device)
         elif not query:
             assert idx.is_contiguous() and idx.dtype == torch.int32
@@ -520,6 +553,6 @@ def sa_fused(xyz, center_xyz, feat_rows, min_radius, max_radius, sample_num, nor
             _lib.check(_lib.load().demf_sa_fused_fwd(
                 _p(xyz), _p(feat_rows), _p(center_xyz), B, N, M, C, float(min_radius),
                 float(max_radius), int(sample_num), int(bool(normalize_xyz)), int(query), _p(wpack),
-                _p(bias), widths[0], widths[1], widths[2], _p(idx), _p(out), _stream()),
+                _p(bias), widths[0], widths[1], widths[2], _p(grid), _p(idx), _p(out), _stream()),
                 "demf_sa_fused_fwd")
     return (out, idx) if return_idx else out

@@ -16,7 +16,8 @@ import torch
 import torch.nn as nn
 
 from . import point_ops as P
-from .bricks import (BaseModule, ConvModule, as_rows, build_conv_layer, conv_module_rows)
+from .bricks import (BaseModule, ConvModule, _foldable, _folded_cached, as_rows, build_conv_layer,
+                     conv_module_rows)
 from .registry import BACKBONES, SA_MODULES
 
 
@@ -100,19 +101,65 @@ class BasePointSAModule(nn.Module):
                 and not (grouper.return_grouped_xyz or grouper.return_grouped_idx
                          or grouper.uniform_sample))
 
-    def forward(self, points_xyz, features=None, indices=None, target_xyz=None):
+    # Inference: the whole level -- ball query, grouping, the three BN-folded 1x1 convolutions
+    # and the max over the neighbourhood -- is ONE tcgen05 kernel (csrc/sa_fused.cu); neither the
+    # grouped tensor nor any activation reaches HBM. `fused_eval = False` keeps the layer-by-layer
+    # path (group rows kernel + library GEMMs), which is also what training uses.
+    fused_eval = True
+
+    def _fused_pack(self, mlp, C):
+        """(wpack, bias, widths) of this MLP for P.sa_fused, rebuilt when a parameter changes."""
+        layers = list(mlp)
+        folded = [_folded_cached(cm, P.group_rows_columns(C) if j == 0 else None)
+                  for j, cm in enumerate(layers)]
+        key = tuple((w.data_ptr(), b.data_ptr()) for w, b in folded)
+        cache = mlp.__dict__.get("_sa_pack")
+        if cache is None or cache[0] != key:
+            cache = (key,) + P.sa_pack_mlp([w for w, _ in folded], [b for _, b in folded])
+            mlp.__dict__["_sa_pack"] = cache
+        return cache[1:]
+
+    def _fused_ok(self, grouper, mlp, points_xyz, C):
+        return (self.fused_eval and self.pool_mod == 'max' and points_xyz.is_cuda
+                and not torch.is_grad_enabled() and len(mlp) == 3
+                and all(isinstance(cm, ConvModule) and _foldable(cm) and cm.with_activation
+                        for cm in mlp)
+                and P.sa_fused_supported(C, grouper.sample_num,
+                                         [cm.conv.out_channels for cm in mlp]))
+
+    # Clouds at least this large are binned into a uniform grid first (P.ball_grid) and the ball
+    # query only tests each centre's 3x3x3 cell neighbourhood -- identical index rows.
+    grid_min_points = 4096
+
+    def ball_grid(self, points_xyz):
+        """Grid workspace for this module's queries on points_xyz, or None for small clouds."""
+        if (not points_xyz.is_cuda or points_xyz.size(1) < self.grid_min_points
+                or not all(self._rows_ok(g) for g in self.groupers)):
+            return None
+        return P.ball_grid(points_xyz.contiguous(), max(g.max_radius for g in self.groupers))
+
+    def forward(self, points_xyz, features=None, indices=None, target_xyz=None, grid=None):
         """points_xyz (B,N,3), features (B,C,N) -> new_xyz (B,M,3), new_features (B,sum C_k,M),
-        indices (B,M)."""
+        indices (B,M). `grid`: a workspace from self.ball_grid(points_xyz) built ahead of time."""
         new_xyz, indices = self._sample_points(points_xyz, features, indices, target_xyz)
         points_xyz = points_xyz.contiguous()
+        if grid is None:
+            grid = self.ball_grid(points_xyz)
         out = []
         for grouper, mlp in zip(self.groupers, self.mlps):
             if self._rows_ok(grouper):
                 feat_rows = None if features is None else as_rows(features)
                 C = 0 if feat_rows is None else feat_rows.size(-1)
+                if self._fused_ok(grouper, mlp, points_xyz, C):
+                    wpack, bias, widths = self._fused_pack(mlp, C)
+                    out.append(P.sa_fused(points_xyz, new_xyz.contiguous(), feat_rows,
+                                          grouper.min_radius, grouper.max_radius,
+                                          grouper.sample_num, grouper.normalize_xyz, wpack, bias,
+                                          widths, grid=grid))
+                    continue
                 _, rows = P.query_and_group_rows(
                     points_xyz, new_xyz.contiguous(), feat_rows, grouper.min_radius,
-                    grouper.max_radius, grouper.sample_num, grouper.normalize_xyz)
+                    grouper.max_radius, grouper.sample_num, grouper.normalize_xyz, grid)
                 B, M, ns, K = rows.shape
                 x = rows.view(B * M * ns, K)
                 for j, layer in enumerate(mlp):
@@ -308,13 +355,17 @@ class PointNet2SASSG(BaseModule):
         levels, seed_fps = self._sampling_chain(xyz) if chained else (None, None)
         indices = torch.arange(num_points, device=xyz.device).unsqueeze(0).repeat(batch, 1).long()
         sa_xyz, sa_features, sa_indices = [xyz], [features], [indices]
+        # the first level's ball-query grid only needs the input cloud: it is binned on the main
+        # stream while the side stream is still busy with the first furthest-point sampling
+        grid0 = self.SA_modules[0].ball_grid(xyz) if levels is not None else None
         for i in range(self.num_sa):
             if levels is not None:
                 idx, new_xyz, ev = levels[i]
                 if ev is not None:
                     torch.cuda.current_stream(xyz.device).wait_event(ev)
                 cur_xyz, cur_features, cur_indices = self.SA_modules[i](
-                    sa_xyz[i], sa_features[i], indices=idx, target_xyz=new_xyz)
+                    sa_xyz[i], sa_features[i], indices=idx, target_xyz=new_xyz,
+                    grid=grid0 if i == 0 else None)
             else:
                 cur_xyz, cur_features, cur_indices = self.SA_modules[i](sa_xyz[i], sa_features[i])
             sa_xyz.append(cur_xyz)

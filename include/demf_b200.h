@@ -132,8 +132,9 @@ int demf_three_interpolate_bwd(const float* grad_out, const int32_t* idx, const 
 int demf_group_rows_width(int C);
 int demf_query_and_group_rows_fwd(const float* xyz, const float* feat_rows, const float* new_xyz,
                                   int B, int N, int M, int C, float min_radius, float max_radius,
-                                  int ns, int normalize_xyz, int query, int32_t* idx, float* out,
-                                  void* stream);
+                                  int ns, int normalize_xyz, int query,
+                                  const void* grid /* demf_ball_grid_build workspace or NULL */,
+                                  int32_t* idx, float* out, void* stream);
 /* grad_out (B,M,ns,K) -> grad_feat_rows (B,N,C) pre-zeroed (may be NULL when C == 0),
  * grad_xyz (B,N,3) pre-zeroed or NULL, grad_centre (B,M,3) fully written or NULL.
  * xyz_scale = 1/max_radius when normalize_xyz was set, else 1. */
@@ -146,6 +147,19 @@ int demf_three_interpolate_rows_fwd(const float* feat_rows, const int32_t* idx, 
                                     int B, int C, int m, int n, float* out, void* stream);
 int demf_three_interpolate_rows_bwd(const float* grad_out, const int32_t* idx, const float* weight,
                                     int B, int C, int n, int m, float* grad_feat_rows, void* stream);
+
+/* ------------------------------------------- exact grid ball query ------- */
+/* The same (B,M,ns) index rows as demf_ball_query, but each centre only tests the points of its
+ * 3x3x3 cell neighbourhood in a uniform grid (cell edge >= radius) instead of the whole cloud.
+ * demf_ball_grid_build bins xyz (B,N,3) once (counting sort, one CTA per scene) into `workspace`
+ * (demf_ball_grid_workspace_bytes(B,N) bytes, 16-byte aligned, caller-owned); the workspace then
+ * answers any query on the same xyz with max_radius <= radius (larger radii fall back to the full
+ * scan inside the kernel). Accepted as the optional `grid` argument of demf_sa_fused_fwd and
+ * demf_query_and_group_rows_fwd. ns <= 256. */
+size_t demf_ball_grid_workspace_bytes(int B, int N);
+int demf_ball_grid_build(const float* xyz, int B, int N, float radius, void* workspace, void* stream);
+int demf_ball_query_grid(const float* xyz, const float* new_xyz, const void* grid, int B, int N, int M,
+                         float min_radius, float max_radius, int ns, int32_t* idx, void* stream);
 
 /* ------------------------- fused set abstraction (inference), tcgen05 --- */
 /* replaces, for one PointSAModule forward in eval mode (mmdet3d
@@ -167,9 +181,14 @@ int demf_sa_pack_weights(const float* w /* (Cout,Cin) device */, int Cout, int C
 int demf_sa_fused_supported(int C, int ns, int c1, int c2, int c3);
 int demf_sa_fused_fwd(const float* xyz, const float* feat_rows, const float* new_xyz, int B, int N, int M,
                       int C, float min_radius, float max_radius, int ns, int normalize_xyz, int query,
-                      const float* wpack, const float* bias, int c1, int c2, int c3, int32_t* idx,
-                      float* out, void* stream);
+                      const float* wpack, const float* bias, int c1, int c2, int c3,
+                      const void* grid /* demf_ball_grid_build workspace of xyz, or NULL */,
+                      int32_t* idx, float* out, void* stream);
 int demf_sa_fused_error(void);
+/* debug only: device buffer of 64 int64 receiving [count, clock64 stamps of one worker thread of
+ * CTA (0,0): start, after ball query, then per tile: gathered, acc0 ready, act1 written, acc1 ready,
+ * act2 written, acc2 ready, stored]; NULL switches it off. */
+int demf_sa_fused_set_profile(long long* device_buffer);
 
 /* ------------------------------------ multi-scale deformable attention --- */
 /* replaces mmcv _ext.ms_deform_attn_forward / ms_deform_attn_backward

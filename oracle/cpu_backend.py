@@ -43,7 +43,7 @@ def _take(rows, idx):
 
 
 def _query_and_group_rows(xyz, center_xyz, feat_rows, min_radius, max_radius, sample_num,
-                          normalize_xyz):
+                          normalize_xyz, grid=None):
     idx = _ball_query(min_radius, max_radius, sample_num, xyz, center_xyz)
     diff = _take(xyz, idx) - center_xyz.unsqueeze(2)
     if normalize_xyz:  # the kernel multiplies by the float32 reciprocal of the radius

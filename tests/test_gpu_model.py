@@ -106,6 +106,45 @@ def test_backbone_forward_matches_cpu_oracle(dev):
     model.cpu()
 
 
+def test_backbone_forward_fused_tf32(dev):
+    """'tf32' mode: every set-abstraction level is ONE tcgen05 kernel (csrc/sa_fused.cu). Index
+    tensors stay bit-exact; features agree with the fp32 CPU port to TF32 accuracy (the
+    arithmetic PyTorch runs the reference's convolutions in by default) and with this package's
+    own layer-by-layer TF32 path."""
+    from demf_b200.mm.pointnet_modules import BasePointSAModule
+    torch.manual_seed(0)
+    model = engine.build_demf_votenet(num_points=4).eval()
+    for m in model.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.5, 1.5)
+    pts = synth.make_points(2, 20000, seed=4, clustered=True)
+    with cpu_backend.oracle_ops(), torch.no_grad():
+        ref = model.pts_backbone(pts)
+    gm = model.to(dev)
+    try:
+        engine.set_gemm_precision("tf32")
+        with torch.no_grad():
+            got = gm.pts_backbone(pts.to(dev))
+            BasePointSAModule.fused_eval = False
+            unfused = gm.pts_backbone(pts.to(dev))
+            torch.cuda.synchronize()
+    finally:
+        engine.set_gemm_precision("fp32")
+    assert _lib.load().demf_sa_fused_error() == 0
+    for k in ("sa_indices", "fp_indices"):
+        for a, b in zip(got[k], ref[k]):
+            assert torch.equal(a.cpu(), b)
+    for a, b, c in zip(got["sa_features"][1:] + got["fp_features"],
+                       ref["sa_features"][1:] + ref["fp_features"],
+                       unfused["sa_features"][1:] + unfused["fp_features"]):
+        scale = b.abs().max().item()
+        assert (a.cpu() - b).abs().max().item() <= 2e-2 * scale
+        assert (a - c).abs().max().item() <= 2e-2 * scale
+        assert (a.cpu() - b).abs().mean().item() <= 2e-3 * scale
+    model.cpu()
+
+
 def test_full_forward_matches_cpu_oracle(dev):
     torch.manual_seed(1)
     model = engine.build_demf_votenet(num_points=4).eval()

@@ -396,3 +396,57 @@ def test_sa_fused_matches_oracle(dev, B, N, M, C, ns, radius, widths):
     out2 = ops.sa_fused(xyz.to(dev), centres.to(dev), feat_rows, 0.0, radius, ns, True, wpack, bias, wd,
                         idx=idx)
     assert torch.equal(out2, out)
+
+
+# ----------------------------------------------------------- exact grid ball query --
+@pytest.mark.parametrize("B,N,M,r,ns,min_r,kind", [
+    (2, 20000, 2048, 0.2, 64, 0.0, "clustered"),   # SA1
+    (2, 20000, 2048, 0.2, 64, 0.0, "uniform"),
+    (1, 20000, 512, 0.4, 32, 0.2, "clustered"),    # dilated ring
+    (2, 5000, 300, 0.6, 16, 0.0, "dense"),         # every ball overflows the hit buffer
+    (1, 6000, 200, 5.0, 64, 0.0, "dense"),         # ball = whole cloud
+    (2, 4099, 257, 0.3, 8, 0.0, "dup"),            # duplicated points, centres on points
+    (1, 1000, 64, 0.25, 200, 0.0, "uniform"),      # nsample > hits
+    (1, 3000, 100, 0.3, 16, 0.0, "far"),           # centres outside the cloud's bounding box
+])
+def test_ball_query_grid_matches_oracle(dev, B, N, M, r, ns, min_r, kind):
+    g = torch.Generator().manual_seed(N + M)
+    if kind == "dense":
+        xyz = (torch.rand(B, N, 3, generator=g) * 0.5).contiguous()
+    elif kind == "dup":
+        base = _xyz(B, N // 2 + 1, seed=3)
+        xyz = torch.cat([base, base], 1)[:, :N].contiguous()
+    else:
+        xyz = _xyz(B, N, seed=N, clustered=(kind == "clustered"))
+    centres = xyz[:, torch.randperm(N, generator=g)[:M]].contiguous()
+    if kind == "far":
+        centres = (centres + torch.tensor([50.0, 0.0, 0.0])).contiguous()
+        centres[:, ::2] = xyz[:, :M:2] + 0.01
+    ref = cref.ball_query(min_r, r, ns, xyz, centres)
+    gx, gc = xyz.to(dev), centres.to(dev)
+    grid = ops.ball_grid(gx, r)
+    got = ops.ball_query_grid(min_r, r, ns, gx, gc, grid)
+    assert torch.equal(got.cpu(), ref)
+    # a query radius beyond the grid's falls back to the full scan inside the kernel
+    small = ops.ball_grid(gx, r * 0.5)
+    assert torch.equal(ops.ball_query_grid(min_r, r, ns, gx, gc, small).cpu(), ref)
+    # the grouping kernel with the grid writes the same rows as without
+    if ns <= 64:
+        feats = torch.randn(B, N, 8, generator=g).to(dev)
+        i0, r0 = ops.query_and_group_rows(gx, gc, feats, min_r, r, ns, True)
+        i1, r1 = ops.query_and_group_rows(gx, gc, feats, min_r, r, ns, True, grid)
+        assert torch.equal(i0.cpu(), ref) and torch.equal(i1, i0) and torch.equal(r1, r0)
+
+
+def test_sa_fused_with_grid_is_identical(dev):
+    sa_module, xyz, centres, feats, weights, biases = _sa_case(2, 20000, 2048, 1, 64, 0.2, (64, 64, 128), seed=5)
+    from demf_b200.mm.bricks import permute_weight_columns
+    w0 = permute_weight_columns(weights[0].to(dev), ops.group_rows_columns(1))
+    wpack, bias, wd = ops.sa_pack_mlp([w0, weights[1].to(dev), weights[2].to(dev)], [b.to(dev) for b in biases])
+    rows = feats.transpose(1, 2).contiguous().to(dev)
+    gx, gc = xyz.to(dev), centres.to(dev)
+    a, ia = ops.sa_fused(gx, gc, rows, 0.0, 0.2, 64, True, wpack, bias, wd, return_idx=True)
+    b, ib = ops.sa_fused(gx, gc, rows, 0.0, 0.2, 64, True, wpack, bias, wd, return_idx=True,
+                         grid=ops.ball_grid(gx, 0.2))
+    assert torch.equal(ia, ib) and torch.equal(a, b)
+    assert _lib.load().demf_sa_fused_error() == 0

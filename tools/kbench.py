@@ -104,6 +104,53 @@ def main():
             med, mn = timeit(lambda: qg(x, c, f), args.reps, flush)
             report("query_and_group", dict(B=B, N=N, M=M, ns=ns, C=C), med, mn,
                    B * (N * 12 + M * 12 + M * ns * 4 + C * N * 4 + (C + 3) * M * ns * 4))
+    if want("sa"):
+        # one set-abstraction level in eval mode: fused tcgen05 kernel vs the unfused rows path
+        # (group rows kernel + 3 cuBLASLt TF32 GEMMs with bias+ReLU epilogue + amax)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        widths_of = {1: (64, 64, 128), 128: (128, 128, 256), 256: (128, 128, 256)}
+        cur = pts
+        for li, (N, M, r, ns, C) in enumerate(geoms):
+            widths = (256, 256, 256) if li == 4 else widths_of[C]
+            x = pts[:, :N].contiguous() if li in (0, 4) else cur[:, :N].contiguous()
+            c = ops.gather_rows(x, ops.furthest_point_sample(x, M)).contiguous()
+            cur = c
+            f = torch.randn(B, N, C, device=dev)
+            K = ops.group_rows_width(C)
+            cin = [K] + list(widths[:-1])
+            ws = [torch.randn(co, ci, device=dev) / ci ** 0.5 for co, ci in zip(widths, cin)]
+            bs = [torch.randn(co, device=dev) * 0.1 for co in widths]
+            wpack, bias, wd = ops.sa_pack_mlp(ws, bs)
+            rows = B * M * ns
+            flops = 2.0 * rows * sum(co * ci for co, ci in zip(widths, cin))
+            hbm = B * (N * 12 + N * C * 4 + M * 12 + M * widths[2] * 4)
+            med, mn = timeit(lambda: ops.sa_fused(x, c, f, 0.0, r, ns, True, wpack, bias, wd),
+                             args.reps, flush)
+            report("sa_fused", dict(B=B, N=N, M=M, ns=ns, C=C, widths=widths,
+                                    TFLOPs_median=round(flops / med / 1e9, 1)), med, mn, hbm)
+            if N >= 2048:
+                med, mn = timeit(lambda: ops.ball_grid(x, r), args.reps, flush)
+                report("ball_grid_build", dict(B=B, N=N, r=r), med, mn, B * N * 28)
+                grid = ops.ball_grid(x, r)
+                med, mn = timeit(lambda: ops.sa_fused(x, c, f, 0.0, r, ns, True, wpack, bias, wd, grid=grid),
+                                 args.reps, flush)
+                report("sa_fused+grid", dict(B=B, N=N, M=M, ns=ns, C=C, widths=widths,
+                                             TFLOPs_median=round(flops / med / 1e9, 1)), med, mn, hbm)
+                med, mn = timeit(lambda: ops.ball_query_grid(0.0, r, ns, x, c, grid), args.reps, flush)
+                report("ball_query_grid", dict(B=B, N=N, M=M, ns=ns), med, mn)
+                med, mn = timeit(lambda: ops.ball_query(0.0, r, ns, x, c), args.reps, flush)
+                report("ball_query_scan", dict(B=B, N=N, M=M, ns=ns), med, mn)
+
+            def unfused():
+                _, g = ops.query_and_group_rows(x, c, f, 0.0, r, ns, True)
+                y = g.view(rows, K)
+                for w, b in zip(ws, bs):
+                    y = torch._addmm_activation(b, y, w.t())
+                return y.view(B, M, ns, -1).amax(dim=2)
+            with torch.no_grad():
+                med, mn = timeit(unfused, args.reps, flush)
+            report("sa_unfused", dict(B=B, N=N, M=M, ns=ns, C=C, widths=widths,
+                                      TFLOPs_median=round(flops / med / 1e9, 1)), med, mn, hbm)
     if want("interp"):
         for n, m in ((512, 256), (1024, 512)):
             a, b = pts[:, :n].contiguous(), pts[:, 5000:5000 + m].contiguous()
