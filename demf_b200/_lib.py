@@ -48,6 +48,7 @@ _SIGNATURES = {
                           _c_int, _c_int, _ptr, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr],
     "demf_sa_fused_error": [],
     "demf_sa_fused_set_profile": [_ptr],
+    "demf_sa_fused_tune": [_c_int, _c_int],
     "demf_msda_fwd": [_ptr, _ptr, _ptr, _ptr, _ptr] + [_c_int] * 7 + [_ptr, _ptr],
     "demf_msda_bwd": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr] + [_c_int] * 7 + [_ptr, _ptr, _ptr, _ptr],
 }

@@ -50,7 +50,9 @@ constexpr int kMaxSlots = 8;
 constexpr int kMaxLanes = 4;
 
 __device__ int g_sa_error = 0;  // sticky: first protocol time-out (never expected)
-long long* g_sa_prof = nullptr;  // host copy of the debug stamp buffer pointer (demf_sa_fused_set_profile)
+long long* g_sa_prof = nullptr;
+int g_sa_max_lanes = kMaxLanes;  // tuning knobs (demf_sa_fused_tune)
+int g_sa_sleep_ns = 0;  // host copy of the debug stamp buffer pointer (demf_sa_fused_set_profile)
 
 struct SaParams {
   const float* xyz;
@@ -69,6 +71,8 @@ struct SaParams {
   int lanes, cpp, npass, lane_act_bytes;  // tile pipelines; A0 chunks per layer-0 pass; passes
   int slots, slot_bytes, resident;
   int tmem_cols, lane_cols, acc_col[3];
+  int sleep_ns;  // back-off between mbarrier polls of the worker warps (0 = spin)
+  int t2;        // layer 2 runs transposed (D^T = W3 * act2^T): lanes = channels, columns = rows
 };
 
 struct SmemLayout {
@@ -93,8 +97,13 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(u);
 }
 
-__device__ __forceinline__ float4 tf32_rna4(float4 v) {
-  return make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+// Round-to-nearest (ties away from zero) to TF32 for an MMA OPERAND in one integer add: the tensor
+// core reads the top 19 bits of the word, so adding half a TF32 ulp to the magnitude is all
+// cvt.rna.tf32 does for finite values (the low 13 bits left behind are ignored by the hardware).
+__device__ __forceinline__ float tf32_operand(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+
+__device__ __forceinline__ float4 tf32_operand4(float4 v) {
+  return make_float4(tf32_operand(v.x), tf32_operand(v.y), tf32_operand(v.z), tf32_operand(v.w));
 }
 
 __device__ __forceinline__ void named_sync(int id, int threads) {
@@ -119,10 +128,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 
 // Bounded wait that also gives up as soon as any thread of the CTA has flagged a failure.
-__device__ __forceinline__ bool wait_or_fail(uint32_t bar, uint32_t parity, volatile int* failed, int code) {
+__device__ __forceinline__ bool wait_or_fail(uint32_t bar, uint32_t parity, volatile int* failed, int code,
+                                             int sleep_ns = 0) {
   if (mbar_try_wait(bar, parity)) return true;
   unsigned long long t0 = 0;
   for (uint32_t spin = 1;; ++spin) {
+    if (sleep_ns) __nanosleep(sleep_ns);
     if (mbar_try_wait(bar, parity)) return true;
     if ((spin & 255u) == 0) {
       if (*failed) return false;
@@ -179,6 +190,57 @@ __device__ __forceinline__ void group_span(const SaParams& p, int nch0, int g, i
   }
 }
 
+struct IssueCtx {
+  uint32_t tmem, act_u32, ring_u32, wfull0, wempty0, acc_full0;
+  int nch0;
+  volatile int* failed;
+};
+
+// Issue the tcgen05.mma instructions of MMA group g of lane `ln` (one thread) and commit the lane's
+// acc_full barrier. Resident weights: chunk `cid` sits in ring slot `cid` for the whole kernel.
+__device__ __forceinline__ bool issue_group(const SaParams& p, const IssueCtx& c, int ln, int g, uint32_t& slot,
+                                            uint32_t& wph) {
+  int layer, ch0, nch;
+  group_span(p, c.nch0, g, layer, ch0, nch);
+  const uint32_t idesc = instr_desc_tf32(kTileRows, p.c[layer]);
+  const int cid = layer == 0 ? ch0 : (layer == 1 ? c.nch0 : c.nch0 + (p.c[0] >> 5));
+  const uint32_t d = c.tmem + ln * p.lane_cols + p.acc_col[layer];
+  const uint32_t a0 = c.act_u32 + ln * p.lane_act_bytes;
+  tc_fence_after_sync();
+  for (int ch = 0; ch < nch; ++ch) {
+    const uint32_t s = p.resident ? (uint32_t)(cid + ch) : slot;
+    if (!wait_or_fail(c.wfull0 + 8 * s, p.resident ? 0u : wph, c.failed, 2)) return false;
+    const int ksteps = layer == 0 ? (min(32, p.K0 - 32 * (ch0 + ch)) >> 3) : 4;
+    // a K step of 8 tf32 = +32 bytes = +2 in the descriptor's (address >> 4) field
+    const uint64_t da = smem_desc_sw128(a0 + ch * kChunkBytes), dw = smem_desc_sw128(c.ring_u32 + s * p.slot_bytes);
+    if (layer == 2 && p.t2) {
+      // D^T[channel, row] += W3[channel, k] * act2[row, k]: the weight chunk is the M operand (128
+      // channels per MMA; the second half of a 256-wide layer sits 128 rows = 16 KB further), the
+      // activation tile the N operand. 128 accumulator columns per 128 channels.
+      const uint32_t it = instr_desc_tf32(128, kTileRows);
+      for (int h = 0; h < (p.c[2] >> 7); ++h) {
+        const uint64_t dwh = dw + (uint64_t)(h * (128 * 128 >> 4));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_tf32(d + h * 128, dwh + 2 * k, da + 2 * k, it, (ch | k) != 0);
+      }
+    } else if (ksteps == 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mma_tf32(d, da + 2 * k, dw + 2 * k, idesc, (ch0 | ch | k) != 0);
+    } else {
+      for (int k = 0; k < ksteps; ++k) mma_tf32(d, da + 2 * k, dw + 2 * k, idesc, (ch0 | ch | k) != 0);
+    }
+    if (!p.resident) {
+      mma_commit(c.wempty0 + 8 * slot);
+      if (++slot == (uint32_t)p.slots) {
+        slot = 0;
+        wph ^= 1;
+      }
+    }
+  }
+  mma_commit(c.acc_full0 + 8 * ln);
+  return true;
+}
+
 __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParams p) {
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned chunks: align the carve-up by hand
@@ -229,41 +291,22 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const int nch0 = (p.K0 + 31) >> 5;
+  const IssueCtx ictx{tmem, act_u32, ring_u32, wfull0, wempty0, acc_full0, nch0, failed};
 
   if (warp == 0) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      uint32_t opp = 0, slot = 0, wph = 0;  // opp: one parity bit per lane
-      for (int r = 0; r < nrounds; ++r) {
-        for (int g = 0; g < ngroups; ++g) {
-          int layer, ch0, nch;
-          group_span(p, nch0, g, layer, ch0, nch);
-          const uint32_t idesc = instr_desc_tf32(kTileRows, p.c[layer]);
-          int cid = layer == 0 ? ch0 : (layer == 1 ? nch0 : nch0 + (p.c[0] >> 5));  // resident slot
-          for (int ln = 0; ln < p.lanes; ++ln) {
+    // Streamed weights only: MMA groups are issued in the fixed order the producer warp mirrors.
+    // (With resident weights every lane issues its own MMAs, see publish() in the worker code.)
+    // The k-th group of a lane waits for the k-th completion of that lane's op_ready barrier.
+    if (lane == 0 && !p.resident) {
+      uint32_t slot = 0, wph = 0;
+      bool ok = true;
+      for (int r = 0; r < nrounds && ok; ++r) {
+        for (int g = 0; g < ngroups && ok; ++g) {
+          for (int ln = 0; ln < p.lanes && ok; ++ln) {
             if (r * p.lanes + ln >= ntiles) break;
-            if (!wait_or_fail(op_ready0 + 8 * ln, (opp >> ln) & 1u, failed, 1)) break;
-            opp ^= 1u << ln;
-            tc_fence_after_sync();
-            const uint32_t d = tmem + ln * p.lane_cols + p.acc_col[layer];
-            const uint32_t a0 = act_u32 + ln * p.lane_act_bytes;
-            for (int ch = 0; ch < nch; ++ch) {
-              const uint32_t s = p.resident ? (uint32_t)(cid + ch) : slot;
-              if (!wait_or_fail(wfull0 + 8 * s, p.resident ? 0u : wph, failed, 2)) break;
-              const int ksteps = layer == 0 ? (min(32, p.K0 - 32 * (ch0 + ch)) >> 3) : 4;
-              const uint32_t a = a0 + ch * kChunkBytes, w = ring_u32 + s * p.slot_bytes;
-              for (int k = 0; k < ksteps; ++k)
-                mma_tf32(d, smem_desc_sw128(a + 32 * k), smem_desc_sw128(w + 32 * k), idesc,
-                         (ch0 | ch | k) != 0);
-              if (!p.resident) {
-                mma_commit(wempty0 + 8 * slot);
-                if (++slot == (uint32_t)p.slots) {
-                  slot = 0;
-                  wph ^= 1;
-                }
-              }
-            }
-            mma_commit(acc_full0 + 8 * ln);
+            ok = wait_or_fail(op_ready0 + 8 * ln, (uint32_t)(r * ngroups + g) & 1u, failed, 1) &&
+                 issue_group(p, ictx, ln, g, slot, wph);
           }
         }
       }
@@ -426,6 +469,23 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
     const float scale = p.normalize_xyz ? p.inv_radius : 1.f;
     uint32_t accp = 0;
     bool ok = true;
+    // The operand of MMA group g of this lane's tile is in shared memory: hand it to the tensor pipe.
+    // Resident weights: the lane's first thread issues the MMAs itself (no hand-off latency, lanes
+    // issue in parallel); streamed weights: signal the issuer warp, which keeps the ring order.
+    auto publish = [&](int g) {
+      fence_proxy_async();
+      tc_fence_before_sync();
+      if (p.resident) {
+        named_sync(2 + ln, lthreads);
+        if (lt == 0) {
+          uint32_t unused_slot = 0, unused_ph = 0;
+          issue_group(p, ictx, ln, g, unused_slot, unused_ph);
+        }
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(op_ready);
+      }
+    };
 
     for (int t = ln; t < ntiles && ok; t += p.lanes) {
       const int32_t* trow = rows + t * kTileRows;  // rows of centre g are contiguous: g*ns
@@ -454,54 +514,63 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
-              if (off[u] >= 0) *reinterpret_cast<float4*>(act + off[u]) = tf32_rna4(v[u]);
+              if (off[u] >= 0) *reinterpret_cast<float4*>(act + off[u]) = tf32_operand4(v[u]);
           }
         }
         // (b) the remaining slots of the pass: unaligned features, the xyz slot, zero padding
         const int t_lo = vec ? max(s_lo, C4) : s_lo;
         if (s_hi > t_lo) {
-          const int w = s_hi - t_lo;
-          for (int e = lt; e < kTileRows * w; e += lthreads) {
-            const int r = e / w;
-            const int j = t_lo + (e - r * w);
-            const int k = trow[r];
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < C4) {
-              const float* f = fb + (long)k * p.C + j * 4;
-              const int left = p.C - j * 4;
-              v.x = __ldg(f);
-              v.y = left > 1 ? __ldg(f + 1) : 0.f;
-              v.z = left > 2 ? __ldg(f + 2) : 0.f;
-              v.w = left > 3 ? __ldg(f + 3) : 0.f;
-            } else if (j == C4) {
-              const float4 c = centres[t * cpt + r / ns];
-              const float* pt = cloud + (long)k * 3;
-              v.x = __fsub_rn(__ldg(pt + 0), c.x);
-              v.y = __fsub_rn(__ldg(pt + 1), c.y);
-              v.z = __fsub_rn(__ldg(pt + 2), c.z);
-              if (p.normalize_xyz) {
-                v.x = __fmul_rn(v.x, scale);
-                v.y = __fmul_rn(v.y, scale);
-                v.z = __fmul_rn(v.z, scale);
+          const int w = s_hi - t_lo, total = kTileRows * w;
+          for (int e0 = lt; e0 < total; e0 += 2 * lthreads) {
+            float4 v[2];
+            int off[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {  // both elements' loads are issued before either store
+              const int e = e0 + u * lthreads;
+              off[u] = -1;
+              v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (e < total) {
+                const int r = e / w;
+                const int j = t_lo + (e - r * w);
+                const int k = trow[r];
+                off[u] = ((j - s_lo) >> 3) * kChunkBytes + sw128_offset(r, j & 7);
+                if (j < C4) {
+                  const float* f = fb + (long)k * p.C + j * 4;
+                  const int left = p.C - j * 4;
+                  v[u].x = __ldg(f);
+                  v[u].y = left > 1 ? __ldg(f + 1) : 0.f;
+                  v[u].z = left > 2 ? __ldg(f + 2) : 0.f;
+                  v[u].w = left > 3 ? __ldg(f + 3) : 0.f;
+                } else if (j == C4) {
+                  const float4 c = centres[t * cpt + r / ns];
+                  const float* pt = cloud + (long)k * 3;
+                  v[u].x = __fsub_rn(__ldg(pt + 0), c.x);
+                  v[u].y = __fsub_rn(__ldg(pt + 1), c.y);
+                  v[u].z = __fsub_rn(__ldg(pt + 2), c.z);
+                  if (p.normalize_xyz) {
+                    v[u].x = __fmul_rn(v[u].x, scale);
+                    v[u].y = __fmul_rn(v[u].y, scale);
+                    v[u].z = __fmul_rn(v[u].z, scale);
+                  }
+                }
               }
             }
-            *reinterpret_cast<float4*>(act + ((j - s_lo) >> 3) * kChunkBytes + sw128_offset(r, j & 7)) = tf32_rna4(v);
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+              if (off[u] >= 0) *reinterpret_cast<float4*>(act + off[u]) = tf32_operand4(v[u]);
           }
         }
-        fence_proxy_async();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(op_ready);
+        publish(pass);
         SA_STAMP();
         if (pass + 1 < p.npass) {  // the next pass overwrites the region: its MMAs must be done
-          ok = wait_or_fail(acc_full, accp, failed, 6);
+          ok = wait_or_fail(acc_full, accp, failed, 6, p.sleep_ns);
           accp ^= 1;
         }
       }
 
       // ---- layers 0 and 1: accumulator -> bias, ReLU, tf32 -> next layer's A operand
       for (int l = 0; l < 2 && ok; ++l) {
-        ok = wait_or_fail(acc_full, accp, failed, 4);
+        ok = wait_or_fail(acc_full, accp, failed, 4, p.sleep_ns);
         accp ^= 1;
         tc_fence_after_sync();
         SA_STAMP();
@@ -511,32 +580,69 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
           tmem_ld32(tmem + lane_base + p.acc_col[l] + blk * 32, u);
           tmem_ld_wait();
           unsigned char* dst = act + blk * kChunkBytes;
+          const float4* bl4 = reinterpret_cast<const float4*>(bl + blk * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
+            const float4 bj = bl4[j];
             float4 v;
-            v.x = tf32_rna(fmaxf(__uint_as_float(u[4 * j + 0]) + bl[blk * 32 + 4 * j + 0], 0.f));
-            v.y = tf32_rna(fmaxf(__uint_as_float(u[4 * j + 1]) + bl[blk * 32 + 4 * j + 1], 0.f));
-            v.z = tf32_rna(fmaxf(__uint_as_float(u[4 * j + 2]) + bl[blk * 32 + 4 * j + 2], 0.f));
-            v.w = tf32_rna(fmaxf(__uint_as_float(u[4 * j + 3]) + bl[blk * 32 + 4 * j + 3], 0.f));
+            v.x = tf32_operand(fmaxf(__uint_as_float(u[4 * j + 0]) + bj.x, 0.f));
+            v.y = tf32_operand(fmaxf(__uint_as_float(u[4 * j + 1]) + bj.y, 0.f));
+            v.z = tf32_operand(fmaxf(__uint_as_float(u[4 * j + 2]) + bj.z, 0.f));
+            v.w = tf32_operand(fmaxf(__uint_as_float(u[4 * j + 3]) + bj.w, 0.f));
             *reinterpret_cast<float4*>(dst + sw128_offset(r_epi, j)) = v;
           }
         }
-        fence_proxy_async();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(op_ready);
+        publish(p.npass + l);
         SA_STAMP();
       }
       if (!ok) break;
 
       // ---- layer 2: max over the ns rows of each centre, then bias + ReLU (both commute with max)
-      ok = wait_or_fail(acc_full, accp, failed, 5);
+      ok = wait_or_fail(acc_full, accp, failed, 5, p.sleep_ns);
       accp ^= 1;
       tc_fence_after_sync();
       SA_STAMP();
       const float* b2 = bias_s + p.c[0] + p.c[1];
       const int c3 = p.c[2];
       const int m_tile = m_base + t * cpt;
+      if (p.t2) {
+        // transposed accumulator: this thread owns channel ch of every 128-channel half, the 128
+        // columns are the tile's grouped rows -> the max over a centre's ns rows is in-thread
+        const int upb = ns == 64 ? 2 : 1;            // 32-column blocks per unit (a centre or a pair)
+        const int nunits = (c3 >> 7) * (4 / upb);
+        for (int uidx = cg; uidx < nunits; uidx += ncg) {
+          const int h = uidx / (4 / upb), blk0 = (uidx - h * (4 / upb)) * upb;
+          const int ch = h * 128 + q * 32 + (int)lane;
+          const float bias_c = b2[ch];
+          uint32_t u[32];
+          tmem_ld32(tmem + lane_base + p.acc_col[2] + h * 128 + blk0 * 32, u);
+          tmem_ld_wait();
+          float m0 = __uint_as_float(u[0]), m1 = __uint_as_float(u[16]);
+#pragma unroll
+          for (int i = 1; i < 16; ++i) {
+            m0 = fmaxf(m0, __uint_as_float(u[i]));
+            m1 = fmaxf(m1, __uint_as_float(u[16 + i]));
+          }
+          if (ns == 16) {
+            const int m = m_tile + blk0 * 2;
+            if (m < p.M) p.out[((long)b * p.M + m) * c3 + ch] = fmaxf(m0 + bias_c, 0.f);
+            if (m + 1 < p.M) p.out[((long)b * p.M + m + 1) * c3 + ch] = fmaxf(m1 + bias_c, 0.f);
+          } else {
+            m0 = fmaxf(m0, m1);
+            if (ns == 64) {
+              tmem_ld32(tmem + lane_base + p.acc_col[2] + h * 128 + (blk0 + 1) * 32, u);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) m0 = fmaxf(m0, __uint_as_float(u[i]));
+            }
+            const int m = m_tile + blk0 / upb;
+            if (m < p.M) p.out[((long)b * p.M + m) * c3 + ch] = fmaxf(m0 + bias_c, 0.f);
+          }
+        }
+        tc_fence_before_sync();
+        SA_STAMP();
+        continue;
+      }
       float keep[8];
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
@@ -634,7 +740,7 @@ bool configure(SaParams& p, int B) {
   const int scratch = p.query ? kCloudTile * 12 : 0;  // phase Q borrows the operand regions
 
   for (int lanes = kMaxLanes; lanes >= 1; lanes >>= 1) {
-    if (lanes > max_tiles) continue;
+    if (lanes > max_tiles || lanes > g_sa_max_lanes) continue;
     const int lane_cols = 512 / lanes;
     if (c1 + c2 > lane_cols || c3 > lane_cols) continue;
     // layer-0 passes of `cpp` chunks: fewer passes first; a pass shorter than the activation
@@ -676,6 +782,7 @@ bool configure(SaParams& p, int B) {
         tiles >>= 1;
       p.tiles = tiles;
       p.G = tiles * cpt;
+      p.t2 = (c3 % 128 == 0) ? 1 : 0;
       return true;
     }
   }
@@ -715,6 +822,14 @@ int demf_sa_fused_supported(int C, int ns, int c1, int c2, int c3) {
 /* debug: device buffer of 64 int64 that receives [count, clock64 stamps...] of one worker thread */
 int demf_sa_fused_set_profile(long long* device_buffer) {
   g_sa_prof = device_buffer;
+  return 0;
+}
+
+/* tuning knobs (development): most tile pipelines per CTA (1, 2 or 4) and the worker warps'
+ * back-off between mbarrier polls in ns (0 = spin) */
+int demf_sa_fused_tune(int max_lanes, int sleep_ns) {
+  g_sa_max_lanes = max_lanes < 1 ? 1 : max_lanes;
+  g_sa_sleep_ns = sleep_ns < 0 ? 0 : sleep_ns;
   return 0;
 }
 
@@ -763,6 +878,7 @@ int demf_sa_fused_fwd(const float* xyz, const float* feat_rows, const float* new
   p.max_r2 = max_radius * max_radius;
   p.inv_radius = 1.0f / max_radius;
   p.prof = g_sa_prof;
+  p.sleep_ns = g_sa_sleep_ns;
   p.grid = (query && ns <= kGridCap) ? grid : nullptr;
   // With a grid and an index buffer from the caller, the neighbour search runs as its own launch:
   // it is a latency-bound index chase that wants 64 warps per SM, while this kernel -- one CTA per

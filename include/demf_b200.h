@@ -189,6 +189,9 @@ int demf_sa_fused_error(void);
  * CTA (0,0): start, after ball query, then per tile: gathered, acc0 ready, act1 written, acc1 ready,
  * act2 written, acc2 ready, stored]; NULL switches it off. */
 int demf_sa_fused_set_profile(long long* device_buffer);
+/* development knobs: most tile pipelines ("lanes") per CTA (1, 2 or 4; default 4) and the worker
+ * warps' back-off between mbarrier polls in ns (default 0 = spin). */
+int demf_sa_fused_tune(int max_lanes, int sleep_ns);
 
 /* ------------------------------------ multi-scale deformable attention --- */
 /* replaces mmcv _ext.ms_deform_attn_forward / ms_deform_attn_backward

@@ -54,11 +54,13 @@ def main():
     ap.add_argument("--reps", type=int, default=30)
     ap.add_argument("--hot", action="store_true", help="no L2 flush between launches")
     ap.add_argument("--only", default="")
+    ap.add_argument("--sa-lanes", type=int, default=4)
+    ap.add_argument("--sa-sleep", type=int, default=0)
     args = ap.parse_args()
     only = set(filter(None, args.only.split(",")))
     want = lambda k: not only or k in only  # noqa: E731
     dev = torch.device("cuda:0")
-    _lib.load()
+    _lib.load().demf_sa_fused_tune(args.sa_lanes, args.sa_sleep)
     B, flush = args.B, not args.hot
     print(json.dumps(dict(device=torch.cuda.get_device_name(0), B=B, flush_l2=flush)), flush=True)
 

@@ -23,7 +23,7 @@ for N, M, r, ns, C, widths in geoms:
     ws = [torch.randn(co, ci, device=dev) / ci ** 0.5 for co, ci in zip(widths, cin)]
     bs = [torch.randn(co, device=dev) * 0.1 for co in widths]
     wpack, bias, wd = ops.sa_pack_mlp(ws, bs)
-    buf = torch.zeros(64, dtype=torch.int64, device=dev)
+    buf = torch.zeros(256, dtype=torch.int64, device=dev)
     grid = ops.ball_grid(x, r) if N >= 4096 else None
     ops.sa_fused(x, c, f, 0.0, r, ns, True, wpack, bias, wd, grid=grid)
     lib.demf_sa_fused_set_profile(buf.data_ptr())
@@ -35,3 +35,9 @@ for N, M, r, ns, C, widths in geoms:
     print(f"N={N} M={M} ns={ns} C={C} widths={widths}: query {t[1] - t[0]} clk")
     nch0 = (((C + 3) // 4 * 4 + 4 + 7) // 8 * 8 + 31) // 32
     print("   stamps:", n, " deltas:", [t[i] - t[i - 1] for i in range(2, n)], " total", t[n - 1] - t[0])
+    iss = st[64:]
+    base = t[0]
+    ev = [(iss[3 * i], iss[3 * i + 1] - base, iss[3 * i + 2] - iss[3 * i + 1]) for i in range(60) if iss[3 * i + 1]]
+    if ev:
+        print("   issuer (lane*100+pos, t_detect-t0, issue clk):", ev[:40])
+        print("   worker stamps rel t0:", [x - base for x in t[:n]])
