@@ -29,6 +29,7 @@ __device__ __forceinline__ float block_reduce(float v, bool want_min, float* scr
 __global__ void __launch_bounds__(kBuildThreads) ball_grid_build_kernel(const float* __restrict__ xyz, int N,
                                                                         float radius, unsigned char* workspace) {
   extern __shared__ int cnt[];  // kGridCells counters, then cursors
+  const unsigned long long trace_t0 = trace_begin();
   __shared__ float scratch[32];
   __shared__ int warp_tot[32];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(kBuildThreads) ball_grid_build_kernel(const fl
     const int pos = atomicAdd(&cnt[cell_of(x, y, z)], 1);
     sorted[pos] = make_float4(x, y, z, __int_as_float(i));
   }
+  trace_end(4, trace_t0);
 }
 
 constexpr int kQueryWarps = 8;
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__(kQueryWarps * 32) ball_query_grid_kernel(
     const float* __restrict__ xyz, const float* __restrict__ new_xyz, const void* __restrict__ grid, int N, int M,
     float min_r2, float max_r2, int ns, int32_t* __restrict__ idx) {
   extern __shared__ int smem_i[];
+  const unsigned long long trace_t0 = trace_begin();
   const unsigned lane = lane_id();
   const int warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(kQueryWarps * 32) ball_query_grid_kernel(
                   buf, hist, lane);
   int32_t* out = idx + ((long)b * M + m) * ns;
   for (int l = lane; l < ns; l += 32) out[l] = row[l];
+  trace_end(3, trace_t0);
 }
 
 }  // namespace
@@ -163,6 +167,7 @@ int launch_ball_query_grid(const float* xyz, const float* new_xyz, const void* g
   return after_launch("ball_query_grid_kernel");
 }
 
+DEMF_DEFINE_TRACE_SETTER(trace_set_grid)
 }  // namespace demf
 
 using namespace demf;

@@ -37,4 +37,17 @@ const char* demf_last_error_string(void) { return demf::g_error; }
 
 uint64_t demf_launch_count(void) { return demf::g_launches.load(std::memory_order_relaxed); }
 
+/* development: CTA-level trace of the instrumented kernels into a caller-owned device buffer of
+ * `capacity` 32-byte records {int kernel, block, smid, pad; u64 start_ns, end_ns} plus a device
+ * counter; NULL switches tracing off. Kernel ids: 1 fps, 2 sa_fused, 3 ball_query_grid,
+ * 4 ball_grid_build, 5 msda_fwd. */
+int demf_trace_set(void* records, unsigned* counter, unsigned capacity) {
+  demf::TraceCtl c{static_cast<demf::TraceRec*>(records), counter, records ? capacity : 0u};
+  demf::trace_set_fps(c);
+  demf::trace_set_sa(c);
+  demf::trace_set_grid(c);
+  demf::trace_set_msda(c);
+  return static_cast<int>(cudaGetLastError());
+}
+
 }  // extern "C"

@@ -46,4 +46,52 @@ __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- CTA-level tracing (development): when a trace buffer is set (demf_trace_set), thread 0 of
+// every CTA of the instrumented kernels appends {kernel id, block, SM id, start ns, end ns}.
+struct TraceRec {
+  int kernel, block, smid, pad;
+  unsigned long long t0, t1;
+};
+struct TraceCtl {
+  TraceRec* recs;
+  unsigned* count;
+  unsigned cap;
+};
+#ifdef __CUDACC__
+// one control block per translation unit (no relocatable device code in this library)
+static __device__ TraceCtl g_trace = {nullptr, nullptr, 0};
+
+__device__ __forceinline__ unsigned long long trace_begin() {
+  unsigned long long t = 0;
+  if (g_trace.recs != nullptr && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_end(int kernel, unsigned long long t0) {
+  if (g_trace.recs != nullptr && threadIdx.x == 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned i = atomicAdd(g_trace.count, 1u);
+    if (i < g_trace.cap) {
+      TraceRec r;
+      r.kernel = kernel;
+      r.block = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+      r.smid = (int)smid;
+      r.pad = 0;
+      r.t0 = t0;
+      r.t1 = t1;
+      g_trace.recs[i] = r;
+    }
+  }
+}
+// each instrumented .cu defines  void trace_set_<tu>(const TraceCtl&)  with this macro
+#define DEMF_DEFINE_TRACE_SETTER(name) \
+  void name(const TraceCtl& c) { cudaMemcpyToSymbol(g_trace, &c, sizeof(TraceCtl)); }
+#endif
+void trace_set_fps(const TraceCtl& c);
+void trace_set_sa(const TraceCtl& c);
+void trace_set_grid(const TraceCtl& c);
+void trace_set_msda(const TraceCtl& c);
+
 }  // namespace demf

@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) fps_cluster_kernel(const float* _
                                                                   int32_t* __restrict__ idx) {
   constexpr int kWarps = kThreads / 32;
   __shared__ FpsSmem<kThreads> sm;
+  const unsigned long long trace_t0 = trace_begin();
 
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned C = cluster.num_blocks();
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) fps_cluster_kernel(const float* _
     if (rank == 0 && tid == 0) out[it] = index_from_inv_priority(win_p, log2T);
   }
   if (C > 1) cluster.sync();  // nobody may exit while peers can still write into its inbox
+  trace_end(1, trace_t0);
 }
 
 // ---- fallback: one CTA per scene, points and running distances in global memory ----------
@@ -409,6 +411,7 @@ bool plan(int B, int N, int* threads, int* C, int* ppt) {
 }
 
 }  // namespace
+DEMF_DEFINE_TRACE_SETTER(trace_set_fps)
 }  // namespace demf
 
 using namespace demf;

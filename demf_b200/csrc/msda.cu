@@ -411,6 +411,7 @@ int launch_bwd(const float* value, const int64_t* shapes, const int64_t* lsi, co
 }
 
 }  // namespace
+DEMF_DEFINE_TRACE_SETTER(trace_set_msda)
 }  // namespace demf
 
 using namespace demf;

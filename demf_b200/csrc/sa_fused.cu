@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
   // SWIZZLE_128B operands need 1024-byte aligned chunks: align the carve-up by hand
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const SmemLayout L = smem_layout(p);
+  const unsigned long long trace_t0 = trace_begin();
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -706,6 +707,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
     __syncwarp();
     tmem_free(tmem, p.tmem_cols);
   }
+  trace_end(2, trace_t0);
 }
 
 // (Cout, Cin) row-major fp32 -> ceil(Cin/32) chunks of Cout x 32 floats in the swizzled K-major
@@ -790,6 +792,7 @@ bool configure(SaParams& p, int B) {
 }
 
 }  // namespace
+DEMF_DEFINE_TRACE_SETTER(trace_set_sa)
 }  // namespace demf
 
 using namespace demf;

@@ -148,6 +148,12 @@ int demf_three_interpolate_rows_fwd(const float* feat_rows, const int32_t* idx, 
 int demf_three_interpolate_rows_bwd(const float* grad_out, const int32_t* idx, const float* weight,
                                     int B, int C, int n, int m, float* grad_feat_rows, void* stream);
 
+/* development: CTA-level trace of the instrumented kernels into a caller-owned DEVICE buffer of
+ * `capacity` 32-byte records {int kernel, block, smid, pad; uint64 start_ns, end_ns} plus a device
+ * counter (zero it first); records == NULL switches tracing off. Kernel ids: 1 fps, 2 sa_fused,
+ * 3 ball_query_grid, 4 ball_grid_build. */
+int demf_trace_set(void* records, unsigned* counter, unsigned capacity);
+
 /* ------------------------------------------- exact grid ball query ------- */
 /* The same (B,M,ns) index rows as demf_ball_query, but each centre only tests the points of its
  * 3x3x3 cell neighbourhood in a uniform grid (cell edge >= radius) instead of the whole cloud.

@@ -16,7 +16,7 @@ engine.set_gemm_precision("tf32")
 torch.manual_seed(1234)
 model = engine.build_demf_votenet(num_points=4).to(dev).eval()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-sets = [engine.synthetic_batch(B, 20000, "S512", seed=1234 + i, device=dev, with_gt=False) for i in range(8)]
+sets = [engine.synthetic_batch(B, 20000, "S512", seed=1234 + i, device=dev, with_gt=False) for i in range(16)]
 
 
 def run(lanes, steps=40, tag=""):
@@ -40,8 +40,13 @@ def run(lanes, steps=40, tag=""):
 with torch.no_grad():
     for _ in range(3):
         model.simple_test(points=sets[0]["points"], img=sets[0]["img"], img_metas=sets[0]["img_metas"])
-for lanes in (1, 2, 4, 6, 8):
+if os.environ.get("PROBE_SERIAL_FPS"):
+    model.pts_backbone.overlap_sampling = False
+quick = os.environ.get("PROBE_QUICK")
+for lanes in ((4, 8, 12, 16) if quick else (1, 2, 4, 6, 8)):
     run(lanes, tag="real FPS  ")
+if quick:
+    sys.exit(0)
 
 # cached indices: the same forward without any furthest-point-sampling kernel
 real_fps = P.furthest_point_sample
