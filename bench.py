@@ -39,9 +39,9 @@ TRAIN_BATCH_PER_GPU = 4
 NUM_POINTS = 20000
 PYRAMID = "S512"
 P_POINTS = 4
-ROTATE = 4  # resident input sets, rotated so that a step never finds its inputs in L2
+ROTATE = 8  # resident input sets, rotated so that a step never finds its inputs in L2
 CPU_SAMPLE_SCENES = 2
-LANES = 4   # forward graphs in flight (engine.ForwardPipeline)
+LANES = 8   # forward graphs in flight (engine.ForwardPipeline)
 
 
 def workload_config(n_gpus):
@@ -61,6 +61,43 @@ def workload_config(n_gpus):
 def msda_algorithmic_bytes(B, Q=256, H=8, D=32, L=4, P=P_POINTS):
     """corner rows + (loc, weight) per sample + output."""
     return B * Q * H * L * P * (4 * D * 4 + 12) + B * Q * H * D * 4
+
+
+def time_sa_levels(model, batch, reps=20):
+    """The fused set-abstraction kernel (csrc/sa_fused.cu: ball query + grouping + 3-layer TF32
+    tcgen05 MLP + max), one level at a time on the model's own tensors: CUDA events around the
+    module call (grid build + query + fused kernel), L2 flushed between repetitions."""
+    import torch
+    bb = model.pts_backbone
+    dev = batch["points"].device
+    with torch.no_grad():
+        out = bb(batch["points"])
+        junk = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        levels = []
+        for i, sa in enumerate(bb.SA_modules):
+            xyz, feats, new_xyz = out["sa_xyz"][i], out["sa_features"][i], out["sa_xyz"][i + 1]
+            idx = out["sa_indices"][i + 1]
+            call = lambda sa=sa, xyz=xyz, feats=feats, idx=idx, new_xyz=new_xyz: sa(  # noqa: E731
+                xyz, feats, indices=idx, target_xyz=new_xyz)
+            for _ in range(3):
+                call()
+            ts = []
+            for _ in range(reps):
+                junk.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                call()
+                b.record()
+                b.synchronize()
+                ts.append(a.elapsed_time(b))
+            ms = statistics.median(ts)
+            B, N = xyz.shape[:2]
+            M, ns = new_xyz.shape[1], sa.groupers[0].sample_num
+            chans = [m.conv.in_channels for m in sa.mlps[0]] + [sa.mlps[0][-1].conv.out_channels]
+            flops = 2.0 * B * M * ns * sum(a * b for a, b in zip(chans[:-1], chans[1:]))
+            levels.append({"level": f"SA{i + 1}", "N": N, "M": M, "nsample": ns, "mlp": chans,
+                           "ms": ms, "tflops": flops / ms / 1e9})
+    return levels
 
 
 def load_peaks():
@@ -327,6 +364,9 @@ def main():
     barrier()
     eager_ms = max_over_ranks(start.elapsed_time(end)) / args.steps
 
+    # ---- extra: the fused set-abstraction kernel per backbone level (isolated, L2 flushed)
+    sa_levels = time_sa_levels(model, sets[0]) if rank == 0 else None
+
     # ---- extra: one training step (forward + backward + all-reduce + AdamW), batch 4/GPU
     train = None
     if not args.no_train:
@@ -414,7 +454,13 @@ def main():
         "execution": f"one CUDA graph launch per step (whole forward captured, FPS chain on a "
                      f"parallel branch); {LANES} independent batches in flight on {LANES} streams",
         "single_batch_latency_ms": serial_ms, "eager_ms_per_step": eager_ms,
-        "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu, "train_step": train,
+        "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu,
+        "sa_fused": {"kernel": "sa_fused_fwd_kernel (ball query + grouping + 3-layer TF32 tcgen05 MLP + "
+                               "max, one launch per level; SA1 with the grid query as its own launch)",
+                     "bound": "tensor/L2 (latency-bound in practice, see DESIGN.md)",
+                     "levels": sa_levels,
+                     "sum_ms": sum(lv["ms"] for lv in sa_levels) if sa_levels else None},
+        "train_step": train,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
