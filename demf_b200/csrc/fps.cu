@@ -28,6 +28,7 @@
 
 #include <cstdlib>
 
+#include "ball_grid.cuh"
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -238,6 +239,175 @@ __global__ void __launch_bounds__(kThreads, 1) fps_cluster_kernel(const float* _
     if (rank == 0 && tid == 0) out[it] = index_from_inv_priority(win_p, log2T);
   }
   if (C > 1) cluster.sync();  // nobody may exit while peers can still write into its inbox
+  trace_end(1, trace_t0);
+}
+
+// ---- grid-pruned FPS: the cloud lives in the SHARED memory of a small cluster ----------------
+// The register-resident kernel above updates every point in every iteration and needs 16 CTAs per
+// 20k-point scene; its cost is the per-iteration latency chain times the 128 SMs it holds. Here the
+// scene is taken in the cell order of the ball-query grid (ball_grid.cuh: points sorted by uniform
+// grid cell), cut into C slabs (one per CTA of a cluster of 2..8) that sit in shared memory
+// (x, y, z, tie-break priority, running min distance), and further into blocks of 32 consecutive
+// points. Each block keeps, in the registers of one lane, its bounding box, the largest running
+// distance of its points and its best (distance, priority) key. A new sample s can only lower a
+// running distance of block b if  lb2(s, box_b) < max_b,  where lb2 is the SAME fma-ordered
+// expression as the point distance evaluated on the box: every rounding step is monotone in the
+// coordinate differences, so lb2 <= d(p, s) for every p in the box and a skipped block provably
+// changes nothing. After a few dozen samples only ~10 blocks of 625 are touched per iteration.
+// The arg-max key and the cluster exchange are those of fps_cluster_kernel: identical indices.
+constexpr int kGridFpsThreads = 512;
+constexpr int kGridFpsWarps = kGridFpsThreads / 32;
+
+__global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const float* __restrict__ xyz,
+                                                                      const void* __restrict__ grid, int N, int m,
+                                                                      int log2T, int cap, int32_t* __restrict__ idx) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  __shared__ FpsSmem<kGridFpsThreads> sm;
+  const unsigned long long trace_t0 = trace_begin();
+  float4* pts = reinterpret_cast<float4*>(gsm);                 // cap entries: x, y, z, inv-priority bits
+  float* tmp = reinterpret_cast<float*>(gsm + (size_t)cap * 16);  // cap running min distances
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned C = cluster.num_blocks();
+  const unsigned rank = cluster.block_rank();
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  const unsigned lane = lane_id();
+  const int warp = tid >> 5;
+  int32_t* out = idx + (long)b * m;
+  const BallGridView g = ball_grid_view(grid, b, N);
+
+  // ---- this CTA's slab of the cell-ordered cloud
+  const int begin = (int)rank * cap;
+  for (int i = tid; i < cap; i += kGridFpsThreads) {
+    const int q = begin + i;
+    if (q < N) {
+      const float4 p = __ldg(g.sorted + q);
+      pts[i] = make_float4(p.x, p.y, p.z, __uint_as_float(inv_priority(__float_as_int(p.w), log2T)));
+      tmp[i] = 1e10f;
+    } else {  // padding: distance pinned to 0, priority 0 -> never wins, never changes
+      pts[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+      tmp[i] = 0.f;
+    }
+  }
+  __syncthreads();
+  // ---- block metadata in registers: lane j of warp w owns block w + 16*j
+  const int nblk = cap >> 5;
+  const int my_blk = warp + kGridFpsWarps * (int)lane;
+  const bool has_blk = my_blk < nblk && begin + my_blk * 32 < N;
+  float lox = 0.f, loy = 0.f, loz = 0.f, hix = 0.f, hiy = 0.f, hiz = 0.f;
+  uint32_t bmax = 0u, bkd = 0u, bkp = 0u;
+  int bli = 0;
+  if (has_blk) {
+    lox = loy = loz = 3.0e38f;
+    hix = hiy = hiz = -3.0e38f;
+    for (int i = 0; i < 32; ++i) {
+      const int q = my_blk * 32 + i;
+      if (begin + q < N) {
+        const float4 p = pts[q];
+        lox = fminf(lox, p.x); hix = fmaxf(hix, p.x);
+        loy = fminf(loy, p.y); hiy = fmaxf(hiy, p.y);
+        loz = fminf(loz, p.z); hiz = fmaxf(hiz, p.z);
+      }
+    }
+    bmax = __float_as_uint(1e10f);
+  }
+  float ox = __ldg(xyz + (long)b * N * 3 + 0), oy = __ldg(xyz + (long)b * N * 3 + 1),
+        oz = __ldg(xyz + (long)b * N * 3 + 2);  // idx[0] = 0
+  if (rank == 0 && tid == 0) out[0] = 0;
+
+  const unsigned tx_bytes = 20u * C;
+  if (tid == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_arrive_expect_tx(&sm.bar[0], tx_bytes);
+    mbar_arrive_expect_tx(&sm.bar[1], tx_bytes);
+  }
+  cluster.sync();
+
+  for (int it = 1; it < m; ++it) {
+    const int par = it & 1;
+    // a. which of this warp's blocks can the new sample change?
+    bool dirty = false;
+    if (has_blk) {
+      const float dx = fmaxf(0.f, fmaxf(__fsub_rn(lox, ox), __fsub_rn(ox, hix)));
+      const float dy = fmaxf(0.f, fmaxf(__fsub_rn(loy, oy), __fsub_rn(oy, hiy)));
+      const float dz = fmaxf(0.f, fmaxf(__fsub_rn(loz, oz), __fsub_rn(oz, hiz)));
+      const float lb2 = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+      dirty = lb2 < __uint_as_float(bmax);
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, dirty);
+    // b. update those blocks, 32 points at a time
+    while (todo) {
+      const int j = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int q = (warp + kGridFpsWarps * j) * 32 + (int)lane;
+      const float4 p = pts[q];
+      const float d = sqdist(p.x, p.y, p.z, ox, oy, oz);
+      const float t = fminf(d, tmp[q]);
+      tmp[q] = t;
+      const uint32_t tb = __float_as_uint(t), pr = __float_as_uint(p.w);
+      const uint32_t wd = __reduce_max_sync(0xffffffffu, tb);
+      const uint32_t wp = __reduce_max_sync(0xffffffffu, tb == wd ? pr : 0u);
+      const int who = __ffs(__ballot_sync(0xffffffffu, tb == wd && pr == wp)) - 1;
+      if ((int)lane == j) {
+        bmax = wd;
+        bkd = wd;
+        bkp = wp;
+        bli = who;
+      }
+    }
+    // c. this warp's candidate = best key over its blocks
+    const uint32_t kd = has_blk ? bkd : 0u, kp = has_blk ? bkp : 0u;
+    const uint32_t wd = __reduce_max_sync(0xffffffffu, kd);
+    const uint32_t wp = __reduce_max_sync(0xffffffffu, kd == wd ? kp : 0u);
+    const unsigned owners = __ballot_sync(0xffffffffu, has_blk && kd == wd && kp == wp);
+    const int src = owners ? __ffs(owners) - 1 : 0;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((int)lane == src && owners) c = pts[my_blk * 32 + bli];
+    c.x = __shfl_sync(0xffffffffu, c.x, src);
+    c.y = __shfl_sync(0xffffffffu, c.y, src);
+    c.z = __shfl_sync(0xffffffffu, c.z, src);
+    if (lane == 0) {
+      sm.warp_xyz[par][warp] = make_float4(c.x, c.y, c.z, 0.f);
+      sm.warp_key[par][warp] = make_uint2(owners ? wd : 0u, owners ? wp : 0u);
+    }
+    __syncthreads();
+    // d. CTA arg-max over the warps, then the cluster exchange (as in fps_cluster_kernel)
+    uint2 key = (lane < (unsigned)kGridFpsWarps) ? sm.warp_key[par][lane] : make_uint2(0u, 0u);
+    const uint32_t cd = __reduce_max_sync(0xffffffffu, key.x);
+    const uint32_t cp = __reduce_max_sync(0xffffffffu, key.x == cd ? key.y : 0u);
+    const unsigned who = __ffs(__ballot_sync(0xffffffffu, lane < (unsigned)kGridFpsWarps && key.x == cd &&
+                                                              key.y == cp)) - 1;
+    const float4 cxyz = sm.warp_xyz[par][who];
+    if (warp == 0 && lane < C) {
+      const uint32_t dst = map_to_cta(smem_u32(&sm.inbox[par][rank]), lane);
+      const uint32_t dbar = map_to_cta(smem_u32(&sm.bar[par]), lane);
+      st_async_v4(dst, cd, cp, __float_as_uint(cxyz.x), __float_as_uint(cxyz.y), dbar);
+      st_async_b32(dst + 16, __float_as_uint(cxyz.z), dbar);
+    }
+    mbar_wait(&sm.bar[par], (unsigned)(((it - 1) >> 1) & 1));
+    if (tid == 0) mbar_arrive_expect_tx(&sm.bar[par], tx_bytes);
+    Packet pk;
+    if (lane < C) {
+      const uint4 qd = *reinterpret_cast<const uint4*>(&sm.inbox[par][lane]);
+      pk.dist_bits = qd.x;
+      pk.inv_prio = qd.y;
+    } else {
+      pk.dist_bits = 0u;
+      pk.inv_prio = 0u;
+    }
+    const uint32_t gd = __reduce_max_sync(0xffffffffu, pk.dist_bits);
+    const uint32_t gp = __reduce_max_sync(0xffffffffu, pk.dist_bits == gd ? pk.inv_prio : 0u);
+    const unsigned srcc = __ffs(__ballot_sync(0xffffffffu, lane < C && pk.dist_bits == gd && pk.inv_prio == gp)) - 1;
+    const Packet* w = &sm.inbox[par][srcc];
+    ox = w->x;
+    oy = w->y;
+    oz = w->z;
+    if (rank == 0 && tid == 0) out[it] = index_from_inv_priority(gp, log2T);
+  }
+  cluster.sync();  // nobody may exit while peers can still write into its inbox
   trace_end(1, trace_t0);
 }
 
@@ -458,6 +628,59 @@ int demf_fps(const float* xyz, int B, int N, int m, void* workspace, int32_t* id
   }
   fps_generic_kernel<<<B, 1024, 0, st>>>(xyz, N, m, log2T, static_cast<float*>(workspace), idx);
   return after_launch("fps_generic_kernel");
+}
+
+/* Grid-pruned FPS: same indices as demf_fps; `grid` = demf_ball_grid_build workspace of the SAME xyz
+ * (any radius). The cloud sits in the shared memory of a 2-, 4- or 8-CTA cluster per scene. */
+int demf_fps_grid(const float* xyz, const void* grid, int B, int N, int m, int32_t* idx, void* stream) {
+  DEMF_REQUIRE_PTR(xyz);
+  DEMF_REQUIRE_PTR(grid);
+  DEMF_REQUIRE_PTR(idx);
+  DEMF_REQUIRE(B >= 0 && N > 0 && m >= 0, DEMF_E_SIZE);
+  DEMF_REQUIRE(B <= 65535 && N < (1 << 30), DEMF_E_SIZE);
+  if (B == 0 || m == 0) return 0;
+  int log2T = floor_log2(N);
+  if (log2T > 10) log2T = 10;
+  // smallest cluster whose slab (20 bytes per point) fits one SM's shared memory: the fewer CTAs,
+  // the cheaper the per-iteration exchange and the fewer SMs a scene holds (measured at N=20000,
+  // 8 forwards in flight: C=2 1.06 ms/step, C=4 1.09, C=8 1.29). A lane owns one block of 32 points:
+  // at most 16 warps x 32 lanes = 512 blocks per CTA.
+  int C = env_int("DEMF_FPS_GRID_CLUSTER", 0);
+  if (C != 2 && C != 4 && C != 8) {
+    C = 2;
+    while (C < 8 && ((((N + C - 1) / C) + 31) / 32 * 32) * 20 > 200 * 1024) C <<= 1;
+  }
+  int cap = (((N + C - 1) / C) + 31) / 32 * 32;
+  DEMF_REQUIRE(cap / 32 <= kGridFpsWarps * 32 && (size_t)cap * 20 <= 200 * 1024, DEMF_E_UNSUPPORTED);
+  const size_t smem = (size_t)cap * 20;
+  static size_t configured = 0;
+  if (smem > configured) {
+    const cudaError_t e = cudaFuncSetAttribute(fps_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("demf_fps_grid: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    configured = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(C, B, 1);
+  cfg.blockDim = dim3(kGridFpsThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, fps_grid_kernel, xyz, grid, N, m, log2T, cap, idx);
+  if (e != cudaSuccess) {
+    set_error("demf_fps_grid: launch failed: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return static_cast<int>(e);
+  }
+  return after_launch("fps_grid_kernel");
 }
 
 }  // extern "C"

@@ -444,6 +444,21 @@ def ball_grid(xyz, radius):
     return ws
 
 
+def furthest_point_sample_grid(xyz, num_points, grid):
+    """furthest_point_sample through a ball_grid workspace of the same xyz (csrc/fps.cu,
+    fps_grid_kernel): the cloud sits cell-ordered in the shared memory of a small cluster and a new
+    sample only revisits the 32-point blocks whose bounding box it can reach. Identical indices."""
+    assert xyz.is_contiguous()
+    _need_cuda(xyz, grid)
+    B, N, _ = xyz.shape
+    with torch.cuda.device_of(xyz):
+        idx = torch.empty(B, num_points, dtype=torch.int32, device=xyz.device)
+        if idx.numel():
+            _lib.check(_lib.load().demf_fps_grid(_p(xyz), _p(grid), B, N, int(num_points), _p(idx),
+                                                 _stream()), "demf_fps_grid")
+    return idx
+
+
 def ball_query_grid(min_radius, max_radius, sample_num, xyz, center_xyz, grid):
     """ball_query through a ball_grid workspace: bit-identical (B,M,ns) int32 rows."""
     assert xyz.is_contiguous() and center_xyz.is_contiguous()

@@ -308,6 +308,7 @@ class PointNet2SASSG(BaseModule):
     # side stream, and the grouping / MLP work of level i on the main stream overlaps the serial
     # FPS iterations of levels > i. Each level publishes an event the main stream waits on.
     prefetch_seed_fps = None   # set by the detector: (fp level whose xyz are the seeds, m)
+    grid_fps = True            # first-level FPS through the ball-query grid (identical indices)
     overlap_sampling = True    # False: run the sampling chain on the current stream
 
     def _side_stream(self, device):
@@ -317,9 +318,10 @@ class PointNet2SASSG(BaseModule):
         return streams[device]
 
     def _sampling_chain(self, xyz):
-        """-> per-level (indices (B,M) i32, new_xyz (B,M,3), ready event), seed fps or None."""
+        """-> per-level (indices (B,M) i32, new_xyz (B,M,3), ready event), seed fps or None, and the
+        ball-query grid of the input cloud (or None)."""
         overlap = xyz.is_cuda and self.overlap_sampling
-        levels, seed_fps = [], None
+        levels, seed_fps, grid0 = [], None, None
         if overlap:
             main = torch.cuda.current_stream(xyz.device)
             side = self._side_stream(xyz.device)
@@ -330,8 +332,14 @@ class PointNet2SASSG(BaseModule):
             ctx = contextlib.nullcontext()
         with ctx:
             cur = xyz
+            # a large input cloud is binned once into the uniform grid that serves both the first
+            # level's ball query and its (grid-pruned) furthest point sampling
+            grid0 = self.SA_modules[0].ball_grid(xyz)
             for i, sa in enumerate(self.SA_modules):
-                idx = P.furthest_point_sample(cur, sa.num_point[0])
+                if i == 0 and grid0 is not None and self.grid_fps:
+                    idx = P.furthest_point_sample_grid(cur, sa.num_point[0], grid0)
+                else:
+                    idx = P.furthest_point_sample(cur, sa.num_point[0])
                 new_xyz = P.gather_rows(cur, idx).contiguous()
                 ev = None
                 if overlap:
@@ -344,7 +352,7 @@ class PointNet2SASSG(BaseModule):
                                 torch.cuda.Event() if overlap else None)
                     if overlap:
                         seed_fps[1].record(side)
-        return levels, seed_fps
+        return levels, seed_fps, grid0
 
     def forward(self, points):
         """points (B,N,3+C) -> dict of fp_xyz / fp_features / fp_indices / sa_*."""
@@ -352,12 +360,9 @@ class PointNet2SASSG(BaseModule):
         batch, num_points = xyz.shape[:2]
         chained = all(getattr(sa, "num_point", None) is not None and len(sa.num_point) == 1
                       for sa in self.SA_modules)
-        levels, seed_fps = self._sampling_chain(xyz) if chained else (None, None)
+        levels, seed_fps, grid0 = self._sampling_chain(xyz) if chained else (None, None, None)
         indices = torch.arange(num_points, device=xyz.device).unsqueeze(0).repeat(batch, 1).long()
         sa_xyz, sa_features, sa_indices = [xyz], [features], [indices]
-        # the first level's ball-query grid only needs the input cloud: it is binned on the main
-        # stream while the side stream is still busy with the first furthest-point sampling
-        grid0 = self.SA_modules[0].ball_grid(xyz) if levels is not None else None
         for i in range(self.num_sa):
             if levels is not None:
                 idx, new_xyz, ev = levels[i]

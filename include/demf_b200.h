@@ -166,6 +166,11 @@ size_t demf_ball_grid_workspace_bytes(int B, int N);
 int demf_ball_grid_build(const float* xyz, int B, int N, float radius, void* workspace, void* stream);
 int demf_ball_query_grid(const float* xyz, const float* new_xyz, const void* grid, int B, int N, int M,
                          float min_radius, float max_radius, int ns, int32_t* idx, void* stream);
+/* Furthest point sampling through the same workspace (any build radius): identical indices to
+ * demf_fps (replaces furthest_point_sampling_wrapper for large clouds). The cloud sits cell-ordered
+ * in the shared memory of a 2/4/8-CTA cluster per scene; a new sample only revisits the 32-point
+ * blocks whose bounding box it can reach. N <= ~80k points. */
+int demf_fps_grid(const float* xyz, const void* grid, int B, int N, int m, int32_t* idx, void* stream);
 
 /* ------------------------- fused set abstraction (inference), tcgen05 --- */
 /* replaces, for one PointSAModule forward in eval mode (mmdet3d

@@ -450,3 +450,26 @@ def test_sa_fused_with_grid_is_identical(dev):
                          grid=ops.ball_grid(gx, 0.2))
     assert torch.equal(ia, ib) and torch.equal(a, b)
     assert _lib.load().demf_sa_fused_error() == 0
+
+
+# ---------------------------------------------------------------- grid-pruned FPS --
+@pytest.mark.parametrize("B,N,m,kind", [
+    (2, 20000, 2048, "clustered"),   # SA1 (configs/demf/demf_votenet.py:51)
+    (2, 20000, 2048, "uniform"),
+    (1, 4099, 300, "clustered"),     # ragged slab / padded last block
+    (3, 8192, 512, "dup"),           # duplicated points: every tie rule exercised
+    (1, 40000, 1000, "uniform"),     # two slabs of 200 KB would not fit: 4-CTA cluster
+    (2, 5000, 5000, "clustered"),    # m == N: every point is picked once
+])
+def test_fps_grid_matches_oracle(dev, B, N, m, kind):
+    if kind == "dup":
+        base = _xyz(B, N // 2, seed=11)
+        xyz = torch.cat([base, base], 1).contiguous()
+    else:
+        xyz = _xyz(B, N, seed=N + m, clustered=(kind == "clustered"))
+    gx = xyz.to(dev)
+    ref = cref.furthest_point_sample(xyz, m)
+    for radius in (0.2, 1.5):     # the grid's cell size only changes which blocks get skipped
+        got = ops.furthest_point_sample_grid(gx, m, ops.ball_grid(gx, radius))
+        assert torch.equal(got.cpu(), ref)
+    assert torch.equal(ops.furthest_point_sample(gx, m).cpu(), ref)

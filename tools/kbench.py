@@ -95,6 +95,10 @@ def main():
             x = pts[:, :N].contiguous()
             med, mn = timeit(lambda: ops.furthest_point_sample(x, m), max(5, args.reps // 3), False)
             report("fps", dict(B=B, N=N, m=m, us_per_iter=round(med * 1e3 / (m - 1), 3)), med, mn)
+            if N >= 2048:
+                grid = ops.ball_grid(x, 0.2 if N > 4096 else 0.4)
+                med, mn = timeit(lambda: ops.furthest_point_sample_grid(x, m, grid), max(5, args.reps // 3), False)
+                report("fps_grid", dict(B=B, N=N, m=m, us_per_iter=round(med * 1e3 / (m - 1), 3)), med, mn)
     if want("ball"):
         for N, M, r, ns, C in geoms:
             x = pts[:, :N].contiguous()
