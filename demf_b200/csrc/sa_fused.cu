@@ -199,7 +199,7 @@ struct IssueCtx {
 // Issue the tcgen05.mma instructions of MMA group g of lane `ln` (one thread) and commit the lane's
 // acc_full barrier. Resident weights: chunk `cid` sits in ring slot `cid` for the whole kernel.
 __device__ __forceinline__ bool issue_group(const SaParams& p, const IssueCtx& c, int ln, int g, uint32_t& slot,
-                                            uint32_t& wph) {
+                                            uint32_t& wph, bool check_w = true) {
   int layer, ch0, nch;
   group_span(p, c.nch0, g, layer, ch0, nch);
   const uint32_t idesc = instr_desc_tf32(kTileRows, p.c[layer]);
@@ -209,7 +209,8 @@ __device__ __forceinline__ bool issue_group(const SaParams& p, const IssueCtx& c
   tc_fence_after_sync();
   for (int ch = 0; ch < nch; ++ch) {
     const uint32_t s = p.resident ? (uint32_t)(cid + ch) : slot;
-    if (!wait_or_fail(c.wfull0 + 8 * s, p.resident ? 0u : wph, c.failed, 2)) return false;
+    // resident weights arrive once: after a lane's first tile their barriers need no second look
+    if (check_w && !wait_or_fail(c.wfull0 + 8 * s, p.resident ? 0u : wph, c.failed, 2)) return false;
     const int ksteps = layer == 0 ? (min(32, p.K0 - 32 * (ch0 + ch)) >> 3) : 4;
     // a K step of 8 tf32 = +32 bytes = +2 in the descriptor's (address >> 4) field
     const uint64_t da = smem_desc_sw128(a0 + ch * kChunkBytes), dw = smem_desc_sw128(c.ring_u32 + s * p.slot_bytes);
@@ -473,14 +474,14 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
     // The operand of MMA group g of this lane's tile is in shared memory: hand it to the tensor pipe.
     // Resident weights: the lane's first thread issues the MMAs itself (no hand-off latency, lanes
     // issue in parallel); streamed weights: signal the issuer warp, which keeps the ring order.
-    auto publish = [&](int g) {
+    auto publish = [&](int g, bool first_tile) {
       fence_proxy_async();
       tc_fence_before_sync();
       if (p.resident) {
         named_sync(2 + ln, lthreads);
         if (lt == 0) {
           uint32_t unused_slot = 0, unused_ph = 0;
-          issue_group(p, ictx, ln, g, unused_slot, unused_ph);
+          issue_group(p, ictx, ln, g, unused_slot, unused_ph, first_tile);
         }
       } else {
         __syncwarp();
@@ -488,6 +489,42 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
       }
     };
 
+    // two tail elements (unaligned feature slot / xyz slot / zero slot) of tile t for this thread
+    auto tail_load = [&](int t, int s_lo, int t_lo, int w, int e0, float4 (&v)[2], int (&off)[2]) {
+      const int32_t* trow = rows + t * kTileRows;
+      const int total = kTileRows * w;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int e = e0 + u * lthreads;
+        off[u] = -1;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < total) {
+          const int r = e / w;
+          const int j = t_lo + (e - r * w);
+          const int k = trow[r];
+          off[u] = ((j - s_lo) >> 3) * kChunkBytes + sw128_offset(r, j & 7);
+          if (j < C4) {
+            const float* f = fb + (long)k * p.C + j * 4;
+            const int left = p.C - j * 4;
+            v[u].x = __ldg(f);
+            v[u].y = left > 1 ? __ldg(f + 1) : 0.f;
+            v[u].z = left > 2 ? __ldg(f + 2) : 0.f;
+            v[u].w = left > 3 ? __ldg(f + 3) : 0.f;
+          } else if (j == C4) {
+            const float4 c = centres[t * cpt + r / ns];
+            const float* pt = cloud + (long)k * 3;
+            v[u].x = __fsub_rn(__ldg(pt + 0), c.x);
+            v[u].y = __fsub_rn(__ldg(pt + 1), c.y);
+            v[u].z = __fsub_rn(__ldg(pt + 2), c.z);
+            if (p.normalize_xyz) {
+              v[u].x = __fmul_rn(v[u].x, scale);
+              v[u].y = __fmul_rn(v[u].y, scale);
+              v[u].z = __fmul_rn(v[u].z, scale);
+            }
+          }
+        }
+      }
+    };
     for (int t = ln; t < ntiles && ok; t += p.lanes) {
       const int32_t* trow = rows + t * kTileRows;  // rows of centre g are contiguous: g*ns
       // ---- layer 0: gather the 128 grouped rows (one pass = `cpp` chunks = 8*cpp slots per row)
@@ -525,43 +562,13 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
           for (int e0 = lt; e0 < total; e0 += 2 * lthreads) {
             float4 v[2];
             int off[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {  // both elements' loads are issued before either store
-              const int e = e0 + u * lthreads;
-              off[u] = -1;
-              v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (e < total) {
-                const int r = e / w;
-                const int j = t_lo + (e - r * w);
-                const int k = trow[r];
-                off[u] = ((j - s_lo) >> 3) * kChunkBytes + sw128_offset(r, j & 7);
-                if (j < C4) {
-                  const float* f = fb + (long)k * p.C + j * 4;
-                  const int left = p.C - j * 4;
-                  v[u].x = __ldg(f);
-                  v[u].y = left > 1 ? __ldg(f + 1) : 0.f;
-                  v[u].z = left > 2 ? __ldg(f + 2) : 0.f;
-                  v[u].w = left > 3 ? __ldg(f + 3) : 0.f;
-                } else if (j == C4) {
-                  const float4 c = centres[t * cpt + r / ns];
-                  const float* pt = cloud + (long)k * 3;
-                  v[u].x = __fsub_rn(__ldg(pt + 0), c.x);
-                  v[u].y = __fsub_rn(__ldg(pt + 1), c.y);
-                  v[u].z = __fsub_rn(__ldg(pt + 2), c.z);
-                  if (p.normalize_xyz) {
-                    v[u].x = __fmul_rn(v[u].x, scale);
-                    v[u].y = __fmul_rn(v[u].y, scale);
-                    v[u].z = __fmul_rn(v[u].z, scale);
-                  }
-                }
-              }
-            }
+            tail_load(t, s_lo, t_lo, w, e0, v, off);  // both elements' loads are issued before either store
 #pragma unroll
             for (int u = 0; u < 2; ++u)
               if (off[u] >= 0) *reinterpret_cast<float4*>(act + off[u]) = tf32_operand4(v[u]);
           }
         }
-        publish(pass);
+        publish(pass, t == ln);
         SA_STAMP();
         if (pass + 1 < p.npass) {  // the next pass overwrites the region: its MMAs must be done
           ok = wait_or_fail(acc_full, accp, failed, 6, p.sleep_ns);
@@ -593,7 +600,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
             *reinterpret_cast<float4*>(dst + sw128_offset(r_epi, j)) = v;
           }
         }
-        publish(p.npass + l);
+        publish(p.npass + l, t == ln);
         SA_STAMP();
       }
       if (!ok) break;

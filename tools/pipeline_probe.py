@@ -60,9 +60,31 @@ def cached_fps(xyz, m):
     return cache[key]
 
 
+real_fps_grid = P.furthest_point_sample_grid
+P.furthest_point_sample_grid = lambda xyz, m, grid: cached_fps(xyz, m)
 P.furthest_point_sample = cached_fps
 with torch.no_grad():
     model.simple_test(points=sets[0]["points"], img=sets[0]["img"], img_metas=sets[0]["img_metas"])
 for lanes in (1, 2, 4, 8):
     run(lanes, tag="cached FPS")
+# ... and without the fused set-abstraction kernels either (cached level outputs): what the
+# vote module, FP modules, head and decoder cost on their own
+real_sa = P.sa_fused
+sa_cache = {}
+
+
+def cached_sa(xyz, center_xyz, feat_rows, *a, **k):
+    key = (xyz.shape[1], center_xyz.shape[1])
+    if key not in sa_cache:
+        sa_cache[key] = real_sa(xyz, center_xyz, feat_rows, *a, **k)
+    return sa_cache[key]
+
+
+P.sa_fused = cached_sa
+with torch.no_grad():
+    model.simple_test(points=sets[0]["points"], img=sets[0]["img"], img_metas=sets[0]["img_metas"])
+for lanes in (1, 4, 8):
+    run(lanes, tag="cached FPS + cached SA")
+P.sa_fused = real_sa
 P.furthest_point_sample = real_fps
+P.furthest_point_sample_grid = real_fps_grid
