@@ -218,8 +218,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="demf_b200", choices=["demf_b200", "reference"])
     ap.add_argument("--no-train", action="store_true", help="skip the extra training-step figure")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -116,7 +116,8 @@ struct FpsSmem {
 template <int kThreads, int kPPT>
 __global__ void __launch_bounds__(kThreads, 1) fps_cluster_kernel(const float* __restrict__ xyz,
                                                                   int N, int m, int log2T,
-                                                                  int32_t* __restrict__ idx) {
+                                                                  int32_t* __restrict__ idx,
+                                                                  float* __restrict__ new_xyz) {
   constexpr int kWarps = kThreads / 32;
   __shared__ FpsSmem<kThreads> sm;
   const unsigned long long trace_t0 = trace_begin();
@@ -150,7 +151,15 @@ __global__ void __launch_bounds__(kThreads, 1) fps_cluster_kernel(const float* _
     }
   }
   float ox = __ldg(cloud + 0), oy = __ldg(cloud + 1), oz = __ldg(cloud + 2);  // idx[0] = 0
-  if (rank == 0 && tid == 0) out[0] = 0;
+  float* oxyz = new_xyz ? new_xyz + (long)b * m * 3 : nullptr;  // optional: coordinates of the picks
+  if (rank == 0 && tid == 0) {
+    out[0] = 0;
+    if (oxyz) {
+      oxyz[0] = ox;
+      oxyz[1] = oy;
+      oxyz[2] = oz;
+    }
+  }
 
   const unsigned tx_bytes = 20u * C;
   if (C > 1) {
@@ -236,7 +245,14 @@ __global__ void __launch_bounds__(kThreads, 1) fps_cluster_kernel(const float* _
       oz = w->z;
       win_p = gp;
     }
-    if (rank == 0 && tid == 0) out[it] = index_from_inv_priority(win_p, log2T);
+    if (rank == 0 && tid == 0) {
+      out[it] = index_from_inv_priority(win_p, log2T);
+      if (oxyz) {
+        oxyz[it * 3 + 0] = ox;
+        oxyz[it * 3 + 1] = oy;
+        oxyz[it * 3 + 2] = oz;
+      }
+    }
   }
   if (C > 1) cluster.sync();  // nobody may exit while peers can still write into its inbox
   trace_end(1, trace_t0);
@@ -260,7 +276,8 @@ constexpr int kGridFpsWarps = kGridFpsThreads / 32;
 
 __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const float* __restrict__ xyz,
                                                                       const void* __restrict__ grid, int N, int m,
-                                                                      int log2T, int cap, int32_t* __restrict__ idx) {
+                                                                      int log2T, int cap, int32_t* __restrict__ idx,
+                                                                      float* __restrict__ new_xyz) {
   extern __shared__ __align__(16) unsigned char gsm[];
   __shared__ FpsSmem<kGridFpsThreads> sm;
   const unsigned long long trace_t0 = trace_begin();
@@ -314,7 +331,15 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
   }
   float ox = __ldg(xyz + (long)b * N * 3 + 0), oy = __ldg(xyz + (long)b * N * 3 + 1),
         oz = __ldg(xyz + (long)b * N * 3 + 2);  // idx[0] = 0
-  if (rank == 0 && tid == 0) out[0] = 0;
+  float* oxyz = new_xyz ? new_xyz + (long)b * m * 3 : nullptr;  // optional: coordinates of the picks
+  if (rank == 0 && tid == 0) {
+    out[0] = 0;
+    if (oxyz) {
+      oxyz[0] = ox;
+      oxyz[1] = oy;
+      oxyz[2] = oz;
+    }
+  }
 
   const unsigned tx_bytes = 20u * C;
   if (tid == 0) {
@@ -405,7 +430,14 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
     ox = w->x;
     oy = w->y;
     oz = w->z;
-    if (rank == 0 && tid == 0) out[it] = index_from_inv_priority(gp, log2T);
+    if (rank == 0 && tid == 0) {
+      out[it] = index_from_inv_priority(gp, log2T);
+      if (oxyz) {
+        oxyz[it * 3 + 0] = ox;
+        oxyz[it * 3 + 1] = oy;
+        oxyz[it * 3 + 2] = oz;
+      }
+    }
   }
   cluster.sync();  // nobody may exit while peers can still write into its inbox
   trace_end(1, trace_t0);
@@ -416,7 +448,8 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
 __global__ void __launch_bounds__(1024, 1) fps_generic_kernel(const float* __restrict__ xyz, int N,
                                                               int m, int log2T,
                                                               float* __restrict__ temp,
-                                                              int32_t* __restrict__ idx) {
+                                                              int32_t* __restrict__ idx,
+                                                              float* __restrict__ new_xyz) {
   __shared__ uint2 warp_key[2][32];
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
@@ -427,7 +460,15 @@ __global__ void __launch_bounds__(1024, 1) fps_generic_kernel(const float* __res
   int32_t* out = idx + (long)b * m;
   for (int k = tid; k < N; k += 1024) tmp[k] = 1e10f;
   int old = 0;
-  if (tid == 0) out[0] = 0;
+  float* oxyz = new_xyz ? new_xyz + (long)b * m * 3 : nullptr;
+  if (tid == 0) {
+    out[0] = 0;
+    if (oxyz) {
+      oxyz[0] = __ldg(cloud + 0);
+      oxyz[1] = __ldg(cloud + 1);
+      oxyz[2] = __ldg(cloud + 2);
+    }
+  }
   for (int it = 1; it < m; ++it) {
     const int par = it & 1;
     const float ox = __ldg(cloud + (long)old * 3), oy = __ldg(cloud + (long)old * 3 + 1),
@@ -451,7 +492,14 @@ __global__ void __launch_bounds__(1024, 1) fps_generic_kernel(const float* __res
     const uint32_t cd = __reduce_max_sync(0xffffffffu, key.x);
     const uint32_t cp = __reduce_max_sync(0xffffffffu, key.x == cd ? key.y : 0u);
     old = index_from_inv_priority(cp, log2T);
-    if (tid == 0) out[it] = old;
+    if (tid == 0) {
+      out[it] = old;
+      if (oxyz) {
+        oxyz[it * 3 + 0] = __ldg(cloud + (long)old * 3);
+        oxyz[it * 3 + 1] = __ldg(cloud + (long)old * 3 + 1);
+        oxyz[it * 3 + 2] = __ldg(cloud + (long)old * 3 + 2);
+      }
+    }
   }
 }
 
@@ -471,7 +519,7 @@ int env_int(const char* name, int dflt) {
 }
 
 template <int kThreads, int kPPT>
-int launch_cluster(const float* xyz, int B, int N, int m, int C, int log2T, int32_t* idx,
+int launch_cluster(const float* xyz, int B, int N, int m, int C, int log2T, int32_t* idx, float* new_xyz,
                    cudaStream_t st, bool probe_only, int* max_clusters) {
   auto kernel = fps_cluster_kernel<kThreads, kPPT>;
   if (C > 8) {
@@ -508,7 +556,7 @@ int launch_cluster(const float* xyz, int B, int N, int m, int C, int log2T, int3
     *max_clusters = cached[C] - 1;
     return 0;
   }
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, xyz, N, m, log2T, idx);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, xyz, N, m, log2T, idx, new_xyz);
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
     set_error("fps_cluster_kernel<%d,%d> C=%d: %s", kThreads, kPPT, C, cudaGetErrorString(e));
@@ -518,12 +566,12 @@ int launch_cluster(const float* xyz, int B, int N, int m, int C, int log2T, int3
 }
 
 template <int kThreads>
-int dispatch_ppt(int ppt, const float* xyz, int B, int N, int m, int C, int log2T, int32_t* idx,
+int dispatch_ppt(int ppt, const float* xyz, int B, int N, int m, int C, int log2T, int32_t* idx, float* new_xyz,
                  cudaStream_t st, bool probe_only, int* max_clusters) {
   switch (ppt) {
 #define DEMF_CASE(p) \
   case p:            \
-    return launch_cluster<kThreads, p>(xyz, B, N, m, C, log2T, idx, st, probe_only, max_clusters);
+    return launch_cluster<kThreads, p>(xyz, B, N, m, C, log2T, idx, new_xyz, st, probe_only, max_clusters);
     DEMF_CASE(1) DEMF_CASE(2) DEMF_CASE(3) DEMF_CASE(4) DEMF_CASE(5) DEMF_CASE(6) DEMF_CASE(8)
     DEMF_CASE(10) DEMF_CASE(12) DEMF_CASE(16) DEMF_CASE(20) DEMF_CASE(24) DEMF_CASE(32) DEMF_CASE(40)
 #undef DEMF_CASE
@@ -532,14 +580,14 @@ int dispatch_ppt(int ppt, const float* xyz, int B, int N, int m, int C, int log2
 }
 
 int dispatch(int threads, int ppt, const float* xyz, int B, int N, int m, int C, int log2T,
-             int32_t* idx, cudaStream_t st, bool probe_only, int* max_clusters) {
+             int32_t* idx, float* new_xyz, cudaStream_t st, bool probe_only, int* max_clusters) {
   switch (threads) {
     case 128:
-      return dispatch_ppt<128>(ppt, xyz, B, N, m, C, log2T, idx, st, probe_only, max_clusters);
+      return dispatch_ppt<128>(ppt, xyz, B, N, m, C, log2T, idx, new_xyz, st, probe_only, max_clusters);
     case 256:
-      return dispatch_ppt<256>(ppt, xyz, B, N, m, C, log2T, idx, st, probe_only, max_clusters);
+      return dispatch_ppt<256>(ppt, xyz, B, N, m, C, log2T, idx, new_xyz, st, probe_only, max_clusters);
     case 512:
-      return dispatch_ppt<512>(ppt, xyz, B, N, m, C, log2T, idx, st, probe_only, max_clusters);
+      return dispatch_ppt<512>(ppt, xyz, B, N, m, C, log2T, idx, new_xyz, st, probe_only, max_clusters);
   }
   return -1;
 }
@@ -596,7 +644,8 @@ size_t demf_fps_workspace_bytes(int B, int N, int m) {
   return (size_t)B * N * sizeof(float);
 }
 
-int demf_fps(const float* xyz, int B, int N, int m, void* workspace, int32_t* idx, void* stream) {
+int demf_fps(const float* xyz, int B, int N, int m, void* workspace, int32_t* idx, float* new_xyz,
+             void* stream) {
   DEMF_REQUIRE_PTR(xyz);
   DEMF_REQUIRE_PTR(idx);
   DEMF_REQUIRE(B >= 0 && N > 0 && m >= 0, DEMF_E_SIZE);
@@ -610,14 +659,14 @@ int demf_fps(const float* xyz, int B, int N, int m, void* workspace, int32_t* id
     // shrink the cluster until every scene's cluster is co-resident on this device
     while (C > 1) {
       int fit = 0;
-      if (dispatch(threads, ppt, xyz, B, N, m, C, log2T, idx, st, true, &fit) == 0 && fit >= B) break;
+      if (dispatch(threads, ppt, xyz, B, N, m, C, log2T, idx, new_xyz, st, true, &fit) == 0 && fit >= B) break;
       C >>= 1;
       const int need = (N + C * threads - 1) / (C * threads);
       ppt = round_up_ppt(need);
       if (ppt < 0) break;
     }
     if (ppt > 0 && !(threads == 512 && ppt > 16)) {
-      const int rc = dispatch(threads, ppt, xyz, B, N, m, C, log2T, idx, st, false, nullptr);
+      const int rc = dispatch(threads, ppt, xyz, B, N, m, C, log2T, idx, new_xyz, st, false, nullptr);
       if (rc != -1) return rc;
     }
   }
@@ -626,13 +675,14 @@ int demf_fps(const float* xyz, int B, int N, int m, void* workspace, int32_t* id
               "bytes of workspace", N, B);
     return DEMF_E_WORKSPACE;
   }
-  fps_generic_kernel<<<B, 1024, 0, st>>>(xyz, N, m, log2T, static_cast<float*>(workspace), idx);
+  fps_generic_kernel<<<B, 1024, 0, st>>>(xyz, N, m, log2T, static_cast<float*>(workspace), idx, new_xyz);
   return after_launch("fps_generic_kernel");
 }
 
 /* Grid-pruned FPS: same indices as demf_fps; `grid` = demf_ball_grid_build workspace of the SAME xyz
  * (any radius). The cloud sits in the shared memory of a 2-, 4- or 8-CTA cluster per scene. */
-int demf_fps_grid(const float* xyz, const void* grid, int B, int N, int m, int32_t* idx, void* stream) {
+int demf_fps_grid(const float* xyz, const void* grid, int B, int N, int m, int32_t* idx, float* new_xyz,
+                  void* stream) {
   DEMF_REQUIRE_PTR(xyz);
   DEMF_REQUIRE_PTR(grid);
   DEMF_REQUIRE_PTR(idx);
@@ -674,7 +724,7 @@ int demf_fps_grid(const float* xyz, const void* grid, int B, int N, int m, int32
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, fps_grid_kernel, xyz, grid, N, m, log2T, cap, idx);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, fps_grid_kernel, xyz, grid, N, m, log2T, cap, idx, new_xyz);
   if (e != cudaSuccess) {
     set_error("demf_fps_grid: launch failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();

@@ -1,0 +1,213 @@
+// Small fused kernels for the glue between the big ops of an eval forward. Each one replaces a
+// chain of 6-12 tiny library launches (index conversions, element-wise arithmetic, concatenations):
+// with several forwards in flight a step is bound by the NUMBER of launches the GPU front end can
+// retire (~2 us per kernel node), not by their work.
+//
+//   chain_indices_kernel    : PointNet2SASSG's `sa_indices[i+1] = gather(sa_indices[i], 1, idx.long())`
+//                             for every level (mmdet3d models/backbones/pointnet2_sa_ssg.py), one launch
+//   interp_cat_rows_kernel  : PointFPModule's  sqrt -> 1/(d+1e-8) -> normalise -> three_interpolate ->
+//                             cat([interpolated, skip])  (mmdet3d ops/pointnet_modules/point_fp_module.py)
+//   decode_boxes_kernel     : softmax(obj)[..., -1], softmax(sem), argmax / gather / class2angle /
+//                             wrap / cat of DeMFClassAgnosticBBoxCoder.decode
+//                             (demf/core/bbox/coders/class_agnostic_bbox_coder.py:168-194) for one
+//                             prediction stage
+#include "common.cuh"
+
+namespace demf {
+namespace {
+
+struct ChainArgs {
+  const int32_t* idx[4];
+  int64_t* out[4];
+  int m[4];
+  int levels;
+};
+
+// One CTA per scene. out[0] = idx[0]; out[l][i] = out[l-1][idx[l][i]].
+__global__ void __launch_bounds__(1024) chain_indices_kernel(const ChainArgs a) {
+  const int b = blockIdx.x;
+  for (int l = 0; l < a.levels; ++l) {
+    const int32_t* idx = a.idx[l] + (long)b * a.m[l];
+    int64_t* out = a.out[l] + (long)b * a.m[l];
+    const int64_t* prev = l ? a.out[l - 1] + (long)b * a.m[l - 1] : nullptr;
+    for (int i = threadIdx.x; i < a.m[l]; i += blockDim.x) {
+      const int k = __ldg(idx + i);
+      out[i] = prev ? prev[k] : (int64_t)k;
+    }
+    __syncthreads();  // this CTA's writes of level l are visible to its reads at level l+1
+  }
+}
+
+// out[b,i,:] = [ sum_k w_k * src[b, idx[b,i,k], :]  |  skip[b,i,:] ],  w_k = r_k / (r_0+r_1+r_2),
+// r_k = 1 / (sqrt(dist2_k) + 1e-8)   (the torch expression of PointFPModule, same operation order)
+__global__ void __launch_bounds__(256) interp_cat_rows_kernel(const float* __restrict__ src,
+                                                              const float* __restrict__ skip,
+                                                              const int32_t* __restrict__ idx,
+                                                              const float* __restrict__ dist2, int m, int n,
+                                                              int C1q, int C2q, long total, float* __restrict__ out) {
+  const int Cq = C1q + C2q;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(e % Cq);
+    const long bi = e / Cq;
+    float4 o;
+    if (j < C1q) {
+      const long b = bi / n;
+      const float4* f = reinterpret_cast<const float4*>(src + b * (long)m * C1q * 4);
+      const int i0 = __ldg(idx + bi * 3), i1 = __ldg(idx + bi * 3 + 1), i2 = __ldg(idx + bi * 3 + 2);
+      const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + bi * 3)), 1e-8f));
+      const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + bi * 3 + 1)), 1e-8f));
+      const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + bi * 3 + 2)), 1e-8f));
+      const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+      const float w0 = __fdiv_rn(r0, norm), w1 = __fdiv_rn(r1, norm), w2 = __fdiv_rn(r2, norm);
+      const float4 p0 = __ldg(f + (long)i0 * C1q + j), p1 = __ldg(f + (long)i1 * C1q + j),
+                   p2 = __ldg(f + (long)i2 * C1q + j);
+      o.x = __fmaf_rn(w2, p2.x, __fmaf_rn(w0, p0.x, __fmul_rn(w1, p1.x)));
+      o.y = __fmaf_rn(w2, p2.y, __fmaf_rn(w0, p0.y, __fmul_rn(w1, p1.y)));
+      o.z = __fmaf_rn(w2, p2.z, __fmaf_rn(w0, p0.z, __fmul_rn(w1, p1.z)));
+      o.w = __fmaf_rn(w2, p2.w, __fmaf_rn(w0, p0.w, __fmul_rn(w1, p1.w)));
+    } else {
+      o = __ldg(reinterpret_cast<const float4*>(skip) + bi * C2q + (j - C1q));
+    }
+    reinterpret_cast<float4*>(out)[e] = o;
+  }
+}
+
+struct DecodeArgs {
+  const float *center, *size, *dir_class, *dir_res, *obj, *sem;
+  int s_center, s_size, s_dir_class, s_dir_res, s_obj, s_sem;  // row strides in floats
+  int Q, bins, classes;
+  int out_rows, out_offset;  // rows per scene of the output tensors and this stage's first row
+  long total;                // B * Q
+  float* box;                // (B, out_rows, 7)
+  float* obj_prob;           // (B, out_rows)
+  float* sem_prob;           // (B, out_rows, classes)
+};
+
+__global__ void __launch_bounds__(256) decode_boxes_kernel(const DecodeArgs a) {
+  const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
+  for (long r = blockIdx.x * (long)blockDim.x + threadIdx.x; r < a.total; r += (long)gridDim.x * blockDim.x) {
+    const long b = r / a.Q;
+    const long q = r - b * a.Q;
+    const long o = b * a.out_rows + a.out_offset + q;
+    // heading: first arg-max bin, its residual, class2angle, wrap to (-pi, pi], then python % 2pi
+    const float* dc = a.dir_class + r * a.s_dir_class;
+    int best = 0;
+    float bv = __ldg(dc);
+    for (int k = 1; k < a.bins; ++k) {
+      const float v = __ldg(dc + k);
+      if (v > bv) {
+        bv = v;
+        best = k;
+      }
+    }
+    const float per = (float)(6.283185307179586 / (double)a.bins);
+    float ang = __fadd_rn(__fmul_rn((float)best, per), __ldg(a.dir_res + r * a.s_dir_res + best));
+    if (ang > pi) ang = __fsub_rn(ang, two_pi);
+    float rem = fmodf(ang, two_pi);
+    if (rem != 0.f && rem < 0.f) rem = __fadd_rn(rem, two_pi);
+    float* box = a.box + o * 7;
+    const float* c = a.center + r * a.s_center;
+    const float* s = a.size + r * a.s_size;
+    box[0] = __ldg(c);
+    box[1] = __ldg(c + 1);
+    box[2] = __ldg(c + 2);
+    box[3] = __ldg(s);
+    box[4] = __ldg(s + 1);
+    box[5] = __ldg(s + 2);
+    box[6] = rem;
+    // objectness: softmax over 2 logits, probability of the last one
+    const float* ob = a.obj + r * a.s_obj;
+    const float o0 = __ldg(ob), o1 = __ldg(ob + 1);
+    const float om = fmaxf(o0, o1);
+    const float e0 = expf(o0 - om), e1 = expf(o1 - om);
+    a.obj_prob[o] = e1 / (e0 + e1);
+    // semantic scores: softmax over `classes` logits
+    const float* sm = a.sem + r * a.s_sem;
+    float mx = __ldg(sm);
+    for (int k = 1; k < a.classes; ++k) mx = fmaxf(mx, __ldg(sm + k));
+    float sum = 0.f;
+    for (int k = 0; k < a.classes; ++k) sum += expf(__ldg(sm + k) - mx);
+    float* sp = a.sem_prob + o * a.classes;
+    for (int k = 0; k < a.classes; ++k) sp[k] = expf(__ldg(sm + k) - mx) / sum;
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline unsigned blocks_for(long total, int threads) {
+  long blocks = (total + threads - 1) / threads;
+  if (blocks > (long)kNumSMs * 16) blocks = (long)kNumSMs * 16;
+  return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace
+}  // namespace demf
+
+using namespace demf;
+
+extern "C" {
+
+int demf_chain_indices(int B, int levels, const int32_t* idx0, int m0, const int32_t* idx1, int m1,
+                       const int32_t* idx2, int m2, const int32_t* idx3, int m3, int64_t* out0,
+                       int64_t* out1, int64_t* out2, int64_t* out3, void* stream) {
+  DEMF_REQUIRE(B >= 0 && levels >= 1 && levels <= 4, DEMF_E_SIZE);
+  ChainArgs a{};
+  const int32_t* in[4] = {idx0, idx1, idx2, idx3};
+  int64_t* out[4] = {out0, out1, out2, out3};
+  const int m[4] = {m0, m1, m2, m3};
+  for (int l = 0; l < levels; ++l) {
+    DEMF_REQUIRE_PTR(in[l]);
+    DEMF_REQUIRE_PTR(out[l]);
+    DEMF_REQUIRE(m[l] > 0, DEMF_E_SIZE);
+    a.idx[l] = in[l];
+    a.out[l] = out[l];
+    a.m[l] = m[l];
+  }
+  a.levels = levels;
+  if (B == 0) return 0;
+  chain_indices_kernel<<<B, 1024, 0, as_stream(stream)>>>(a);
+  return after_launch("chain_indices_kernel");
+}
+
+int demf_interp_cat_rows_fwd(const float* src_rows, const float* skip_rows, const int32_t* idx,
+                             const float* dist2, int B, int C1, int C2, int m, int n, float* out,
+                             void* stream) {
+  DEMF_REQUIRE_PTR(src_rows);
+  DEMF_REQUIRE_PTR(idx);
+  DEMF_REQUIRE_PTR(dist2);
+  DEMF_REQUIRE_PTR(out);
+  if (C2 > 0) DEMF_REQUIRE_PTR(skip_rows);
+  DEMF_REQUIRE(B >= 0 && C1 > 0 && C2 >= 0 && m > 0 && n >= 0, DEMF_E_SIZE);
+  DEMF_REQUIRE(C1 % 4 == 0 && C2 % 4 == 0 && aligned16(src_rows) && aligned16(out) &&
+                   (C2 == 0 || aligned16(skip_rows)),
+               DEMF_E_UNSUPPORTED);
+  const long total = (long)B * n * ((C1 + C2) / 4);
+  if (total == 0) return 0;
+  interp_cat_rows_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(
+      src_rows, skip_rows, idx, dist2, m, n, C1 / 4, C2 / 4, total, out);
+  return after_launch("interp_cat_rows_kernel");
+}
+
+int demf_decode_boxes(const float* center, int s_center, const float* size, int s_size,
+                      const float* dir_class, int s_dir_class, const float* dir_res, int s_dir_res,
+                      const float* obj, int s_obj, const float* sem, int s_sem, int B, int Q, int bins,
+                      int classes, int out_rows, int out_offset, float* box, float* obj_prob,
+                      float* sem_prob, void* stream) {
+  DEMF_REQUIRE_PTR(center);
+  DEMF_REQUIRE_PTR(size);
+  DEMF_REQUIRE_PTR(dir_class);
+  DEMF_REQUIRE_PTR(dir_res);
+  DEMF_REQUIRE_PTR(obj);
+  DEMF_REQUIRE_PTR(sem);
+  DEMF_REQUIRE_PTR(box);
+  DEMF_REQUIRE_PTR(obj_prob);
+  DEMF_REQUIRE_PTR(sem_prob);
+  DEMF_REQUIRE(B >= 0 && Q > 0 && bins > 0 && classes > 0 && out_offset >= 0 && out_offset + Q <= out_rows,
+               DEMF_E_SIZE);
+  if (B == 0) return 0;
+  DecodeArgs a{center, size, dir_class, dir_res, obj, sem, s_center, s_size, s_dir_class, s_dir_res,
+               s_obj, s_sem, Q, bins, classes, out_rows, out_offset, (long)B * Q, box, obj_prob, sem_prob};
+  decode_boxes_kernel<<<blocks_for(a.total, 256), 256, 0, as_stream(stream)>>>(a);
+  return after_launch("decode_boxes_kernel");
+}
+
+}  // extern "C"

@@ -174,14 +174,19 @@ class MultiheadAttention(BaseModule):
             identity = query
         if key_pos is None and query_pos is not None and query_pos.shape == key.shape:
             key_pos = query_pos
+        shared_qk = key is query and key_pos is query_pos   # self attention: q and k are one tensor
         if query_pos is not None:
             query = query + query_pos
-        if key_pos is not None:
+        if shared_qk:
+            key = query
+        elif key_pos is not None:
             key = key + key_pos
         if self.batch_first:
             query, key, value = (t.transpose(0, 1) for t in (query, key, value))
+        # the attention map itself is never used: without it PyTorch takes its fused
+        # scaled-dot-product path instead of mul + bmm + softmax + bmm + mean
         out = self.attn(query=query, key=key, value=value, attn_mask=attn_mask,
-                        key_padding_mask=key_padding_mask)[0]
+                        key_padding_mask=key_padding_mask, need_weights=False)[0]
         if self.batch_first:
             out = out.transpose(0, 1)
         return identity + self.dropout_layer(self.proj_drop(out))

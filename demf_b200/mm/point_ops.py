@@ -45,7 +45,7 @@ class FurthestPointSampling(Function):
             ws = (torch.empty(ws_bytes // 4, dtype=torch.float32, device=points_xyz.device)
                   if ws_bytes else None)
             if idx.numel():
-                _lib.check(lib.demf_fps(_p(points_xyz), B, N, num_points, _p(ws), _p(idx),
+                _lib.check(lib.demf_fps(_p(points_xyz), B, N, num_points, _p(ws), _p(idx), None,
                                         _stream()), "demf_fps")
         ctx.mark_non_differentiable(idx)
         return idx
@@ -56,6 +56,31 @@ class FurthestPointSampling(Function):
 
 
 furthest_point_sample = FurthestPointSampling.apply
+
+
+def furthest_point_sample_xyz(points_xyz, num_points, grid=None):
+    """furthest_point_sample that also returns the picked points' coordinates (B,m,3): the kernel
+    has them in registers when it writes an index, so the separate gather launch (and the int64
+    index copy in front of it) disappears. `grid` = ball_grid workspace: grid-pruned kernel.
+    Sampling is not differentiable; use gather on the indices when gradients must flow to xyz."""
+    assert points_xyz.is_contiguous()
+    _need_cuda(points_xyz, grid)
+    B, N = points_xyz.shape[:2]
+    lib = _lib.load()
+    with torch.cuda.device_of(points_xyz):
+        idx = torch.empty(B, num_points, dtype=torch.int32, device=points_xyz.device)
+        new_xyz = torch.empty(B, num_points, 3, dtype=torch.float32, device=points_xyz.device)
+        if idx.numel():
+            if grid is not None:
+                _lib.check(lib.demf_fps_grid(_p(points_xyz), _p(grid), B, N, int(num_points), _p(idx),
+                                             _p(new_xyz), _stream()), "demf_fps_grid")
+            else:
+                ws_bytes = lib.demf_fps_workspace_bytes(B, N, num_points)
+                ws = (torch.empty(ws_bytes // 4, dtype=torch.float32, device=points_xyz.device)
+                      if ws_bytes else None)
+                _lib.check(lib.demf_fps(_p(points_xyz), B, N, int(num_points), _p(ws), _p(idx),
+                                        _p(new_xyz), _stream()), "demf_fps")
+    return idx, new_xyz
 
 
 class BallQuery(Function):
@@ -455,7 +480,7 @@ def furthest_point_sample_grid(xyz, num_points, grid):
         idx = torch.empty(B, num_points, dtype=torch.int32, device=xyz.device)
         if idx.numel():
             _lib.check(_lib.load().demf_fps_grid(_p(xyz), _p(grid), B, N, int(num_points), _p(idx),
-                                                 _stream()), "demf_fps_grid")
+                                                 None, _stream()), "demf_fps_grid")
     return idx
 
 
@@ -571,3 +596,62 @@ def sa_fused(xyz, center_xyz, feat_rows, min_radius, max_radius, sample_num, nor
                 _p(bias), widths[0], widths[1], widths[2], _p(grid), _p(idx), _p(out), _stream()),
                 "demf_sa_fused_fwd")
     return (out, idx) if return_idx else out
+
+
+# --------------------------------------------------- fused glue kernels (inference) --
+def chain_indices(level_indices):
+    """[idx_0 (B,M0) i32, idx_1 (B,M1) i32, ...] (each indexing the previous level's points) ->
+    [(B,M_l) i64 indices into the ORIGINAL cloud], one launch (csrc/glue.cu). Equals upstream's
+    `sa_indices[i+1] = torch.gather(sa_indices[i], 1, idx.long())` chain started from arange."""
+    assert 1 <= len(level_indices) <= 4
+    _need_cuda(*level_indices)
+    B = level_indices[0].size(0)
+    outs = [torch.empty(t.shape, dtype=torch.int64, device=t.device) for t in level_indices]
+    pad = 4 - len(level_indices)
+    ins = [t.contiguous() for t in level_indices]
+    args = [B, len(ins)]
+    for t in ins:
+        args += [_p(t), t.size(1)]
+    args += [None, 0] * pad
+    args += [_p(o) for o in outs] + [None] * pad
+    with torch.cuda.device_of(ins[0]):
+        _lib.check(_lib.load().demf_chain_indices(*args, _stream()), "demf_chain_indices")
+    return outs
+
+
+def interp_cat_rows(src_rows, skip_rows, indices, dist2):
+    """three_nn squared distances + indices -> inverse-distance weights -> interpolation of
+    src_rows (B,m,C1) -> concatenated with skip_rows (B,n,C2) (or None): (B,n,C1+C2), one launch
+    (csrc/glue.cu; PointFPModule's sqrt/reciprocal/sum/div/three_interpolate/cat). Inference only."""
+    assert src_rows.is_contiguous() and indices.is_contiguous() and dist2.is_contiguous()
+    assert skip_rows is None or skip_rows.is_contiguous()
+    _need_cuda(src_rows, skip_rows, indices, dist2)
+    B, m, C1 = src_rows.shape
+    n = indices.size(1)
+    C2 = 0 if skip_rows is None else skip_rows.size(2)
+    with torch.cuda.device_of(src_rows):
+        out = torch.empty(B, n, C1 + C2, dtype=torch.float32, device=src_rows.device)
+        if out.numel():
+            _lib.check(_lib.load().demf_interp_cat_rows_fwd(
+                _p(src_rows), _p(skip_rows), _p(indices), _p(dist2), B, C1, C2, m, n, _p(out),
+                _stream()), "demf_interp_cat_rows_fwd")
+    return out
+
+
+def decode_boxes(res, num_dir_bins, box, obj_prob, sem_prob, row_offset):
+    """One prediction stage `res` (split_pred dict of (B,Q,*) row tensors, views allowed) ->
+    box (7), objectness probability and semantic probabilities written at rows
+    [row_offset, row_offset+Q) of the (B,R,7)/(B,R)/(B,R,classes) outputs, one launch."""
+    names = ("center", "size", "dir_class", "dir_res", "obj_scores", "sem_scores")
+    ts = [res[k] for k in names]
+    _need_cuda(*ts)
+    B, Q = ts[0].shape[:2]
+    for t in ts:  # row tensors: (B,Q,c) with unit channel stride and b-stride = Q * q-stride
+        assert t.stride(2) == 1 and t.stride(0) == Q * t.stride(1), t.stride()
+    args = []
+    for t in ts:
+        args += [_p(t), t.stride(1)]
+    with torch.cuda.device_of(box):
+        _lib.check(_lib.load().demf_decode_boxes(
+            *args, B, Q, int(num_dir_bins), ts[5].size(2), box.size(1), int(row_offset), _p(box),
+            _p(obj_prob), _p(sem_prob), _stream()), "demf_decode_boxes")

@@ -231,6 +231,18 @@ class PointFPModule(BaseModule):
         """target (B,n,3), source (B,m,3), target_feats (B,C1,n), source_feats (B,C2,m)
         -> (B,M,n)."""
         src_rows = as_rows(source_feats)
+        if (source is not None and src_rows.is_cuda and not torch.is_grad_enabled()
+                and src_rows.size(-1) % 4 == 0
+                and (target_feats is None or target_feats.size(1) % 4 == 0)):
+            # inference: weights, interpolation and the skip concatenation in one launch
+            d2, idx = P.three_nn_squared(target.contiguous(), source.contiguous())
+            x = P.interp_cat_rows(src_rows, None if target_feats is None else as_rows(target_feats),
+                                  idx, d2)
+            B, n, C = x.shape
+            x = x.view(B * n, C)
+            for layer in self.mlps:
+                x = conv_module_rows(layer, x)
+            return x.view(B, n, -1).transpose(1, 2)
         if source is not None:
             dist, idx = P.three_nn(target.contiguous(), source.contiguous())
             dist_reciprocal = 1.0 / (dist + 1e-8)
@@ -296,6 +308,14 @@ class PointNet2SASSG(BaseModule):
                 fp_source_channel = cur_fp_mlps[-1]
                 fp_target_channel = skip_channel_list.pop()
 
+    def _identity_indices(self, batch, num_points, device):
+        """(B,N) int64 arange rows (sa_indices[0]); constant, so built once per shape and device."""
+        cache = self.__dict__.setdefault("_arange_cache", {})
+        key = (batch, num_points, str(device))
+        if key not in cache:
+            cache[key] = torch.arange(num_points, device=device).unsqueeze(0).repeat(batch, 1).long()
+        return cache[key]
+
     @staticmethod
     def _split_point_feats(points):
         xyz = points[..., 0:3].contiguous()
@@ -336,11 +356,12 @@ class PointNet2SASSG(BaseModule):
             # level's ball query and its (grid-pruned) furthest point sampling
             grid0 = self.SA_modules[0].ball_grid(xyz)
             for i, sa in enumerate(self.SA_modules):
-                if i == 0 and grid0 is not None and self.grid_fps:
-                    idx = P.furthest_point_sample_grid(cur, sa.num_point[0], grid0)
+                if cur.is_cuda:   # the kernel writes the picked coordinates next to the indices
+                    idx, new_xyz = P.furthest_point_sample_xyz(
+                        cur, sa.num_point[0], grid0 if (i == 0 and self.grid_fps) else None)
                 else:
                     idx = P.furthest_point_sample(cur, sa.num_point[0])
-                new_xyz = P.gather_rows(cur, idx).contiguous()
+                    new_xyz = P.gather_rows(cur, idx).contiguous()
                 ev = None
                 if overlap:
                     ev = torch.cuda.Event()
@@ -361,8 +382,11 @@ class PointNet2SASSG(BaseModule):
         chained = all(getattr(sa, "num_point", None) is not None and len(sa.num_point) == 1
                       for sa in self.SA_modules)
         levels, seed_fps, grid0 = self._sampling_chain(xyz) if chained else (None, None, None)
-        indices = torch.arange(num_points, device=xyz.device).unsqueeze(0).repeat(batch, 1).long()
+        indices = self._identity_indices(batch, num_points, xyz.device)
         sa_xyz, sa_features, sa_indices = [xyz], [features], [indices]
+        # indices of every level into the ORIGINAL cloud: on CUDA one launch for the whole chain,
+        # issued after the loop (the main stream has then waited for every level's sampling)
+        chain_on_device = levels is not None and xyz.is_cuda and len(levels) <= 4
         for i in range(self.num_sa):
             if levels is not None:
                 idx, new_xyz, ev = levels[i]
@@ -375,7 +399,10 @@ class PointNet2SASSG(BaseModule):
                 cur_xyz, cur_features, cur_indices = self.SA_modules[i](sa_xyz[i], sa_features[i])
             sa_xyz.append(cur_xyz)
             sa_features.append(cur_features)
-            sa_indices.append(torch.gather(sa_indices[-1], 1, cur_indices.long()))
+            if not chain_on_device:
+                sa_indices.append(torch.gather(sa_indices[-1], 1, cur_indices.long()))
+        if chain_on_device:
+            sa_indices += P.chain_indices([lv[0] for lv in levels])
         fp_xyz, fp_features, fp_indices = [sa_xyz[-1]], [sa_features[-1]], [sa_indices[-1]]
         for i in range(self.num_fp):
             fp_features.append(self.FP_modules[i](sa_xyz[self.num_sa - i - 1],

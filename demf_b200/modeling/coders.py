@@ -76,16 +76,18 @@ class DeMFClassAgnosticBBoxCoder:
         cls_t = cls_preds.transpose(2, 1)
         reg_t = reg_preds.transpose(2, 1)
         nb = self.num_dir_bins
+        # the slices stay VIEWS of the two row tensors (upstream copies each with .contiguous():
+        # seven tiny launches per stage); every consumer here takes strided inputs
         results = dict(
-            center=base_xyz + reg_t[..., 0:3].contiguous(),
-            size=reg_t[..., 3:6].contiguous(),
-            dir_class=reg_t[..., 6:6 + nb].contiguous())
-        dir_res_norm = reg_t[..., 6 + nb:6 + 2 * nb].contiguous()
+            center=base_xyz + reg_t[..., 0:3],
+            size=reg_t[..., 3:6],
+            dir_class=reg_t[..., 6:6 + nb])
+        dir_res_norm = reg_t[..., 6 + nb:6 + 2 * nb]
         results['dir_res_norm'] = dir_res_norm
         results['dir_res'] = dir_res_norm * (np.pi / nb)
-        results['obj_scores'] = cls_t[..., 0:2].contiguous()
+        results['obj_scores'] = cls_t[..., 0:2]
         if cls_t.shape[-1] > 2:
-            results['sem_scores'] = cls_t[..., 2:].contiguous()
+            results['sem_scores'] = cls_t[..., 2:]
         return results
 
     def decode_corners(self, center, size):

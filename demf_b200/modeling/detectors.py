@@ -171,6 +171,21 @@ class DeMFVoteNet(BaseModule):
         _, bbox_preds = self._forward_head(points, img, img_metas,
                                            self.test_cfg['pts']['sample_mod'], projection)
         head = self.pts_bbox_head
+        layers = list(head.test_cfg['ensemble_layers'])
+        first = bbox_preds['decode_res_all'][layers[0]]
+        coder = head.bbox_coder
+        if first['center'].is_cuda and coder.with_rot and 'sem_scores' in first:
+            # one launch per ensembled stage: softmaxes, heading decode and the concatenations
+            from ..mm import point_ops as P
+            B, Q = first['center'].shape[:2]
+            R = Q * len(layers)
+            dev = first['center'].device
+            box = torch.empty(B, R, 7, device=dev)
+            obj = torch.empty(B, R, device=dev)
+            sem = torch.empty(B, R, first['sem_scores'].size(-1), device=dev)
+            for n, i in enumerate(layers):
+                P.decode_boxes(bbox_preds['decode_res_all'][i], coder.num_dir_bins, box, obj, sem, n * Q)
+            return box, obj, sem
         obj, sem, box = [], [], []
         for i in head.test_cfg['ensemble_layers']:
             res = bbox_preds['decode_res_all'][i]

@@ -65,7 +65,8 @@ uint64_t demf_launch_count(void);
  * upstream block-tree tie rule (see oracle/demf_oracle.c: demf_ref_fps).
  * `workspace` is only read when demf_fps_workspace_bytes() > 0. */
 size_t demf_fps_workspace_bytes(int B, int N, int m);
-int demf_fps(const float* xyz, int B, int N, int m, void* workspace, int32_t* idx, void* stream);
+int demf_fps(const float* xyz, int B, int N, int m, void* workspace, int32_t* idx,
+             float* new_xyz /* optional (B,m,3): coordinates of the picked points, or NULL */, void* stream);
 
 /* ----------------------------------------------------------- ball query -- */
 /* replaces mmdet3d ball_query_ext.ball_query_wrapper (QueryAndGroup inside each
@@ -170,7 +171,8 @@ int demf_ball_query_grid(const float* xyz, const float* new_xyz, const void* gri
  * demf_fps (replaces furthest_point_sampling_wrapper for large clouds). The cloud sits cell-ordered
  * in the shared memory of a 2/4/8-CTA cluster per scene; a new sample only revisits the 32-point
  * blocks whose bounding box it can reach. N <= ~80k points. */
-int demf_fps_grid(const float* xyz, const void* grid, int B, int N, int m, int32_t* idx, void* stream);
+int demf_fps_grid(const float* xyz, const void* grid, int B, int N, int m, int32_t* idx,
+                  float* new_xyz /* optional (B,m,3) or NULL */, void* stream);
 
 /* ------------------------- fused set abstraction (inference), tcgen05 --- */
 /* replaces, for one PointSAModule forward in eval mode (mmdet3d
@@ -203,6 +205,29 @@ int demf_sa_fused_set_profile(long long* device_buffer);
 /* development knobs: most tile pipelines ("lanes") per CTA (1, 2 or 4; default 4) and the worker
  * warps' back-off between mbarrier polls in ns (default 0 = spin). */
 int demf_sa_fused_tune(int max_lanes, int sleep_ns);
+
+/* ----------------------------------------------------- fused glue (inference) --- */
+/* Each replaces a chain of tiny library launches in the upstream Python modules:
+ *  demf_chain_indices: PointNet2SASSG's sa_indices[i+1] = gather(sa_indices[i], 1, idx.long()) for
+ *    up to 4 levels (mmdet3d models/backbones/pointnet2_sa_ssg.py); idx_l (B,m_l) i32 -> out_l i64.
+ *  demf_interp_cat_rows_fwd: PointFPModule's sqrt -> 1/(d+1e-8) -> normalise -> three_interpolate ->
+ *    cat([interpolated, skip]) from three_nn's SQUARED distances: src_rows (B,m,C1), skip_rows (B,n,C2)
+ *    or NULL, idx (B,n,3), dist2 (B,n,3) -> out (B,n,C1+C2); C1, C2 multiples of 4.
+ *  demf_decode_boxes: one prediction stage of DeMFClassAgnosticBBoxCoder.decode + the score softmaxes
+ *    (demf/core/bbox/coders/class_agnostic_bbox_coder.py:168-194; upstream VoteHead.get_bboxes):
+ *    row tensors (B,Q,*) given as pointer + row stride in floats -> box (B,out_rows,7),
+ *    obj_prob (B,out_rows), sem_prob (B,out_rows,classes) at rows [out_offset, out_offset+Q). */
+int demf_chain_indices(int B, int levels, const int32_t* idx0, int m0, const int32_t* idx1, int m1,
+                       const int32_t* idx2, int m2, const int32_t* idx3, int m3, int64_t* out0,
+                       int64_t* out1, int64_t* out2, int64_t* out3, void* stream);
+int demf_interp_cat_rows_fwd(const float* src_rows, const float* skip_rows, const int32_t* idx,
+                             const float* dist2, int B, int C1, int C2, int m, int n, float* out,
+                             void* stream);
+int demf_decode_boxes(const float* center, int s_center, const float* size, int s_size,
+                      const float* dir_class, int s_dir_class, const float* dir_res, int s_dir_res,
+                      const float* obj, int s_obj, const float* sem, int s_sem, int B, int Q, int bins,
+                      int classes, int out_rows, int out_offset, float* box, float* obj_prob,
+                      float* sem_prob, void* stream);
 
 /* ------------------------------------ multi-scale deformable attention --- */
 /* replaces mmcv _ext.ms_deform_attn_forward / ms_deform_attn_backward

@@ -95,11 +95,11 @@ def test_fps_large_cloud_uses_workspace_kernel(dev):
 
 def test_fps_rejects_bad_arguments(dev):
     lib = _lib.load()
-    assert lib.demf_fps(None, 1, 10, 2, None, None, None) == -1
+    assert lib.demf_fps(None, 1, 10, 2, None, None, None, None) == -1
     assert "NULL" in lib.demf_last_error_string().decode()
     x = torch.zeros(1, 10, 3, device=dev)
     i = torch.zeros(1, 2, dtype=torch.int32, device=dev)
-    assert lib.demf_fps(x.data_ptr(), 1, 0, 2, None, i.data_ptr(), None) == -2
+    assert lib.demf_fps(x.data_ptr(), 1, 0, 2, None, i.data_ptr(), None, None) == -2
     with pytest.raises(AssertionError):
         ops.furthest_point_sample(torch.zeros(1, 3, 10, device=dev).transpose(1, 2), 2)
     with pytest.raises(RuntimeError, match="CUDA"):
@@ -473,3 +473,72 @@ def test_fps_grid_matches_oracle(dev, B, N, m, kind):
         got = ops.furthest_point_sample_grid(gx, m, ops.ball_grid(gx, radius))
         assert torch.equal(got.cpu(), ref)
     assert torch.equal(ops.furthest_point_sample(gx, m).cpu(), ref)
+
+
+# ------------------------------------------------------------ fused glue kernels --
+def test_fps_xyz_output_equals_gather(dev):
+    xyz = _xyz(3, 5000, seed=21, clustered=True)
+    gx = xyz.to(dev)
+    ref = cref.furthest_point_sample(xyz, 700)
+    want = torch.gather(xyz, 1, ref.long()[..., None].expand(-1, -1, 3))
+    for grid in (None, ops.ball_grid(gx, 0.3)):
+        idx, new_xyz = ops.furthest_point_sample_xyz(gx, 700, grid)
+        assert torch.equal(idx.cpu(), ref) and torch.equal(new_xyz.cpu(), want)
+
+
+def test_chain_indices_equals_gather_chain(dev):
+    g = torch.Generator().manual_seed(3)
+    sizes = [20000, 2048, 1024, 512, 256]
+    idx = [torch.stack([torch.randperm(sizes[l], generator=g)[:sizes[l + 1]] for _ in range(4)]).int()
+           for l in range(4)]
+    cur = torch.arange(sizes[0]).unsqueeze(0).repeat(4, 1)
+    want = []
+    for t in idx:
+        cur = torch.gather(cur, 1, t.long())
+        want.append(cur)
+    got = ops.chain_indices([t.to(dev) for t in idx])
+    for a, b in zip(got, want):
+        assert a.dtype == torch.int64 and torch.equal(a.cpu(), b)
+
+
+@pytest.mark.parametrize("B,n,m,C1,C2", [(2, 512, 256, 256, 256), (2, 1024, 512, 256, 256), (1, 33, 7, 8, 0)])
+def test_interp_cat_rows_matches_torch_chain(dev, B, n, m, C1, C2):
+    g = torch.Generator().manual_seed(n)
+    tgt, src = _xyz(B, n, seed=1).to(dev), _xyz(B, m, seed=2).to(dev)
+    feats = torch.randn(B, m, C1, generator=g).to(dev)
+    skip = torch.randn(B, n, C2, generator=g).to(dev) if C2 else None
+    d2, idx = ops.three_nn_squared(tgt, src)
+    got = ops.interp_cat_rows(feats, skip, idx, d2)
+    dist = torch.sqrt(d2)                      # PointFPModule's torch expression
+    recip = 1.0 / (dist + 1e-8)
+    w = (recip / recip.sum(2, keepdim=True)).contiguous()
+    ref = ops.three_interpolate_rows(feats, idx, w)
+    if skip is not None:
+        ref = torch.cat([ref, skip], -1)
+    torch.testing.assert_close(got, ref, atol=1e-6, rtol=1e-6)
+    if skip is not None:
+        assert torch.equal(got[..., C1:], skip)
+
+
+def test_decode_boxes_matches_coder(dev):
+    import numpy as np
+    from demf_b200.modeling.coders import DeMFClassAgnosticBBoxCoder
+    g = torch.Generator().manual_seed(5)
+    B, Q, nb, nc = 3, 256, 12, 10
+    coder = DeMFClassAgnosticBBoxCoder(nb, nc, [[1.0, 1.0, 1.0]] * nc)
+    # as BaseConvBboxHead emits them: (B,C,Q) views of point-major rows
+    reg = (torch.randn(B, Q, 6 + 2 * nb, generator=g) * 2).to(dev).transpose(1, 2)
+    cls = (torch.randn(B, Q, 2 + nc, generator=g) * 3).to(dev).transpose(1, 2)
+    base = torch.randn(B, Q, 3, generator=g).to(dev)
+    res = coder.split_pred(cls, reg, base)
+    want_box = coder.decode(res)
+    want_obj = torch.softmax(res['obj_scores'], -1)[..., -1]
+    want_sem = torch.softmax(res['sem_scores'], -1)
+    box = torch.zeros(B, 2 * Q, 7, device=dev)
+    obj = torch.zeros(B, 2 * Q, device=dev)
+    sem = torch.zeros(B, 2 * Q, nc, device=dev)
+    ops.decode_boxes(res, nb, box, obj, sem, Q)
+    torch.testing.assert_close(box[:, Q:], want_box, atol=1e-6, rtol=1e-6)
+    torch.testing.assert_close(obj[:, Q:], want_obj, atol=1e-6, rtol=1e-5)
+    torch.testing.assert_close(sem[:, Q:], want_sem, atol=1e-6, rtol=1e-5)
+    assert box[:, :Q].abs().sum() == 0 and (box[..., 6] >= 0).all() and (box[..., 6] < 2 * np.pi + 1e-6).all()

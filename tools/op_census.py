@@ -21,7 +21,7 @@ with torch.no_grad():
     for _ in range(3):
         model.simple_test(points=batch["points"], img=batch["img"], img_metas=batch["img_metas"], projection=proj)
     torch.cuda.synchronize()
-    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as prof:
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
         model.simple_test(points=batch["points"], img=batch["img"], img_metas=batch["img_metas"], projection=proj)
         torch.cuda.synchronize()
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -40,6 +40,11 @@ for ev in prof.events():
             break
     sites[(where.split(" ")[0] if where != "?" else "?", ev.name)] += n_k
     kernels[ev.name] += n_k
+print("---- launching ops in order (name, input shapes)")
+seq = [ev for ev in prof.events() if ev.device_type != torch.autograd.DeviceType.CUDA and getattr(ev, "kernels", None)]
+seq.sort(key=lambda e: e.time_range.start)
+for ev in seq:
+    print(f"  {ev.name:32s} {str(ev.input_shapes)[:110]}")
 print("kernel launches by op:", sum(kernels.values()))
 for k, v in kernels.most_common(25):
     print(f"  {v:4d}  {k}")
