@@ -205,3 +205,50 @@ def test_fps_duplicate_points_golden_differs_from_index_order_rule(golden):
     z = golden("fps_dup_n300_m100")
     naive = ops_numpy.furthest_point_sample(z["xyz"].numpy(), 100)
     assert not np.array_equal(naive, z["idx"].numpy())
+
+
+# ------------------------------------------------ set-abstraction module oracle --
+def test_tf32_rna_emulation_bit_patterns():
+    """cvt.rna.tf32.f32: 10 mantissa bits kept, round to nearest, ties AWAY from zero."""
+    from oracle.sa_module import tf32_rna
+    x = torch.tensor([1.0, 1.0 + 2 ** -11, 1.0 + 2 ** -11 - 2 ** -20, 1.0 + 3 * 2 ** -11, -1.0 - 2 ** -11,
+                      0.0, 3.0e-39, 65504.0])
+    y = tf32_rna(x)
+    want = torch.tensor([1.0, 1.0 + 2 ** -10, 1.0, 1.0 + 2 ** -9, -1.0 - 2 ** -10, 0.0, 3.0e-39, 65504.0])
+    # (the denormal only loses low bits; compare through the rounding rule)
+    assert torch.equal(y[:6], want[:6]) and y[7] == want[7]
+    assert (y.view(torch.int32) & 0x1FFF).abs().sum() == 0        # low 13 mantissa bits cleared
+    r = torch.randn(10000) * 7
+    assert ((tf32_rna(r) - r).abs() <= r.abs() * 2 ** -11 + 1e-45).all()
+
+
+def test_sa_module_oracle_matches_the_mm_module_on_cpu():
+    """Two formulations of one PointSAModule forward in eval mode: oracle/sa_module.py (grouped
+    tensor in upstream channel order, folded (W, b) pairs) vs the package's own PointSAModule run
+    on CPU through the oracle ops (rows layout, its own BN folding)."""
+    from demf_b200.mm.bricks import _fold_conv_bn
+    from demf_b200.mm.pointnet_modules import PointSAModule
+    from oracle import sa_module
+    from oracle.cpu_backend import oracle_ops
+    torch.manual_seed(3)
+    sa = PointSAModule(mlp_channels=[8, 32, 32, 64], num_point=40, radius=0.5, num_sample=16,
+                       normalize_xyz=True).eval()
+    for m in sa.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.running_mean.normal_(0, 0.2)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.1)
+    xyz = synth.make_points(2, 600, seed=2)[..., :3].contiguous()
+    feats = torch.randn(2, 8, 600)
+    with oracle_ops(), torch.no_grad():
+        new_xyz, out, idx = sa(xyz, feats)
+    folded = [_fold_conv_bn(cm, None) for cm in sa.mlps[0]]
+    ridx, ref = sa_module.sa_forward(xyz, new_xyz, feats, 0.0, 0.5, 16, True,
+                                     [w for w, _ in folded], [b for _, b in folded])
+    assert torch.equal(idx, cref.furthest_point_sample(xyz, 40))
+    torch.testing.assert_close(out, ref, atol=1e-5, rtol=1e-5)
+    _, ref32 = sa_module.sa_forward(xyz, new_xyz, feats, 0.0, 0.5, 16, True,
+                                    [w for w, _ in folded], [b for _, b in folded], tf32=True)
+    assert (ref32 - ref).abs().max() <= 1e-2 * ref.abs().max()     # TF32 operands: ~3 decimal digits
+    assert not torch.equal(ref32, ref)
