@@ -1,0 +1,41 @@
+"""Pick the headline metrics out of an `ncu --set full` report into a small JSON (runs anywhere).
+
+    python tools/ncu_metrics.py gpurun_out/x.ncu-rep "note" > profiles/x.json
+"""
+import csv
+import json
+import subprocess
+import sys
+
+KEEP = [
+    "gpu__time_duration.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__cluster_size",
+    "launch__shared_mem_per_block_dynamic", "launch__waves_per_multiprocessor", "sm__cycles_elapsed.max",
+    "smsp__pcsamp_warps_issue_stalled_long_scoreboard", "smsp__pcsamp_warps_issue_stalled_barrier",
+    "smsp__pcsamp_warps_issue_stalled_wait", "smsp__pcsamp_warps_issue_stalled_short_scoreboard",
+    "smsp__pcsamp_warps_issue_stalled_selected", "smsp__pcsamp_warps_issue_stalled_not_selected",
+    "smsp__pcsamp_warps_issue_stalled_math_pipe_throttle", "smsp__pcsamp_warps_issue_stalled_branch_resolving",
+    "smsp__pcsamp_warps_issue_stalled_no_instructions", "smsp__pcsamp_warps_issue_stalled_mio_throttle",
+]
+
+
+def main():
+    rep, note = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "")
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    launches = []
+    for vals in rows[2:]:
+        d = {h: f"{v} {u}".strip() for h, u, v in zip(hdr, units, vals) if h in KEEP}
+        d["kernel"] = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else ""
+        launches.append(d)
+    print(json.dumps({"source": rep, "how": "ncu --set full --clock-control none --import-source on",
+                      "note": note, "launches": launches}, indent=1))
+
+
+if __name__ == "__main__":
+    main()
