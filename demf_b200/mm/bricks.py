@@ -176,11 +176,17 @@ class MultiheadAttention(BaseModule):
             key_pos = query_pos
         shared_qk = key is query and key_pos is query_pos   # self attention: q and k are one tensor
         if query_pos is not None:
-            query = query + query_pos
+            if torch.is_grad_enabled():
+                query = query + query_pos
+            else:  # a dense result: the input projections then are single addmm launches
+                query = torch.add(query, query_pos, out=torch.empty(
+                    query.shape, dtype=query.dtype, device=query.device))
         if shared_qk:
             key = query
         elif key_pos is not None:
             key = key + key_pos
+        if not torch.is_grad_enabled() and not value.is_contiguous():
+            value = value.contiguous()
         if self.batch_first:
             query, key, value = (t.transpose(0, 1) for t in (query, key, value))
         # the attention map itself is never used: without it PyTorch takes its fused

@@ -169,6 +169,18 @@ class MultiScaleDeformableAttention(BaseModule):
         nn.init.constant_(self.output_proj.bias, 0.)
         self._is_init = True
 
+    def _fused_query_proj(self):
+        """[sampling_offsets; attention_weights] as one (W, b), rebuilt when a parameter changes."""
+        ts = (self.sampling_offsets.weight, self.sampling_offsets.bias, self.attention_weights.weight,
+              self.attention_weights.bias)
+        key = tuple((t.data_ptr(), t._version) for t in ts)
+        cache = self.__dict__.get("_qproj_cache")
+        if cache is None or cache[0] != key:
+            cache = (key, torch.cat([ts[0], ts[2]], 0).detach().contiguous(),
+                     torch.cat([ts[1], ts[3]], 0).detach().contiguous())
+            self.__dict__["_qproj_cache"] = cache
+        return cache[1], cache[2]
+
     def forward(self, query, key=None, value=None, identity=None, query_pos=None,
                 key_padding_mask=None, reference_points=None, spatial_shapes=None,
                 level_start_index=None, **kwargs):
@@ -189,10 +201,21 @@ class MultiScaleDeformableAttention(BaseModule):
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
         value = value.view(bs, num_value, self.num_heads, -1)
-        sampling_offsets = self.sampling_offsets(query).view(
-            bs, num_query, self.num_heads, self.num_levels, self.num_points, 2)
-        attention_weights = self.attention_weights(query).view(
-            bs, num_query, self.num_heads, self.num_levels * self.num_points)
+        if not torch.is_grad_enabled():
+            # inference: the offset and weight projections read the same rows -- one GEMM over the
+            # concatenated (cached) weights on a contiguous copy of the permuted query
+            w, b = self._fused_query_proj()
+            proj = torch.addmm(b, query.reshape(bs * num_query, -1), w.t())
+            n_off = self.sampling_offsets.out_features
+            sampling_offsets = proj[:, :n_off].view(
+                bs, num_query, self.num_heads, self.num_levels, self.num_points, 2)
+            attention_weights = proj[:, n_off:].view(
+                bs, num_query, self.num_heads, self.num_levels * self.num_points)
+        else:
+            sampling_offsets = self.sampling_offsets(query).view(
+                bs, num_query, self.num_heads, self.num_levels, self.num_points, 2)
+            attention_weights = self.attention_weights(query).view(
+                bs, num_query, self.num_heads, self.num_levels * self.num_points)
         attention_weights = attention_weights.softmax(-1).view(
             bs, num_query, self.num_heads, self.num_levels, self.num_points)
         if reference_points.shape[-1] == 2:
