@@ -271,6 +271,9 @@ __global__ void __launch_bounds__(kThreads, 1) fps_cluster_kernel(const float* _
 // coordinate differences, so lb2 <= d(p, s) for every p in the box and a skipped block provably
 // changes nothing. After a few dozen samples only ~10 blocks of 625 are touched per iteration.
 // The arg-max key and the cluster exchange are those of fps_cluster_kernel: identical indices.
+#ifdef DEMF_FPS_STATS
+__device__ unsigned long long g_fps_stats[4];
+#endif
 constexpr int kGridFpsThreads = 512;
 constexpr int kGridFpsWarps = kGridFpsThreads / 32;
 
@@ -280,6 +283,7 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
                                                                       float* __restrict__ new_xyz) {
   extern __shared__ __align__(16) unsigned char gsm[];
   __shared__ FpsSmem<kGridFpsThreads> sm;
+  __shared__ __align__(16) Packet flat_inbox[2][32];  // [iteration parity][source CTA * 16 + warp]
   const unsigned long long trace_t0 = trace_begin();
   float4* pts = reinterpret_cast<float4*>(gsm);                 // cap entries: x, y, z, inv-priority bits
   float* tmp = reinterpret_cast<float*>(gsm + (size_t)cap * 16);  // cap running min distances
@@ -341,7 +345,8 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
     }
   }
 
-  const unsigned tx_bytes = 20u * C;
+  const bool flat = C * kGridFpsWarps <= 32;
+  const unsigned tx_bytes = flat ? 20u * C * kGridFpsWarps : 20u * C;
   if (tid == 0) {
     mbar_init(&sm.bar[0], 1);
     mbar_init(&sm.bar[1], 1);
@@ -363,6 +368,13 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
       dirty = lb2 < __uint_as_float(bmax);
     }
     unsigned todo = __ballot_sync(0xffffffffu, dirty);
+#ifdef DEMF_FPS_STATS
+    if (lane == 0) {
+      atomicAdd(&g_fps_stats[0], (unsigned long long)__popc(todo));
+      atomicMax(&g_fps_stats[1], (unsigned long long)__popc(todo));
+      if (it >= 64) atomicAdd(&g_fps_stats[2], (unsigned long long)__popc(todo));
+    }
+#endif
     // b. update those blocks, 32 points at a time
     while (todo) {
       const int j = __ffs(todo) - 1;
@@ -394,42 +406,70 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
     c.x = __shfl_sync(0xffffffffu, c.x, src);
     c.y = __shfl_sync(0xffffffffu, c.y, src);
     c.z = __shfl_sync(0xffffffffu, c.z, src);
-    if (lane == 0) {
-      sm.warp_xyz[par][warp] = make_float4(c.x, c.y, c.z, 0.f);
-      sm.warp_key[par][warp] = make_uint2(owners ? wd : 0u, owners ? wp : 0u);
-    }
-    __syncthreads();
-    // d. CTA arg-max over the warps, then the cluster exchange (as in fps_cluster_kernel)
-    uint2 key = (lane < (unsigned)kGridFpsWarps) ? sm.warp_key[par][lane] : make_uint2(0u, 0u);
-    const uint32_t cd = __reduce_max_sync(0xffffffffu, key.x);
-    const uint32_t cp = __reduce_max_sync(0xffffffffu, key.x == cd ? key.y : 0u);
-    const unsigned who = __ffs(__ballot_sync(0xffffffffu, lane < (unsigned)kGridFpsWarps && key.x == cd &&
-                                                              key.y == cp)) - 1;
-    const float4 cxyz = sm.warp_xyz[par][who];
-    if (warp == 0 && lane < C) {
-      const uint32_t dst = map_to_cta(smem_u32(&sm.inbox[par][rank]), lane);
-      const uint32_t dbar = map_to_cta(smem_u32(&sm.bar[par]), lane);
-      st_async_v4(dst, cd, cp, __float_as_uint(cxyz.x), __float_as_uint(cxyz.y), dbar);
-      st_async_b32(dst + 16, __float_as_uint(cxyz.z), dbar);
-    }
-    mbar_wait(&sm.bar[par], (unsigned)(((it - 1) >> 1) & 1));
-    if (tid == 0) mbar_arrive_expect_tx(&sm.bar[par], tx_bytes);
-    Packet pk;
-    if (lane < C) {
-      const uint4 qd = *reinterpret_cast<const uint4*>(&sm.inbox[par][lane]);
-      pk.dist_bits = qd.x;
-      pk.inv_prio = qd.y;
+    uint32_t gp;
+    if (flat) {
+      // d'. flat exchange (C * 16 warps <= 32): every warp pushes its candidate straight into the
+      // inbox of every CTA of the cluster (its own included) and every warp reduces the <= 32
+      // candidates itself: no CTA barrier and no second exchange stage in the loop
+      if (lane < C) {
+        const uint32_t dst = map_to_cta(smem_u32(&flat_inbox[par][rank * kGridFpsWarps + warp]), lane);
+        const uint32_t dbar = map_to_cta(smem_u32(&sm.bar[par]), lane);
+        st_async_v4(dst, owners ? wd : 0u, owners ? wp : 0u, __float_as_uint(c.x), __float_as_uint(c.y), dbar);
+        st_async_b32(dst + 16, __float_as_uint(c.z), dbar);
+      }
+      mbar_wait(&sm.bar[par], (unsigned)(((it - 1) >> 1) & 1));
+      if (tid == 0) mbar_arrive_expect_tx(&sm.bar[par], tx_bytes);
+      uint32_t pd = 0u, pp = 0u;
+      if (lane < C * kGridFpsWarps) {
+        const uint2 q2 = *reinterpret_cast<const uint2*>(&flat_inbox[par][lane]);
+        pd = q2.x;
+        pp = q2.y;
+      }
+      const uint32_t gd = __reduce_max_sync(0xffffffffu, pd);
+      gp = __reduce_max_sync(0xffffffffu, pd == gd ? pp : 0u);
+      const unsigned srcc = __ffs(__ballot_sync(0xffffffffu, lane < C * kGridFpsWarps && pd == gd && pp == gp)) - 1;
+      const Packet* w = &flat_inbox[par][srcc];
+      ox = w->x;
+      oy = w->y;
+      oz = w->z;
     } else {
-      pk.dist_bits = 0u;
-      pk.inv_prio = 0u;
+      if (lane == 0) {
+        sm.warp_xyz[par][warp] = make_float4(c.x, c.y, c.z, 0.f);
+        sm.warp_key[par][warp] = make_uint2(owners ? wd : 0u, owners ? wp : 0u);
+      }
+      __syncthreads();
+      // d. CTA arg-max over the warps, then the cluster exchange (as in fps_cluster_kernel)
+      uint2 key = (lane < (unsigned)kGridFpsWarps) ? sm.warp_key[par][lane] : make_uint2(0u, 0u);
+      const uint32_t cd = __reduce_max_sync(0xffffffffu, key.x);
+      const uint32_t cp = __reduce_max_sync(0xffffffffu, key.x == cd ? key.y : 0u);
+      const unsigned who = __ffs(__ballot_sync(0xffffffffu, lane < (unsigned)kGridFpsWarps && key.x == cd &&
+                                                                key.y == cp)) - 1;
+      const float4 cxyz = sm.warp_xyz[par][who];
+      if (warp == 0 && lane < C) {
+        const uint32_t dst = map_to_cta(smem_u32(&sm.inbox[par][rank]), lane);
+        const uint32_t dbar = map_to_cta(smem_u32(&sm.bar[par]), lane);
+        st_async_v4(dst, cd, cp, __float_as_uint(cxyz.x), __float_as_uint(cxyz.y), dbar);
+        st_async_b32(dst + 16, __float_as_uint(cxyz.z), dbar);
+      }
+      mbar_wait(&sm.bar[par], (unsigned)(((it - 1) >> 1) & 1));
+      if (tid == 0) mbar_arrive_expect_tx(&sm.bar[par], tx_bytes);
+      Packet pk;
+      if (lane < C) {
+        const uint4 qd = *reinterpret_cast<const uint4*>(&sm.inbox[par][lane]);
+        pk.dist_bits = qd.x;
+        pk.inv_prio = qd.y;
+      } else {
+        pk.dist_bits = 0u;
+        pk.inv_prio = 0u;
+      }
+      const uint32_t gd = __reduce_max_sync(0xffffffffu, pk.dist_bits);
+      gp = __reduce_max_sync(0xffffffffu, pk.dist_bits == gd ? pk.inv_prio : 0u);
+      const unsigned srcc = __ffs(__ballot_sync(0xffffffffu, lane < C && pk.dist_bits == gd && pk.inv_prio == gp)) - 1;
+      const Packet* w = &sm.inbox[par][srcc];
+      ox = w->x;
+      oy = w->y;
+      oz = w->z;
     }
-    const uint32_t gd = __reduce_max_sync(0xffffffffu, pk.dist_bits);
-    const uint32_t gp = __reduce_max_sync(0xffffffffu, pk.dist_bits == gd ? pk.inv_prio : 0u);
-    const unsigned srcc = __ffs(__ballot_sync(0xffffffffu, lane < C && pk.dist_bits == gd && pk.inv_prio == gp)) - 1;
-    const Packet* w = &sm.inbox[par][srcc];
-    ox = w->x;
-    oy = w->y;
-    oz = w->z;
     if (rank == 0 && tid == 0) {
       out[it] = index_from_inv_priority(gp, log2T);
       if (oxyz) {
@@ -678,6 +718,14 @@ int demf_fps(const float* xyz, int B, int N, int m, void* workspace, int32_t* id
   fps_generic_kernel<<<B, 1024, 0, st>>>(xyz, N, m, log2T, static_cast<float*>(workspace), idx, new_xyz);
   return after_launch("fps_generic_kernel");
 }
+
+#ifdef DEMF_FPS_STATS
+unsigned long long demf_fps_stat(int i) {
+  unsigned long long v[4];
+  cudaMemcpyFromSymbol(v, g_fps_stats, sizeof(v));
+  return v[i];
+}
+#endif
 
 /* Grid-pruned FPS: same indices as demf_fps; `grid` = demf_ball_grid_build workspace of the SAME xyz
  * (any radius). The cloud sits in the shared memory of a 2-, 4- or 8-CTA cluster per scene. */
