@@ -66,6 +66,34 @@ __device__ __forceinline__ int ball_grid_coord(float v, float v0, float inv_h) {
   return __float2int_rd(__fmul_rn(__fsub_rn(v, v0), inv_h));
 }
 
+// Smallest index bound (a multiple of the histogram bucket width) below which at least `ns` of the
+// histogrammed hits lie; *below = how many exactly. Returns 0 when fewer than ns hits were counted.
+__device__ __forceinline__ int hist_bound(const int* hist, int ns, int shift, unsigned lane, int* below = nullptr) {
+  const int h0 = hist[2 * lane], h1 = hist[2 * lane + 1];
+  int incl = h0 + h1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((int)lane >= o) incl += t;
+  }
+  const int excl = incl - h0 - h1;
+  int cand = kGridHist, cnt = 0;  // first bucket whose inclusive prefix reaches ns
+  if (excl + h0 >= ns && excl < ns) {
+    cand = 2 * lane;
+    cnt = excl + h0;
+  } else if (incl >= ns && excl + h0 < ns) {
+    cand = 2 * lane + 1;
+    cnt = incl;
+  }
+  const unsigned who = __ballot_sync(0xffffffffu, cand < kGridHist);
+  if (!who) return 0;
+  const int src = __ffs(who) - 1;
+  cand = __shfl_sync(0xffffffffu, cand, src);
+  cnt = __shfl_sync(0xffffffffu, cnt, src);
+  if (below) *below = cnt;
+  return (cand + 1) << shift;
+}
+
 // One warp, one centre. Writes the full index row (ns entries) to `row` and returns the number of
 // distinct hits kept (min(hits, ns)), or -1 when the caller must fall back to the full scan.
 // buf: kGridCap ints, hist: kGridHist ints -- per-warp scratch (shared memory).
@@ -81,46 +109,88 @@ __device__ __forceinline__ int ball_grid_query_warp(const BallGridView& g, int N
   int shift = 0;
   while (((N - 1) >> shift) >= kGridHist) ++shift;
 
+  // The 3x3 cell columns (contiguous in z) of the neighbourhood as one flat candidate range: lane
+  // l < 9 fetches column l's [begin, end) -- one round trip instead of nine dependent ones -- and
+  // every lane keeps the nine (offset, begin) pairs, so that candidate t of the flat range maps to
+  // sorted[begin_c + t - offset_c] and consecutive lanes test consecutive candidates.
+  int cbeg = 0, clen = 0;
+  if (lane < 9 && zlo <= zhi) {
+    const int x = ix - 1 + (int)lane / 3, y = iy - 1 + (int)lane % 3;
+    if (x >= 0 && x < g.h.nx && y >= 0 && y < g.h.ny) {
+      const int c0 = (x * kGridY + y) * kGridZ;
+      cbeg = __ldg(g.cell_start + c0 + zlo);
+      clen = __ldg(g.cell_start + c0 + zhi + 1) - cbeg;
+    }
+  }
+  int incl = clen;
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((int)lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 8);
+  int coff[9], cb[9];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) {
+    coff[c] = __shfl_sync(0xffffffffu, incl - clen, c);
+    cb[c] = __shfl_sync(0xffffffffu, cbeg, c);
+  }
+  (void)xlo; (void)xhi; (void)ylo; (void)yhi;
+
   int bound = 0x7fffffff;  // keep hits with index < bound
   for (int pass = 0; pass < 2; ++pass) {
     for (int l = lane; l < kGridHist; l += 32) hist[l] = 0;
     __syncwarp();
     int cnt = 0;
-    if (zlo <= zhi) {
-      for (int x = xlo; x <= xhi; ++x) {
-        for (int y = ylo; y <= yhi; ++y) {
-          const int c0 = (x * kGridY + y) * kGridZ;
-          const int beg = __ldg(g.cell_start + c0 + zlo), end = __ldg(g.cell_start + c0 + zhi + 1);
-          for (int j = beg; j < end; j += 32) {
-            const int q = j + lane;
-            bool hit = false;
-            int k = 0;
-            if (q < end) {
-              const float4 p = __ldg(g.sorted + q);
-              k = __float_as_int(p.w);
-              const float d2 = sqdist(cx, cy, cz, p.x, p.y, p.z);
-              hit = ((d2 == 0.f) || (d2 >= min_r2 && d2 < max_r2)) && k < bound;
-            }
-            const unsigned ballot = __ballot_sync(0xffffffffu, hit);
-            if (ballot) {
-              const int pos = cnt + __popc(ballot & ((1u << lane) - 1u));
-              if (hit) {
-                if (pos < kGridCap) buf[pos] = k;
-                atomicAdd(&hist[k >> shift], 1);
-              }
-              cnt += __popc(ballot);
-            }
-          }
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      const int t = t0 + (int)lane;
+      bool hit = false;
+      int k = 0;
+      if (t < total) {
+        int q = cb[0] + t;
+#pragma unroll
+        for (int c = 1; c < 9; ++c)
+          if (t >= coff[c]) q = cb[c] + (t - coff[c]);
+        const float4 p = __ldg(g.sorted + q);
+        k = __float_as_int(p.w);
+        const float d2 = sqdist(cx, cy, cz, p.x, p.y, p.z);
+        hit = ((d2 == 0.f) || (d2 >= min_r2 && d2 < max_r2)) && k < bound;
+      }
+      const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+      if (ballot) {
+        const int pos = cnt + __popc(ballot & ((1u << lane) - 1u));
+        if (hit) {
+          if (pos < kGridCap) buf[pos] = k;
+          atomicAdd(&hist[k >> shift], 1);
         }
+        cnt += __popc(ballot);
       }
     }
     __syncwarp();
     if (cnt <= kGridCap) {
-      // rank = number of hits with a smaller index (indices are distinct)
-      for (int e = lane; e < cnt; e += 32) {
+      int n = cnt;
+      if (cnt > ns + 32) {
+        // many more hits than wanted: the histogram gives an index bound below which >= ns of them
+        // lie; only those compete for the ns smallest (ranking is quadratic in the candidates)
+        const int lim = hist_bound(hist, ns, shift, lane);
+        if (lim > 0) {
+          n = 0;
+          for (int e0 = 0; e0 < cnt; e0 += 32) {
+            const int e = e0 + (int)lane;
+            const int v = e < cnt ? buf[e] : 0x7fffffff;
+            const unsigned keep = __ballot_sync(0xffffffffu, v < lim);
+            __syncwarp();
+            if (v < lim) buf[n + __popc(keep & ((1u << lane) - 1u))] = v;   // n <= e0: never ahead of the reads
+            n += __popc(keep);
+            __syncwarp();
+          }
+        }
+      }
+      // rank = number of kept hits with a smaller index (indices are distinct)
+      for (int e = lane; e < n; e += 32) {
         const int v = buf[e];
         int rank = 0;
-        for (int j = 0; j < cnt; ++j) rank += buf[j] < v;
+        for (int j = 0; j < n; ++j) rank += buf[j] < v;
         if (rank < ns) row[rank] = v;
       }
       __syncwarp();
@@ -132,31 +202,12 @@ __device__ __forceinline__ int ball_grid_query_warp(const BallGridView& g, int N
     }
     if (pass == 1) return -1;
     // more hits than the buffer holds: smallest index bound with >= ns hits below it
-    const int h0 = hist[2 * lane], h1 = hist[2 * lane + 1];
-    int incl = h0 + h1;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if ((int)lane >= o) incl += t;
-    }
-    const int excl = incl - h0 - h1;
-    int cand = kGridHist;  // first bucket whose inclusive prefix reaches ns
     int below = 0;
-    if (excl + h0 >= ns && excl < ns) {
-      cand = 2 * lane;
-      below = excl + h0;
-    } else if (incl >= ns && excl + h0 < ns) {
-      cand = 2 * lane + 1;
-      below = incl;
-    }
-    const unsigned who = __ballot_sync(0xffffffffu, cand < kGridHist);
-    if (!who) return -1;  // cannot happen: cnt > cap >= ns
-    const int src = __ffs(who) - 1;
-    cand = __shfl_sync(0xffffffffu, cand, src);
-    below = __shfl_sync(0xffffffffu, below, src);
-    if (below > kGridCap) return -1;
-    bound = (cand + 1) << shift;
+    const int lim = hist_bound(hist, ns, shift, lane, &below);
+    if (lim <= 0 || below > kGridCap) return -1;
+    bound = lim;
     __syncwarp();
+    continue;
   }
   return -1;
 }
