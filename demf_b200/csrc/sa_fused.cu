@@ -52,7 +52,8 @@ constexpr int kMaxLanes = 4;
 __device__ int g_sa_error = 0;  // sticky: first protocol time-out (never expected)
 long long* g_sa_prof = nullptr;
 int g_sa_max_lanes = kMaxLanes;  // tuning knobs (demf_sa_fused_tune)
-int g_sa_sleep_ns = 0;  // host copy of the debug stamp buffer pointer (demf_sa_fused_set_profile)
+int g_sa_sleep_ns = 0;
+int g_sa_pair = 0;       // CTA pairs for streamed weights (demf_sa_fused_tune_pair): correct, not yet faster  // host copy of the debug stamp buffer pointer (demf_sa_fused_set_profile)
 
 struct SaParams {
   const float* xyz;
@@ -73,6 +74,7 @@ struct SaParams {
   int tmem_cols, lane_cols, acc_col[3];
   int sleep_ns;  // back-off between mbarrier polls of the worker warps (0 = spin)
   int t2;        // layer 2 runs transposed (D^T = W3 * act2^T): lanes = channels, columns = rows
+  int pair;      // CTA pairs (cta_group::2): one MMA covers the tiles of two CTAs, each CTA streams half the weights
 };
 
 struct SmemLayout {
@@ -87,7 +89,7 @@ __host__ __device__ inline SmemLayout smem_layout(const SaParams& p) {
   L.bias = L.centres + p.G * 16;
   L.part = L.bias + (p.c[0] + p.c[1] + p.c[2]) * 4;
   L.bars = (L.part + (p.ns == 64 ? p.lanes * 2 * p.c[2] * 4 : 0) + 15) & ~15;
-  L.total = L.bars + (2 * kMaxSlots + 2 * kMaxLanes) * 8 + 16 + 1024;  // + alignment slack
+  L.total = L.bars + (3 * kMaxSlots + 2 * kMaxLanes) * 8 + 16 + 1024;  // + alignment slack
   return L;
 }
 
@@ -242,6 +244,43 @@ __device__ __forceinline__ bool issue_group(const SaParams& p, const IssueCtx& c
   return true;
 }
 
+// CTA-pair version (leader CTA only): every instruction covers the lane-`ln` tiles of BOTH CTAs
+// (M = 256); each CTA's ring slot holds its half of the weight chunk (layers 0/1: half of the output
+// channels = N split; transposed layer 2: its 128 channels = M split, the two activation tiles are
+// the N halves). A slot is ready when the local copy landed (wfull) and the peer forwarded its own
+// (pfull); commits are multicast to the barriers of both CTAs.
+__device__ __forceinline__ bool issue_group_pair(const SaParams& p, const IssueCtx& c, uint32_t pfull0, int ln,
+                                                 int g, uint32_t& slot, uint32_t& wph) {
+  int layer, ch0, nch;
+  group_span(p, c.nch0, g, layer, ch0, nch);
+  const uint32_t idesc = layer == 2 ? instr_desc_tf32(256, 2 * kTileRows) : instr_desc_tf32(256, p.c[layer]);
+  const uint32_t d = c.tmem + ln * p.lane_cols + p.acc_col[layer];
+  const uint32_t a0 = c.act_u32 + ln * p.lane_act_bytes;
+  tc_fence_after_sync();
+  for (int ch = 0; ch < nch; ++ch) {
+    if (!wait_or_fail(c.wfull0 + 8 * slot, wph, c.failed, 2)) return false;
+    if (!wait_or_fail(pfull0 + 8 * slot, wph, c.failed, 7)) return false;
+    tc_fence_after_sync();
+    const int ksteps = layer == 0 ? (min(32, p.K0 - 32 * (ch0 + ch)) >> 3) : 4;
+    const uint64_t da = smem_desc_sw128(a0 + ch * kChunkBytes), dw = smem_desc_sw128(c.ring_u32 + slot * p.slot_bytes);
+    if (layer == 2) {
+      for (int k = 0; k < 4; ++k) mma2_tf32(d, dw + 2 * k, da + 2 * k, idesc, (ch | k) != 0);
+    } else {
+      for (int k = 0; k < ksteps; ++k) mma2_tf32(d, da + 2 * k, dw + 2 * k, idesc, (ch0 | ch | k) != 0);
+    }
+    mma2_commit(c.wempty0 + 8 * slot);
+    if (++slot == (uint32_t)p.slots) {
+      slot = 0;
+      wph ^= 1;
+    }
+  }
+  mma2_commit(c.acc_full0 + 8 * ln);
+  return true;
+}
+
+// kPair: the CTA-pair variant. A kernel that contains cta_group::2 instructions can only be launched
+// with an even cluster size, so the unpaired variant is compiled without them.
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParams p) {
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned chunks: align the carve-up by hand
@@ -255,7 +294,9 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
   const int b = blockIdx.y;
   const int m_base = blockIdx.x * p.G;
   const int cpt = kTileRows / p.ns;  // centres per tile
-  const int ntiles = min(p.tiles, (min(p.G, p.M - m_base) + cpt - 1) / cpt);
+  const uint32_t crank = kPair ? cluster_ctarank() : 0u;  // CTA pairs: both CTAs run the leader's tile count
+  const int m_lead = m_base - (int)crank * p.G;
+  const int ntiles = min(p.tiles, (min(p.G, p.M - m_lead) + cpt - 1) / cpt);
   const int nrounds = (ntiles + p.lanes - 1) / p.lanes;
   const int ngroups = p.npass + 2;
 
@@ -264,10 +305,11 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
   float4* centres = reinterpret_cast<float4*>(smem + L.centres);
   float* bias_s = reinterpret_cast<float*>(smem + L.bias);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSlots + 2 * kMaxLanes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kMaxSlots + 2 * kMaxLanes);
   volatile int* failed = reinterpret_cast<volatile int*>(tmem_slot + 1);
   const uint32_t wfull0 = smem_u32(&bars[0]), wempty0 = smem_u32(&bars[kMaxSlots]);
   const uint32_t op_ready0 = smem_u32(&bars[2 * kMaxSlots]), acc_full0 = smem_u32(&bars[2 * kMaxSlots + kMaxLanes]);
+  const uint32_t pfull0 = smem_u32(&bars[2 * kMaxSlots + 2 * kMaxLanes]);  // CTA pairs: the peer's copy landed
   const uint32_t act_u32 = smem_u32(smem), ring_u32 = smem_u32(ring);
   const int wpl = kWorkerWarps / p.lanes;  // worker warps per lane
 
@@ -276,20 +318,23 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
     for (int s = 0; s < kMaxSlots; ++s) {
       mbar_init(wfull0 + 8 * s, 1);
       mbar_init(wempty0 + 8 * s, 1);
+      mbar_init(pfull0 + 8 * s, 1);
     }
     for (int l = 0; l < kMaxLanes; ++l) {
-      mbar_init(op_ready0 + 8 * l, wpl);
+      mbar_init(op_ready0 + 8 * l, p.pair ? 2 * wpl : wpl);  // pairs: the leader hears both CTAs' lanes
       mbar_init(acc_full0 + 8 * l, 1);
     }
     mbar_fence_init();
   }
   if (warp == 0) {
     __syncwarp();
-    tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+    if constexpr (kPair) tmem_alloc2(smem_u32(tmem_slot), p.tmem_cols);
+    else tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
   }
   for (int i = tid; i < p.c[0] + p.c[1] + p.c[2]; i += kThreads) bias_s[i] = __ldg(p.bias + i);
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();  // the peer's barriers exist before anything arrives on them
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const int nch0 = (p.K0 + 31) >> 5;
@@ -300,15 +345,38 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
     // Streamed weights only: MMA groups are issued in the fixed order the producer warp mirrors.
     // (With resident weights every lane issues its own MMAs, see publish() in the worker code.)
     // The k-th group of a lane waits for the k-th completion of that lane's op_ready barrier.
-    if (lane == 0 && !p.resident) {
+    if (lane == 0 && !p.resident && crank == 0) {
       uint32_t slot = 0, wph = 0;
       bool ok = true;
       for (int r = 0; r < nrounds && ok; ++r) {
         for (int g = 0; g < ngroups && ok; ++g) {
           for (int ln = 0; ln < p.lanes && ok; ++ln) {
             if (r * p.lanes + ln >= ntiles) break;
-            ok = wait_or_fail(op_ready0 + 8 * ln, (uint32_t)(r * ngroups + g) & 1u, failed, 1) &&
-                 issue_group(p, ictx, ln, g, slot, wph);
+            ok = wait_or_fail(op_ready0 + 8 * ln, (uint32_t)(r * ngroups + g) & 1u, failed, 1);
+            if constexpr (kPair) ok = ok && issue_group_pair(p, ictx, pfull0, ln, g, slot, wph);
+            else ok = ok && issue_group(p, ictx, ln, g, slot, wph);
+          }
+        }
+      }
+    } else if (kPair && lane == 0 && crank == 1) {
+      // peer CTA of a pair: tell the leader when each of OUR weight copies has landed
+      uint32_t slot = 0, wph = 0;
+      bool ok = true;
+      for (int r = 0; r < nrounds && ok; ++r) {
+        for (int g = 0; g < ngroups && ok; ++g) {
+          int layer, ch0, nch;
+          group_span(p, nch0, g, layer, ch0, nch);
+          for (int ln = 0; ln < p.lanes && ok; ++ln) {
+            if (r * p.lanes + ln >= ntiles) break;
+            for (int ch = 0; ch < nch; ++ch) {
+              ok = wait_or_fail(wfull0 + 8 * slot, wph, failed, 8);
+              if (!ok) break;
+              mbar_arrive_remote(map_to_rank(pfull0 + 8 * slot, 0));
+              if (++slot == (uint32_t)p.slots) {
+                slot = 0;
+                wph ^= 1;
+              }
+            }
           }
         }
       }
@@ -336,6 +404,9 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
             int layer, ch0, nch;
             group_span(p, nch0, g, layer, ch0, nch);
             const uint32_t bytes = p.c[layer] * 128;
+            // CTA pairs: this CTA's half of every chunk (half of the rows = output channels)
+            const uint32_t ld_bytes = p.pair ? bytes >> 1 : bytes;
+            const uint32_t ld_off = p.pair ? crank * (ld_bytes >> 2) : 0u;
             // chunk offsets in wpack: layer 0 at 0, layer 1 after nch0 chunks of c0 rows, ...
             const float* base = p.wpack;
             if (layer >= 1) base += (size_t)nch0 * p.c[0] * 32;
@@ -345,9 +416,9 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
               for (int ch = 0; ch < nch; ++ch) {
                 ok = wait_or_fail(wempty0 + 8 * slot, ph ^ 1, failed, 3);
                 if (!ok) break;
-                mbar_expect_tx(wfull0 + 8 * slot, bytes);
-                bulk_g2s(ring_u32 + slot * p.slot_bytes, base + (size_t)(ch0 + ch) * (bytes >> 2), bytes,
-                         wfull0 + 8 * slot);
+                mbar_expect_tx(wfull0 + 8 * slot, ld_bytes);
+                bulk_g2s(ring_u32 + slot * p.slot_bytes, base + (size_t)(ch0 + ch) * (bytes >> 2) + ld_off,
+                         ld_bytes, wfull0 + 8 * slot);
                 if (++slot == (uint32_t)p.slots) {
                   slot = 0;
                   ph ^= 1;
@@ -485,7 +556,10 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
         }
       } else {
         __syncwarp();
-        if (lane == 0) mbar_arrive(op_ready);
+        if (lane == 0) {
+          if (!kPair || crank == 0) mbar_arrive(op_ready);
+          else mbar_arrive_remote(map_to_rank(op_ready, 0));  // the leader CTA issues for both
+        }
       }
     };
 
@@ -620,7 +694,10 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
         const int nunits = (c3 >> 7) * (4 / upb);
         for (int uidx = cg; uidx < nunits; uidx += ncg) {
           const int h = uidx / (4 / upb), blk0 = (uidx - h * (4 / upb)) * upb;
-          const int ch = h * 128 + q * 32 + (int)lane;
+          // CTA pairs: this CTA's TMEM holds ITS 128 channels for the tile rows of both CTAs
+          // (columns [0,128) = the leader's tile, [128,256) = the peer's)
+          const int ch = (p.pair ? (int)crank : h) * 128 + q * 32 + (int)lane;
+          const int mt = p.pair ? m_lead + h * p.G + t * cpt : m_tile;
           const float bias_c = b2[ch];
           uint32_t u[32];
           tmem_ld32(tmem + lane_base + p.acc_col[2] + h * 128 + blk0 * 32, u);
@@ -632,7 +709,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
             m1 = fmaxf(m1, __uint_as_float(u[16 + i]));
           }
           if (ns == 16) {
-            const int m = m_tile + blk0 * 2;
+            const int m = mt + blk0 * 2;
             if (m < p.M) p.out[((long)b * p.M + m) * c3 + ch] = fmaxf(m0 + bias_c, 0.f);
             if (m + 1 < p.M) p.out[((long)b * p.M + m + 1) * c3 + ch] = fmaxf(m1 + bias_c, 0.f);
           } else {
@@ -643,7 +720,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
 #pragma unroll
               for (int i = 0; i < 32; ++i) m0 = fmaxf(m0, __uint_as_float(u[i]));
             }
-            const int m = m_tile + blk0 / upb;
+            const int m = mt + blk0 / upb;
             if (m < p.M) p.out[((long)b * p.M + m) * c3 + ch] = fmaxf(m0 + bias_c, 0.f);
           }
         }
@@ -709,10 +786,12 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
 
   // ---- teardown
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();  // the peer may still be reading this CTA's operands / TMEM pair
+  else __syncthreads();
   if (warp == 0) {
     __syncwarp();
-    tmem_free(tmem, p.tmem_cols);
+    if constexpr (kPair) tmem_free2(tmem, p.tmem_cols);
+    else tmem_free(tmem, p.tmem_cols);
   }
   trace_end(2, trace_t0);
 }
@@ -766,9 +845,18 @@ bool configure(SaParams& p, int B) {
       p.G = max_tiles * cpt;
       // resident weights if they fit, else the deepest ring (>= 2 slots) that does
       p.resident = 1;
+      p.pair = 0;
       p.slots = total_chunks;
+      p.slot_bytes = cmax * 128;
       if (total_chunks > kMaxSlots || smem_layout(p).total > budget) {
         p.resident = 0;
+        // streamed weights: CTA pairs when the shapes allow (each CTA then streams half of every
+        // chunk -- 16 KB ring entries -- for twice the rows per byte that crosses L2 -> SM)
+        p.pair = (g_sa_pair && c3 == 256 && c1 % 16 == 0 && c2 % 16 == 0 && c1 <= 256 && c2 <= 256) ? 1 : 0;
+        if (p.pair) {
+          const int h1 = c1 / 2, h2 = c2 / 2;
+          p.slot_bytes = (h1 > h2 ? (h1 > 128 ? h1 : 128) : (h2 > 128 ? h2 : 128)) * 128;
+        }
         p.slots = 0;
         for (int sl = kMaxSlots; sl >= 2; --sl) {
           p.slots = sl;
@@ -837,6 +925,11 @@ int demf_sa_fused_set_profile(long long* device_buffer) {
 
 /* tuning knobs (development): most tile pipelines per CTA (1, 2 or 4) and the worker warps'
  * back-off between mbarrier polls in ns (0 = spin) */
+int demf_sa_fused_tune_pair(int enable) {
+  g_sa_pair = enable ? 1 : 0;
+  return 0;
+}
+
 int demf_sa_fused_tune(int max_lanes, int sleep_ns) {
   g_sa_max_lanes = max_lanes < 1 ? 1 : max_lanes;
   g_sa_sleep_ns = sleep_ns < 0 ? 0 : sleep_ns;
@@ -904,19 +997,41 @@ int demf_sa_fused_fwd(const float* xyz, const float* feat_rows, const float* new
   DEMF_REQUIRE(configure(p, B), DEMF_E_UNSUPPORTED);
   const SmemLayout L = smem_layout(p);
 
-  static int configured_smem = 0;
-  if (L.total > configured_smem) {
-    cudaError_t e = cudaFuncSetAttribute(sa_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L.total);
+  auto kernel = p.pair ? sa_fused_fwd_kernel<true> : sa_fused_fwd_kernel<false>;
+  static int configured_smem[2] = {0, 0};
+  if (L.total > configured_smem[p.pair]) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
     if (e != cudaSuccess) {
       set_error("demf_sa_fused_fwd: cannot reserve %d bytes of shared memory: %s", L.total,
                 cudaGetErrorString(e));
       return static_cast<int>(e);
     }
-    configured_smem = L.total;
+    configured_smem[p.pair] = L.total;
   }
   dim3 grid_dim((M + p.G - 1) / p.G, B);
-  sa_fused_fwd_kernel<<<grid_dim, kThreads, L.total, as_stream(stream)>>>(p);
+  // CTA pairs: clusters of two CTAs along x (an odd tail gets a CTA without centres: it still feeds
+  // its pair). The kernel contains cluster instructions, so it is always launched with an explicit
+  // cluster dimension (1 when unpaired).
+  if (p.pair) grid_dim.x = (grid_dim.x + 1) & ~1u;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid_dim;
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = L.total;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.pair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
+  if (e != cudaSuccess) {
+    set_error("demf_sa_fused_fwd: launch failed: %s (grid %u x %u, cluster %d, %d B smem, lanes %d, slots %d, resident %d)",
+              cudaGetErrorString(e), grid_dim.x, grid_dim.y, p.pair ? 2 : 1, L.total, p.lanes, p.slots, p.resident);
+    (void)cudaGetLastError();
+    return static_cast<int>(e);
+  }
   return after_launch("sa_fused_fwd_kernel");
 }
 

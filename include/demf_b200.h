@@ -205,6 +205,7 @@ int demf_sa_fused_set_profile(long long* device_buffer);
 /* development knobs: most tile pipelines ("lanes") per CTA (1, 2 or 4; default 4) and the worker
  * warps' back-off between mbarrier polls in ns (default 0 = spin). */
 int demf_sa_fused_tune(int max_lanes, int sleep_ns);
+int demf_sa_fused_tune_pair(int enable); /* CTA pairs (cta_group::2) for streamed weights; default off */
 
 /* ----------------------------------------------------- fused glue (inference) --- */
 /* Each replaces a chain of tiny library launches in the upstream Python modules:

@@ -542,3 +542,35 @@ def test_decode_boxes_matches_coder(dev):
     torch.testing.assert_close(obj[:, Q:], want_obj, atol=1e-6, rtol=1e-5)
     torch.testing.assert_close(sem[:, Q:], want_sem, atol=1e-6, rtol=1e-5)
     assert box[:, :Q].abs().sum() == 0 and (box[..., 6] >= 0).all() and (box[..., 6] < 2 * np.pi + 1e-6).all()
+
+
+@pytest.mark.parametrize("B,N,M,C,ns,radius,widths", [
+    (2, 2048, 1024, 128, 32, 0.4, (128, 128, 256)),   # SA2
+    (2, 1024, 512, 256, 16, 0.8, (128, 128, 256)),    # SA3
+    (2, 1024, 250, 256, 16, 0.3, (256, 256, 256)),    # vote aggregation, ragged: a pair with a centre-less CTA
+    (1, 512, 100, 256, 16, 1.2, (128, 128, 256)),     # odd number of CTAs along x
+])
+def test_sa_fused_cta_pairs_match_oracle(dev, B, N, M, C, ns, radius, widths):
+    """The cta_group::2 variant (two CTAs per MMA, each streaming half of every weight chunk;
+    off by default, demf_sa_fused_tune_pair) gives the same rows and features."""
+    sa_module, xyz, centres, feats, weights, biases = _sa_case(B, N, M, C, ns, radius, widths, seed=N + M + 1)
+    from demf_b200.mm.bricks import permute_weight_columns
+    w0 = permute_weight_columns(weights[0].to(dev), ops.group_rows_columns(C))
+    wpack, bias, wd = ops.sa_pack_mlp([w0, weights[1].to(dev), weights[2].to(dev)], [b.to(dev) for b in biases])
+    rows = feats.transpose(1, 2).contiguous().to(dev)
+    lib = _lib.load()
+    single, idx1 = ops.sa_fused(xyz.to(dev), centres.to(dev), rows, 0.0, radius, ns, True, wpack, bias, wd,
+                                return_idx=True)
+    try:
+        lib.demf_sa_fused_tune_pair(1)
+        paired, idx2 = ops.sa_fused(xyz.to(dev), centres.to(dev), rows, 0.0, radius, ns, True, wpack, bias, wd,
+                                    return_idx=True)
+        torch.cuda.synchronize()
+    finally:
+        lib.demf_sa_fused_tune_pair(0)
+    assert lib.demf_sa_fused_error() == 0
+    ref_idx, ref = sa_module.sa_forward(xyz, centres, feats, 0.0, radius, ns, True, weights, biases, tf32=True)
+    assert torch.equal(idx2.cpu(), ref_idx) and torch.equal(idx1, idx2)
+    scale = ref.abs().max().item()
+    assert (paired.cpu().transpose(1, 2) - ref).abs().max().item() <= 1e-3 * scale
+    assert (paired - single).abs().max().item() <= 1e-4 * scale    # same operands, other summation order

@@ -56,11 +56,13 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--sa-lanes", type=int, default=4)
     ap.add_argument("--sa-sleep", type=int, default=0)
+    ap.add_argument("--sa-pair", type=int, default=0)
     args = ap.parse_args()
     only = set(filter(None, args.only.split(",")))
     want = lambda k: not only or k in only  # noqa: E731
     dev = torch.device("cuda:0")
     _lib.load().demf_sa_fused_tune(args.sa_lanes, args.sa_sleep)
+    _lib.load().demf_sa_fused_tune_pair(args.sa_pair)
     B, flush = args.B, not args.hot
     print(json.dumps(dict(device=torch.cuda.get_device_name(0), B=B, flush_l2=flush)), flush=True)
 
