@@ -3,6 +3,10 @@
 # The frozen image branch (img_backbone / img_neck / img_encoder, inherited upstream from
 # configs/deformdetr/imvotenet_image.py) is outside this repository's scope: BASELINE.json feeds
 # synthetic 4-level pyramids in its place, so only its type names are kept for reference.
+# The encoder itself (demf/modeling/layers/deform_detr_encoder.py) IS implemented: `img_encoder_cfg`
+# below restates configs/demf/demf_votenet.py:28-47; put it in `model.img_encoder` (or call
+# demf_b200.engine.build_demf_votenet(img_encoder=True)) and the pyramids handed to the detector are
+# treated as the neck's output and run through it.
 # `num_points` of the deformable cross attention is 2 in the reference file (line 83); the
 # BASELINE.json configs quote 4 (the mmcv default) -- override with
 # Config.merge_from_dict({'model.pts_bbox_head.decoder.transformerlayers.attn_cfgs.1.num_points': 4})
@@ -23,11 +27,26 @@ _mean_sizes = [[2.114256, 1.620300, 0.927272], [0.791118, 1.279516, 0.718182],
                [0.528526, 1.002642, 1.172878], [0.500618, 0.632163, 0.683424],
                [0.404671, 1.071108, 1.688889], [0.76584, 1.398258, 0.472728]]
 
+img_encoder_cfg = dict(
+    type='DeformableDetrEncoder',
+    encoder=dict(
+        type='DetrTransformerEncoder',
+        num_layers=6,
+        transformerlayers=dict(
+            type='BaseTransformerLayer',
+            attn_cfgs=dict(type='MultiScaleDeformableAttention', embed_dims=256),
+            feedforward_channels=1024,
+            ffn_dropout=0.1,
+            operation_order=('self_attn', 'norm', 'ffn', 'norm'))),
+    positional_encoding=dict(type='SinePositionalEncoding', num_feats=128, normalize=True, offset=-0.5),
+    num_feature_levels=4,
+    embed_dims=256)
+
 model = dict(
     type='DeMFVoteNet',
     img_backbone=dict(type='ResNet'),                 # frozen, not built here
     img_neck=dict(type='ChannelMapper'),              # frozen, not built here
-    img_encoder=dict(type='DeformableDetrEncoder'),   # frozen, not built here
+    img_encoder=dict(type='DeformableDetrEncoder'),   # name only; see img_encoder_cfg
     pts_backbone=dict(
         type='PointNet2SASSG',
         in_channels=4,

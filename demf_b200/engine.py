@@ -22,12 +22,15 @@ from .mm.registry import build_model
 CONFIG = os.path.join(os.path.dirname(os.path.abspath(__file__)), "configs", "demf_votenet.py")
 
 
-def build_demf_votenet(num_points=4, cfg_options=None, init=True):
+def build_demf_votenet(num_points=4, cfg_options=None, init=True, img_encoder=False):
     """DeMFVoteNet from demf_b200/configs/demf_votenet.py. `num_points` = sampling points per
     level and head of the deformable cross attention (2 in the reference config, 4 in
-    BASELINE.json's configs)."""
+    BASELINE.json's configs). `img_encoder=True` also builds the frozen Deformable-DETR encoder of
+    the image branch; the pyramids given to the model are then the neck's output."""
     cfg = Config.fromfile(CONFIG)
     model_cfg = cfg.model.to_dict()
+    if img_encoder:
+        model_cfg["img_encoder"] = cfg.img_encoder_cfg.to_dict()
     model_cfg["pts_bbox_head"]["decoder"]["transformerlayers"]["attn_cfgs"][1]["num_points"] = num_points
     if cfg_options:
         c = Config(dict(model=model_cfg))

@@ -8,13 +8,15 @@ mmdet's DetrTransformerDecoderLayer. Dense projections are plain library GEMMs (
 torch); the sm_100a kernels live behind point_ops.py and ms_deform_attn.py.
 """
 import copy
+import math
 import warnings
 
 import torch
 import torch.nn as nn
 
 from .config import ConfigDict
-from .registry import (ATTENTION, FEEDFORWARD_NETWORK, TRANSFORMER_LAYER, build_attention,
+from .registry import (ATTENTION, FEEDFORWARD_NETWORK, POSITIONAL_ENCODING, TRANSFORMER_LAYER,
+                       TRANSFORMER_LAYER_SEQUENCE, build_transformer_layer, build_attention,
                        build_feedforward_network)
 
 
@@ -337,6 +339,95 @@ class DetrTransformerDecoderLayer(BaseTransformerLayer):
                          norm_cfg=norm_cfg, ffn_num_fcs=ffn_num_fcs, **kwargs)
         assert len(operation_order) == 6
         assert set(operation_order) == {"self_attn", "norm", "cross_attn", "ffn"}
+
+
+@TRANSFORMER_LAYER_SEQUENCE.register_module()
+class TransformerLayerSequence(BaseModule):
+    """mmcv TransformerLayerSequence: `num_layers` layers built from one config (or a list of
+    configs), applied in order with the same keyword arguments."""
+
+    def __init__(self, transformerlayers=None, num_layers=None, init_cfg=None):
+        super().__init__(init_cfg)
+        if isinstance(transformerlayers, dict):
+            transformerlayers = [copy.deepcopy(transformerlayers) for _ in range(num_layers)]
+        else:
+            assert isinstance(transformerlayers, list) and len(transformerlayers) == num_layers
+        self.num_layers = num_layers
+        self.layers = ModuleList()
+        for i in range(num_layers):
+            self.layers.append(build_transformer_layer(transformerlayers[i]))
+        self.embed_dims = self.layers[0].embed_dims
+        self.pre_norm = self.layers[0].pre_norm
+
+    def forward(self, query, key, value, query_pos=None, key_pos=None, attn_masks=None,
+                query_key_padding_mask=None, key_padding_mask=None, **kwargs):
+        for layer in self.layers:
+            query = layer(query, key, value, query_pos=query_pos, key_pos=key_pos,
+                          attn_masks=attn_masks, query_key_padding_mask=query_key_padding_mask,
+                          key_padding_mask=key_padding_mask, **kwargs)
+        return query
+
+
+@TRANSFORMER_LAYER_SEQUENCE.register_module()
+class DetrTransformerEncoder(TransformerLayerSequence):
+    """mmdet DetrTransformerEncoder: the layer sequence plus a final LayerNorm that exists only
+    for pre-norm layers (the reference's post-norm encoder has none)."""
+
+    def __init__(self, *args, post_norm_cfg=dict(type="LN"), **kwargs):
+        super().__init__(*args, **kwargs)
+        if post_norm_cfg is not None:
+            self.post_norm = build_norm_layer(post_norm_cfg, self.embed_dims)[1] \
+                if self.pre_norm else None
+        else:
+            assert not self.pre_norm, f"Use prenorm in {self.__class__.__name__}, Please specify post_norm_cfg"
+            self.post_norm = None
+
+    def forward(self, *args, **kwargs):
+        x = super().forward(*args, **kwargs)
+        if self.post_norm is not None:
+            x = self.post_norm(x)
+        return x
+
+
+@POSITIONAL_ENCODING.register_module()
+class SinePositionalEncoding(BaseModule):
+    """mmdet SinePositionalEncoding: mask (B,H,W), nonzero = padding -> (B, 2*num_feats, H, W);
+    first half encodes the row coordinate, second half the column coordinate, each coordinate the
+    running count of valid pixels, optionally normalised to [0, scale]."""
+
+    def __init__(self, num_feats, temperature=10000, normalize=False, scale=2 * math.pi, eps=1e-6,
+                 offset=0., init_cfg=None):
+        super().__init__(init_cfg)
+        if normalize:
+            assert isinstance(scale, (float, int)), \
+                f"when normalize is set, scale should be provided and in float or int type, found {type(scale)}"
+        self.num_feats = num_feats
+        self.temperature = temperature
+        self.normalize = normalize
+        self.scale = scale
+        self.eps = eps
+        self.offset = offset
+
+    def forward(self, mask):
+        mask = mask.to(torch.int)
+        not_mask = 1 - mask
+        y_embed = not_mask.cumsum(1, dtype=torch.float32)
+        x_embed = not_mask.cumsum(2, dtype=torch.float32)
+        if self.normalize:
+            y_embed = (y_embed + self.offset) / (y_embed[:, -1:, :] + self.eps) * self.scale
+            x_embed = (x_embed + self.offset) / (x_embed[:, :, -1:] + self.eps) * self.scale
+        dim_t = torch.arange(self.num_feats, dtype=torch.float32, device=mask.device)
+        dim_t = self.temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / self.num_feats)
+        pos_x = x_embed[:, :, :, None] / dim_t
+        pos_y = y_embed[:, :, :, None] / dim_t
+        B, H, W = mask.size()
+        pos_x = torch.stack((pos_x[:, :, :, 0::2].sin(), pos_x[:, :, :, 1::2].cos()), dim=4).view(B, H, W, -1)
+        pos_y = torch.stack((pos_y[:, :, :, 0::2].sin(), pos_y[:, :, :, 1::2].cos()), dim=4).view(B, H, W, -1)
+        return torch.cat((pos_y, pos_x), dim=3).permute(0, 3, 1, 2)
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}(num_feats={self.num_feats}, temperature={self.temperature}, "
+                f"normalize={self.normalize}, scale={self.scale}, eps={self.eps})")
 
 
 def to_config_dict(cfg):

@@ -41,7 +41,9 @@ class DeMFVoteNet(BaseModule):
             self.img_backbone = build_backbone(img_backbone)
         if _registered(img_neck, NECKS):
             self.img_neck = build_neck(img_neck)
-        if _registered(img_encoder, HEADS):
+        # the shipped config keeps `img_encoder=dict(type='DeformableDetrEncoder')` as a name-only
+        # placeholder (BASELINE.json's pyramids are post-encoder); a full config builds it
+        if _registered(img_encoder, HEADS) and img_encoder.get('encoder') is not None:
             self.img_encoder = build_head(img_encoder)
         self.freeze_img_branch = freeze_img_branch
         if freeze_img_branch:
@@ -112,7 +114,9 @@ class DeMFVoteNet(BaseModule):
         """img: (B,3,H,W) image batch when an image branch is built, else the list of pyramid
         levels itself."""
         if isinstance(img, (list, tuple)) and not self.with_img_backbone:
-            return list(img)
+            # a pyramid handed in directly is the neck's output when the encoder is built
+            # (demfnet.py:118-125 runs backbone -> neck -> encoder), else the encoder's output
+            return self.img_encoder(list(img), img_metas) if self.with_img_encoder else list(img)
         x = self.img_backbone(img)
         if self.with_img_neck:
             x = self.img_neck(x)

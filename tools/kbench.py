@@ -1,6 +1,6 @@
 """Per-kernel timings of libdemf_b200.so at the DeMF geometries (development tool, GPU only).
 
-    python tools/kbench.py [--B 8] [--reps 30] [--only msda,fps,...]
+    python tools/kbench.py [--B 8] [--reps 30] [--only msda,msda_self,encoder,fps,...]
 
 CUDA events on the launching stream; an L2 flush (write of a 256 MB buffer) precedes every
 timed launch unless --hot. Prints one JSON line per kernel/config: median and min ms plus the
@@ -88,6 +88,56 @@ def main():
                 med, mn = timeit(bwd, args.reps, flush)
                 report("msda_bwd", dict(pyramid=name, P=P, B=Bm), med, mn, 2 * nbytes)
                 del v, gv
+
+    if want("msda_self"):
+        # encoder regime (demf/modeling/layers/deform_detr_encoder.py): every pixel of the pyramid is a
+        # query (Q = S) sampling around its own position. Compulsory HBM bytes = value + locations +
+        # weights read once, output written once; `sample_MB` is what the gathers request from L1/L2.
+        for name in ("S512", "REAL", "XL"):
+            Bm = B if name != "XL" else 1
+            shapes = synth.PYRAMIDS[name]
+            S, H, D, L, P = synth.pyramid_tokens(name), 8, 32, 4, 4
+            g = torch.Generator().manual_seed(5)
+            v = torch.randn(Bm, S, H, D, generator=g).to(dev)
+            ref = torch.cat([torch.stack(torch.meshgrid(
+                (torch.arange(w) + 0.5) / w, (torch.arange(h) + 0.5) / h, indexing="xy"), -1).reshape(-1, 2)
+                for h, w in shapes], 0)
+            loc = (ref[None, :, None, None, None, :] + 0.03 * torch.randn(Bm, S, H, L, P, 2, generator=g)).to(dev)
+            at = torch.softmax(torch.randn(Bm, S, H, L * P, generator=g), -1).view(Bm, S, H, L, P).to(dev)
+            sh = torch.tensor(shapes, dtype=torch.int64, device=dev)
+            lsi = torch.cat([sh.new_zeros(1), sh.prod(1).cumsum(0)[:-1]])
+            nbytes = v.numel() * 4 * 2 + loc.numel() * 4 + at.numel() * 4
+            med, mn = timeit(lambda: MSDA.apply(v, sh, lsi, loc, at, 64), args.reps, flush)
+            report("msda_self_fwd", dict(pyramid=name, B=Bm, Q=S, sample_MB=round(
+                Bm * S * H * L * P * 4 * D * 4 / 1e6, 1)), med, mn, nbytes)
+            del v, loc, at
+
+    if want("encoder"):
+        from demf_b200 import engine
+        from demf_b200.mm.config import Config
+        from demf_b200.mm.registry import build_head
+        torch.manual_seed(0)
+        enc = build_head(Config.fromfile(engine.CONFIG).img_encoder_cfg.to_dict())
+        enc.init_weights()
+        enc = enc.to(dev).eval()
+        for name in ("S512", "REAL"):
+            feats = [f.to(dev) for f in synth.make_pyramid(B, name)]
+            metas = synth.make_img_metas(B, name)
+            with torch.no_grad():
+                med, mn = timeit(lambda: enc(feats, metas), max(5, args.reps // 3), False)
+                report("img_encoder_eager", dict(pyramid=name, B=B, S=synth.pyramid_tokens(name)), med, mn)
+                side = torch.cuda.Stream()
+                with torch.cuda.stream(side):
+                    for _ in range(3):
+                        enc(feats, metas)
+                side.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out = enc(feats, metas)  # noqa: F841
+                med, mn = timeit(graph.replay, max(5, args.reps // 3), False)
+                report("img_encoder_graph", dict(pyramid=name, B=B, S=synth.pyramid_tokens(name),
+                                                 images_per_s=round(B / med * 1e3, 1)), med, mn)
+            del graph, out
 
     pts = synth.make_points(B, 20000, seed=0, clustered=True)[..., :3].contiguous().to(dev)
     geoms = [(20000, 2048, 0.2, 64, 1), (2048, 1024, 0.4, 32, 128), (1024, 512, 0.8, 16, 256),
