@@ -95,12 +95,21 @@ __device__ __forceinline__ float bil(float w1, float v1, float w2, float v2, flo
 
 // ------------------------------------------------------------------ forward, fast path --
 // kLanes = D/4 lanes per (b,q,h) tuple; 32/kLanes tuples per warp.
-template <int kLanes>
+//
+// kProj = true is the same kernel fed by the attention module's raw projections instead of finished
+// locations and weights (what mmcv computes with five elementwise launches between the Linear
+// layers and the sampling kernel, multi_scale_deform_attn.py:322-349): `loc` then points at rows
+// (B*Q, H*L*P*3) = [offsets (H,L,P,2) | logits (H,L,P)] and `ref` at reference points (B,Q,L,refdim);
+// phase 1 forms  loc = ref + off / (W_l, H_l)   (refdim 2)  or  ref.xy + off / P * ref.wh * 0.5
+// (refdim 4) with the same IEEE operations in the same order as the torch expressions, and the
+// softmax over the L*P logits of a tuple with torch's own reduction shape (xor butterfly over
+// L*P lanes: max, exp(x - max), sum, divide), so the result equals the unfused composition.
+template <int kLanes, bool kProj>
 __global__ void __launch_bounds__(kThreads) msda_fwd_kernel(
     const float* __restrict__ value, const int64_t* __restrict__ shapes,
     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
-    const float* __restrict__ attn, int S, int H, int Q, int L, int P, long tuples,
-    float* __restrict__ out) {
+    const float* __restrict__ attn, const float* __restrict__ ref, int refdim, int S, int H, int Q,
+    int L, int P, long tuples, float* __restrict__ out) {
   constexpr int D = kLanes * 4;
   constexpr int kTuplesPerWarp = 32 / kLanes;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -124,19 +133,63 @@ __global__ void __launch_bounds__(kThreads) msda_fwd_kernel(
 
   // ---- phase 1: one lane per sample
   const int nrec = ntup * LP;
-  for (int r = lane; r < nrec; r += 32) {
-    const int t = r / LP;
-    const int j = r - t * LP;
-    const int l = j / P;
-    const long tuple = tuple0 + t;
-    const int head = (int)(tuple % H);
-    const long s = tuple * LP + j;
-    const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + s);
-    const float a = __ldg(attn + s);
-    const Bilinear bl = setup_sample(xy.x, xy.y, lv.h[l], lv.w[l], lv.start[l], H, D, head);
-    s_off[r] = make_int4(bl.off[0], bl.off[1], bl.off[2], bl.off[3]);
-    s_w[r] = make_float4(bl.w[0], bl.w[1], bl.w[2], bl.w[3]);
-    s_a[r] = a;
+  if constexpr (!kProj) {
+    for (int r = lane; r < nrec; r += 32) {
+      const int t = r / LP;
+      const int j = r - t * LP;
+      const int l = j / P;
+      const long tuple = tuple0 + t;
+      const int head = (int)(tuple % H);
+      const long s = tuple * LP + j;
+      const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + s);
+      const float a = __ldg(attn + s);
+      const Bilinear bl = setup_sample(xy.x, xy.y, lv.h[l], lv.w[l], lv.start[l], H, D, head);
+      s_off[r] = make_int4(bl.off[0], bl.off[1], bl.off[2], bl.off[3]);
+      s_w[r] = make_float4(bl.w[0], bl.w[1], bl.w[2], bl.w[3]);
+      s_a[r] = a;
+    }
+  } else {
+    const int HLP = H * LP;
+    const float inv_p = 1.f / (float)P;
+    // LP is a power of two <= 32 here (host check): the LP samples of a tuple sit in LP adjacent lanes
+    for (int r0 = 0; r0 < nrec; r0 += 32) {
+      const int r = r0 + lane;
+      const bool active = r < nrec;
+      float logit = -INFINITY;
+      float lx = 0.f, ly = 0.f;
+      int l = 0, head = 0;
+      if (active) {
+        const int t = r / LP;
+        const int j = r - t * LP;
+        l = j / P;
+        const long tuple = tuple0 + t;
+        head = (int)(tuple % H);
+        const long row = tuple / H;  // b*Q + q
+        const float* pr = loc + row * (long)HLP * 3;
+        const float ox = __ldg(pr + ((long)head * LP + j) * 2);
+        const float oy = __ldg(pr + ((long)head * LP + j) * 2 + 1);
+        logit = __ldg(pr + (long)HLP * 2 + head * LP + j);
+        const float* rp = ref + (row * L + l) * refdim;
+        if (refdim == 2) {
+          lx = __fadd_rn(__ldg(rp), __fdiv_rn(ox, (float)lv.w[l]));
+          ly = __fadd_rn(__ldg(rp + 1), __fdiv_rn(oy, (float)lv.h[l]));
+        } else {
+          lx = __fadd_rn(__ldg(rp), __fmul_rn(__fmul_rn(__fmul_rn(ox, inv_p), __ldg(rp + 2)), 0.5f));
+          ly = __fadd_rn(__ldg(rp + 1), __fmul_rn(__fmul_rn(__fmul_rn(oy, inv_p), __ldg(rp + 3)), 0.5f));
+        }
+      }
+      float mx = logit;
+      for (int o = LP >> 1; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float e = active ? expf(logit - mx) : 0.f;
+      float sum = e;
+      for (int o = LP >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (active) {
+        const Bilinear bl = setup_sample(lx, ly, lv.h[l], lv.w[l], lv.start[l], H, D, head);
+        s_off[r] = make_int4(bl.off[0], bl.off[1], bl.off[2], bl.off[3]);
+        s_w[r] = make_float4(bl.w[0], bl.w[1], bl.w[2], bl.w[3]);
+        s_a[r] = __fdiv_rn(e, sum);
+      }
+    }
   }
   __syncwarp();
 
@@ -381,21 +434,21 @@ inline bool fast_path_lanes(int D, int* lanes) {
   return true;
 }
 
-template <int kLanes>
+template <int kLanes, bool kProj = false>
 int launch_fwd(const float* value, const int64_t* shapes, const int64_t* lsi, const float* loc,
                const float* attn, int S, int H, int Q, int L, int P, long tuples, float* out,
-               cudaStream_t st) {
+               cudaStream_t st, const float* ref = nullptr, int refdim = 0) {
   constexpr int tpw = 32 / kLanes;
   const size_t smem = (size_t)kWarps * tpw * L * P * 36;
-  auto k = msda_fwd_kernel<kLanes>;
+  auto k = msda_fwd_kernel<kLanes, kProj>;
   if (smem > 48 * 1024) {
     if (smem > 200 * 1024) return -1;  // caller falls back to the scalar path
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
   const long blocks = (tuples + (long)kWarps * tpw - 1) / ((long)kWarps * tpw);
-  k<<<(unsigned)blocks, kThreads, smem, st>>>(value, shapes, lsi, loc, attn, S, H, Q, L, P, tuples,
-                                             out);
-  return after_launch("msda_fwd_kernel");
+  k<<<(unsigned)blocks, kThreads, smem, st>>>(value, shapes, lsi, loc, attn, ref, refdim, S, H, Q, L, P,
+                                             tuples, out);
+  return after_launch(kProj ? "msda_fwd_kernel<proj>" : "msda_fwd_kernel");
 }
 
 template <int kLanes>
@@ -453,6 +506,56 @@ int demf_msda_fwd(const float* value, const int64_t* spatial_shapes,
       value, spatial_shapes, level_start_index, sampling_loc, attn_weight, S, H, D, Q, L, P, total,
       out);
   return after_launch("msda_fwd_generic_kernel");
+}
+
+int demf_msda_proj_fwd_supported(int D, int L, int P) {
+  int lanes = 0;
+  const long lp = (long)L * P;
+  // one tuple's L*P samples must fill whole shuffle groups and a warp's records whole passes
+  return fast_path_lanes(D, &lanes) && lp >= 1 && lp <= 32 && (lp & (lp - 1)) == 0 &&
+         ((32 / lanes) * lp) % 32 == 0 && L <= kMaxLevels;
+}
+
+int demf_msda_proj_fwd(const float* value, const int64_t* spatial_shapes,
+                       const int64_t* level_start_index, const float* proj, const float* ref_points,
+                       int ref_dim, int B, int S, int H, int D, int Q, int L, int P, float* out,
+                       void* stream) {
+  DEMF_REQUIRE_PTR(value);
+  DEMF_REQUIRE_PTR(spatial_shapes);
+  DEMF_REQUIRE_PTR(level_start_index);
+  DEMF_REQUIRE_PTR(proj);
+  DEMF_REQUIRE_PTR(ref_points);
+  DEMF_REQUIRE_PTR(out);
+  if (int rc = check_dims(B, S, H, D, Q, L, P)) return rc;
+  if (ref_dim != 2 && ref_dim != 4) {
+    set_error("demf_msda_proj_fwd: ref_dim must be 2 or 4 (got %d)", ref_dim);
+    return DEMF_E_SIZE;
+  }
+  if (!demf_msda_proj_fwd_supported(D, L, P) || !aligned16(value) || !aligned16(out)) {
+    set_error("demf_msda_proj_fwd: unsupported D=%d, L*P=%d or unaligned buffers "
+              "(see demf_msda_proj_fwd_supported)", D, L * P);
+    return DEMF_E_UNSUPPORTED;
+  }
+  const long tuples = (long)B * Q * H;
+  if (tuples == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  int lanes = 0;
+  fast_path_lanes(D, &lanes);
+  int rc = -1;
+  switch (lanes) {
+#define DEMF_CASE(n)                                                                                 \
+  case n:                                                                                            \
+    rc = launch_fwd<n, true>(value, spatial_shapes, level_start_index, proj, nullptr, S, H, Q, L, P, \
+                             tuples, out, st, ref_points, ref_dim);                                  \
+    break;
+    DEMF_CASE(1) DEMF_CASE(2) DEMF_CASE(4) DEMF_CASE(8) DEMF_CASE(16) DEMF_CASE(32)
+#undef DEMF_CASE
+  }
+  if (rc == -1) {
+    set_error("demf_msda_proj_fwd: shared memory request too large for L*P=%d", L * P);
+    return DEMF_E_UNSUPPORTED;
+  }
+  return rc;
 }
 
 int demf_msda_bwd(const float* value, const int64_t* spatial_shapes,

@@ -113,6 +113,30 @@ class MultiScaleDeformableAttnFunction(Function):
         return grad_value, None, None, grad_loc, grad_attn, None
 
 
+def msda_proj_supported(head_dim, num_levels, num_points):
+    return bool(_lib.load().demf_msda_proj_fwd_supported(head_dim, num_levels, num_points))
+
+
+def msda_from_projections(value, spatial_shapes, level_start_index, proj, reference_points,
+                          num_levels, num_points):
+    """Inference MSDA straight from the query projections: softmax of the logits, sampling
+    locations and sampling in ONE launch (csrc/msda.cu, kProj).
+    value (B,S,H,D); proj (B*Q, H*L*P*3) = [offsets | logits]; reference_points (B,Q,L,2|4)."""
+    B, S, H, D = value.shape
+    Q = reference_points.shape[1]
+    assert value.is_cuda and value.dtype == torch.float32 and value.is_contiguous()
+    assert proj.is_contiguous() and proj.shape == (B * Q, H * num_levels * num_points * 3)
+    assert reference_points.is_contiguous() and reference_points.dtype == torch.float32
+    assert reference_points.shape[2] == num_levels
+    out = torch.empty(B, Q, H * D, dtype=value.dtype, device=value.device)
+    with torch.cuda.device_of(value):
+        _lib.check(_lib.load().demf_msda_proj_fwd(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), proj.data_ptr(),
+            reference_points.data_ptr(), reference_points.shape[-1], B, S, H, D, Q, num_levels,
+            num_points, out.data_ptr(), _stream()), "demf_msda_proj_fwd")
+    return out
+
+
 _validated_shapes = {}
 
 
@@ -130,6 +154,8 @@ def _check_num_value(spatial_shapes, num_value):
 @ATTENTION.register_module()
 class MultiScaleDeformableAttention(BaseModule):
     """mmcv MultiScaleDeformableAttention (Deformable-DETR attention), same ctor and forward."""
+
+    fused_eval = True   # inference: projections -> output in one launch (msda_from_projections)
 
     def __init__(self, embed_dims=256, num_heads=8, num_levels=4, num_points=4, im2col_step=64,
                  dropout=0.1, batch_first=False, norm_cfg=None, init_cfg=None):
@@ -206,6 +232,17 @@ class MultiScaleDeformableAttention(BaseModule):
             # concatenated (cached) weights on a contiguous copy of the permuted query
             w, b = self._fused_query_proj()
             proj = torch.addmm(b, query.reshape(bs * num_query, -1), w.t())
+            if self.fused_eval and value.is_cuda and value.dtype == torch.float32 \
+                    and reference_points.shape[-1] in (2, 4) \
+                    and msda_proj_supported(value.shape[-1], self.num_levels, self.num_points):
+                # softmax, sampling locations and sampling in one launch
+                output = msda_from_projections(
+                    value.contiguous(), spatial_shapes, level_start_index, proj,
+                    reference_points.contiguous().float(), self.num_levels, self.num_points)
+                output = self.output_proj(output.to(query.dtype))
+                if not self.batch_first:
+                    output = output.permute(1, 0, 2)
+                return self.dropout(output) + identity
             n_off = self.sampling_offsets.out_features
             sampling_offsets = proj[:, :n_off].view(
                 bs, num_query, self.num_heads, self.num_levels, self.num_points, 2)

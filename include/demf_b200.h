@@ -242,6 +242,20 @@ int demf_decode_boxes(const float* center, int s_center, const float* size, int 
 int demf_msda_fwd(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
                   const float* sampling_loc, const float* attn_weight,
                   int B, int S, int H, int D, int Q, int L, int P, float* out, void* stream);
+/* Inference form fed by the attention module's projections: replaces, in one launch, the chain
+ * mmcv's MultiScaleDeformableAttention.forward runs between its Linear layers and the sampling
+ * kernel (multi_scale_deform_attn.py:322-349: view, softmax over L*P, offsets / (W_l,H_l),
+ * + reference points, contiguous, ms_deform_attn_forward).
+ *   proj (B*Q, H*L*P*3) f32 rows = [sampling_offsets (H,L,P,2) | attention logits (H,L,P)];
+ *   ref_points (B,Q,L,ref_dim) f32, ref_dim 2 (x,y) or 4 (x,y,w,h), already scaled by valid ratios;
+ *   -> out (B,Q,H*D).
+ * Supported when D = 4*2^k <= 128 and L*P is a power of two <= 32 dividing the warp's record count
+ * (demf_msda_proj_fwd_supported returns 1); anything else returns DEMF_E_UNSUPPORTED and the
+ * caller composes the steps around demf_msda_fwd. */
+int demf_msda_proj_fwd_supported(int D, int L, int P);
+int demf_msda_proj_fwd(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                       const float* proj, const float* ref_points, int ref_dim,
+                       int B, int S, int H, int D, int Q, int L, int P, float* out, void* stream);
 int demf_msda_bwd(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
                   const float* sampling_loc, const float* attn_weight, const float* grad_out,
                   int B, int S, int H, int D, int Q, int L, int P,

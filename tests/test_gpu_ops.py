@@ -337,6 +337,105 @@ def test_msda_rejects_bad_input(dev):
     assert rc == -3 and "levels" in lib.demf_last_error_string().decode()
 
 
+def _proj_inputs(B, Q, H, D, shapes, P, refdim, seed):
+    g = torch.Generator().manual_seed(seed)
+    L = len(shapes)
+    S = sum(h * w for h, w in shapes)
+    value = torch.randn(B, S, H, D, generator=g)
+    proj = torch.cat([torch.randn(B * Q, H * L * P * 2, generator=g) * 3.0,      # offsets in pixels
+                      torch.randn(B * Q, H * L * P, generator=g) * 2.0], 1).contiguous()
+    ref = torch.rand(B, Q, L, refdim, generator=g)
+    if refdim == 4:
+        ref[..., 2:] = ref[..., 2:] * 0.3 + 0.05
+    sh = torch.tensor(shapes, dtype=torch.int64)
+    lsi = torch.cat([sh.new_zeros(1), sh.prod(1).cumsum(0)[:-1]])
+    return value, sh, lsi, proj, ref
+
+
+def _compose_from_projections(value, sh, proj, ref, H, L, P):
+    """mmcv multi_scale_deform_attn.py:322-349, statement by statement."""
+    B, Q = ref.shape[:2]
+    n_off = H * L * P * 2
+    off = proj[:, :n_off].view(B, Q, H, L, P, 2)
+    w = proj[:, n_off:].view(B, Q, H, L * P).softmax(-1).view(B, Q, H, L, P)
+    if ref.shape[-1] == 2:
+        normalizer = torch.stack([sh[..., 1], sh[..., 0]], -1)
+        loc = ref[:, :, None, :, None, :] + off / normalizer[None, None, None, :, None, :]
+    else:
+        loc = ref[:, :, None, :, None, :2] + off / P * ref[:, :, None, :, None, 2:] * 0.5
+    return loc.contiguous(), w.contiguous()
+
+
+@pytest.mark.parametrize("B,Q,H,D,shapes,P,refdim", [
+    (2, 256, 8, 32, synth.PYRAMIDS["S512"], 4, 2),            # DeMF head cross attention
+    (2, 256, 8, 32, synth.PYRAMIDS["S512"], 2, 2),            # reference config: 2 points
+    (1, 3, 8, 32, ((5, 7), (3, 4), (2, 2), (1, 1)), 4, 2),    # ragged: fewer tuples than a block
+    (2, 37, 4, 64, ((9, 6), (4, 3)), 8, 4),                   # box reference points, D=64
+    (1, 50, 8, 16, ((6, 6), (3, 3), (2, 2), (1, 1)), 1, 2),   # L*P = 4, D=16
+    (1, 777, 2, 128, ((16, 12),), 32, 2),                     # one level, 32 points, D=128
+])
+def test_msda_from_projections_equals_composition(dev, B, Q, H, D, shapes, P, refdim):
+    """One-launch inference form against (a) the same steps composed with torch on the GPU and fed
+    to the plain kernel -- expected identical up to the last bit of softmax -- and (b) the CPU oracle
+    (1e-4 absolute, north_star's MSDA tolerance)."""
+    L = len(shapes)
+    assert msda_mod.msda_proj_supported(D, L, P)
+    value, sh, lsi, proj, ref = _proj_inputs(B, Q, H, D, shapes, P, refdim, seed=Q + D)
+    got = msda_mod.msda_from_projections(value.to(dev), sh.to(dev), lsi.to(dev), proj.to(dev), ref.to(dev), L, P)
+    loc_g, w_g = _compose_from_projections(value.to(dev), sh.to(dev), proj.to(dev), ref.to(dev), H, L, P)
+    composed = msda_mod.MultiScaleDeformableAttnFunction.apply(value.to(dev), sh.to(dev), lsi.to(dev), loc_g, w_g, 64)
+    assert (got - composed).abs().max().item() <= 2e-6
+    loc_c, w_c = _compose_from_projections(value, sh, proj, ref, H, L, P)
+    want = cref.ms_deform_attn_forward(value, sh, lsi, loc_c, w_c)
+    assert (got.cpu() - want).abs().max().item() <= 1e-4
+
+
+def test_msda_from_projections_encoder_regime(dev):
+    """Q = S (every pixel a query, as in the image-branch encoder) at BASELINE's pyramid."""
+    shapes = synth.PYRAMIDS["S512"]
+    S = synth.pyramid_tokens("S512")
+    value, sh, lsi, proj, ref = _proj_inputs(2, S, 8, 32, shapes, 4, 2, seed=3)
+    got = msda_mod.msda_from_projections(value.to(dev), sh.to(dev), lsi.to(dev), proj.to(dev), ref.to(dev), 4, 4)
+    loc_g, w_g = _compose_from_projections(value.to(dev), sh.to(dev), proj.to(dev), ref.to(dev), 8, 4, 4)
+    composed = msda_mod.MultiScaleDeformableAttnFunction.apply(value.to(dev), sh.to(dev), lsi.to(dev), loc_g, w_g, 64)
+    assert (got - composed).abs().max().item() <= 2e-6
+    loc_c, w_c = _compose_from_projections(value[:1], sh, proj[:S], ref[:1], 8, 4, 4)
+    want = cref.ms_deform_attn_forward(value[:1].contiguous(), sh, lsi, loc_c, w_c)
+    assert (got[:1].cpu() - want).abs().max().item() <= 1e-4
+
+
+def test_msda_module_fused_and_composed_paths_agree(dev):
+    torch.manual_seed(0)
+    m = msda_mod.MultiScaleDeformableAttention(embed_dims=256, num_heads=8, num_levels=4, num_points=4).to(dev).eval()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    shapes = synth.PYRAMIDS["S512"]
+    S = synth.pyramid_tokens("S512")
+    sh = torch.tensor(shapes, dtype=torch.int64, device=dev)
+    lsi = torch.cat([sh.new_zeros(1), sh.prod(1).cumsum(0)[:-1]])
+    q = torch.randn(256, 2, 256, device=dev)
+    v = torch.randn(S, 2, 256, device=dev)
+    ref = torch.rand(2, 256, 4, 2, device=dev)
+    kw = dict(value=v, reference_points=ref, spatial_shapes=sh, level_start_index=lsi)
+    with torch.no_grad():
+        fused = m(q, **kw)
+        try:
+            msda_mod.MultiScaleDeformableAttention.fused_eval = False
+            composed = m(q, **kw)
+        finally:
+            msda_mod.MultiScaleDeformableAttention.fused_eval = True
+    assert (fused - composed).abs().max().item() <= 1e-5
+    # unsupported geometry (L*P = 12) keeps the composed path
+    assert not msda_mod.msda_proj_supported(32, 3, 4)
+    lib = _lib.load()
+    rc = lib.demf_msda_proj_fwd(v.data_ptr(), sh.data_ptr(), lsi.data_ptr(), v.data_ptr(), ref.data_ptr(), 2,
+                                1, 4, 8, 32, 4, 3, 4, v.data_ptr(), None)
+    assert rc == -3 and "unsupported" in lib.demf_last_error_string().decode()
+    assert lib.demf_msda_proj_fwd(v.data_ptr(), sh.data_ptr(), lsi.data_ptr(), v.data_ptr(), ref.data_ptr(), 3,
+                                  1, 4, 8, 32, 4, 4, 4, v.data_ptr(), None) != 0
+
+
 def test_empty_batches_are_noops(dev):
     assert ops.furthest_point_sample(torch.zeros(0, 5, 3, device=dev), 2).shape == (0, 2)
     assert ops.ball_query(0.0, 1.0, 4, torch.zeros(2, 5, 3, device=dev),
