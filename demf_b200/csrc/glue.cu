@@ -11,6 +11,10 @@
 //                             wrap / cat of DeMFClassAgnosticBBoxCoder.decode
 //                             (demf/core/bbox/coders/class_agnostic_bbox_coder.py:168-194) for one
 //                             prediction stage
+//   bias_layer_norm_rows_kernel : LayerNorm(x [+ bias] [+ residual]) over rows, one warp per row held in
+//                             registers: the `dropout(out) + identity` add and the LayerNorm that follow
+//                             every attention / FFN block of a post-norm transformer layer (mmcv
+//                             BaseTransformerLayer) in one pass -- read once, write once
 #include "common.cuh"
 
 namespace demf {
@@ -139,6 +143,60 @@ inline unsigned blocks_for(long total, int threads) {
   return (unsigned)(blocks < 1 ? 1 : blocks);
 }
 
+// y[r,:] = (t - mean(t)) * rsqrt(var(t) + eps) * gamma + beta,  t = x[r,:] (+ bias) (+ res[r,:]).
+// kVec float4 per lane: C = 128 * kVec. Two-pass statistics on the register copy (biased variance).
+template <int kVec>
+__global__ void __launch_bounds__(256) bias_layer_norm_rows_kernel(
+    const float* __restrict__ x, const float* __restrict__ bias, const float* __restrict__ res,
+    const float* __restrict__ gamma, const float* __restrict__ beta, long rows, float eps,
+    float* __restrict__ out) {
+  constexpr int C = 128 * kVec;
+  const unsigned lane = lane_id();
+  const long warps = (long)gridDim.x * (blockDim.x >> 5);
+  for (long r = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+    float4 v[kVec];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      v[i] = *reinterpret_cast<const float4*>(x + r * C + c);
+      if (bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c));
+        v[i].x += b.x; v[i].y += b.y; v[i].z += b.z; v[i].w += b.w;
+      }
+      if (res) {
+        const float4 q = *reinterpret_cast<const float4*>(res + r * C + c);
+        v[i].x += q.x; v[i].y += q.y; v[i].z += q.z; v[i].w += q.w;
+      }
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.f / C);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.f / C) + eps);
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * g.x + b.x;
+      y.y = (v[i].y - mean) * rstd * g.y + b.y;
+      y.z = (v[i].z - mean) * rstd * g.z + b.z;
+      y.w = (v[i].w - mean) * rstd * g.w + b.w;
+      *reinterpret_cast<float4*>(out + r * C + c) = y;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace demf
 
@@ -208,6 +266,34 @@ int demf_decode_boxes(const float* center, int s_center, const float* size, int 
                s_obj, s_sem, Q, bins, classes, out_rows, out_offset, (long)B * Q, box, obj_prob, sem_prob};
   decode_boxes_kernel<<<blocks_for(a.total, 256), 256, 0, as_stream(stream)>>>(a);
   return after_launch("decode_boxes_kernel");
+}
+
+int demf_bias_layer_norm_rows(const float* x, const float* bias, const float* residual, const float* gamma,
+                              const float* beta, long rows, int C, float eps, float* out, void* stream) {
+  DEMF_REQUIRE_PTR(x);
+  DEMF_REQUIRE_PTR(gamma);
+  DEMF_REQUIRE_PTR(beta);
+  DEMF_REQUIRE_PTR(out);
+  DEMF_REQUIRE(rows >= 0 && C > 0, DEMF_E_SIZE);
+  DEMF_REQUIRE(C % 128 == 0 && C <= 1024, DEMF_E_UNSUPPORTED);
+  DEMF_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                 reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(residual) |
+                 reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15u) == 0,
+               DEMF_E_UNSUPPORTED);
+  if (rows == 0) return 0;
+  long blocks = (rows + 7) / 8;
+  if (blocks > (long)kNumSMs * 16) blocks = (long)kNumSMs * 16;
+  cudaStream_t st = as_stream(stream);
+  switch (C / 128) {
+#define DEMF_CASE(n)                                                                                      \
+  case n:                                                                                                 \
+    bias_layer_norm_rows_kernel<n><<<(unsigned)blocks, 256, 0, st>>>(x, bias, residual, gamma, beta, rows, \
+                                                                     eps, out);                           \
+    break;
+    DEMF_CASE(1) DEMF_CASE(2) DEMF_CASE(3) DEMF_CASE(4) DEMF_CASE(5) DEMF_CASE(6) DEMF_CASE(7) DEMF_CASE(8)
+#undef DEMF_CASE
+  }
+  return after_launch("bias_layer_norm_rows_kernel");
 }
 
 }  // extern "C"

@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(kThreads) msda_fwd_kernel(
     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
     const float* __restrict__ attn, const float* __restrict__ ref, int refdim, int S, int H, int Q,
     int L, int P, long tuples, float* __restrict__ out) {
+  // kProj: `attn`, when given, is a second projection tensor of the same shape added to `loc`'s rows
+  // (the positional half of the query projection, constant per image geometry)
   constexpr int D = kLanes * 4;
   constexpr int kTuplesPerWarp = 32 / kLanes;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -166,9 +168,15 @@ __global__ void __launch_bounds__(kThreads) msda_fwd_kernel(
         head = (int)(tuple % H);
         const long row = tuple / H;  // b*Q + q
         const float* pr = loc + row * (long)HLP * 3;
-        const float ox = __ldg(pr + ((long)head * LP + j) * 2);
-        const float oy = __ldg(pr + ((long)head * LP + j) * 2 + 1);
+        float ox = __ldg(pr + ((long)head * LP + j) * 2);
+        float oy = __ldg(pr + ((long)head * LP + j) * 2 + 1);
         logit = __ldg(pr + (long)HLP * 2 + head * LP + j);
+        if (attn) {
+          const float* pa = attn + row * (long)HLP * 3;
+          ox = __fadd_rn(ox, __ldg(pa + ((long)head * LP + j) * 2));
+          oy = __fadd_rn(oy, __ldg(pa + ((long)head * LP + j) * 2 + 1));
+          logit = __fadd_rn(logit, __ldg(pa + (long)HLP * 2 + head * LP + j));
+        }
         const float* rp = ref + (row * L + l) * refdim;
         if (refdim == 2) {
           lx = __fadd_rn(__ldg(rp), __fdiv_rn(ox, (float)lv.w[l]));
@@ -517,9 +525,9 @@ int demf_msda_proj_fwd_supported(int D, int L, int P) {
 }
 
 int demf_msda_proj_fwd(const float* value, const int64_t* spatial_shapes,
-                       const int64_t* level_start_index, const float* proj, const float* ref_points,
-                       int ref_dim, int B, int S, int H, int D, int Q, int L, int P, float* out,
-                       void* stream) {
+                       const int64_t* level_start_index, const float* proj, const float* proj_add,
+                       const float* ref_points, int ref_dim, int B, int S, int H, int D, int Q, int L,
+                       int P, float* out, void* stream) {
   DEMF_REQUIRE_PTR(value);
   DEMF_REQUIRE_PTR(spatial_shapes);
   DEMF_REQUIRE_PTR(level_start_index);
@@ -545,7 +553,7 @@ int demf_msda_proj_fwd(const float* value, const int64_t* spatial_shapes,
   switch (lanes) {
 #define DEMF_CASE(n)                                                                                 \
   case n:                                                                                            \
-    rc = launch_fwd<n, true>(value, spatial_shapes, level_start_index, proj, nullptr, S, H, Q, L, P, \
+    rc = launch_fwd<n, true>(value, spatial_shapes, level_start_index, proj, proj_add, S, H, Q, L, P, \
                              tuples, out, st, ref_points, ref_dim);                                  \
     break;
     DEMF_CASE(1) DEMF_CASE(2) DEMF_CASE(4) DEMF_CASE(8) DEMF_CASE(16) DEMF_CASE(32)

@@ -118,21 +118,24 @@ def msda_proj_supported(head_dim, num_levels, num_points):
 
 
 def msda_from_projections(value, spatial_shapes, level_start_index, proj, reference_points,
-                          num_levels, num_points):
+                          num_levels, num_points, proj_add=None):
     """Inference MSDA straight from the query projections: softmax of the logits, sampling
     locations and sampling in ONE launch (csrc/msda.cu, kProj).
-    value (B,S,H,D); proj (B*Q, H*L*P*3) = [offsets | logits]; reference_points (B,Q,L,2|4)."""
+    value (B,S,H,D); proj (B*Q, H*L*P*3) = [offsets | logits]; reference_points (B,Q,L,2|4);
+    proj_add: optional tensor of proj's shape added to it inside the kernel."""
     B, S, H, D = value.shape
     Q = reference_points.shape[1]
     assert value.is_cuda and value.dtype == torch.float32 and value.is_contiguous()
     assert proj.is_contiguous() and proj.shape == (B * Q, H * num_levels * num_points * 3)
     assert reference_points.is_contiguous() and reference_points.dtype == torch.float32
     assert reference_points.shape[2] == num_levels
+    assert proj_add is None or (proj_add.is_contiguous() and proj_add.shape == proj.shape
+                                and proj_add.dtype == proj.dtype)
     out = torch.empty(B, Q, H * D, dtype=value.dtype, device=value.device)
     with torch.cuda.device_of(value):
         _lib.check(_lib.load().demf_msda_proj_fwd(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), proj.data_ptr(),
-            reference_points.data_ptr(), reference_points.shape[-1], B, S, H, D, Q, num_levels,
+            proj_add.data_ptr() if proj_add is not None else None, reference_points.data_ptr(), reference_points.shape[-1], B, S, H, D, Q, num_levels,
             num_points, out.data_ptr(), _stream()), "demf_msda_proj_fwd")
     return out
 

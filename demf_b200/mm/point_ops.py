@@ -655,3 +655,19 @@ def decode_boxes(res, num_dir_bins, box, obj_prob, sem_prob, row_offset):
         _lib.check(_lib.load().demf_decode_boxes(
             *args, B, Q, int(num_dir_bins), ts[5].size(2), box.size(1), int(row_offset), _p(box),
             _p(obj_prob), _p(sem_prob), _stream()), "demf_decode_boxes")
+
+
+def bias_layer_norm_rows(x, gamma, beta, eps, bias=None, residual=None, out=None):
+    """LayerNorm(x + bias + residual) over the last axis of contiguous rows x (R, C) in one pass
+    (csrc/glue.cu); C a multiple of 128 up to 1024. `out` may be x itself."""
+    _need_cuda(x, gamma, beta)
+    R, C = x.shape
+    assert x.is_contiguous() and x.dtype == torch.float32
+    assert residual is None or (residual.is_contiguous() and residual.shape == x.shape)
+    if out is None:
+        out = torch.empty_like(x)
+    with torch.cuda.device_of(x):
+        _lib.check(_lib.load().demf_bias_layer_norm_rows(
+            _p(x), _p(bias) if bias is not None else None, _p(residual) if residual is not None else None,
+            _p(gamma), _p(beta), R, C, float(eps), _p(out), _stream()), "demf_bias_layer_norm_rows")
+    return out

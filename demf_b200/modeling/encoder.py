@@ -109,6 +109,82 @@ class DeformableDetrEncoder(BaseModule):
         self._geometry_cache[key] = geo
         return geo
 
+    # ------------------------------------------------------- inference on token rows ----
+    fused_eval = True
+
+    def _rows_path_ok(self, feat):
+        """The frozen branch as configured upstream: post-norm (self_attn, norm, ffn, norm) layers of
+        deformable attention + 2-layer ReLU FFN + LayerNorm, no gradients, fp32 on the GPU."""
+        from ..mm.ms_deform_attn import MultiScaleDeformableAttention, msda_proj_supported
+        if torch.is_grad_enabled() or not feat.is_cuda or feat.dtype != torch.float32 or self.training:
+            return False
+        ok = self.__dict__.get('_rows_ok')
+        if ok is None:
+            ok = getattr(self.encoder, 'post_norm', None) is None
+            for layer in self.encoder.layers:
+                att = layer.attentions[0] if len(layer.attentions) == 1 else None
+                ffn = layer.ffns[0] if len(layer.ffns) == 1 else None
+                ok = ok and layer.operation_order == ('self_attn', 'norm', 'ffn', 'norm') \
+                    and isinstance(att, MultiScaleDeformableAttention) and not att.batch_first \
+                    and msda_proj_supported(att.embed_dims // att.num_heads, att.num_levels, att.num_points) \
+                    and ffn is not None and ffn.num_fcs == 2 and ffn.add_identity \
+                    and type(ffn.layers[0][1]) is nn.ReLU and isinstance(ffn.dropout_layer, nn.Identity) \
+                    and all(type(n) is nn.LayerNorm and n.elementwise_affine for n in layer.norms) \
+                    and self.embed_dims % 128 == 0 and self.embed_dims <= 1024
+            self.__dict__['_rows_ok'] = bool(ok)
+        return ok
+
+    def _pos_projection(self, li, att, pos_rows, geo):
+        """(pos + level_embed) @ [W_off; W_attn]^T + b for layer `li`: the positional half of the
+        query projection is the same for every image of this geometry -- computed once and added
+        to x @ W^T inside the sampling kernel."""
+        w, b = att._fused_query_proj()
+        key = (w.data_ptr(), w._version, b.data_ptr(), b._version, self.level_embeds._version,
+               self.level_embeds.data_ptr())
+        cache = geo.setdefault('pos_proj', {})
+        hit = cache.get(li)
+        if hit is None or hit[0] != key:
+            hit = (key, torch.addmm(b, pos_rows, w.t()))
+            cache[li] = hit
+        return hit[1], w
+
+    def _encode_rows(self, mlvl_feats, pos, geo):
+        """All layers on contiguous token rows (B*S, C): per layer 5 GEMMs (bias and ReLU in their
+        epilogues), one projection-fed MSDA launch and two bias + residual + LayerNorm passes;
+        nothing else touches the activations."""
+        from ..mm import point_ops as P
+        from ..mm.ms_deform_attn import msda_from_projections
+        bs, c = mlvl_feats[0].shape[:2]
+        x = torch.cat([f.flatten(2) for f in mlvl_feats], 2).transpose(1, 2).reshape(-1, c)   # (B*S,C)
+        S = x.shape[0] // bs
+        pos_rows = geo.get('pos_rows')
+        key = (self.level_embeds._version, self.level_embeds.data_ptr())
+        if pos_rows is None or pos_rows[0] != key:
+            rows = torch.cat([p + self.level_embeds[lvl].view(1, 1, -1) for lvl, p in enumerate(pos)], 1)
+            pos_rows = (key, rows.reshape(-1, c).contiguous())
+            geo['pos_rows'] = pos_rows
+        pos_rows = pos_rows[1]
+        mask = geo['mask_flatten'].reshape(-1, 1) if geo['any_padding'] else None
+        ref = geo['reference_points']
+        for li, layer in enumerate(self.encoder.layers):
+            att, ffn, (n1, n2) = layer.attentions[0], layer.ffns[0], layer.norms
+            pos_proj, wq = self._pos_projection(li, att, pos_rows, geo)
+            proj = torch.mm(x, wq.t())               # + pos_proj inside the kernel = (x + pos) @ Wq^T + bq
+            value = torch.addmm(att.value_proj.bias, x, att.value_proj.weight.t())
+            if mask is not None:
+                value.masked_fill_(mask, 0.0)
+            o = msda_from_projections(value.view(bs, S, att.num_heads, -1), geo['spatial_shapes'],
+                                      geo['level_start_index'], proj, ref, att.num_levels, att.num_points,
+                                      proj_add=pos_proj)
+            t = torch.mm(o.view(-1, c), att.output_proj.weight.t())
+            x = P.bias_layer_norm_rows(t, n1.weight, n1.bias, n1.eps, bias=att.output_proj.bias,
+                                       residual=x, out=t)              # LN(identity + out_proj(o))
+            fc1, fc2 = ffn.layers[0][0], ffn.layers[1]
+            h = torch._addmm_activation(fc1.bias, x, fc1.weight.t())        # ReLU in the epilogue
+            t = torch.mm(h, fc2.weight.t())
+            x = P.bias_layer_norm_rows(t, n2.weight, n2.bias, n2.eps, bias=fc2.bias, residual=x, out=t)
+        return x
+
     # ------------------------------------------------------------------- forward ----
     def forward(self, mlvl_feats, img_metas):
         """mlvl_feats: L tensors (B,C,H_l,W_l); img_metas[i]: 'batch_input_shape' (H,W) of the padded
@@ -136,6 +212,13 @@ class DeformableDetrEncoder(BaseModule):
                        mask_flatten=torch.cat([m.flatten(1) for m in mlvl_masks], 1),
                        any_padding=True,
                        reference_points=self.get_reference_points(shapes, valid_ratios, device))
+        if self.fused_eval and self._rows_path_ok(mlvl_feats[0]) and not kwargs:
+            memory = self._encode_rows(mlvl_feats, pos, geo).view(bs, -1, c).permute(0, 2, 1)   # (B,C,S)
+            outs, start = [], 0
+            for h, w in shapes:
+                outs.append(memory[:, :, start:start + h * w].reshape(bs, c, h, w))
+                start += h * w
+            return outs
         feat_flatten = torch.cat([f.flatten(2) for f in mlvl_feats], 2).permute(2, 0, 1)   # (S,B,C)
         lvl_pos = torch.cat([p + self.level_embeds[lvl].view(1, 1, -1) for lvl, p in enumerate(pos)], 1)
         lvl_pos = lvl_pos.permute(1, 0, 2)                                                # (S,B,C)

@@ -230,6 +230,15 @@ int demf_decode_boxes(const float* center, int s_center, const float* size, int 
                       int classes, int out_rows, int out_offset, float* box, float* obj_prob,
                       float* sem_prob, void* stream);
 
+/* LayerNorm over rows with the preceding bias / residual adds folded in: replaces, for inference, the
+ * `dropout(out) + identity` add and the nn.LayerNorm after every attention and FFN block of mmcv's
+ * BaseTransformerLayer (post-norm) that the image-branch encoder runs
+ * (demf/modeling/layers/deform_detr_encoder.py:141-151, configs/demf/demf_votenet.py:33-39).
+ *   out[r,:] = LN(x[r,:] + bias[:] + residual[r,:]) * gamma + beta; bias and residual may be NULL.
+ * C a multiple of 128 up to 1024, pointers 16-byte aligned; out may alias x. */
+int demf_bias_layer_norm_rows(const float* x, const float* bias, const float* residual, const float* gamma,
+                              const float* beta, long rows, int C, float eps, float* out, void* stream);
+
 /* ------------------------------------ multi-scale deformable attention --- */
 /* replaces mmcv _ext.ms_deform_attn_forward / ms_deform_attn_backward
  * (MultiScaleDeformableAttnFunction; reached from transformer.py:73-78).
@@ -247,6 +256,8 @@ int demf_msda_fwd(const float* value, const int64_t* spatial_shapes, const int64
  * kernel (multi_scale_deform_attn.py:322-349: view, softmax over L*P, offsets / (W_l,H_l),
  * + reference points, contiguous, ms_deform_attn_forward).
  *   proj (B*Q, H*L*P*3) f32 rows = [sampling_offsets (H,L,P,2) | attention logits (H,L,P)];
+ *   proj_add: NULL, or a second tensor of proj's shape added to it element by element first (the
+ *   projection of the positional embedding, which is constant per image geometry);
  *   ref_points (B,Q,L,ref_dim) f32, ref_dim 2 (x,y) or 4 (x,y,w,h), already scaled by valid ratios;
  *   -> out (B,Q,H*D).
  * Supported when D = 4*2^k <= 128 and L*P is a power of two <= 32 dividing the warp's record count
@@ -254,7 +265,7 @@ int demf_msda_fwd(const float* value, const int64_t* spatial_shapes, const int64
  * caller composes the steps around demf_msda_fwd. */
 int demf_msda_proj_fwd_supported(int D, int L, int P);
 int demf_msda_proj_fwd(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
-                       const float* proj, const float* ref_points, int ref_dim,
+                       const float* proj, const float* proj_add, const float* ref_points, int ref_dim,
                        int B, int S, int H, int D, int Q, int L, int P, float* out, void* stream);
 int demf_msda_bwd(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
                   const float* sampling_loc, const float* attn_weight, const float* grad_out,

@@ -271,6 +271,31 @@ def test_encoder_gpu_matches_cpu_oracle(padded):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("padded", [True, False])
+def test_encoder_rows_path_equals_layer_sequence(padded):
+    """The inference path on token rows (fused projections, MSDA from projections, bias + residual +
+    LayerNorm kernel) against the module-by-module layer sequence on the same device."""
+    from demf_b200.modeling.encoder import DeformableDetrEncoder
+    engine.set_gemm_precision("fp32")
+    try:
+        enc = _encoder(num_layers=3).cuda()
+        feats, metas = _inputs(B=2, padded=padded)
+        feats = [f.cuda() for f in feats]
+        with torch.no_grad():
+            assert enc._rows_path_ok(feats[0])
+            fast = enc(feats, metas)
+            DeformableDetrEncoder.fused_eval = False
+            slow = enc(feats, metas)
+    finally:
+        DeformableDetrEncoder.fused_eval = True
+        engine.set_gemm_precision("tf32")
+    masks = enc._geometry(SHAPES, metas, feats[0].device)["masks"]
+    for a, b, m in zip(fast, slow, masks):
+        keep = ~m[:, None].expand_as(a)
+        torch.testing.assert_close(a[keep], b[keep], atol=2e-5, rtol=0)
+
+
+@pytest.mark.gpu
 def test_encoder_gpu_full_size_properties():
     """Six layers at BASELINE's pyramid (S = 5440 tokens, batch 8): finite, deterministic, and
     independent of what lies under the padding mask (values there are zeroed before sampling)."""

@@ -399,6 +399,12 @@ def test_msda_from_projections_encoder_regime(dev):
     loc_g, w_g = _compose_from_projections(value.to(dev), sh.to(dev), proj.to(dev), ref.to(dev), 8, 4, 4)
     composed = msda_mod.MultiScaleDeformableAttnFunction.apply(value.to(dev), sh.to(dev), lsi.to(dev), loc_g, w_g, 64)
     assert (got - composed).abs().max().item() <= 2e-6
+    # split projection: proj = a + b given as two tensors
+    a = (proj * 0.25).contiguous()
+    b = (proj - a).contiguous()
+    split = msda_mod.msda_from_projections(value.to(dev), sh.to(dev), lsi.to(dev), a.to(dev), ref.to(dev), 4, 4,
+                                           proj_add=b.to(dev))
+    assert (split - got).abs().max().item() <= 1e-5
     loc_c, w_c = _compose_from_projections(value[:1], sh, proj[:S], ref[:1], 8, 4, 4)
     want = cref.ms_deform_attn_forward(value[:1].contiguous(), sh, lsi, loc_c, w_c)
     assert (got[:1].cpu() - want).abs().max().item() <= 1e-4
@@ -429,11 +435,33 @@ def test_msda_module_fused_and_composed_paths_agree(dev):
     # unsupported geometry (L*P = 12) keeps the composed path
     assert not msda_mod.msda_proj_supported(32, 3, 4)
     lib = _lib.load()
-    rc = lib.demf_msda_proj_fwd(v.data_ptr(), sh.data_ptr(), lsi.data_ptr(), v.data_ptr(), ref.data_ptr(), 2,
+    rc = lib.demf_msda_proj_fwd(v.data_ptr(), sh.data_ptr(), lsi.data_ptr(), v.data_ptr(), None, ref.data_ptr(), 2,
                                 1, 4, 8, 32, 4, 3, 4, v.data_ptr(), None)
     assert rc == -3 and "unsupported" in lib.demf_last_error_string().decode()
-    assert lib.demf_msda_proj_fwd(v.data_ptr(), sh.data_ptr(), lsi.data_ptr(), v.data_ptr(), ref.data_ptr(), 3,
+    assert lib.demf_msda_proj_fwd(v.data_ptr(), sh.data_ptr(), lsi.data_ptr(), v.data_ptr(), None, ref.data_ptr(), 3,
                                   1, 4, 8, 32, 4, 4, 4, v.data_ptr(), None) != 0
+
+
+@pytest.mark.parametrize("R,C", [(1, 128), (43, 256), (1000, 384), (5441, 256), (77, 1024)])
+def test_bias_layer_norm_rows(dev, R, C):
+    """LN(x + bias + residual) in one pass against torch.nn.functional.layer_norm in float64."""
+    g = torch.Generator().manual_seed(R + C)
+    x = torch.randn(R, C, generator=g) * 3 + 1
+    res = torch.randn(R, C, generator=g)
+    bias, gamma, beta = (torch.randn(C, generator=g) for _ in range(3))
+    want = torch.nn.functional.layer_norm((x + bias + res).double(), (C,), gamma.double(), beta.double(), 1e-5)
+    got = ops.bias_layer_norm_rows(x.to(dev), gamma.to(dev), beta.to(dev), 1e-5, bias=bias.to(dev),
+                                   residual=res.to(dev))
+    assert (got.cpu().double() - want).abs().max().item() <= 5e-6
+    plain = ops.bias_layer_norm_rows(x.to(dev), gamma.to(dev), beta.to(dev), 1e-5)
+    ref32 = torch.nn.functional.layer_norm(x.to(dev), (C,), gamma.to(dev), beta.to(dev), 1e-5)
+    assert (plain - ref32).abs().max().item() <= 5e-6
+    xd = x.to(dev)
+    assert ops.bias_layer_norm_rows(xd, gamma.to(dev), beta.to(dev), 1e-5, out=xd) is xd      # in place
+    assert torch.equal(xd, plain)
+    with pytest.raises(RuntimeError):
+        ops.bias_layer_norm_rows(torch.zeros(4, 100, device=dev), torch.ones(100, device=dev),
+                                 torch.zeros(100, device=dev), 1e-5)
 
 
 def test_empty_batches_are_noops(dev):

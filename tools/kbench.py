@@ -57,6 +57,8 @@ def main():
     ap.add_argument("--sa-lanes", type=int, default=4)
     ap.add_argument("--sa-sleep", type=int, default=0)
     ap.add_argument("--sa-pair", type=int, default=0)
+    ap.add_argument("--gemm", default="tf32", choices=("tf32", "fp32"), help="library GEMM arithmetic (encoder)")
+    ap.add_argument("--profile", action="store_true", help="encoder: print the per-kernel time table")
     args = ap.parse_args()
     only = set(filter(None, args.only.split(",")))
     want = lambda k: not only or k in only  # noqa: E731
@@ -117,15 +119,25 @@ def main():
         from demf_b200.mm.config import Config
         from demf_b200.mm.registry import build_head
         torch.manual_seed(0)
+        engine.set_gemm_precision(args.gemm)
         enc = build_head(Config.fromfile(engine.CONFIG).img_encoder_cfg.to_dict())
         enc.init_weights()
         enc = enc.to(dev).eval()
         for name in ("S512", "REAL"):
             feats = [f.to(dev) for f in synth.make_pyramid(B, name)]
             metas = synth.make_img_metas(B, name)
+            if args.profile:
+                from torch.profiler import ProfilerActivity, profile
+                with torch.no_grad():
+                    enc(feats, metas)
+                    torch.cuda.synchronize()
+                    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                        enc(feats, metas)
+                        torch.cuda.synchronize()
+                print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))
             with torch.no_grad():
                 med, mn = timeit(lambda: enc(feats, metas), max(5, args.reps // 3), False)
-                report("img_encoder_eager", dict(pyramid=name, B=B, S=synth.pyramid_tokens(name)), med, mn)
+                report("img_encoder_eager", dict(pyramid=name, B=B, S=synth.pyramid_tokens(name), gemm=args.gemm), med, mn)
                 side = torch.cuda.Stream()
                 with torch.cuda.stream(side):
                     for _ in range(3):
