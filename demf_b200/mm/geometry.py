@@ -215,6 +215,28 @@ class DepthBoxes:
         return points_in_boxes_batch(points[None, :, :3], self.tensor[None])[0]
 
 
+def box_corner_minmax(boxes):
+    """boxes (...,7) bottom-centre (x,y,z,dx,dy,dz,yaw) -> (...,6) = (min xyz, max xyz) over the 8 corners
+    of `DepthInstance3DBoxes.corners` (mmdet3d 0.18.1 core/bbox/structures/depth_box3d.py: dims * corner
+    pattern relative to (0.5,0.5,0), rotated about z by rotation_3d_in_axis, + bottom centre), which is
+    what multiclass_nms_single feeds to aligned_3d_nms."""
+    dims, yaw = boxes[..., 3:6], boxes[..., 6]
+    cosa, sina = torch.cos(yaw)[..., None], torch.sin(yaw)[..., None]
+    sx = boxes.new_tensor([-0.5, -0.5, 0.5, 0.5]) * dims[..., 0:1]       # 4 footprint corners
+    sy = boxes.new_tensor([-0.5, 0.5, 0.5, -0.5]) * dims[..., 1:2]
+    rx = sx * cosa + sy * sina + boxes[..., 0:1]
+    ry = -sx * sina + sy * cosa + boxes[..., 1:2]
+    z0 = boxes[..., 2] + dims[..., 2] * 0.0
+    z1 = boxes[..., 2] + dims[..., 2] * 1.0
+    return torch.stack([rx.min(-1)[0], ry.min(-1)[0], torch.minimum(z0, z1),
+                        rx.max(-1)[0], ry.max(-1)[0], torch.maximum(z0, z1)], -1)
+
+
+def bbox3d2result(bboxes, scores, labels):
+    """mmdet3d.core.bbox3d2result: detections of one scene as a dict of CPU tensors."""
+    return dict(boxes_3d=bboxes.to('cpu'), scores_3d=scores.cpu(), labels_3d=labels.cpu())
+
+
 def points_in_boxes_batch(xyz, boxes):
     """xyz (B,N,3), boxes (B,G,7) [bottom-centre] -> (B,N,G) int32 membership.
     Local frame test of mmdet3d roiaware_pool3d points_in_boxes: z within [bottom, bottom+dz]

@@ -133,10 +133,17 @@ def msda_from_projections(value, spatial_shapes, level_start_index, proj, refere
                                 and proj_add.dtype == proj.dtype)
     out = torch.empty(B, Q, H * D, dtype=value.dtype, device=value.device)
     with torch.cuda.device_of(value):
+        if KERNEL_TIMER.enabled:
+            ext = dict(external=True) if torch.cuda.is_current_stream_capturing() else {}
+            ev = (torch.cuda.Event(enable_timing=True, **ext), torch.cuda.Event(enable_timing=True, **ext))
+            ev[0].record()
         _lib.check(_lib.load().demf_msda_proj_fwd(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), proj.data_ptr(),
             proj_add.data_ptr() if proj_add is not None else None, reference_points.data_ptr(), reference_points.shape[-1], B, S, H, D, Q, num_levels,
             num_points, out.data_ptr(), _stream()), "demf_msda_proj_fwd")
+        if KERNEL_TIMER.enabled:
+            ev[1].record()
+            KERNEL_TIMER.pairs.append(ev)
     return out
 
 

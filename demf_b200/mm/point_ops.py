@@ -671,3 +671,38 @@ def bias_layer_norm_rows(x, gamma, beta, eps, bias=None, residual=None, out=None
             _p(x), _p(bias) if bias is not None else None, _p(residual) if residual is not None else None,
             _p(gamma), _p(beta), R, C, float(eps), _p(out), _stream()), "demf_bias_layer_norm_rows")
     return out
+
+
+def box_point_count(points, boxes):
+    """points (B,N,3+) rows, boxes (B,K,7) bottom-centre -> (B,K) int32 number of points inside each
+    box (column sums of mmdet3d `points_in_boxes`), one launch for the batch."""
+    _need_cuda(points, boxes)
+    B, N = points.shape[:2]
+    K = boxes.shape[1]
+    assert points.dtype == torch.float32
+    assert N == 0 or (points.stride(2) == 1 and points.stride(0) == N * points.stride(1)), points.stride()
+    boxes = boxes.contiguous().float()
+    counts = torch.zeros(B, K, dtype=torch.int32, device=points.device)
+    if B == 0 or K == 0 or N == 0:
+        return counts
+    with torch.cuda.device_of(points):
+        _lib.check(_lib.load().demf_box_point_count(_p(points), points.stride(1), _p(boxes), B, N, K, _p(counts),
+                                                    _stream()), "demf_box_point_count")
+    return counts
+
+
+def aligned_3d_nms(minmax, scores, classes, valid, thresh):
+    """Batched mmdet3d `aligned_3d_nms`: minmax (B,K,6), scores (B,K), classes (B,K) int64, valid (B,K)
+    bool -> (B,K) bool mask of the boxes the greedy class-aware sweep keeps (one CTA per scene)."""
+    _need_cuda(minmax, scores, classes, valid)
+    B, K = scores.shape
+    minmax, scores = minmax.contiguous().float(), scores.contiguous().float()
+    classes = classes.contiguous().long()
+    valid8 = valid.contiguous().to(torch.uint8)
+    keep = torch.zeros(B, K, dtype=torch.uint8, device=scores.device)
+    if B == 0 or K == 0:
+        return keep.bool()
+    with torch.cuda.device_of(scores):
+        _lib.check(_lib.load().demf_aligned_3d_nms(_p(minmax), _p(scores), _p(classes), _p(valid8), B, K,
+                                                   float(thresh), _p(keep), _stream()), "demf_aligned_3d_nms")
+    return keep.bool()

@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from ..mm.bricks import BaseModule
+from ..mm.geometry import bbox3d2result
 from ..mm.registry import BACKBONES, DETECTORS, HEADS, NECKS, build_backbone, build_head, build_neck
 
 
@@ -169,34 +170,19 @@ class DeMFVoteNet(BaseModule):
         return self._forward_head(points, img, img_metas, self.test_cfg['pts']['sample_mod'])[1]
 
     def simple_test(self, points=None, img_metas=None, img=None, bboxes_2d=None, rescale=False,
-                    projection=None, **kwargs):
-        """Forward + box decoding of the ensemble layers (NMS is out of scope):
-        returns (boxes (B, len(ensemble)*Q, 7), objectness (B, .), semantic scores (B, ., C))."""
+                    projection=None, nms=False, **kwargs):
+        """Forward + decoding of the ensemble layers. nms=False (what bench.py times, BASELINE.json's
+        scenes/s of the forward path): (boxes (B, len(ensemble)*Q, 7), objectness, semantic scores).
+        nms=True: the reference's return value (demfnet.py:254-283) -- per scene a dict of CPU
+        boxes_3d / scores_3d / labels_3d after DeMFVoteHead.get_bboxes."""
         _, bbox_preds = self._forward_head(points, img, img_metas,
                                            self.test_cfg['pts']['sample_mod'], projection)
         head = self.pts_bbox_head
-        layers = list(head.test_cfg['ensemble_layers'])
-        first = bbox_preds['decode_res_all'][layers[0]]
-        coder = head.bbox_coder
-        if first['center'].is_cuda and coder.with_rot and 'sem_scores' in first:
-            # one launch per ensembled stage: softmaxes, heading decode and the concatenations
-            from ..mm import point_ops as P
-            B, Q = first['center'].shape[:2]
-            R = Q * len(layers)
-            dev = first['center'].device
-            box = torch.empty(B, R, 7, device=dev)
-            obj = torch.empty(B, R, device=dev)
-            sem = torch.empty(B, R, first['sem_scores'].size(-1), device=dev)
-            for n, i in enumerate(layers):
-                P.decode_boxes(bbox_preds['decode_res_all'][i], coder.num_dir_bins, box, obj, sem, n * Q)
-            return box, obj, sem
-        obj, sem, box = [], [], []
-        for i in head.test_cfg['ensemble_layers']:
-            res = bbox_preds['decode_res_all'][i]
-            obj.append(torch.softmax(res['obj_scores'], dim=-1)[..., -1])
-            sem.append(torch.softmax(res['sem_scores'], dim=-1))
-            box.append(head.bbox_coder.decode(res))
-        return torch.cat(box, 1), torch.cat(obj, 1), torch.cat(sem, 1)
+        if not nms:
+            return head.decode_ensemble(bbox_preds)
+        pts = torch.stack(points) if isinstance(points, (list, tuple)) else points
+        bbox_list = head.get_bboxes(pts, bbox_preds, img_metas, rescale=rescale)
+        return [bbox3d2result(b, s, l) for b, s, l in bbox_list]
 
     def forward(self, return_loss=True, **kwargs):
         return self.forward_train(**kwargs) if return_loss else self.simple_test(**kwargs)

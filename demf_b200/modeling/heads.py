@@ -225,6 +225,86 @@ class DeMFVoteHead(BaseModule):
         return (feat_flatten, mask_flatten, reference_points, spatial_shapes, level_start_index,
                 valid_ratios)
 
+    # ------------------------------------------------------------ post-processing ---
+    def decode_ensemble(self, bbox_preds):
+        """Decoded boxes (B,R,7) [gravity centre], objectness (B,R) and semantic probabilities (B,R,C)
+        of the `test_cfg.ensemble_layers` stages, R = len(layers) * num_proposal (reference :720-736)."""
+        layers = list(self.test_cfg['ensemble_layers'])
+        stages = bbox_preds['decode_res_all']
+        first = stages[layers[0]]
+        coder = self.bbox_coder
+        if first['center'].is_cuda and coder.with_rot and 'sem_scores' in first:
+            # one launch per ensembled stage: softmaxes, heading decode and the concatenations
+            B, Q = first['center'].shape[:2]
+            R = Q * len(layers)
+            dev = first['center'].device
+            box = torch.empty(B, R, 7, device=dev)
+            obj = torch.empty(B, R, device=dev)
+            sem = torch.empty(B, R, first['sem_scores'].size(-1), device=dev)
+            for n, i in enumerate(layers):
+                P.decode_boxes(stages[i], coder.num_dir_bins, box, obj, sem, n * Q)
+            return box, obj, sem
+        obj, sem, box = [], [], []
+        for i in layers:
+            res = stages[i]
+            obj.append(torch.softmax(res['obj_scores'], dim=-1)[..., -1])
+            sem.append(torch.softmax(res['sem_scores'], dim=-1))
+            box.append(coder.decode(res))
+        return torch.cat(box, 1), torch.cat(obj, 1), torch.cat(sem, 1)
+
+    def get_bboxes(self, points, bbox_preds, input_metas, rescale=False, use_nms=True):
+        """Reference :714-754. points (B,N,3+); returns per scene (boxes, scores, labels) after
+        class-aware 3D NMS, or the raw (B,R,7) boxes when use_nms is False."""
+        bbox3d, obj_scores, sem_scores = self.decode_ensemble(bbox_preds)
+        if not use_nms:
+            return bbox3d
+        selected = self.multiclass_nms_batch(obj_scores, sem_scores, bbox3d, points[..., :3])
+        results = []
+        for b, (boxes, scores, labels) in enumerate(selected):
+            box_type = input_metas[b].get('box_type_3d', geometry.DepthBoxes) if input_metas else geometry.DepthBoxes
+            results.append((box_type(boxes, box_dim=boxes.shape[-1], with_yaw=self.bbox_coder.with_rot),
+                            scores, labels))
+        return results
+
+    def multiclass_nms_single(self, obj_scores, sem_scores, bbox, points, input_meta=None):
+        """One scene, upstream signature (mmdet3d 0.18.1 VoteHead.multiclass_nms_single):
+        obj_scores (R,), sem_scores (R,C), bbox (R,7) gravity centre, points (N,3)."""
+        return self.multiclass_nms_batch(obj_scores[None], sem_scores[None], bbox[None], points[None])[0]
+
+    def multiclass_nms_batch(self, obj_scores, sem_scores, bbox, points):
+        """multiclass_nms_single for the whole batch with ONE host synchronisation (upstream: a Python
+        loop over scenes around a Python loop over kept boxes). Steps, in upstream's order:
+        boxes to bottom-centre form; drop boxes holding <= 5 points; class-aware NMS on the
+        axis-aligned hulls of the survivors by objectness; drop objectness <= score_thr; with
+        per_class_proposal every kept box is emitted once per class with score obj * sem[k]."""
+        cfg = self.test_cfg
+        boxes_bc = bbox.clone()
+        boxes_bc[..., 2] = boxes_bc[..., 2] - boxes_bc[..., 5] * 0.5      # origin (.5,.5,.5) -> (.5,.5,0)
+        counts = P.box_point_count(points, boxes_bc)
+        nonempty = counts > 5
+        minmax = geometry.box_corner_minmax(boxes_bc)
+        classes = torch.argmax(sem_scores, -1)
+        keep = P.aligned_3d_nms(minmax, obj_scores, classes, nonempty, cfg['nms_thr'])
+        selected = keep & (obj_scores > cfg['score_thr'])
+        rows = selected.nonzero(as_tuple=False)                           # the host sync
+        per_scene = torch.bincount(rows[:, 0], minlength=bbox.shape[0]).tolist()
+        box_sel = boxes_bc[rows[:, 0], rows[:, 1]]
+        obj_sel = obj_scores[rows[:, 0], rows[:, 1]]
+        sem_sel = sem_scores[rows[:, 0], rows[:, 1]]
+        cls_sel = classes[rows[:, 0], rows[:, 1]]
+        out, start = [], 0
+        C = sem_scores.shape[-1]
+        for n in per_scene:
+            sl = slice(start, start + n)
+            start += n
+            if cfg['per_class_proposal']:
+                out.append((box_sel[sl].repeat(C, 1),
+                            (obj_sel[sl, None] * sem_sel[sl]).t().reshape(-1),
+                            torch.arange(C, device=bbox.device, dtype=cls_sel.dtype).repeat_interleave(n)))
+            else:
+                out.append((box_sel[sl], obj_sel[sl], cls_sel[sl]))
+        return out
+
     # --------------------------------------------------------------------- loss ---
     def loss(self, bbox_preds, *args, **kwargs):
         """Average of _loss over the num_fusion_layers+1 prediction stages (reference :596-620).

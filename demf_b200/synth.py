@@ -107,3 +107,37 @@ def make_msda_inputs(B=8, Q=256, H=8, D=32, name="S512", P=4, seed=0, shapes=Non
     loc = (ref + 0.05 * torch.randn(B, Q, H, L, P, 2, generator=g)).contiguous()
     attn = torch.softmax(torch.randn(B, Q, H, L * P, generator=g), -1).view(B, Q, H, L, P)
     return value, spatial_shapes, level_start_index, loc, attn.contiguous()
+
+
+def make_box_predictions(B, K, seed, classes=10):
+    """Decoded head outputs for post-processing tests and timings: (B,K,7) gravity-centre boxes clustered
+    around a dozen objects per scene (so that NMS has work to do), objectness (B,K) ~U(0,1) and semantic
+    probabilities (B,K,classes) peaked at the object's class."""
+    g = torch.Generator().manual_seed(seed)
+    nobj = 12
+    centre = torch.rand(B, nobj, 3, generator=g) * torch.tensor([5.0, 5.0, 1.5]) - torch.tensor([2.5, 2.5, 0.0])
+    size = torch.rand(B, nobj, 3, generator=g) * 1.2 + 0.3
+    yaw = torch.rand(B, nobj, generator=g) * 2 * math.pi
+    which = torch.randint(0, nobj, (B, K), generator=g)
+    take = lambda t: torch.gather(t, 1, which[..., None].expand(-1, -1, t.shape[-1]))  # noqa: E731
+    box = torch.cat([take(centre) + 0.08 * torch.randn(B, K, 3, generator=g),
+                     take(size) * (1 + 0.1 * torch.randn(B, K, 3, generator=g)).clamp(0.5, 1.5),
+                     (torch.gather(yaw, 1, which) + 0.1 * torch.randn(B, K, generator=g))[..., None] % (2 * math.pi)], -1)
+    obj = torch.rand(B, K, generator=g)
+    sem = torch.softmax(torch.randn(B, K, classes, generator=g) + 3 * torch.nn.functional.one_hot(
+        which % classes, classes), -1)
+    return box, obj, sem
+
+
+def make_points_in_boxes(B, N, box, seed):
+    """(B,N,3) points: half uniform in the room, half inside boxes drawn from the first third of `box`
+    (the rest of the boxes stay nearly empty and are filtered by the > 5 points rule)."""
+    g = torch.Generator().manual_seed(seed + 99)
+    K = box.shape[1]
+    uni = torch.rand(B, N // 2, 3, generator=g) * torch.tensor([6.0, 6.0, 2.5]) - torch.tensor([3.0, 3.0, 0.0])
+    which = torch.randint(0, K // 3, (B, N - N // 2), generator=g)       # only the first third of the boxes
+    bsel = torch.gather(box, 1, which[..., None].expand(-1, -1, 7))
+    u = (torch.rand(B, N - N // 2, 3, generator=g) - 0.5) * bsel[..., 3:6]
+    c, s = torch.cos(bsel[..., 6]), torch.sin(bsel[..., 6])
+    local = torch.stack([u[..., 0] * c + u[..., 1] * s, -u[..., 0] * s + u[..., 1] * c, u[..., 2]], -1)
+    return torch.cat([uni, local + bsel[..., :3]], 1).contiguous()

@@ -230,6 +230,21 @@ int demf_decode_boxes(const float* center, int s_center, const float* size, int 
                       int classes, int out_rows, int out_offset, float* box, float* obj_prob,
                       float* sem_prob, void* stream);
 
+/* ------------------------------------------- inference post-processing --- */
+/* The two per-scene loops of mmdet3d 0.18.1 VoteHead.multiclass_nms_single, reached from
+ * DeMFVoteHead.get_bboxes (demf/modeling/heads/class_agnostic_vote_head.py:739-743):
+ * demf_box_point_count replaces `bbox.points_in_boxes(points).T.sum(1)` (roiaware_pool3d
+ * points_in_boxes_batch): counts (B,K) i32 = points of scene b inside box k; boxes (B,K,7) =
+ * (x,y,z_bottom,dx,dy,dz,yaw), points rows of point_stride floats starting with xyz.
+ * demf_aligned_3d_nms replaces mmdet3d core/post_processing aligned_3d_nms for a whole batch:
+ * minmax (B,K,6) axis-aligned (x1,y1,z1,x2,y2,z2); scores (B,K); classes (B,K) i64; valid (B,K) u8 =
+ * boxes taking part; keep (B,K) u8 <- 1 for picked boxes. Greedy by descending score (ties: larger
+ * index first), a box is dropped unless iou * (same class) <= thresh. K <= 4096. */
+int demf_box_point_count(const float* points, int point_stride, const float* boxes, int B, int N, int K,
+                         int32_t* counts, void* stream);
+int demf_aligned_3d_nms(const float* minmax, const float* scores, const int64_t* classes, const uint8_t* valid,
+                        int B, int K, float thresh, uint8_t* keep, void* stream);
+
 /* LayerNorm over rows with the preceding bias / residual adds folded in: replaces, for inference, the
  * `dropout(out) + identity` add and the nn.LayerNorm after every attention and FFN block of mmcv's
  * BaseTransformerLayer (post-norm) that the image-branch encoder runs

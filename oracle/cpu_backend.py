@@ -80,6 +80,22 @@ def _three_interpolate(features, idx, weight):
     return _three_interpolate_rows(features.transpose(1, 2), idx, weight).transpose(1, 2)
 
 
+def _box_point_count(points, boxes):
+    from .postprocess import points_in_boxes_depth
+    return torch.stack([points_in_boxes_depth(points[b, :, :3], boxes[b]).sum(0).to(torch.int32)
+                        for b in range(points.shape[0])])
+
+
+def _aligned_3d_nms(minmax, scores, classes, valid, thresh):
+    from .postprocess import aligned_3d_nms
+    keep = torch.zeros_like(valid, dtype=torch.bool)
+    for b in range(scores.shape[0]):
+        inds = torch.nonzero(valid[b], as_tuple=False).flatten()
+        picked = aligned_3d_nms(minmax[b][inds], scores[b][inds], classes[b][inds], thresh)
+        keep[b, inds[picked]] = True
+    return keep
+
+
 class _MsdaCpu:
     """Stand-in for MultiScaleDeformableAttnFunction with the same .apply signature."""
 
@@ -100,6 +116,7 @@ def oracle_ops():
         "three_interpolate_rows": _three_interpolate_rows,
         "grouping_operation": _grouping_operation, "gather_points": _gather_points,
         "three_interpolate": _three_interpolate,
+        "box_point_count": _box_point_count, "aligned_3d_nms": _aligned_3d_nms,
     }
     saved = {k: getattr(P, k) for k in patched}
     saved_fn = msda_mod.MultiScaleDeformableAttnFunction
