@@ -58,7 +58,10 @@ _SIGNATURES = {
     "demf_msda_fwd": [_ptr, _ptr, _ptr, _ptr, _ptr] + [_c_int] * 7 + [_ptr, _ptr],
     "demf_box_point_count": [_ptr, _c_int, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr],
     "demf_aligned_3d_nms": [_ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_float, _ptr, _ptr],
-    "demf_bias_layer_norm_rows": [_ptr, _ptr, _ptr, _ptr, _ptr, ctypes.c_long, _c_int, _c_float, _ptr, _ptr],
+    "demf_vote_tail": [_ptr, _c_int, _ptr, _ptr, ctypes.c_long, _c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr],
+    "demf_levels_to_rows": [_ptr, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr],
+    "demf_bias_layer_norm_rows": [_ptr, _ptr, _ptr, _ptr, _ptr, ctypes.c_long, _c_int, _c_float, _ptr, _ptr, _ptr,
+                                  _ptr],
     "demf_msda_proj_fwd_supported": [_c_int] * 3,
     "demf_msda_proj_fwd": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr] + [_c_int] * 8 + [_ptr, _ptr],
     "demf_msda_bwd": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr] + [_c_int] * 7 + [_ptr, _ptr, _ptr, _ptr],

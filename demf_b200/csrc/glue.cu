@@ -143,13 +143,106 @@ inline unsigned blocks_for(long total, int threads) {
   return (unsigned)(blocks < 1 ? 1 : blocks);
 }
 
+// VoteModule tail (mmdet3d models/model_utils/vote_module.py forward, vote_per_seed = 1): from the
+// conv_out rows votes (R, ldv) = [offset(3) | residual(C)] form
+//   offset' = clamp(offset, +-range)      vote_xyz = seed_xyz + offset'
+//   vote_feat = (seed_feat + residual) / ||seed_feat + residual||_2      (norm_feats)
+// one warp per row, the row in registers (C = 128 * kVec).
+template <int kVec>
+__global__ void __launch_bounds__(256) vote_tail_kernel(const float* __restrict__ votes, int ldv,
+                                                        const float* __restrict__ seed_xyz,
+                                                        const float* __restrict__ seed_rows, long rows,
+                                                        float rx, float ry, float rz, int norm_feats,
+                                                        float* __restrict__ vote_xyz, float* __restrict__ offset,
+                                                        float* __restrict__ vote_rows) {
+  constexpr int C = 128 * kVec;
+  const unsigned lane = lane_id();
+  const long warps = (long)gridDim.x * (blockDim.x >> 5);
+  for (long r = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+    const float* v = votes + r * ldv;
+    if (lane < 3) {
+      const float lim = lane == 0 ? rx : (lane == 1 ? ry : rz);
+      float o = v[lane];
+      if (lim >= 0.f) o = fminf(fmaxf(o, -lim), lim);
+      offset[r * 3 + lane] = o;
+      vote_xyz[r * 3 + lane] = __fadd_rn(seed_xyz[r * 3 + lane], o);
+    }
+    float x[kVec * 4];
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      const float4 s4 = *reinterpret_cast<const float4*>(seed_rows + r * C + c);
+      // the residual starts at column 3 of the vote row: not 16-byte aligned, scalar loads
+      x[i * 4 + 0] = __fadd_rn(s4.x, v[3 + c]);
+      x[i * 4 + 1] = __fadd_rn(s4.y, v[4 + c]);
+      x[i * 4 + 2] = __fadd_rn(s4.z, v[5 + c]);
+      x[i * 4 + 3] = __fadd_rn(s4.w, v[6 + c]);
+      sq += (x[i * 4] * x[i * 4] + x[i * 4 + 1] * x[i * 4 + 1]) + (x[i * 4 + 2] * x[i * 4 + 2] + x[i * 4 + 3] * x[i * 4 + 3]);
+    }
+    float scale = 1.f;
+    if (norm_feats) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      scale = sqrtf(sq);
+    }
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      float4 y;
+      y.x = norm_feats ? __fdiv_rn(x[i * 4 + 0], scale) : x[i * 4 + 0];
+      y.y = norm_feats ? __fdiv_rn(x[i * 4 + 1], scale) : x[i * 4 + 1];
+      y.z = norm_feats ? __fdiv_rn(x[i * 4 + 2], scale) : x[i * 4 + 2];
+      y.w = norm_feats ? __fdiv_rn(x[i * 4 + 3], scale) : x[i * 4 + 3];
+      *reinterpret_cast<float4*>(vote_rows + r * C + c) = y;
+    }
+  }
+}
+
+// Pyramid levels (B,C,H_l*W_l) -> token rows (B,S,C), all levels in one launch: 32x32 tiles through
+// shared memory so that both the reads (along the pixels) and the writes (along the channels) are
+// coalesced 128-byte lines. blockIdx.x enumerates (level, pixel tile), blockIdx.y channel tiles,
+// blockIdx.z the batch.
+struct LevelsArgs {
+  const float* src[8];
+  int hw[8];
+  int start[8];       // first token row of the level
+  int tile_start[9];  // prefix sum of ceil(hw/32) over the levels
+  int levels;
+};
+
+__global__ void __launch_bounds__(256) levels_to_rows_kernel(const LevelsArgs a, int C, int S,
+                                                             float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  int l = 0;
+  while (l + 1 < a.levels && (int)blockIdx.x >= a.tile_start[l + 1]) ++l;
+  const int p0 = ((int)blockIdx.x - a.tile_start[l]) * 32;
+  const int c0 = blockIdx.y * 32;
+  const int b = blockIdx.z;
+  const int hw = a.hw[l];
+  const float* src = a.src[l] + (long)b * C * hw;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + i * 8, p = p0 + tx;
+    if (c < C && p < hw) tile[ty + i * 8][tx] = __ldg(src + (long)c * hw + p);
+  }
+  __syncthreads();
+  float* dst = out + ((long)b * S + a.start[l]) * C;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = p0 + ty + i * 8, c = c0 + tx;
+    if (c < C && p < hw) dst[(long)p * C + c] = tile[tx][ty + i * 8];
+  }
+}
+
 // y[r,:] = (t - mean(t)) * rsqrt(var(t) + eps) * gamma + beta,  t = x[r,:] (+ bias) (+ res[r,:]).
 // kVec float4 per lane: C = 128 * kVec. Two-pass statistics on the register copy (biased variance).
 template <int kVec>
 __global__ void __launch_bounds__(256) bias_layer_norm_rows_kernel(
     const float* __restrict__ x, const float* __restrict__ bias, const float* __restrict__ res,
     const float* __restrict__ gamma, const float* __restrict__ beta, long rows, float eps,
-    float* __restrict__ out) {
+    float* __restrict__ out, const float* __restrict__ post_add, float* __restrict__ out2) {
   constexpr int C = 128 * kVec;
   const unsigned lane = lane_id();
   const long warps = (long)gridDim.x * (blockDim.x >> 5);
@@ -193,6 +286,10 @@ __global__ void __launch_bounds__(256) bias_layer_norm_rows_kernel(
       y.z = (v[i].z - mean) * rstd * g.z + b.z;
       y.w = (v[i].w - mean) * rstd * g.w + b.w;
       *reinterpret_cast<float4*>(out + r * C + c) = y;
+      if (out2) {  // the next attention's query = y + positional embedding, written alongside
+        const float4 p = *reinterpret_cast<const float4*>(post_add + r * C + c);
+        *reinterpret_cast<float4*>(out2 + r * C + c) = make_float4(y.x + p.x, y.y + p.y, y.z + p.z, y.w + p.w);
+      }
     }
   }
 }
@@ -268,8 +365,71 @@ int demf_decode_boxes(const float* center, int s_center, const float* size, int 
   return after_launch("decode_boxes_kernel");
 }
 
+int demf_vote_tail(const float* votes, int ldv, const float* seed_xyz, const float* seed_rows, long rows, int C,
+                   const float* xyz_range, int norm_feats, float* vote_xyz, float* offset, float* vote_rows,
+                   void* stream) {
+  DEMF_REQUIRE_PTR(votes);
+  DEMF_REQUIRE_PTR(seed_xyz);
+  DEMF_REQUIRE_PTR(seed_rows);
+  DEMF_REQUIRE_PTR(vote_xyz);
+  DEMF_REQUIRE_PTR(offset);
+  DEMF_REQUIRE_PTR(vote_rows);
+  DEMF_REQUIRE(rows >= 0 && C > 0 && ldv >= C + 3, DEMF_E_SIZE);
+  DEMF_REQUIRE(C % 128 == 0 && C <= 512, DEMF_E_UNSUPPORTED);
+  DEMF_REQUIRE(((reinterpret_cast<uintptr_t>(seed_rows) | reinterpret_cast<uintptr_t>(vote_rows)) & 15u) == 0,
+               DEMF_E_UNSUPPORTED);
+  if (rows == 0) return 0;
+  // xyz_range: HOST pointer to 3 floats or NULL (no clamp)
+  const float rx = xyz_range ? xyz_range[0] : -1.f, ry = xyz_range ? xyz_range[1] : -1.f,
+              rz = xyz_range ? xyz_range[2] : -1.f;
+  long blocks = (rows + 7) / 8;
+  if (blocks > (long)kNumSMs * 16) blocks = (long)kNumSMs * 16;
+  cudaStream_t st = as_stream(stream);
+  switch (C / 128) {
+#define DEMF_CASE(n)                                                                                          \
+  case n:                                                                                                     \
+    vote_tail_kernel<n><<<(unsigned)blocks, 256, 0, st>>>(votes, ldv, seed_xyz, seed_rows, rows, rx, ry, rz,   \
+                                                          norm_feats, vote_xyz, offset, vote_rows);           \
+    break;
+    DEMF_CASE(1) DEMF_CASE(2) DEMF_CASE(3) DEMF_CASE(4)
+#undef DEMF_CASE
+  }
+  return after_launch("vote_tail_kernel");
+}
+
+int demf_levels_to_rows(const float* const* levels, const int* hw, int num_levels, int B, int C, float* out,
+                        void* stream) {
+  DEMF_REQUIRE_PTR(levels);
+  DEMF_REQUIRE_PTR(hw);
+  DEMF_REQUIRE_PTR(out);
+  DEMF_REQUIRE(num_levels >= 1 && num_levels <= 8 && B >= 0 && C > 0, DEMF_E_SIZE);
+  DEMF_REQUIRE(B <= 65535 && (C + 31) / 32 <= 65535, DEMF_E_SIZE);
+  LevelsArgs a{};
+  int S = 0, tiles = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    DEMF_REQUIRE_PTR(levels[l]);
+    DEMF_REQUIRE(hw[l] > 0, DEMF_E_SIZE);
+    a.src[l] = levels[l];
+    a.hw[l] = hw[l];
+    a.start[l] = S;
+    a.tile_start[l] = tiles;
+    S += hw[l];
+    tiles += (hw[l] + 31) / 32;
+  }
+  a.tile_start[num_levels] = tiles;
+  a.levels = num_levels;
+  if (B == 0) return 0;
+  dim3 grid(tiles, (C + 31) / 32, B);
+  levels_to_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(a, C, S, out);
+  return after_launch("levels_to_rows_kernel");
+}
+
 int demf_bias_layer_norm_rows(const float* x, const float* bias, const float* residual, const float* gamma,
-                              const float* beta, long rows, int C, float eps, float* out, void* stream) {
+                              const float* beta, long rows, int C, float eps, float* out, const float* post_add,
+                              float* out2, void* stream) {
+  DEMF_REQUIRE((post_add == nullptr) == (out2 == nullptr), DEMF_E_SIZE);
+  DEMF_REQUIRE(((reinterpret_cast<uintptr_t>(post_add) | reinterpret_cast<uintptr_t>(out2)) & 15u) == 0,
+               DEMF_E_UNSUPPORTED);
   DEMF_REQUIRE_PTR(x);
   DEMF_REQUIRE_PTR(gamma);
   DEMF_REQUIRE_PTR(beta);
@@ -288,7 +448,7 @@ int demf_bias_layer_norm_rows(const float* x, const float* bias, const float* re
 #define DEMF_CASE(n)                                                                                      \
   case n:                                                                                                 \
     bias_layer_norm_rows_kernel<n><<<(unsigned)blocks, 256, 0, st>>>(x, bias, residual, gamma, beta, rows, \
-                                                                     eps, out);                           \
+                                                                     eps, out, post_add, out2);           \
     break;
     DEMF_CASE(1) DEMF_CASE(2) DEMF_CASE(3) DEMF_CASE(4) DEMF_CASE(5) DEMF_CASE(6) DEMF_CASE(7) DEMF_CASE(8)
 #undef DEMF_CASE

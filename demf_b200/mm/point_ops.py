@@ -657,20 +657,24 @@ def decode_boxes(res, num_dir_bins, box, obj_prob, sem_prob, row_offset):
             _p(obj_prob), _p(sem_prob), _stream()), "demf_decode_boxes")
 
 
-def bias_layer_norm_rows(x, gamma, beta, eps, bias=None, residual=None, out=None):
+def bias_layer_norm_rows(x, gamma, beta, eps, bias=None, residual=None, out=None, post_add=None):
     """LayerNorm(x + bias + residual) over the last axis of contiguous rows x (R, C) in one pass
-    (csrc/glue.cu); C a multiple of 128 up to 1024. `out` may be x itself."""
+    (csrc/glue.cu); C a multiple of 128 up to 1024. `out` may be x itself. With `post_add` (R, C)
+    also returns out + post_add (the next attention's query + positional embedding)."""
     _need_cuda(x, gamma, beta)
     R, C = x.shape
     assert x.is_contiguous() and x.dtype == torch.float32
     assert residual is None or (residual.is_contiguous() and residual.shape == x.shape)
+    assert post_add is None or (post_add.is_contiguous() and post_add.shape == x.shape)
     if out is None:
         out = torch.empty_like(x)
+    out2 = torch.empty_like(x) if post_add is not None else None
     with torch.cuda.device_of(x):
         _lib.check(_lib.load().demf_bias_layer_norm_rows(
             _p(x), _p(bias) if bias is not None else None, _p(residual) if residual is not None else None,
-            _p(gamma), _p(beta), R, C, float(eps), _p(out), _stream()), "demf_bias_layer_norm_rows")
-    return out
+            _p(gamma), _p(beta), R, C, float(eps), _p(out), _p(post_add) if post_add is not None else None,
+            _p(out2) if out2 is not None else None, _stream()), "demf_bias_layer_norm_rows")
+    return out if out2 is None else (out, out2)
 
 
 def box_point_count(points, boxes):
@@ -706,3 +710,43 @@ def aligned_3d_nms(minmax, scores, classes, valid, thresh):
         _lib.check(_lib.load().demf_aligned_3d_nms(_p(minmax), _p(scores), _p(classes), _p(valid8), B, K,
                                                    float(thresh), _p(keep), _stream()), "demf_aligned_3d_nms")
     return keep.bool()
+
+
+def levels_to_rows(levels, out=None):
+    """Pyramid levels, each (B,C,H,W) contiguous -> token rows (B, sum H*W, C) in level order, one launch
+    (the flatten(2).transpose(1,2) + cat of the reference's multi-level flatten)."""
+    import ctypes
+    _need_cuda(*levels)
+    B, C = levels[0].shape[:2]
+    assert 1 <= len(levels) <= 8
+    for f in levels:
+        assert f.is_contiguous() and f.dtype == torch.float32 and f.shape[:2] == (B, C)
+    hw = [f.shape[2] * f.shape[3] for f in levels]
+    if out is None:
+        out = torch.empty(B, sum(hw), C, dtype=torch.float32, device=levels[0].device)
+    assert out.is_contiguous() and out.shape == (B, sum(hw), C)
+    ptrs = (ctypes.c_void_p * len(levels))(*[f.data_ptr() for f in levels])
+    sizes = (ctypes.c_int * len(levels))(*hw)
+    with torch.cuda.device_of(out):
+        _lib.check(_lib.load().demf_levels_to_rows(ptrs, sizes, len(levels), B, C, _p(out), _stream()),
+                   "demf_levels_to_rows")
+    return out
+
+
+def vote_tail(votes, seed_xyz, seed_rows, xyz_range=None, norm_feats=True):
+    """VoteModule tail for one vote per seed: votes (R, >=3+C) rows of conv_out, seed_xyz (B,N,3),
+    seed_rows (B,N,C) -> vote_xyz (B,N,3), offset (B,N,3), vote_rows (B,N,C); one launch."""
+    import ctypes
+    _need_cuda(votes, seed_xyz, seed_rows)
+    B, N, C = seed_rows.shape
+    assert votes.dim() == 2 and votes.stride(1) == 1 and votes.shape[0] == B * N and votes.shape[1] >= C + 3
+    assert seed_xyz.is_contiguous() and seed_rows.is_contiguous() and seed_xyz.shape == (B, N, 3)
+    vote_xyz = torch.empty_like(seed_xyz)
+    offset = torch.empty_like(seed_xyz)
+    vote_rows = torch.empty_like(seed_rows)
+    rng = (ctypes.c_float * 3)(*[float(v) for v in xyz_range]) if xyz_range is not None else None
+    with torch.cuda.device_of(votes):
+        _lib.check(_lib.load().demf_vote_tail(_p(votes), votes.stride(0), _p(seed_xyz), _p(seed_rows), B * N, C,
+                                              rng, int(bool(norm_feats)), _p(vote_xyz), _p(offset), _p(vote_rows),
+                                              _stream()), "demf_vote_tail")
+    return vote_xyz, offset, vote_rows

@@ -454,6 +454,21 @@ class VoteModule(nn.Module):
             out_channel = 3 * self.vote_per_seed
         self.conv_out = nn.Conv1d(prev_channels, out_channel, 1)
 
+    fused_eval = True
+
+    def _padded_conv_out(self):
+        """conv_out's (3+C, C) weight and bias zero-padded to a multiple of 4 output rows, rebuilt when a
+        parameter changes."""
+        w, b = self.conv_out.weight, self.conv_out.bias
+        key = (w.data_ptr(), w._version, b.data_ptr(), b._version)
+        cache = self.__dict__.get('_conv_out_pad')
+        if cache is None or cache[0] != key:
+            pad = (-w.shape[0]) % 4
+            cache = (key, torch.nn.functional.pad(w.detach().flatten(1), (0, 0, 0, pad)).contiguous(),
+                     torch.nn.functional.pad(b.detach(), (0, pad)).contiguous())
+            self.__dict__['_conv_out_pad'] = cache
+        return cache[1], cache[2]
+
     def forward(self, seed_points, seed_feats):
         """seed_points (B,N,3), seed_feats (B,C,N) -> vote_points (B,N*vps,3),
         vote_feats (B,C,N*vps), offset (B,3,N*vps)."""
@@ -469,6 +484,19 @@ class VoteModule(nn.Module):
         x = seed_rows.reshape(batch_size * num_seed, feat_channels)
         for layer in self.vote_conv:
             x = conv_module_rows(layer, x)
+        if self.fused_eval and not torch.is_grad_enabled() and x.is_cuda and self.vote_per_seed == 1 \
+                and self.with_res_feat and feat_channels % 128 == 0 and feat_channels <= 512 \
+                and x.dtype == torch.float32:
+            # inference: conv_out as ONE aligned GEMM (3+C outputs padded to a multiple of 4 so that the
+            # library picks its tcgen05 kernel instead of the unaligned sm80 fallback), then offset clamp,
+            # seed + offset, seed_feat + residual and the L2 normalisation in one launch
+            w, b = self._padded_conv_out()
+            votes = torch.addmm(b, x, w.t())
+            seed_xyz = seed_points.contiguous()
+            seed_c = seed_rows.contiguous()
+            vote_points, offset, vote_rows = P.vote_tail(votes, seed_xyz, seed_c, self.vote_xyz_range,
+                                                         self.norm_feats)
+            return vote_points, vote_rows.transpose(2, 1), offset.transpose(2, 1)
         votes = torch.nn.functional.linear(x, self.conv_out.weight.flatten(1), self.conv_out.bias)
         votes = votes.view(batch_size, num_seed, self.vote_per_seed, -1)
         offset = votes[:, :, :, 0:3]

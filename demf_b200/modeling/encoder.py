@@ -155,7 +155,10 @@ class DeformableDetrEncoder(BaseModule):
         from ..mm import point_ops as P
         from ..mm.ms_deform_attn import msda_from_projections
         bs, c = mlvl_feats[0].shape[:2]
-        x = torch.cat([f.flatten(2) for f in mlvl_feats], 2).transpose(1, 2).reshape(-1, c)   # (B*S,C)
+        if len(mlvl_feats) <= 8 and all(f.is_contiguous() for f in mlvl_feats):
+            x = P.levels_to_rows(list(mlvl_feats)).view(-1, c)                                # (B*S,C)
+        else:
+            x = torch.cat([f.flatten(2) for f in mlvl_feats], 2).transpose(1, 2).reshape(-1, c)
         S = x.shape[0] // bs
         pos_rows = geo.get('pos_rows')
         key = (self.level_embeds._version, self.level_embeds.data_ptr())

@@ -201,9 +201,13 @@ class DeMFVoteHead(BaseModule):
         starts = np.concatenate([[0], np.cumsum([h * w for h, w in shapes])])
         num_value = int(starts[-1])
 
-        pyramid = mlvl_feats[0].new_empty(batch_size, num_value, channels)
-        for lvl, feat in enumerate(mlvl_feats):
-            pyramid[:, starts[lvl]:starts[lvl + 1]].copy_(feat.flatten(2).transpose(1, 2))
+        if dev.type == 'cuda' and len(mlvl_feats) <= 8 and all(
+                f.is_contiguous() and f.dtype == torch.float32 and not f.requires_grad for f in mlvl_feats):
+            pyramid = P.levels_to_rows(list(mlvl_feats))     # one coalesced transpose launch
+        else:
+            pyramid = mlvl_feats[0].new_empty(batch_size, num_value, channels)
+            for lvl, feat in enumerate(mlvl_feats):
+                pyramid[:, starts[lvl]:starts[lvl + 1]].copy_(feat.flatten(2).transpose(1, 2))
         feat_flatten = pyramid.permute(1, 0, 2)
 
         input_img_h, input_img_w = img_metas[0]['batch_input_shape']

@@ -245,14 +245,33 @@ int demf_box_point_count(const float* points, int point_stride, const float* box
 int demf_aligned_3d_nms(const float* minmax, const float* scores, const int64_t* classes, const uint8_t* valid,
                         int B, int K, float thresh, uint8_t* keep, void* stream);
 
+/* Tail of mmdet3d VoteModule.forward (models/model_utils/vote_module.py; built by DeMFVoteHead,
+ * class_agnostic_vote_head.py:371) for vote_per_seed = 1, inference: from the conv_out rows
+ * votes (rows, ldv) = [offset(3) | residual(C) | padding] to vote_xyz (rows,3) = seed_xyz + clamp(offset),
+ * offset (rows,3) and vote_rows (rows,C) = (seed_rows + residual), L2-normalised per row when norm_feats.
+ * xyz_range: HOST pointer to 3 floats (vote_xyz_range) or NULL. C a multiple of 128 up to 512. */
+int demf_vote_tail(const float* votes, int ldv, const float* seed_xyz, const float* seed_rows, long rows, int C,
+                   const float* xyz_range, int norm_feats, float* vote_xyz, float* offset, float* vote_rows,
+                   void* stream);
+
+/* Image pyramid (num_levels <= 8 tensors (B,C,H_l*W_l) f32, HOST array of device pointers and HOST array of
+ * H_l*W_l) -> token rows out (B, sum H_l*W_l, C): the flatten(2).transpose(1,2) + cat of
+ * DeMFVoteHead.prepare_decoder_inputs (demf/modeling/heads/class_agnostic_vote_head.py:570-591) and of
+ * DeformableDetrEncoder.transformer (deform_detr_encoder.py:107-121) in one coalesced launch. */
+int demf_levels_to_rows(const float* const* levels, const int* hw, int num_levels, int B, int C, float* out,
+                        void* stream);
+
 /* LayerNorm over rows with the preceding bias / residual adds folded in: replaces, for inference, the
  * `dropout(out) + identity` add and the nn.LayerNorm after every attention and FFN block of mmcv's
  * BaseTransformerLayer (post-norm) that the image-branch encoder runs
  * (demf/modeling/layers/deform_detr_encoder.py:141-151, configs/demf/demf_votenet.py:33-39).
  *   out[r,:] = LN(x[r,:] + bias[:] + residual[r,:]) * gamma + beta; bias and residual may be NULL.
+ *   post_add / out2 (both or neither): out2[r,:] = out[r,:] + post_add[r,:], the `query + query_pos` of the
+ *   attention that follows (mmcv MultiScaleDeformableAttention / MultiheadAttention forward).
  * C a multiple of 128 up to 1024, pointers 16-byte aligned; out may alias x. */
 int demf_bias_layer_norm_rows(const float* x, const float* bias, const float* residual, const float* gamma,
-                              const float* beta, long rows, int C, float eps, float* out, void* stream);
+                              const float* beta, long rows, int C, float eps, float* out, const float* post_add,
+                              float* out2, void* stream);
 
 /* ------------------------------------ multi-scale deformable attention --- */
 /* replaces mmcv _ext.ms_deform_attn_forward / ms_deform_attn_backward

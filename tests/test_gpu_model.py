@@ -277,3 +277,39 @@ def test_graphed_train_step_equals_eager(dev):
     assert ((g0 - g1).norm() / g0.norm()).item() <= 1e-3
     assert abs(l0[1] - l1[1]) <= 5e-2 * abs(l0[1]), (l0, l1)
     assert l0[0] != l0[2]
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_decoder_layer_rows_path_equals_module_path(dev, masked):
+    """DeMFTransformerDecoderLayer inference on (B*Q, C) rows (packed q/k projection, fused attention,
+    projection-fed MSDA, bias + residual + LayerNorm kernel) against the module-by-module layer."""
+    from demf_b200.modeling.layers import DeMFTransformerDecoderLayer
+    torch.manual_seed(5)
+    model = engine.build_demf_votenet(num_points=4).to(dev).eval()
+    layer = model.pts_bbox_head.decoder[0]
+    with torch.no_grad():
+        for p in layer.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    B, Q, C = 2, 256, 256
+    g = torch.Generator().manual_seed(9)
+    rows = torch.randn(B, Q, C, generator=g).to(dev)
+    query = rows.permute(1, 0, 2)                                     # (Q,B,C) view of rows, as the head passes it
+    query_pos = torch.rand(B, Q, 6, generator=g).to(dev)
+    pyr = torch.randn(B, synth.pyramid_tokens("S512"), C, generator=g).to(dev)
+    shapes = torch.tensor(synth.PYRAMIDS["S512"], dtype=torch.long, device=dev)
+    lsi = torch.cat([shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]])
+    ref = torch.rand(B, Q, 2, generator=g).to(dev)
+    valid = (0.5 + 0.5 * torch.rand(B, 4, 2, generator=g)).to(dev)
+    mask = (torch.rand(B, pyr.shape[1], generator=g) < 0.2).to(dev) if masked else None
+    kw = dict(query=query, key=None, value=pyr.permute(1, 0, 2), query_pos=query_pos, key_padding_mask=mask,
+              reference_points=ref, spatial_shapes=shapes, level_start_index=lsi, valid_ratios=valid)
+    with torch.no_grad():
+        assert layer._rows_path_ok(query, kw["value"], kw)
+        fast = layer(**kw)
+        try:
+            DeMFTransformerDecoderLayer.fused_eval = False
+            slow = layer(**kw)
+        finally:
+            DeMFTransformerDecoderLayer.fused_eval = True
+    assert fast.shape == slow.shape == (Q, B, C)
+    torch.testing.assert_close(fast, slow, atol=3e-5, rtol=0)

@@ -464,6 +464,45 @@ def test_bias_layer_norm_rows(dev, R, C):
                                  torch.zeros(100, device=dev), 1e-5)
 
 
+@pytest.mark.parametrize("B,C,shapes", [(2, 256, synth.PYRAMIDS["S512"]), (1, 256, synth.PYRAMIDS["REAL"]),
+                                        (3, 70, ((5, 7), (3, 3), (1, 1))), (1, 33, ((1, 1),)),
+                                        (2, 8, tuple((k + 1, 2) for k in range(8)))])
+def test_levels_to_rows(dev, B, C, shapes):
+    g = torch.Generator().manual_seed(C)
+    levels = [torch.randn(B, C, h, w, generator=g) for h, w in shapes]
+    want = torch.cat([f.flatten(2).transpose(1, 2) for f in levels], 1)
+    got = ops.levels_to_rows([f.to(dev) for f in levels])
+    assert got.shape == want.shape and torch.equal(got.cpu(), want)
+    with pytest.raises(AssertionError):
+        ops.levels_to_rows([levels[0].to(dev)[:, ::2]])
+
+
+@pytest.mark.parametrize("C,rng,norm", [(256, None, True), (128, (0.5, 0.5, 0.25), True), (384, None, False)])
+def test_vote_module_fused_tail_equals_composed(dev, C, rng, norm):
+    """VoteModule inference tail (padded conv_out GEMM + one launch for clamp / seed + offset / residual /
+    L2 normalisation) against the statement-by-statement path of the same module."""
+    from demf_b200.mm.pointnet_modules import VoteModule
+    torch.manual_seed(C)
+    m = VoteModule(C, conv_channels=(C, C), norm_feats=norm, vote_xyz_range=rng).to(dev).eval()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    seeds = torch.rand(2, 300, 3, device=dev) * 4 - 2
+    feats = torch.randn(2, C, 300, device=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            fused = m(seeds, feats)
+            VoteModule.fused_eval = False
+            composed = m(seeds, feats)
+    finally:
+        VoteModule.fused_eval = True
+        torch.backends.cuda.matmul.allow_tf32 = True
+    for a, b in zip(fused, composed):
+        assert a.shape == b.shape
+        torch.testing.assert_close(a, b, atol=2e-6, rtol=1e-5)
+
+
 def test_empty_batches_are_noops(dev):
     assert ops.furthest_point_sample(torch.zeros(0, 5, 3, device=dev), 2).shape == (0, 2)
     assert ops.ball_query(0.0, 1.0, 4, torch.zeros(2, 5, 3, device=dev),
