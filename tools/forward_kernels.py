@@ -1,0 +1,46 @@
+"""Ordered kernel list of ONE warm eval forward (torch.profiler / CUPTI; eager launches on one stream, so
+the durations are warm-cache but serialised). Usage: python tools/forward_kernels.py [--batch 8]"""
+import argparse
+import os
+import re
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import demf_b200  # noqa: E402,F401
+from demf_b200 import engine  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8)
+    args = ap.parse_args()
+    from torch.profiler import ProfilerActivity, profile
+    dev = torch.device("cuda:0")
+    engine.set_gemm_precision("tf32")
+    torch.manual_seed(0)
+    model = engine.build_demf_votenet(num_points=4).to(dev).eval()
+    batch = engine.synthetic_batch(args.batch, 20000, "S512", seed=1, device=dev, with_gt=False)
+    kw = dict(points=batch["points"], img_metas=batch["img_metas"], img=batch["img"])
+    with torch.no_grad():
+        for _ in range(3):
+            model.simple_test(**kw)
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            model.simple_test(**kw)
+            torch.cuda.synchronize()
+    evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA),
+                 key=lambda e: e.time_range.start)
+    total = 0.0
+    for e in evs:
+        name = e.name.replace("(anonymous namespace)::", "").replace("void ", "").replace("at::native::", "")
+        name = re.sub(r"\(.*", "", name)
+        dur = e.time_range.end - e.time_range.start
+        total += dur
+        print(f"{dur:9.1f} us  {name[:110]}")
+    print(f"{len(evs)} kernels, {total:.1f} us summed")
+
+
+if __name__ == "__main__":
+    main()
