@@ -451,16 +451,17 @@ def main():
         eager_tms = max_over_ranks(start.elapsed_time(end)) / tsteps
         gstep = engine.GraphedTrainStep(trainer, tsets[0], max_gt=16)
         for i in range(3):
-            gstep(tsets[i % ROTATE])
+            gstep(tsets[i % ROTATE], next_batch=tsets[(i + 1) % ROTATE])
         barrier()
         start.record()
-        for i in range(tsteps):
-            loss, _ = gstep(tsets[i % ROTATE])
+        for i in range(tsteps):   # the next batch's sampling chain runs on a second stream under this step
+            loss, _ = gstep(tsets[i % ROTATE], next_batch=tsets[(i + 1) % ROTATE])
         end.record()
         barrier()
         tms = max_over_ranks(start.elapsed_time(end))
         train = {"workload": "forward+backward+grad all-reduce+clip+AdamW (BASELINE.json configs[3]), "
-                             "whole step as one CUDA graph, inputs copied device-to-device per step",
+                             "whole step as one CUDA graph + the next batch's sampling chain as a second graph on its own stream, "
+                             "inputs copied device-to-device per step",
                  "batch_per_gpu": TRAIN_BATCH_PER_GPU, "steps": tsteps,
                  "ms_per_step": tms / tsteps, "eager_ms_per_step": eager_tms,
                  "scenes_per_s": TRAIN_BATCH_PER_GPU * n_gpus * tsteps / (tms * 1e-3),

@@ -231,7 +231,7 @@ class GraphedTrainStep:
     step 1 of training.
     """
 
-    def __init__(self, trainer, example, max_gt=16, warmup=3):
+    def __init__(self, trainer, example, max_gt=16, warmup=3, pipeline_sampling=True):
         import copy
         from .mm import geometry
         model = trainer.model
@@ -239,6 +239,8 @@ class GraphedTrainStep:
         dev = example["points"].device
         self.trainer = trainer
         self.max_gt = max_gt
+        self.presampled = None
+        self._prefetched = None
         self._fold = geometry.fold_projection
         self.points = example["points"].clone()
         self.levels = [lv.clone() for lv in example["img"]]
@@ -252,6 +254,8 @@ class GraphedTrainStep:
 
         snapshot = copy.deepcopy(model.state_dict())
         self.stream = torch.cuda.Stream(device=dev)
+        if pipeline_sampling:
+            self._capture_sampler(model, dev, warmup)
         self.stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(self.stream):
             for _ in range(warmup):
@@ -270,12 +274,55 @@ class GraphedTrainStep:
                         v.zero_()
         torch.cuda.synchronize(dev)
 
+    # ---- sampling one batch ahead ------------------------------------------------------------
+    # Furthest point sampling is ~2 ms of strictly sequential iterations on a handful of SMs and depends
+    # only on the coordinates. Inside the step graph it sits on the critical path in front of the first
+    # set-abstraction level; as its own graph on a second stream it runs for batch i+1 underneath the
+    # backward pass of batch i. The step graph reads the indices from static buffers.
+    @staticmethod
+    def _sampling_tensors(samp):
+        levels, seed_fps, grid0 = samp
+        ts = [t for idx, xyz, _ in levels for t in (idx, xyz)]
+        if seed_fps is not None:
+            ts.append(seed_fps[0])
+        if grid0 is not None:
+            ts.append(grid0)
+        return ts
+
+    def _capture_sampler(self, model, dev, warmup):
+        mod = model.train_cfg['pts']['sample_mod']
+        self.points_next = self.points.clone()
+        self.sample_stream = torch.cuda.Stream(device=dev)
+        self.sample_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.sample_stream), torch.no_grad():
+            for _ in range(warmup):
+                model.presample(self.points_next, mod)
+        torch.cuda.current_stream(dev).wait_stream(self.sample_stream)
+        torch.cuda.synchronize(dev)
+        self.sample_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.sample_graph, stream=self.sample_stream), torch.no_grad():
+            nxt = model.presample(self.points_next, mod)
+        self._next_tensors = self._sampling_tensors(nxt)
+        # the step graph's own copy: (idx, new_xyz, no event) per level, seed indices, grid
+        levels, seed_fps, grid0 = nxt
+        self.presampled = ([(idx.clone(), xyz.clone(), None) for idx, xyz, _ in levels],
+                           None if seed_fps is None else (seed_fps[0].clone(), None),
+                           None if grid0 is None else grid0.clone())
+        self._cur_tensors = self._sampling_tensors(self.presampled)
+        self._sampled = torch.cuda.Event()
+        self._consumed = torch.cuda.Event()
+
+    def _sample_into_next(self, points, stream):
+        with torch.cuda.stream(stream):
+            self.points_next.copy_(points, non_blocking=True)
+            self.sample_graph.replay()
+
     def _eager(self):
         t = self.trainer
         t.flat.zero()
         losses = t.model.forward_train(points=self.points, img=self.levels, img_metas=self.metas,
                                        gt_bboxes_3d=self.box, gt_labels_3d=self.label,
-                                       projection=(self.mats, self.affs))
+                                       projection=(self.mats, self.affs), presampled=self.presampled)
         total = sum(losses.values())
         total.backward()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(t.group) > 1:
@@ -307,10 +354,30 @@ class GraphedTrainStep:
             self.box.copy_(self._box_host, non_blocking=True)
             self.label.copy_(self._label_host, non_blocking=True)
 
-    def __call__(self, batch=None):
-        """Run one step (on the current stream) and return the static (total loss, loss dict)."""
+    def __call__(self, batch=None, next_batch=None):
+        """Run one step (on the current stream) and return the static (total loss, loss dict).
+        `next_batch`: the batch of the following call; its sampling chain is started on the second
+        stream right away so that it overlaps this step."""
         if batch is not None:
             self.load(batch)
+        if self.presampled is not None:
+            dev = self.points.device
+            main = torch.cuda.current_stream(dev)
+            if batch is not None:
+                if self._prefetched is not None and self._prefetched is batch["points"]:
+                    main.wait_event(self._sampled)
+                else:   # nothing prefetched for this batch: sample in line
+                    self._sample_into_next(batch["points"], main)
+                for dst, src in zip(self._cur_tensors, self._next_tensors):
+                    dst.copy_(src, non_blocking=True)
+                self._consumed.record(main)
+            self._prefetched = None
+            if next_batch is not None:
+                self.sample_stream.wait_event(self._consumed)
+                self.sample_stream.wait_stream(main)     # next_batch's points may be produced on main
+                self._sample_into_next(next_batch["points"], self.sample_stream)
+                self._sampled.record(self.sample_stream)
+                self._prefetched = next_batch["points"]
         self.graph.replay()
         return self.loss, self.losses
 

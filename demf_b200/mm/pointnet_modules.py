@@ -337,10 +337,20 @@ class PointNet2SASSG(BaseModule):
             streams[device] = torch.cuda.Stream(device=device)
         return streams[device]
 
-    def _sampling_chain(self, xyz):
+    presampled = None   # result of sample() on the cloud the next forward() will see (see below)
+
+    def sample(self, points):
+        """The sampling chain of forward(points) on the current stream: it depends on the coordinates
+        only, not on any weight, so a caller may run it AHEAD of the forward (e.g. for the next batch
+        while this batch's backward runs) and hand the result over through `self.presampled`."""
+        xyz, _ = self._split_point_feats(points)
+        return self._sampling_chain(xyz, overlap=False)
+
+    def _sampling_chain(self, xyz, overlap=None):
         """-> per-level (indices (B,M) i32, new_xyz (B,M,3), ready event), seed fps or None, and the
         ball-query grid of the input cloud (or None)."""
-        overlap = xyz.is_cuda and self.overlap_sampling
+        if overlap is None:
+            overlap = xyz.is_cuda and self.overlap_sampling
         levels, seed_fps, grid0 = [], None, None
         if overlap:
             main = torch.cuda.current_stream(xyz.device)
@@ -381,7 +391,10 @@ class PointNet2SASSG(BaseModule):
         batch, num_points = xyz.shape[:2]
         chained = all(getattr(sa, "num_point", None) is not None and len(sa.num_point) == 1
                       for sa in self.SA_modules)
-        levels, seed_fps, grid0 = self._sampling_chain(xyz) if chained else (None, None, None)
+        if self.presampled is not None:
+            levels, seed_fps, grid0 = self.presampled
+        else:
+            levels, seed_fps, grid0 = self._sampling_chain(xyz) if chained else (None, None, None)
         indices = self._identity_indices(batch, num_points, xyz.device)
         sa_xyz, sa_features, sa_indices = [xyz], [features], [indices]
         # indices of every level into the ORIGINAL cloud: on CUDA one launch for the whole chain,

@@ -125,10 +125,24 @@ class DeMFVoteNet(BaseModule):
             x = self.img_encoder(x, img_metas)
         return x
 
-    def extract_pts_feat(self, pts, sample_mod=None):
+    def presample(self, points, sample_mod):
+        """Every index the forward of `points` will need from furthest point sampling (backbone levels,
+        the head's seed sampling) plus the first level's ball-query grid, on the current stream.
+        Weight-independent: hand the result to forward_train / simple_test as `presampled=` to take
+        the sampling chain off that step's critical path."""
         prefetch = sample_mod == 'seed' and hasattr(self, '_seed_fps_level')
         self.pts_backbone.prefetch_seed_fps = self._seed_fps_level if prefetch else None
-        x = self.pts_backbone(pts)
+        points = torch.stack(list(points)) if not torch.is_tensor(points) else points
+        return self.pts_backbone.sample(points)
+
+    def extract_pts_feat(self, pts, sample_mod=None, presampled=None):
+        prefetch = sample_mod == 'seed' and hasattr(self, '_seed_fps_level')
+        self.pts_backbone.prefetch_seed_fps = self._seed_fps_level if prefetch else None
+        self.pts_backbone.presampled = presampled
+        try:
+            x = self.pts_backbone(pts)
+        finally:
+            self.pts_backbone.presampled = None
         self._seed_fps_indices = x.get('seed_fps_indices') if isinstance(x, dict) else None
         if self.with_pts_neck:
             x = self.pts_neck(x)
@@ -142,11 +156,11 @@ class DeMFVoteNet(BaseModule):
         for meta in img_metas:
             meta['batch_input_shape'] = shape
 
-    def _forward_head(self, points, img, img_metas, sample_mod, projection=None):
+    def _forward_head(self, points, img, img_metas, sample_mod, projection=None, presampled=None):
         self._batch_input_shape(img, img_metas)
         img_features = self.extract_img_feat(img, img_metas)
         points = torch.stack(list(points)) if not torch.is_tensor(points) else points
-        seeds_3d, seed_3d_features, seed_indices = self.extract_pts_feat(points, sample_mod)
+        seeds_3d, seed_3d_features, seed_indices = self.extract_pts_feat(points, sample_mod, presampled)
         feat_dict = dict(seed_points=seeds_3d, seed_features=seed_3d_features,
                          seed_indices=seed_indices)
         if self._seed_fps_indices is not None:
@@ -158,9 +172,9 @@ class DeMFVoteNet(BaseModule):
 
     def forward_train(self, points=None, img=None, img_metas=None, gt_bboxes_ignore=None,
                       gt_bboxes_3d=None, gt_labels_3d=None, pts_semantic_mask=None,
-                      pts_instance_mask=None, projection=None, **kwargs):
+                      pts_instance_mask=None, projection=None, presampled=None, **kwargs):
         points, bbox_preds = self._forward_head(points, img, img_metas,
-                                                self.train_cfg['pts']['sample_mod'], projection)
+                                                self.train_cfg['pts']['sample_mod'], projection, presampled)
         loss_inputs = (points, gt_bboxes_3d, gt_labels_3d, pts_semantic_mask, pts_instance_mask,
                        img_metas)
         return self.pts_bbox_head.loss(bbox_preds, *loss_inputs, gt_bboxes_ignore=gt_bboxes_ignore)

@@ -250,16 +250,25 @@ def test_graphed_train_step_equals_eager(dev):
     engine.set_gemm_precision("fp32")
     batches = [engine.synthetic_batch(2, 20000, "S512", seed=20 + i, device=dev) for i in range(2)]
     results = []
-    for graphed in (False, True):
+    for graphed in (False, "inline", "ahead"):
         torch.manual_seed(4)
         model = engine.build_demf_votenet(num_points=4).to(dev).train()
         _no_dropout(model)
         trainer = engine.Trainer(model, capturable=True)
-        step = engine.GraphedTrainStep(trainer, batches[0], max_gt=16) if graphed else None
+        step = engine.GraphedTrainStep(trainer, batches[0], max_gt=16,
+                                       pipeline_sampling=graphed == "ahead") if graphed else None
         losses, grad1 = [], None
         for i in range(3):
             batch = batches[i % 2]
-            if graphed:
+            if graphed == "ahead":   # the next batch's sampling chain runs under this step
+                total, _ = step(batch, next_batch=batches[(i + 1) % 2] if i != 1 else None)
+                # the indices the step graph just consumed are those of THIS batch
+                with torch.no_grad():
+                    want = step._sampling_tensors(model.presample(batch["points"], "seed"))
+                for got_t, want_t in zip(step._cur_tensors, want):
+                    if got_t.dtype != torch.uint8:   # the grid workspace orders a cell's points by atomics
+                        assert torch.equal(got_t, want_t)
+            elif graphed:
                 total, _ = step(batch)
             else:
                 box, lab = engine.pad_gt(batch["gt_bboxes_3d"], batch["gt_labels_3d"], 16, dev)
@@ -268,7 +277,12 @@ def test_graphed_train_step_equals_eager(dev):
             if i == 0:
                 grad1 = trainer.flat.buffer.clone()   # clipped gradient of step 1
         results.append((losses, grad1))
-    (l0, g0), (l1, g1) = results
+    (l0, g0), (l1, g1), (l2, g2) = results
+    # sampling ahead of the step (own graph, second stream; step 3 falls back to in-line sampling) changes
+    # no index: same first loss and gradient as the single-graph step
+    assert abs(l1[0] - l2[0]) <= 1e-5 * abs(l1[0]), (l1, l2)
+    assert ((g1 - g2).norm() / g1.norm()).item() <= 1e-3
+    assert abs(l1[1] - l2[1]) <= 1e-1 * abs(l1[1]) and abs(l1[2] - l2[2]) <= 1e-1 * abs(l1[2]), (l1, l2)
     # Step 1 sees identical weights: same loss and -- up to the order of the float atomics in the
     # backward kernels (as upstream's) -- the same clipped gradient. Later steps are only
     # statistically equal: AdamW's first updates are +-lr*sign(g), so a rounding-level difference
