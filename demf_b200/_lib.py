@@ -56,6 +56,12 @@ _SIGNATURES = {
     "demf_sa_fused_tune": [_c_int, _c_int],
     "demf_sa_fused_tune_pair": [_c_int],
     "demf_msda_fwd": [_ptr, _ptr, _ptr, _ptr, _ptr] + [_c_int] * 7 + [_ptr, _ptr],
+    "demf_bn_rows_supported": [_c_int],
+    "demf_bn_rows_state_bytes": [_c_int],
+    "demf_bn_rows_fwd": [_ptr, ctypes.c_long, _c_int, _ptr, _ptr, _c_float, _c_float, _c_int, _ptr, _ptr, _ptr, _ptr,
+                         _ptr, _ptr, _ptr],
+    "demf_bn_rows_bwd": [_ptr, _ptr, _ptr, ctypes.c_long, _c_int, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr,
+                         _ptr, _ptr],
     "demf_box_point_count": [_ptr, _c_int, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr],
     "demf_aligned_3d_nms": [_ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_float, _ptr, _ptr],
     "demf_vote_tail": [_ptr, _c_int, _ptr, _ptr, ctypes.c_long, _c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr],
@@ -72,6 +78,7 @@ _RESTYPES = {
     "demf_fps_workspace_bytes": ctypes.c_size_t,
     "demf_sa_pack_floats": ctypes.c_long,
     "demf_ball_grid_workspace_bytes": ctypes.c_size_t,
+    "demf_bn_rows_state_bytes": ctypes.c_long,
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

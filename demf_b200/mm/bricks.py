@@ -528,11 +528,39 @@ def conv_module_rows(cm, x, cols=None):
     if cols is not None:
         w = permute_weight_columns(w, cols)
     y = torch.nn.functional.linear(x, w, cm.conv.bias)
+    if cm.with_norm and _fused_bn_ok(cm, y):
+        # training: batch statistics + normalise + ReLU in two launches (two more in backward)
+        from . import point_ops as P
+        bn = cm.norm
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        state = bn.__dict__.get("_rows_state")
+        if state is None or state.device != y.device:
+            state = P.bn_rows_state(bn.num_features, y.device)
+            bn.__dict__["_rows_state"] = state
+        return P.batch_norm_relu_rows(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum,
+                                      bn.eps, cm.with_activation, state)
     if cm.with_norm:
         y = batch_norm_rows(cm.norm, y)
     if cm.with_activation:
         y = cm.activate(y)
     return y
+
+
+FUSED_BN_TRAIN = True
+
+
+def _fused_bn_ok(cm, y):
+    """Batch-statistics BatchNorm (+ ReLU or nothing) on contiguous fp32 CUDA rows of a supported width."""
+    bn = cm.norm
+    if not (FUSED_BN_TRAIN and y.is_cuda and y.dtype == torch.float32 and y.dim() == 2 and y.is_contiguous()
+            and y.shape[0] > 1 and isinstance(bn, nn.modules.batchnorm._BatchNorm) and bn.training
+            and bn.affine and bn.track_running_stats and bn.momentum is not None):
+        return False
+    if cm.with_activation and type(cm.activate) is not nn.ReLU:
+        return False
+    from . import point_ops as P
+    return P.bn_rows_supported(bn.num_features)
 
 
 def as_rows(features):

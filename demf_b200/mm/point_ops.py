@@ -750,3 +750,55 @@ def vote_tail(votes, seed_xyz, seed_rows, xyz_range=None, norm_feats=True):
                                               rng, int(bool(norm_feats)), _p(vote_xyz), _p(offset), _p(vote_rows),
                                               _stream()), "demf_vote_tail")
     return vote_xyz, offset, vote_rows
+
+
+class _BatchNormReluRows(torch.autograd.Function):
+    """Training-mode BatchNorm (+ ReLU) on rows, two launches forward and two backward (csrc/bn_rows.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, relu, state):
+        R, C = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=x.device)
+        invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+        with torch.cuda.device_of(x):
+            _lib.check(_lib.load().demf_bn_rows_fwd(
+                _p(x), R, C, _p(gamma), _p(beta), float(eps), float(momentum), int(relu),
+                _p(running_mean) if running_mean is not None else None,
+                _p(running_var) if running_var is not None else None, _p(state), _p(mean), _p(invstd), _p(y),
+                _stream()), "demf_bn_rows_fwd")
+        ctx.save_for_backward(x, y, gamma, mean, invstd, state)
+        ctx.relu = bool(relu)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_y):
+        x, y, gamma, mean, invstd, state = ctx.saved_tensors
+        R, C = x.shape
+        grad_y = grad_y.contiguous()
+        grad_x = torch.empty_like(x)
+        grads = torch.empty(4, C, dtype=torch.float32, device=x.device)     # grad_gamma, grad_beta, coef(2)
+        with torch.cuda.device_of(x):
+            _lib.check(_lib.load().demf_bn_rows_bwd(
+                _p(grad_y), _p(y), _p(x), R, C, _p(gamma), _p(mean), _p(invstd), int(ctx.relu), _p(state),
+                _p(grads[2:]), _p(grad_x), _p(grads[0]), _p(grads[1]), _stream()), "demf_bn_rows_bwd")
+        return grad_x, grads[0], grads[1], None, None, None, None, None, None
+
+
+def bn_rows_supported(channels):
+    return bool(_lib.load().demf_bn_rows_supported(int(channels)))
+
+
+def bn_rows_state(channels, device):
+    """Zeroed persistent accumulator block a BatchNorm layer owns for batch_norm_relu_rows."""
+    nbytes = int(_lib.load().demf_bn_rows_state_bytes(int(channels)))
+    return torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=device)
+
+
+def batch_norm_relu_rows(x, gamma, beta, running_mean, running_var, momentum, eps, relu, state):
+    """y = [relu](batch_norm(x)) with batch statistics over the rows of x (R, C), differentiable in x,
+    gamma, beta; running statistics updated in place. `state` from bn_rows_state(C, device)."""
+    _need_cuda(x, gamma, beta)
+    assert x.dim() == 2 and x.is_contiguous() and x.dtype == torch.float32 and x.shape[0] > 0
+    return _BatchNormReluRows.apply(x, gamma, beta, running_mean, running_var, momentum, eps, relu, state)

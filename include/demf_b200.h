@@ -230,6 +230,27 @@ int demf_decode_boxes(const float* center, int s_center, const float* size, int 
                       int classes, int out_rows, int out_offset, float* box, float* obj_prob,
                       float* sem_prob, void* stream);
 
+/* ------------------------------------------------ training BatchNorm rows --- */
+/* Training-mode BatchNorm (+ ReLU) over point-major rows x (R,C): replaces, for the 1x1-conv ConvModules of
+ * the shared MLPs (mmcv ConvModule conv -> BN -> ReLU as built by mmdet3d PointSAModule / PointFPModule /
+ * VoteModule / BaseConvBboxHead), torch's batch_norm collect_statistics / update_stats / transform_input /
+ * clamp forward and threshold / backward_reduce / backward_elemt backward kernels by two launches each way.
+ *   fwd: y = [relu]((x - mean_batch) * invstd * gamma + beta); save_mean / save_invstd (C) for backward;
+ *        running_mean / running_var (may both be NULL) updated with `momentum` (unbiased variance).
+ *   bwd: grad_x (R,C), grad_gamma (C), grad_beta (C) from grad_y, the forward's y (ReLU mask), x and the
+ *        saved statistics; coef = scratch of 2*C floats.
+ * state: persistent device block of demf_bn_rows_state_bytes(C) bytes owned by the layer, ZERO before the
+ * first call (each call leaves it zero); calls sharing a state must be stream-ordered.
+ * C = 4 * 2^k <= 1024 (demf_bn_rows_supported), all pointers 16-byte aligned. */
+int demf_bn_rows_supported(int C);
+long demf_bn_rows_state_bytes(int C);
+int demf_bn_rows_fwd(const float* x, long R, int C, const float* gamma, const float* beta, float eps,
+                     float momentum, int relu, float* running_mean, float* running_var, void* state,
+                     float* save_mean, float* save_invstd, float* y, void* stream);
+int demf_bn_rows_bwd(const float* grad_y, const float* y, const float* x, long R, int C, const float* gamma,
+                     const float* save_mean, const float* save_invstd, int relu, void* state, float* coef,
+                     float* grad_x, float* grad_gamma, float* grad_beta, void* stream);
+
 /* ------------------------------------------- inference post-processing --- */
 /* The two per-scene loops of mmdet3d 0.18.1 VoteHead.multiclass_nms_single, reached from
  * DeMFVoteHead.get_bboxes (demf/modeling/heads/class_agnostic_vote_head.py:739-743):

@@ -503,6 +503,70 @@ def test_vote_module_fused_tail_equals_composed(dev, C, rng, norm):
         torch.testing.assert_close(a, b, atol=2e-6, rtol=1e-5)
 
 
+@pytest.mark.parametrize("R,C,relu", [(1000, 64, True), (4097, 256, True), (33, 128, False), (5000, 1024, True),
+                                      (777, 4, True), (2, 8, True), (300000, 64, True)])
+def test_batch_norm_relu_rows_forward_backward(dev, R, C, relu):
+    """Training BatchNorm (+ReLU) on rows against torch's batch_norm + relu evaluated in float64:
+    outputs, running statistics and all three gradients; twice in a row (the layer's accumulator
+    block must come back zeroed)."""
+    g = torch.Generator().manual_seed(R + C)
+    x = (torch.randn(R, C, generator=g) * 2 + 0.7)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    gy = torch.randn(R, C, generator=g)
+    xd = x.double().requires_grad_(True)
+    gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    rm, rv = torch.zeros(C, dtype=torch.float64), torch.ones(C, dtype=torch.float64)
+    want = torch.nn.functional.batch_norm(xd, rm, rv, gd, bd, True, 0.1, 1e-5)
+    if relu:
+        want = torch.relu(want)
+    want.backward(gy.double())
+    state = ops.bn_rows_state(C, dev)
+    assert ops.bn_rows_supported(C) and not ops.bn_rows_supported(C + 4 if C != 4 else 12)
+    for rep in range(2):
+        xg = x.to(dev).requires_grad_(True)
+        gg, bg = gamma.to(dev).requires_grad_(True), beta.to(dev).requires_grad_(True)
+        rmg, rvg = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+        got = ops.batch_norm_relu_rows(xg, gg, bg, rmg, rvg, 0.1, 1e-5, relu, state)
+        got.backward(gy.to(dev))
+        assert (got.detach().cpu().double() - want.detach()).abs().max().item() <= 2e-5
+        assert (rmg.cpu().double() - rm).abs().max().item() <= 1e-6
+        assert (rvg.cpu().double() - rv).abs().max().item() <= 1e-5
+        for a, b in ((xg.grad, xd.grad), (gg.grad, gd.grad), (bg.grad, bd.grad)):
+            scale = b.abs().max().item() + 1e-12
+            assert (a.cpu().double() - b).abs().max().item() <= 2e-5 * scale + 2e-5   # R = 2 cancels to ~0
+        assert state.abs().sum().item() == 0.0
+
+
+def test_conv_module_rows_training_uses_fused_bn_and_matches_torch(dev):
+    from demf_b200.mm import bricks
+    torch.manual_seed(0)
+    cm = bricks.ConvModule(32, 64, 1, conv_cfg=dict(type="Conv1d"), norm_cfg=dict(type="BN1d"), bias=True).to(dev).train()
+    ref = bricks.ConvModule(32, 64, 1, conv_cfg=dict(type="Conv1d"), norm_cfg=dict(type="BN1d"), bias=True).to(dev).train()
+    ref.load_state_dict(cm.state_dict())
+    x = torch.randn(5000, 32, device=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        n0 = _lib.launch_count()
+        y = bricks.conv_module_rows(cm, x)
+        y.square().sum().backward()
+        assert _lib.launch_count() - n0 == 4          # stats, apply, backward reduce, backward apply
+        bricks.FUSED_BN_TRAIN = False
+        yr = bricks.conv_module_rows(ref, x)
+        yr.square().sum().backward()
+    finally:
+        bricks.FUSED_BN_TRAIN = True
+        torch.backends.cuda.matmul.allow_tf32 = True
+    torch.testing.assert_close(y, yr, atol=2e-5, rtol=0)
+    wscale = ref.conv.weight.grad.abs().max().item()
+    for (n, p), (_, q) in zip(cm.named_parameters(), ref.named_parameters()):
+        if n == "conv.bias":   # a bias in front of BatchNorm has zero gradient: both are rounding noise
+            assert p.grad.abs().max().item() <= 1e-4 * wscale and q.grad.abs().max().item() <= 1e-4 * wscale
+        else:
+            torch.testing.assert_close(p.grad, q.grad, atol=2e-3 * q.grad.abs().max().item() + 1e-5, rtol=0)
+    torch.testing.assert_close(cm.norm.running_var, ref.norm.running_var, atol=1e-5, rtol=0)
+    assert int(cm.norm.num_batches_tracked) == 1
+
+
 def test_empty_batches_are_noops(dev):
     assert ops.furthest_point_sample(torch.zeros(0, 5, 3, device=dev), 2).shape == (0, 2)
     assert ops.ball_query(0.0, 1.0, 4, torch.zeros(2, 5, 3, device=dev),

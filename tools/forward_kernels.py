@@ -12,14 +12,47 @@ import demf_b200  # noqa: E402,F401
 from demf_b200 import engine  # noqa: E402
 
 
+def train_step(args, dev):
+    from collections import defaultdict
+    from torch.profiler import ProfilerActivity, profile
+    model = engine.build_demf_votenet(num_points=4).to(dev).train()
+    trainer = engine.Trainer(model, capturable=True)
+    batch = engine.synthetic_batch(args.batch, 20000, "S512", seed=1, device=dev)
+    box, lab = engine.pad_gt(batch["gt_bboxes_3d"], batch["gt_labels_3d"], 16, dev)
+    batch = dict(batch, gt_bboxes_3d=box, gt_labels_3d=lab)
+    for _ in range(3):
+        trainer.step(batch)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        trainer.step(batch)
+        torch.cuda.synchronize()
+    agg = defaultdict(lambda: [0, 0.0])
+    n = 0
+    for e in prof.events():
+        if e.device_type != torch.autograd.DeviceType.CUDA:
+            continue
+        name = e.name.replace("(anonymous namespace)::", "").replace("void ", "").replace("at::native::", "")
+        name = re.sub(r"\(.*", "", name)[:120]
+        agg[name][0] += 1
+        agg[name][1] += e.time_range.end - e.time_range.start
+        n += 1
+    total = sum(v[1] for v in agg.values())
+    print(f"{n} kernels, {total:.1f} us summed (warm, serialised)")
+    for name, (cnt, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
+        print(f"{us:9.1f} us {100 * us / total:5.1f}%  x{cnt:4d}  {name}")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--train", action="store_true", help="one training step instead; prints per-kernel totals")
     args = ap.parse_args()
     from torch.profiler import ProfilerActivity, profile
     dev = torch.device("cuda:0")
     engine.set_gemm_precision("tf32")
     torch.manual_seed(0)
+    if args.train:
+        return train_step(args, dev)
     model = engine.build_demf_votenet(num_points=4).to(dev).eval()
     batch = engine.synthetic_batch(args.batch, 20000, "S512", seed=1, device=dev, with_gt=False)
     kw = dict(points=batch["points"], img_metas=batch["img_metas"], img=batch["img"])
