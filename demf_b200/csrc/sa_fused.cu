@@ -75,10 +75,11 @@ struct SaParams {
   int sleep_ns;  // back-off between mbarrier polls of the worker warps (0 = spin)
   int t2;        // layer 2 runs transposed (D^T = W3 * act2^T): lanes = channels, columns = rows
   int pair;      // CTA pairs (cta_group::2): one MMA covers the tiles of two CTAs, each CTA streams half the weights
+  int pre0;      // layer 0 pre-projected per POINT: feat = (B,N,c0) rows of W1_feat * feat_j, bias carries W1_xyz
 };
 
 struct SmemLayout {
-  int ring, rows, centres, bias, part, bars, total;
+  int ring, rows, centres, bias, part, drow, bars, total;
 };
 
 __host__ __device__ inline SmemLayout smem_layout(const SaParams& p) {
@@ -87,8 +88,9 @@ __host__ __device__ inline SmemLayout smem_layout(const SaParams& p) {
   L.rows = L.ring + p.slots * p.slot_bytes;
   L.centres = L.rows + p.G * p.ns * 4;
   L.bias = L.centres + p.G * 16;
-  L.part = L.bias + (p.c[0] + p.c[1] + p.c[2]) * 4;
-  L.bars = (L.part + (p.ns == 64 ? p.lanes * 2 * p.c[2] * 4 : 0) + 15) & ~15;
+  L.part = L.bias + (p.c[0] + p.c[1] + p.c[2] + (p.pre0 ? 3 * p.c[0] : 0)) * 4;
+  L.drow = (L.part + (p.ns == 64 ? p.lanes * 2 * p.c[2] * 4 : 0) + 15) & ~15;
+  L.bars = (L.drow + (p.pre0 ? p.lanes * kTileRows * 16 : 0) + 15) & ~15;
   L.total = L.bars + (3 * kMaxSlots + 2 * kMaxLanes) * 8 + 16 + 1024;  // + alignment slack
   return L;
 }
@@ -331,7 +333,8 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
     if constexpr (kPair) tmem_alloc2(smem_u32(tmem_slot), p.tmem_cols);
     else tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
   }
-  for (int i = tid; i < p.c[0] + p.c[1] + p.c[2]; i += kThreads) bias_s[i] = __ldg(p.bias + i);
+  for (int i = tid; i < p.c[0] + p.c[1] + p.c[2] + (p.pre0 ? 3 * p.c[0] : 0); i += kThreads)
+    bias_s[i] = __ldg(p.bias + i);
   tc_fence_before_sync();
   if constexpr (kPair) cluster_sync_all();  // the peer's barriers exist before anything arrives on them
   else __syncthreads();
@@ -652,6 +655,68 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
 
       // ---- layers 0 and 1: accumulator -> bias, ReLU, tf32 -> next layer's A operand
       for (int l = 0; l < 2 && ok; ++l) {
+        if (l == 0 && p.pre0) {
+          // Layer 0 is linear in its input [feat_j | (xyz_j - c_i)/r]: the feature half W1f * feat_j does
+          // not depend on the centre and was computed once per POINT (N rows) instead of once per grouped
+          // row (M*ns rows) -- p.feat holds those c0-wide rows. What is left per grouped row is a K = 3
+          // product, done here in fp32 FMAs on TF32-rounded operands while the row is gathered:
+          //   act1[r, c] = relu(P[idx_r, c] + W1x[c] . d_r + b0[c])
+          // written straight into layer 1's A operand. No layer-0 MMA, no W1 stream, no epilogue 0.
+          float4* drow = reinterpret_cast<float4*>(smem + L.drow) + ln * kTileRows;
+          for (int r = lt; r < kTileRows; r += lthreads) {
+            const float4 c = centres[t * cpt + r / ns];
+            const float* pt = cloud + (long)trow[r] * 3;
+            float dx = __fsub_rn(__ldg(pt + 0), c.x), dy = __fsub_rn(__ldg(pt + 1), c.y),
+                  dz = __fsub_rn(__ldg(pt + 2), c.z);
+            if (p.normalize_xyz) {
+              dx = __fmul_rn(dx, scale);
+              dy = __fmul_rn(dy, scale);
+              dz = __fmul_rn(dz, scale);
+            }
+            drow[r] = make_float4(tf32_rna(dx), tf32_rna(dy), tf32_rna(dz), 0.f);
+          }
+          named_sync(2 + ln, lthreads);
+          const int c0 = p.c[0], w = c0 >> 2, total = kTileRows * w;
+          const int w_shift = 31 - __clz(w);  // c0 is a multiple of 32 ...
+          const bool pow2 = (w & (w - 1)) == 0;
+          const float4* b0v = reinterpret_cast<const float4*>(bias_s);
+          const float4* wxv = reinterpret_cast<const float4*>(bias_s + p.c[0] + p.c[1] + p.c[2]);
+          const float4* wyv = wxv + w;
+          const float4* wzv = wyv + w;
+          constexpr int U = 2;
+          for (int e0 = lt; e0 < total; e0 += lthreads * U) {
+            float4 v[U];
+            int rr[U], jj[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int e = e0 + u * lthreads;
+              rr[u] = -1;
+              if (e < total) {
+                const int r = pow2 ? (e >> w_shift) : (e / w);
+                const int j = e - r * w;
+                v[u] = __ldg(reinterpret_cast<const float4*>(fb + (long)trow[r] * c0) + j);
+                rr[u] = r;
+                jj[u] = j;
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (rr[u] < 0) continue;
+              const float4 d = drow[rr[u]];
+              const float4 wx = wxv[jj[u]], wy = wyv[jj[u]], wz = wzv[jj[u]], bb = b0v[jj[u]];
+              float4 o;
+              o.x = fmaxf(v[u].x + fmaf(wz.x, d.z, fmaf(wy.x, d.y, wx.x * d.x)) + bb.x, 0.f);
+              o.y = fmaxf(v[u].y + fmaf(wz.y, d.z, fmaf(wy.y, d.y, wx.y * d.x)) + bb.y, 0.f);
+              o.z = fmaxf(v[u].z + fmaf(wz.z, d.z, fmaf(wy.z, d.y, wx.z * d.x)) + bb.z, 0.f);
+              o.w = fmaxf(v[u].w + fmaf(wz.w, d.z, fmaf(wy.w, d.y, wx.w * d.x)) + bb.w, 0.f);
+              *reinterpret_cast<float4*>(act + (jj[u] >> 3) * kChunkBytes + sw128_offset(rr[u], jj[u] & 7)) =
+                  tf32_operand4(o);
+            }
+          }
+          publish(p.npass + l, t == ln);
+          SA_STAMP();
+          continue;
+        }
         ok = wait_or_fail(acc_full, accp, failed, 4, p.sleep_ns);
         accp ^= 1;
         tc_fence_after_sync();
@@ -818,7 +883,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 bool configure(SaParams& p, int B) {
   const int c1 = p.c[0], c2 = p.c[1], c3 = p.c[2];
   const int cpt = kTileRows / p.ns;
-  const int nch0 = (p.K0 + 31) / 32, nch1 = c1 / 32, nch2 = c2 / 32;
+  const int nch0 = (p.K0 + 31) / 32, nch1 = c1 / 32, nch2 = c2 / 32;   // K0 = 0 with a pre-projected layer 0
   const int total_chunks = nch0 + nch1 + nch2;
   const int cmax = c1 > c2 ? (c1 > c3 ? c1 : c3) : (c2 > c3 ? c2 : c3);
   const int act_chunks = nch1 > nch2 ? nch1 : nch2;
@@ -830,14 +895,14 @@ bool configure(SaParams& p, int B) {
   for (int lanes = kMaxLanes; lanes >= 1; lanes >>= 1) {
     if (lanes > max_tiles || lanes > g_sa_max_lanes) continue;
     const int lane_cols = 512 / lanes;
-    if (c1 + c2 > lane_cols || c3 > lane_cols) continue;
+    if ((p.pre0 ? c2 : c1 + c2) > lane_cols || c3 > lane_cols) continue;
     // layer-0 passes of `cpp` chunks: fewer passes first; a pass shorter than the activation
     // region would not shrink the lane's operand region any further
     const int cpp_min = nch0 < act_chunks ? nch0 : act_chunks;
     for (int cpp = nch0; cpp >= cpp_min; --cpp) {
       p.lanes = lanes;
       p.cpp = cpp;
-      p.npass = (nch0 + cpp - 1) / cpp;
+      p.npass = cpp > 0 ? (nch0 + cpp - 1) / cpp : 0;  // pre-projected layer 0: no layer-0 MMA passes
       int region = (cpp > act_chunks ? cpp : act_chunks) * kChunkBytes;
       while (lanes * region < scratch) region += kChunkBytes;
       p.lane_act_bytes = region;
@@ -852,7 +917,7 @@ bool configure(SaParams& p, int B) {
         p.resident = 0;
         // streamed weights: CTA pairs when the shapes allow (each CTA then streams half of every
         // chunk -- 16 KB ring entries -- for twice the rows per byte that crosses L2 -> SM)
-        p.pair = (g_sa_pair && c3 == 256 && c1 % 16 == 0 && c2 % 16 == 0 && c1 <= 256 && c2 <= 256) ? 1 : 0;
+        p.pair = (g_sa_pair && !p.pre0 && c3 == 256 && c1 % 16 == 0 && c2 % 16 == 0 && c1 <= 256 && c2 <= 256) ? 1 : 0;
         if (p.pair) {
           const int h1 = c1 / 2, h2 = c2 / 2;
           p.slot_bytes = (h1 > h2 ? (h1 > 128 ? h1 : 128) : (h2 > 128 ? h2 : 128)) * 128;
@@ -866,10 +931,11 @@ bool configure(SaParams& p, int B) {
       }
       if (p.slots == 0) continue;
       p.lane_cols = lane_cols;
+      const int a1 = p.pre0 ? 0 : c1;   // no layer-0 accumulator when layer 0 is pre-projected
       p.acc_col[0] = 0;
-      p.acc_col[1] = c1;
-      p.acc_col[2] = (c1 + c2 + c3 <= lane_cols) ? c1 + c2 : 0;
-      const int top = p.acc_col[2] + c3 > c1 + c2 ? p.acc_col[2] + c3 : c1 + c2;
+      p.acc_col[1] = a1;
+      p.acc_col[2] = (a1 + c2 + c3 <= lane_cols) ? a1 + c2 : 0;
+      const int top = p.acc_col[2] + c3 > a1 + c2 ? p.acc_col[2] + c3 : a1 + c2;
       const int used = (lanes - 1) * lane_cols + top;
       p.tmem_cols = used <= 32 ? 32 : used <= 64 ? 64 : used <= 128 ? 128 : used <= 256 ? 256 : 512;
       // fewer tiles per CTA when the grid would not fill the GPU (but keep every lane busy)
@@ -942,10 +1008,10 @@ int demf_sa_fused_error(void) {
   return e;
 }
 
-int demf_sa_fused_fwd(const float* xyz, const float* feat_rows, const float* new_xyz, int B, int N, int M,
-                      int C, float min_radius, float max_radius, int ns, int normalize_xyz, int query,
-                      const float* wpack, const float* bias, int c1, int c2, int c3, const void* grid,
-                      int32_t* idx, float* out, void* stream) {
+static int sa_fused_launch(const float* xyz, const float* feat_rows, const float* new_xyz, int B, int N, int M,
+                           int C, float min_radius, float max_radius, int ns, int normalize_xyz, int query,
+                           const float* wpack, const float* bias, int c1, int c2, int c3, const void* grid,
+                           int32_t* idx, float* out, void* stream, int pre0) {
   DEMF_REQUIRE_PTR(xyz);
   DEMF_REQUIRE_PTR(new_xyz);
   DEMF_REQUIRE_PTR(wpack);
@@ -971,7 +1037,8 @@ int demf_sa_fused_fwd(const float* xyz, const float* feat_rows, const float* new
   p.M = M;
   p.C = C;
   p.ns = ns;
-  p.K0 = ((((C + 3) / 4) * 4 + 4) + 7) / 8 * 8;
+  p.pre0 = pre0;
+  p.K0 = pre0 ? 0 : ((((C + 3) / 4) * 4 + 4) + 7) / 8 * 8;
   p.c[0] = c1;
   p.c[1] = c2;
   p.c[2] = c3;
@@ -1033,6 +1100,25 @@ int demf_sa_fused_fwd(const float* xyz, const float* feat_rows, const float* new
     return static_cast<int>(e);
   }
   return after_launch("sa_fused_fwd_kernel");
+}
+
+int demf_sa_fused_fwd(const float* xyz, const float* feat_rows, const float* new_xyz, int B, int N, int M,
+                      int C, float min_radius, float max_radius, int ns, int normalize_xyz, int query,
+                      const float* wpack, const float* bias, int c1, int c2, int c3, const void* grid,
+                      int32_t* idx, float* out, void* stream) {
+  return sa_fused_launch(xyz, feat_rows, new_xyz, B, N, M, C, min_radius, max_radius, ns, normalize_xyz, query,
+                         wpack, bias, c1, c2, c3, grid, idx, out, stream, 0);
+}
+
+/* Layer 0 pre-projected per point: proj_rows (B,N,c1) = feat_rows * W1_feat^T (no bias), wpack = the packed
+ * images of W2 and W3 only, bias = [b1(c1) | b2(c2) | b3(c3) | W1_xyz^T (3 x c1, TF32-rounded)]. */
+int demf_sa_fused_pre_fwd(const float* xyz, const float* proj_rows, const float* new_xyz, int B, int N, int M,
+                          float min_radius, float max_radius, int ns, int normalize_xyz, int query,
+                          const float* wpack, const float* bias, int c1, int c2, int c3, const void* grid,
+                          int32_t* idx, float* out, void* stream) {
+  DEMF_REQUIRE_PTR(proj_rows);
+  return sa_fused_launch(xyz, proj_rows, new_xyz, B, N, M, c1, min_radius, max_radius, ns, normalize_xyz, query,
+                         wpack, bias, c1, c2, c3, grid, idx, out, stream, 1);
 }
 
 }  // extern "C"

@@ -198,6 +198,19 @@ def main():
                              args.reps, flush)
             report("sa_fused", dict(B=B, N=N, M=M, ns=ns, C=C, widths=widths,
                                     TFLOPs_median=round(flops / med / 1e9, 1)), med, mn, hbm)
+            if C >= 32:
+                # first layer pre-projected per point (one GEMM over N rows) + the kernel without layer 0
+                w0 = torch.cat([ws[0][:, K - 4:K - 1], ws[0][:, :C]], 1)      # upstream order [xyz | feat]
+                w_feat_t, wpack2, bias2, wd2 = ops.sa_pack_mlp_pre(w0, [ws[1], ws[2]], bs)
+
+                def pre():
+                    torch.backends.cuda.matmul.allow_tf32 = False
+                    proj = (f.view(B * N, C) @ w_feat_t).view(B, N, -1)
+                    torch.backends.cuda.matmul.allow_tf32 = True
+                    return ops.sa_fused_pre(x, c, proj, 0.0, r, ns, True, wpack2, bias2, wd2)
+                med, mn = timeit(pre, args.reps, flush)
+                report("sa_fused_pre", dict(B=B, N=N, M=M, ns=ns, C=C, widths=widths,
+                                            TFLOPs_median=round(flops / med / 1e9, 1)), med, mn, hbm)
             if N >= 2048:
                 med, mn = timeit(lambda: ops.ball_grid(x, r), args.reps, flush)
                 report("ball_grid_build", dict(B=B, N=N, r=r), med, mn, B * N * 28)
