@@ -57,6 +57,7 @@ _SIGNATURES = {
     "demf_sa_fused_set_profile": [_ptr],
     "demf_sa_fused_tune": [_c_int, _c_int],
     "demf_sa_fused_tune_pair": [_c_int],
+    "demf_sa_fused_tune_bias_init": [_c_int],
     "demf_msda_fwd": [_ptr, _ptr, _ptr, _ptr, _ptr] + [_c_int] * 7 + [_ptr, _ptr],
     "demf_bn_rows_supported": [_c_int],
     "demf_bn_rows_state_bytes": [_c_int],
@@ -67,6 +68,7 @@ _SIGNATURES = {
     "demf_box_point_count": [_ptr, _c_int, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr],
     "demf_aligned_3d_nms": [_ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_float, _ptr, _ptr],
     "demf_vote_tail": [_ptr, _c_int, _ptr, _ptr, ctypes.c_long, _c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr],
+    "demf_project_points": [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr, _ptr],
     "demf_levels_to_rows": [_ptr, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr],
     "demf_bias_layer_norm_rows": [_ptr, _ptr, _ptr, _ptr, _ptr, ctypes.c_long, _c_int, _c_float, _ptr, _ptr, _ptr,
                                   _ptr],

@@ -199,6 +199,31 @@ __global__ void __launch_bounds__(256) vote_tail_kernel(const float* __restrict_
   }
 }
 
+// Proposal centres -> normalised image coordinates (DeMFVoteHead.get_reference_points,
+// demf/modeling/heads/class_agnostic_vote_head.py:524-547, with the per-scene chain of inverse 3D
+// augmentation, depth2img, 2D augmentation and normalisation folded on the host into mats (B,3,4) and
+// affs (B,4) = (su, sv, ou, ov)):  h = M [x y z 1]^T;  uv = clamp((h.xy / h.z) * s + o, 0, 1).
+// One thread per proposal, fp32 FMAs (the library path was a batched GEMM + four element-wise launches).
+__global__ void __launch_bounds__(256) project_points_kernel(const float* __restrict__ xyz,
+                                                             const float* __restrict__ mats,
+                                                             const float* __restrict__ affs, int Q, long total,
+                                                             float* __restrict__ out) {
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const long b = e / Q;
+    const float* m = mats + b * 12;
+    const float* a = affs + b * 4;
+    const float x = __ldg(xyz + e * 3), y = __ldg(xyz + e * 3 + 1), z = __ldg(xyz + e * 3 + 2);
+    const float hu = fmaf(z, __ldg(m + 2), fmaf(y, __ldg(m + 1), fmaf(x, __ldg(m + 0), __ldg(m + 3))));
+    const float hv = fmaf(z, __ldg(m + 6), fmaf(y, __ldg(m + 5), fmaf(x, __ldg(m + 4), __ldg(m + 7))));
+    const float hw = fmaf(z, __ldg(m + 10), fmaf(y, __ldg(m + 9), fmaf(x, __ldg(m + 8), __ldg(m + 11))));
+    const float u = fmaf(__fdiv_rn(hu, hw), __ldg(a + 0), __ldg(a + 2));
+    const float v = fmaf(__fdiv_rn(hv, hw), __ldg(a + 1), __ldg(a + 3));
+    // torch.clamp semantics: NaN stays NaN
+    out[e * 2] = u != u ? u : fminf(fmaxf(u, 0.f), 1.f);
+    out[e * 2 + 1] = v != v ? v : fminf(fmaxf(v, 0.f), 1.f);
+  }
+}
+
 // Pyramid levels (B,C,H_l*W_l) -> token rows (B,S,C), all levels in one launch: 32x32 tiles through
 // shared memory so that both the reads (along the pixels) and the writes (along the channels) are
 // coalesced 128-byte lines. blockIdx.x enumerates (level, pixel tile), blockIdx.y channel tiles,
@@ -395,6 +420,19 @@ int demf_vote_tail(const float* votes, int ldv, const float* seed_xyz, const flo
 #undef DEMF_CASE
   }
   return after_launch("vote_tail_kernel");
+}
+
+int demf_project_points(const float* xyz, const float* mats, const float* affs, int B, int Q, float* out,
+                        void* stream) {
+  DEMF_REQUIRE_PTR(xyz);
+  DEMF_REQUIRE_PTR(mats);
+  DEMF_REQUIRE_PTR(affs);
+  DEMF_REQUIRE_PTR(out);
+  DEMF_REQUIRE(B >= 0 && Q >= 0, DEMF_E_SIZE);
+  const long total = (long)B * Q;
+  if (total == 0) return 0;
+  project_points_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(xyz, mats, affs, Q, total, out);
+  return after_launch("project_points_kernel");
 }
 
 int demf_levels_to_rows(const float* const* levels, const int* hw, int num_levels, int B, int C, float* out,

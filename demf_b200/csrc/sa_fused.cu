@@ -53,6 +53,7 @@ __device__ int g_sa_error = 0;  // sticky: first protocol time-out (never expect
 long long* g_sa_prof = nullptr;
 int g_sa_max_lanes = kMaxLanes;  // tuning knobs (demf_sa_fused_tune)
 int g_sa_sleep_ns = 0;
+int g_sa_bias_init = 0;  // layers 0/1: bias stored into the TMEM accumulator instead of added in the epilogue (no faster)
 int g_sa_pair = 0;       // CTA pairs for streamed weights (demf_sa_fused_tune_pair): correct, not yet faster  // host copy of the debug stamp buffer pointer (demf_sa_fused_set_profile)
 
 struct SaParams {
@@ -76,6 +77,7 @@ struct SaParams {
   int t2;        // layer 2 runs transposed (D^T = W3 * act2^T): lanes = channels, columns = rows
   int pair;      // CTA pairs (cta_group::2): one MMA covers the tiles of two CTAs, each CTA streams half the weights
   int pre0;      // layer 0 pre-projected per POINT: feat = (B,N,c0) rows of W1_feat * feat_j, bias carries W1_xyz
+  int bias_init; // layers 0/1: the workers store the bias into the TMEM accumulator before the MMAs accumulate onto it
 };
 
 struct SmemLayout {
@@ -216,6 +218,7 @@ __device__ __forceinline__ bool issue_group(const SaParams& p, const IssueCtx& c
     // resident weights arrive once: after a lane's first tile their barriers need no second look
     if (check_w && !wait_or_fail(c.wfull0 + 8 * s, p.resident ? 0u : wph, c.failed, 2)) return false;
     const int ksteps = layer == 0 ? (min(32, p.K0 - 32 * (ch0 + ch)) >> 3) : 4;
+    const uint32_t acc0 = layer < 2 ? (uint32_t)p.bias_init : 0u;  // accumulate from the first K step on
     // a K step of 8 tf32 = +32 bytes = +2 in the descriptor's (address >> 4) field
     const uint64_t da = smem_desc_sw128(a0 + ch * kChunkBytes), dw = smem_desc_sw128(c.ring_u32 + s * p.slot_bytes);
     if (layer == 2 && p.t2) {
@@ -229,10 +232,11 @@ __device__ __forceinline__ bool issue_group(const SaParams& p, const IssueCtx& c
         for (int k = 0; k < 4; ++k) mma_tf32(d + h * 128, dwh + 2 * k, da + 2 * k, it, (ch | k) != 0);
       }
     } else if (ksteps == 4) {
+      // layers 0 and 1 accumulate onto columns the workers initialised with the bias (p.bias_init)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) mma_tf32(d, da + 2 * k, dw + 2 * k, idesc, (ch0 | ch | k) != 0);
+      for (int k = 0; k < 4; ++k) mma_tf32(d, da + 2 * k, dw + 2 * k, idesc, acc0 | ch0 | ch | k);
     } else {
-      for (int k = 0; k < ksteps; ++k) mma_tf32(d, da + 2 * k, dw + 2 * k, idesc, (ch0 | ch | k) != 0);
+      for (int k = 0; k < ksteps; ++k) mma_tf32(d, da + 2 * k, dw + 2 * k, idesc, acc0 | ch0 | ch | k);
     }
     if (!p.resident) {
       mma_commit(c.wempty0 + 8 * slot);
@@ -566,6 +570,24 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
       }
     };
 
+    // Bias of layer l into this warp's part of the lane's accumulator (every row gets the same vector):
+    // the MMAs then accumulate onto it and the epilogue has no bias add left (32 FADD + 8 LDS per 32
+    // columns per thread, a quarter of its instructions). Exact: the bias never passes through TF32.
+    auto init_acc = [&](int l) {
+      const float* bl = bias_s + (l == 0 ? 0 : p.c[0]);
+      for (int blk = cg; blk < (p.c[l] >> 5); blk += ncg) {
+        uint32_t u[32];
+        const uint4* bl4 = reinterpret_cast<const uint4*>(bl + blk * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 b = bl4[j];
+          u[4 * j + 0] = b.x; u[4 * j + 1] = b.y; u[4 * j + 2] = b.z; u[4 * j + 3] = b.w;
+        }
+        tmem_st32(tmem + lane_base + p.acc_col[l] + blk * 32, u);
+      }
+      tmem_st_wait();
+    };
+
     // two tail elements (unaligned feature slot / xyz slot / zero slot) of tile t for this thread
     auto tail_load = [&](int t, int s_lo, int t_lo, int w, int e0, float4 (&v)[2], int (&off)[2]) {
       const int32_t* trow = rows + t * kTileRows;
@@ -604,6 +626,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
     };
     for (int t = ln; t < ntiles && ok; t += p.lanes) {
       const int32_t* trow = rows + t * kTileRows;  // rows of centre g are contiguous: g*ns
+      if (p.bias_init && !p.pre0) init_acc(0);      // (the previous tile's last epilogue has read these columns)
       // ---- layer 0: gather the 128 grouped rows (one pass = `cpp` chunks = 8*cpp slots per row)
       for (int pass = 0; pass < p.npass && ok; ++pass) {
         const int s_lo = pass * p.cpp * 8, s_hi = min(S4, s_lo + p.cpp * 8);
@@ -713,6 +736,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
                   tf32_operand4(o);
             }
           }
+          if (p.bias_init) init_acc(1);
           publish(p.npass + l, t == ln);
           SA_STAMP();
           continue;
@@ -722,6 +746,24 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
         tc_fence_after_sync();
         SA_STAMP();
         const float* bl = bias_s + (l == 0 ? 0 : p.c[0]);
+        if (p.bias_init) {
+          for (int blk = cg; blk < (p.c[l] >> 5); blk += ncg) {
+            uint32_t u[32];
+            tmem_ld32(tmem + lane_base + p.acc_col[l] + blk * 32, u);
+            tmem_ld_wait();
+            unsigned char* dst = act + blk * kChunkBytes;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 v;
+              v.x = tf32_operand(fmaxf(__uint_as_float(u[4 * j + 0]), 0.f));
+              v.y = tf32_operand(fmaxf(__uint_as_float(u[4 * j + 1]), 0.f));
+              v.z = tf32_operand(fmaxf(__uint_as_float(u[4 * j + 2]), 0.f));
+              v.w = tf32_operand(fmaxf(__uint_as_float(u[4 * j + 3]), 0.f));
+              *reinterpret_cast<float4*>(dst + sw128_offset(r_epi, j)) = v;
+            }
+          }
+          if (l == 0) init_acc(1);  // layer 1's columns are free: its previous epilogue is long done
+        } else
         for (int blk = cg; blk < (p.c[l] >> 5); blk += ncg) {
           uint32_t u[32];
           tmem_ld32(tmem + lane_base + p.acc_col[l] + blk * 32, u);
@@ -991,6 +1033,11 @@ int demf_sa_fused_set_profile(long long* device_buffer) {
 
 /* tuning knobs (development): most tile pipelines per CTA (1, 2 or 4) and the worker warps'
  * back-off between mbarrier polls in ns (0 = spin) */
+int demf_sa_fused_tune_bias_init(int enable) {
+  g_sa_bias_init = enable ? 1 : 0;
+  return 0;
+}
+
 int demf_sa_fused_tune_pair(int enable) {
   g_sa_pair = enable ? 1 : 0;
   return 0;
@@ -1038,6 +1085,7 @@ static int sa_fused_launch(const float* xyz, const float* feat_rows, const float
   p.C = C;
   p.ns = ns;
   p.pre0 = pre0;
+  p.bias_init = g_sa_bias_init;
   p.K0 = pre0 ? 0 : ((((C + 3) / 4) * 4 + 4) + 7) / 8 * 8;
   p.c[0] = c1;
   p.c[1] = c2;
@@ -1062,6 +1110,7 @@ static int sa_fused_launch(const float* xyz, const float* feat_rows, const float
   }
   static_assert(kWorkerWarps * (kGridCap + kGridHist) * 4 <= kCloudTile * 12, "grid scratch fits the tile");
   DEMF_REQUIRE(configure(p, B), DEMF_E_UNSUPPORTED);
+  if (p.pair) p.bias_init = 0;
   const SmemLayout L = smem_layout(p);
 
   auto kernel = p.pair ? sa_fused_fwd_kernel<true> : sa_fused_fwd_kernel<false>;

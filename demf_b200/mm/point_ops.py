@@ -853,3 +853,17 @@ def batch_norm_relu_rows(x, gamma, beta, running_mean, running_var, momentum, ep
     _need_cuda(x, gamma, beta)
     assert x.dim() == 2 and x.is_contiguous() and x.dtype == torch.float32 and x.shape[0] > 0
     return _BatchNormReluRows.apply(x, gamma, beta, running_mean, running_var, momentum, eps, relu, state)
+
+
+def project_points(xyz, mats, affs):
+    """xyz (B,Q,3), mats (B,3,4), affs (B,4) -> (B,Q,2) normalised, clamped image coordinates; one launch
+    (geometry.project_batched: batched GEMM, divide, scale, shift, clamp). Inference only."""
+    _need_cuda(xyz, mats, affs)
+    xyz, mats, affs = xyz.contiguous(), mats.contiguous(), affs.contiguous()
+    B, Q = xyz.shape[:2]
+    assert mats.shape == (B, 3, 4) and affs.shape == (B, 4) and xyz.dtype == torch.float32
+    out = torch.empty(B, Q, 2, dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device_of(xyz):
+        _lib.check(_lib.load().demf_project_points(_p(xyz), _p(mats), _p(affs), B, Q, _p(out), _stream()),
+                   "demf_project_points")
+    return out

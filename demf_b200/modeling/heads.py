@@ -177,6 +177,8 @@ class DeMFVoteHead(BaseModule):
             mats, affs = geometry.fold_projection(img_metas)
             dev = seeds_3d_batch.device
             projection = (mats.to(dev, non_blocking=True), affs.to(dev, non_blocking=True))
+        if seeds_3d_batch.is_cuda and not torch.is_grad_enabled() and seeds_3d_batch.dtype == torch.float32:
+            return P.project_points(seeds_3d_batch, *projection)
         return geometry.project_batched(seeds_3d_batch, *projection)
 
     _level_cache = {}

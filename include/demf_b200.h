@@ -218,6 +218,7 @@ int demf_sa_fused_set_profile(long long* device_buffer);
  * warps' back-off between mbarrier polls in ns (default 0 = spin). */
 int demf_sa_fused_tune(int max_lanes, int sleep_ns);
 int demf_sa_fused_tune_pair(int enable); /* CTA pairs (cta_group::2) for streamed weights; default off */
+int demf_sa_fused_tune_bias_init(int enable); /* layers 1-2: bias stored into the TMEM accumulator; default off */
 
 /* ----------------------------------------------------- fused glue (inference) --- */
 /* Each replaces a chain of tiny library launches in the upstream Python modules:
@@ -286,6 +287,12 @@ int demf_aligned_3d_nms(const float* minmax, const float* scores, const int64_t*
 int demf_vote_tail(const float* votes, int ldv, const float* seed_xyz, const float* seed_rows, long rows, int C,
                    const float* xyz_range, int norm_feats, float* vote_xyz, float* offset, float* vote_rows,
                    void* stream);
+
+/* DeMFVoteHead.get_reference_points (class_agnostic_vote_head.py:524-547) for the whole batch: xyz (B,Q,3)
+ * proposal centres, mats (B,3,4) and affs (B,4) = the per-scene projection chain folded on the host
+ * (geometry.fold_projection) -> out (B,Q,2) image coordinates normalised to [0,1] and clamped. */
+int demf_project_points(const float* xyz, const float* mats, const float* affs, int B, int Q, float* out,
+                        void* stream);
 
 /* Image pyramid (num_levels <= 8 tensors (B,C,H_l*W_l) f32, HOST array of device pointers and HOST array of
  * H_l*W_l) -> token rows out (B, sum H_l*W_l, C): the flatten(2).transpose(1,2) + cat of

@@ -567,6 +567,21 @@ def test_conv_module_rows_training_uses_fused_bn_and_matches_torch(dev):
     assert int(cm.norm.num_batches_tracked) == 1
 
 
+def test_project_points_matches_host_projection(dev):
+    """Reference points in one launch against geometry.project_batched evaluated in float64."""
+    from demf_b200.mm import geometry
+    B, Q = 4, 256
+    metas = synth.make_img_metas(B, "S512", seed=3)
+    mats, affs = geometry.fold_projection(metas)
+    g = torch.Generator().manual_seed(1)
+    xyz = torch.rand(B, Q, 3, generator=g) * torch.tensor([6.0, 6.0, 2.5]) - torch.tensor([3.0, 0.5, 0.0])
+    want = geometry.project_batched(xyz.double(), mats.double(), affs.double())
+    got = ops.project_points(xyz.to(dev), mats.to(dev), affs.to(dev))
+    assert got.shape == (B, Q, 2)
+    assert (got.cpu().double() - want).abs().max().item() <= 2e-6
+    assert ((want > 0) & (want < 1)).any() and (got >= 0).all() and (got <= 1).all()
+
+
 def test_empty_batches_are_noops(dev):
     assert ops.furthest_point_sample(torch.zeros(0, 5, 3, device=dev), 2).shape == (0, 2)
     assert ops.ball_query(0.0, 1.0, 4, torch.zeros(2, 5, 3, device=dev),

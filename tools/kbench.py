@@ -57,6 +57,7 @@ def main():
     ap.add_argument("--sa-lanes", type=int, default=4)
     ap.add_argument("--sa-sleep", type=int, default=0)
     ap.add_argument("--sa-pair", type=int, default=0)
+    ap.add_argument("--sa-bias-init", type=int, default=0)
     ap.add_argument("--gemm", default="tf32", choices=("tf32", "fp32"), help="library GEMM arithmetic (encoder)")
     ap.add_argument("--profile", action="store_true", help="encoder: print the per-kernel time table")
     args = ap.parse_args()
@@ -65,6 +66,7 @@ def main():
     dev = torch.device("cuda:0")
     _lib.load().demf_sa_fused_tune(args.sa_lanes, args.sa_sleep)
     _lib.load().demf_sa_fused_tune_pair(args.sa_pair)
+    _lib.load().demf_sa_fused_tune_bias_init(args.sa_bias_init)
     B, flush = args.B, not args.hot
     print(json.dumps(dict(device=torch.cuda.get_device_name(0), B=B, flush_l2=flush)), flush=True)
 
