@@ -630,6 +630,20 @@ class BaseConvBboxHead(BaseModule):
                            bias=self.bias, inplace=True))
         return conv_layers
 
+    def _merged_out(self):
+        """[conv_cls; conv_reg] as one zero-padded (W, b), rebuilt when a parameter changes."""
+        ts = (self.conv_cls.weight, self.conv_cls.bias, self.conv_reg.weight, self.conv_reg.bias)
+        key = tuple((t.data_ptr(), t._version) for t in ts)
+        cache = self.__dict__.get("_merged_out_cache")
+        if cache is None or cache[0] != key:
+            w = torch.cat([ts[0].detach().flatten(1), ts[2].detach().flatten(1)], 0)
+            b = torch.cat([ts[1].detach(), ts[3].detach()], 0)
+            pad = (-w.shape[0]) % 4
+            cache = (key, torch.nn.functional.pad(w, (0, 0, 0, pad)).contiguous(),
+                     torch.nn.functional.pad(b, (0, pad)).contiguous(), ts[0].shape[0], ts[2].shape[0])
+            self.__dict__["_merged_out_cache"] = cache
+        return cache[1:]
+
     def forward(self, feats):
         """feats (B,C,N) -> cls_score (B,num_cls,N), bbox_pred (B,num_reg,N)."""
         rows = as_rows(feats)
@@ -639,6 +653,12 @@ class BaseConvBboxHead(BaseModule):
             for layer in self.shared_convs:
                 x = conv_module_rows(layer, x)
         x_cls = x_reg = x
+        if not torch.is_grad_enabled() and x.is_cuda and not self.cls_conv_channels and not self.reg_conv_channels:
+            # inference: both output convs read the same rows -> ONE GEMM over the concatenated weights,
+            # padded to a multiple of 4 outputs so that the library takes an aligned tcgen05 kernel
+            w, b, n_cls, n_reg = self._merged_out()
+            out = torch.addmm(b, x, w.t()).view(B, N, -1)
+            return out[..., :n_cls].transpose(1, 2), out[..., n_cls:n_cls + n_reg].transpose(1, 2)
         if len(self.cls_conv_channels) > 0:
             for layer in self.cls_convs:
                 x_cls = conv_module_rows(layer, x_cls)

@@ -321,16 +321,60 @@ class DeMFVoteHead(BaseModule):
                                              'vote_points')}
         targets = self.get_targets(args[0], args[1], args[2], bbox_preds=common)
         assert self.num_fusion_layers + 1 == len(decode_res_all)
+        first = decode_res_all[0]['center']
+        if self.parallel_stage_loss and first.is_cuda and len(decode_res_all) > 1:
+            # Each stage's loss is ~150 tiny dependent kernels (and as many again in backward): latency, not
+            # work. The stages are independent, so every stage after the first runs on its own stream --
+            # parallel branches of the captured step graph; autograd replays each backward on the stream
+            # its forward ran on.
+            dev = first.device
+            cur = torch.cuda.current_stream(dev)
+            stages = [None] * len(decode_res_all)
+            # the vote loss does not depend on the stage (upstream recomputes it per stage and averages
+            # identical values): once, shared
+            vote_loss = self._vote_loss(common, targets)
+            for i in range(1, len(decode_res_all)):
+                side = self._stage_stream(dev, i)
+                side.wait_stream(cur)
+                # tensors allocated on the main stream and read on the side stream: tell the allocator
+                for t in list(common.values()) + list(decode_res_all[i].values()) + list(targets):
+                    if torch.is_tensor(t) and t.is_cuda:
+                        t.record_stream(side)
+                with torch.cuda.stream(side):
+                    stages[i] = self._loss(dict(common, **decode_res_all[i]), *args, targets=targets,
+                                           vote_loss=vote_loss, **kwargs)
+            stages[0] = self._loss(dict(common, **decode_res_all[0]), *args, targets=targets,
+                                   vote_loss=vote_loss, **kwargs)
+            for i in range(1, len(decode_res_all)):
+                cur.wait_stream(self._stage_stream(dev, i))
+                for v in stages[i].values():
+                    v.record_stream(cur)
+        else:
+            stages = [self._loss(dict(common, **decode_res), *args, targets=targets, **kwargs)
+                      for decode_res in decode_res_all]
         losses = dict()
-        for decode_res in decode_res_all:
-            stage = self._loss(dict(common, **decode_res), *args, targets=targets, **kwargs)
+        for stage in stages:
             for k, v in stage.items():
                 losses[k] = losses.get(k, 0) + v / (self.num_fusion_layers + 1)
         return losses
 
+    parallel_stage_loss = True
+    _stage_streams = {}
+
+    @classmethod
+    def _stage_stream(cls, device, i):
+        key = (str(device), i)
+        if key not in cls._stage_streams:
+            cls._stage_streams[key] = torch.cuda.Stream(device=device)
+        return cls._stage_streams[key]
+
+    def _vote_loss(self, bbox_preds, targets):
+        return self.vote_module.get_loss(bbox_preds['seed_points'], bbox_preds['vote_points'],
+                                         bbox_preds['seed_indices'], targets[1], targets[0])
+
     def _loss(self, bbox_preds, points, gt_bboxes_3d, gt_labels_3d, pts_semantic_mask=None,
               pts_instance_mask=None, img_metas=None, gt_bboxes_ignore=None, ret_target=False,
-              targets=None):
+              targets=None, vote_loss=None):
         if targets is None:
             targets = self.get_targets(points, gt_bboxes_3d, gt_labels_3d, pts_semantic_mask,
                                        pts_instance_mask, bbox_preds)
@@ -338,9 +382,8 @@ class DeMFVoteHead(BaseModule):
          objectness_targets, objectness_weights, box_loss_weights, distance_targets, dir_targets,
          size_targets, center_targets) = targets
 
-        vote_loss = self.vote_module.get_loss(bbox_preds['seed_points'], bbox_preds['vote_points'],
-                                              bbox_preds['seed_indices'], vote_target_masks,
-                                              vote_targets)
+        if vote_loss is None:
+            vote_loss = self._vote_loss(bbox_preds, targets)
         objectness_loss = self.objectness_loss(bbox_preds['obj_scores'].transpose(2, 1),
                                                objectness_targets, weight=objectness_weights)
         w3 = box_loss_weights.unsqueeze(-1).expand(-1, -1, 3)
