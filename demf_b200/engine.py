@@ -206,10 +206,12 @@ class Trainer:
         self.group = group
 
     def step(self, batch, sync_collective=False):
+        from .mm.bricks import async_weight_grads
         self.flat.zero()
-        losses = self.model.forward_train(**batch)
-        total = sum(losses.values())
-        total.backward()
+        with async_weight_grads(self.flat.buffer.device):   # dW GEMMs on a second stream, joined on exit
+            losses = self.model.forward_train(**batch)
+            total = sum(losses.values())
+            total.backward()
         work = self.flat.all_reduce_mean(self.group)
         if work is not None:
             work.wait()
@@ -318,13 +320,15 @@ class GraphedTrainStep:
             self.sample_graph.replay()
 
     def _eager(self):
+        from .mm.bricks import async_weight_grads
         t = self.trainer
         t.flat.zero()
-        losses = t.model.forward_train(points=self.points, img=self.levels, img_metas=self.metas,
-                                       gt_bboxes_3d=self.box, gt_labels_3d=self.label,
-                                       projection=(self.mats, self.affs), presampled=self.presampled)
-        total = sum(losses.values())
-        total.backward()
+        with async_weight_grads(self.points.device):
+            losses = t.model.forward_train(points=self.points, img=self.levels, img_metas=self.metas,
+                                           gt_bboxes_3d=self.box, gt_labels_3d=self.label,
+                                           projection=(self.mats, self.affs), presampled=self.presampled)
+            total = sum(losses.values())
+            total.backward()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(t.group) > 1:
             t.flat.buffer.div_(dist.get_world_size(t.group))
             dist.all_reduce(t.flat.buffer, op=dist.ReduceOp.SUM, group=t.group)

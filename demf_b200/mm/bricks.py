@@ -527,7 +527,9 @@ def conv_module_rows(cm, x, cols=None):
     w = cm.conv.weight.flatten(1)
     if cols is not None:
         w = permute_weight_columns(w, cols)
-    y = torch.nn.functional.linear(x, w, cm.conv.bias)
+        y = torch.nn.functional.linear(x, w, cm.conv.bias)
+    else:
+        y = _linear_rows(cm, x, w)
     if cm.with_norm and _fused_bn_ok(cm, y):
         # training: batch statistics + normalise + ReLU in two launches (two more in backward)
         from . import point_ops as P
@@ -548,6 +550,77 @@ def conv_module_rows(cm, x, cols=None):
 
 
 FUSED_BN_TRAIN = True
+
+
+# ------------------------------------------------ weight gradients off the critical path --
+# In backward, a 1x1 convolution on rows needs dX = dY W (the next link of the chain) and dW = dY^T X,
+# which nothing downstream waits for. Autograd runs both on one stream, so the bandwidth-heavy dW GEMMs
+# (K = all grouped rows of the level) sit between the many small latency-bound kernels of the chain.
+# A trainer that owns the gradient buffers can ask for dW on a second stream instead: it is accumulated
+# straight into `param.grad` there (no autograd accumulation node, no extra add) and the trainer joins the
+# stream before it reads any gradient. Off unless a `with async_weight_grads(device):` block is active.
+_ASYNC_WGRAD = {"on": False, "streams": {}}
+
+
+def _wgrad_stream(device):
+    key = str(device)
+    if key not in _ASYNC_WGRAD["streams"]:
+        _ASYNC_WGRAD["streams"][key] = torch.cuda.Stream(device=device)
+    return _ASYNC_WGRAD["streams"][key]
+
+
+class async_weight_grads:
+    """Context for forward + backward of one step: weight gradients of the rows convolutions are computed
+    on a side stream into the pre-allocated `param.grad` buffers; leaving the block joins that stream."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+
+    def __enter__(self):
+        self.prev = _ASYNC_WGRAD["on"]
+        _ASYNC_WGRAD["on"] = self.device.type == "cuda"
+        return self
+
+    def __exit__(self, *exc):
+        _ASYNC_WGRAD["on"] = self.prev
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).wait_stream(_wgrad_stream(self.device))
+        return False
+
+
+class _LinearRowsAsyncWgrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight2d, bias, conv):
+        ctx.save_for_backward(x, weight2d)
+        ctx.conv = conv
+        return torch.nn.functional.linear(x, weight2d, bias)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        conv = ctx.conv
+        gy = gy.contiguous()
+        gx = gy.mm(w) if ctx.needs_input_grad[0] else None
+        cur = torch.cuda.current_stream(gy.device)
+        side = _wgrad_stream(gy.device)
+        side.wait_stream(cur)
+        gy.record_stream(side)
+        x.record_stream(side)
+        with torch.cuda.stream(side):
+            conv.weight.grad.view(w.shape).addmm_(gy.t(), x)
+            if conv.bias is not None and conv.bias.grad is not None:
+                conv.bias.grad.add_(gy.sum(0))
+        return gx, None, None, None
+
+
+def _linear_rows(cm, x, w):
+    """x @ w^T + bias for a ConvModule's 1x1 convolution; `w` is the flattened view of cm.conv.weight."""
+    conv = cm.conv
+    if (_ASYNC_WGRAD["on"] and x.is_cuda and torch.is_grad_enabled() and conv.weight.requires_grad
+            and conv.weight.grad is not None and (conv.bias is None or conv.bias.grad is not None)):
+        return _LinearRowsAsyncWgrad.apply(x, w, conv.bias, conv)
+    return torch.nn.functional.linear(x, w, conv.bias)
 
 
 def _fused_bn_ok(cm, y):

@@ -328,3 +328,30 @@ def test_decoder_layer_rows_path_equals_module_path(dev, masked):
             DeMFTransformerDecoderLayer.fused_eval = True
     assert fast.shape == slow.shape == (Q, B, C)
     torch.testing.assert_close(fast, slow, atol=3e-5, rtol=0)
+
+
+def test_async_weight_gradients_equal_autograd(dev):
+    """Trainer.step computes the weight gradients of the rows convolutions on a second stream, straight into
+    the flat buffer; the plain autograd backward of the same step must give the same flat gradient."""
+    from demf_b200.mm import bricks
+    batch = engine.synthetic_batch(2, 20000, "S512", seed=31, device=dev)
+    box, lab = engine.pad_gt(batch["gt_bboxes_3d"], batch["gt_labels_3d"], 16, dev)
+    batch = dict(batch, gt_bboxes_3d=box, gt_labels_3d=lab)
+    grads = []
+    for use_async in (True, False):
+        torch.manual_seed(11)
+        model = engine.build_demf_votenet(num_points=4).to(dev).train()
+        _no_dropout(model)
+        trainer = engine.Trainer(model, capturable=True)
+        trainer.flat.zero()
+        if use_async:
+            with bricks.async_weight_grads(dev):
+                sum(model.forward_train(**batch).values()).backward()
+            assert not bricks._ASYNC_WGRAD["on"]
+        else:
+            sum(model.forward_train(**batch).values()).backward()
+        torch.cuda.synchronize()
+        grads.append(trainer.flat.buffer.clone())
+    a, b = grads
+    assert b.abs().max().item() > 0
+    assert ((a - b).norm() / b.norm()).item() <= 1e-3      # float atomics in the backward kernels reorder sums
