@@ -283,12 +283,11 @@ class GraphedTrainStep:
     # backward pass of batch i. The step graph reads the indices from static buffers.
     @staticmethod
     def _sampling_tensors(samp):
-        levels, seed_fps, grid0 = samp
+        levels, seed_fps, grids = samp
         ts = [t for idx, xyz, _ in levels for t in (idx, xyz)]
         if seed_fps is not None:
             ts.append(seed_fps[0])
-        if grid0 is not None:
-            ts.append(grid0)
+        ts += [g for g in grids if g is not None]
         return ts
 
     def _capture_sampler(self, model, dev, warmup):
@@ -306,10 +305,10 @@ class GraphedTrainStep:
             nxt = model.presample(self.points_next, mod)
         self._next_tensors = self._sampling_tensors(nxt)
         # the step graph's own copy: (idx, new_xyz, no event) per level, seed indices, grid
-        levels, seed_fps, grid0 = nxt
+        levels, seed_fps, grids = nxt
         self.presampled = ([(idx.clone(), xyz.clone(), None) for idx, xyz, _ in levels],
                            None if seed_fps is None else (seed_fps[0].clone(), None),
-                           None if grid0 is None else grid0.clone())
+                           [None if g is None else g.clone() for g in grids])
         self._cur_tensors = self._sampling_tensors(self.presampled)
         self._sampled = torch.cuda.Event()
         self._consumed = torch.cuda.Event()

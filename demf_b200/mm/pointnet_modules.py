@@ -147,7 +147,7 @@ class BasePointSAModule(nn.Module):
 
     # Clouds at least this large are binned into a uniform grid first (P.ball_grid) and the ball
     # query only tests each centre's 3x3x3 cell neighbourhood -- identical index rows.
-    grid_min_points = 4096
+    grid_min_points = 2048
 
     def ball_grid(self, points_xyz):
         """Grid workspace for this module's queries on points_xyz, or None for small clouds."""
@@ -384,7 +384,7 @@ class PointNet2SASSG(BaseModule):
         ball-query grid of the input cloud (or None)."""
         if overlap is None:
             overlap = xyz.is_cuda and self.overlap_sampling
-        levels, seed_fps, grid0 = [], None, None
+        levels, seed_fps, grids = [], None, []
         if overlap:
             main = torch.cuda.current_stream(xyz.device)
             side = self._side_stream(xyz.device)
@@ -398,6 +398,7 @@ class PointNet2SASSG(BaseModule):
             # a large input cloud is binned once into the uniform grid that serves both the first
             # level's ball query and its (grid-pruned) furthest point sampling
             grid0 = self.SA_modules[0].ball_grid(xyz)
+            grids.append(grid0)
             for i, sa in enumerate(self.SA_modules):
                 if cur.is_cuda:   # the kernel writes the picked coordinates next to the indices
                     idx, new_xyz = P.furthest_point_sample_xyz(
@@ -409,14 +410,19 @@ class PointNet2SASSG(BaseModule):
                 if overlap:
                     ev = torch.cuda.Event()
                     ev.record(side)
-                levels.append((idx, new_xyz, ev))
                 cur = new_xyz
+                # the next level's ball-query grid over the centres just picked (None for small clouds):
+                # built here, off the main stream; the NEXT level's event (recorded later on this
+                # stream) covers it
+                if i + 1 < len(self.SA_modules):
+                    grids.append(self.SA_modules[i + 1].ball_grid(cur))
+                levels.append((idx, new_xyz, ev))
                 if self.prefetch_seed_fps is not None and self.prefetch_seed_fps[0] == i + 1:
                     seed_fps = (P.furthest_point_sample(cur, self.prefetch_seed_fps[1]),
                                 torch.cuda.Event() if overlap else None)
                     if overlap:
                         seed_fps[1].record(side)
-        return levels, seed_fps, grid0
+        return levels, seed_fps, grids
 
     def forward(self, points):
         """points (B,N,3+C) -> dict of fp_xyz / fp_features / fp_indices / sa_*."""
@@ -425,9 +431,9 @@ class PointNet2SASSG(BaseModule):
         chained = all(getattr(sa, "num_point", None) is not None and len(sa.num_point) == 1
                       for sa in self.SA_modules)
         if self.presampled is not None:
-            levels, seed_fps, grid0 = self.presampled
+            levels, seed_fps, grids = self.presampled
         else:
-            levels, seed_fps, grid0 = self._sampling_chain(xyz) if chained else (None, None, None)
+            levels, seed_fps, grids = self._sampling_chain(xyz) if chained else (None, None, None)
         indices = self._identity_indices(batch, num_points, xyz.device)
         sa_xyz, sa_features, sa_indices = [xyz], [features], [indices]
         # indices of every level into the ORIGINAL cloud: on CUDA one launch for the whole chain,
@@ -440,7 +446,7 @@ class PointNet2SASSG(BaseModule):
                     torch.cuda.current_stream(xyz.device).wait_event(ev)
                 cur_xyz, cur_features, cur_indices = self.SA_modules[i](
                     sa_xyz[i], sa_features[i], indices=idx, target_xyz=new_xyz,
-                    grid=grid0 if i == 0 else None)
+                    grid=grids[i] if i < len(grids) else None)
             else:
                 cur_xyz, cur_features, cur_indices = self.SA_modules[i](sa_xyz[i], sa_features[i])
             sa_xyz.append(cur_xyz)
