@@ -65,7 +65,9 @@ _SIGNATURES = {
                          _ptr, _ptr, _ptr],
     "demf_bn_rows_bwd": [_ptr, _ptr, _ptr, ctypes.c_long, _c_int, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr,
                          _ptr, _ptr],
-    "demf_box_point_count": [_ptr, _c_int, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr],
+    "demf_box_point_count": [_ptr, _c_int, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
+    "demf_nms_select": [_ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, _ptr, _ptr, _ptr,
+                        _ptr, _ptr, _ptr],
     "demf_aligned_3d_nms": [_ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_float, _ptr, _ptr],
     "demf_vote_tail": [_ptr, _c_int, _ptr, _ptr, ctypes.c_long, _c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr],
     "demf_project_points": [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr, _ptr],

@@ -21,9 +21,12 @@ namespace {
 constexpr int kBoxesPerWarp = 4;
 
 // boxes (B,K,7) = (x, y, z_bottom, dx, dy, dz, yaw); points rows of `stride` floats (xyz first).
+// gravity != 0: boxes carry the GRAVITY centre (origin (0.5,0.5,0.5), what the coder decodes); the bottom
+// centre is formed first exactly as the host conversion would (z - dz*0.5), so counts do not depend on
+// which form the caller hands over.
 __global__ void __launch_bounds__(256) box_point_count_kernel(const float* __restrict__ points, int stride,
                                                               const float* __restrict__ boxes, int N, int K,
-                                                              int* __restrict__ counts) {
+                                                              int gravity, int* __restrict__ counts) {
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5;
   const unsigned lane = lane_id();
@@ -39,7 +42,8 @@ __global__ void __launch_bounds__(256) box_point_count_kernel(const float* __res
     const float dz = __ldg(bx + 5);
     cx[i] = __ldg(bx);
     cy[i] = __ldg(bx + 1);
-    cz[i] = __fadd_rn(__ldg(bx + 2), __fmul_rn(dz, 0.5f));
+    const float zb = gravity ? __fsub_rn(__ldg(bx + 2), __fmul_rn(dz, 0.5f)) : __ldg(bx + 2);
+    cz[i] = __fadd_rn(zb, __fmul_rn(dz, 0.5f));
     hx[i] = __fmul_rn(__ldg(bx + 3), 0.5f);
     hy[i] = __fmul_rn(__ldg(bx + 4), 0.5f);
     hz[i] = __fmul_rn(dz, 0.5f);
@@ -165,6 +169,65 @@ __global__ void __launch_bounds__(kNmsThreads) aligned_nms_kernel(const float* _
   }
 }
 
+// Everything multiclass_nms_single derives per box before the NMS, one thread per box: the axis-aligned hull
+// of the rotated box (DepthInstance3DBoxes.corners -> min / max, same fp32 operations in the same order as
+// geometry.box_corner_minmax), the semantic class (first maximum), and whether it holds more than
+// `min_points` points. boxes: gravity-centre (B*K,7).
+__global__ void __launch_bounds__(256) nms_prepare_kernel(const float* __restrict__ boxes,
+                                                          const float* __restrict__ sem, int C,
+                                                          const int* __restrict__ counts, int min_points, long total,
+                                                          float* __restrict__ minmax, int64_t* __restrict__ classes,
+                                                          uint8_t* __restrict__ valid) {
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const float* bx = boxes + e * 7;
+    const float x = __ldg(bx), y = __ldg(bx + 1), dx = __ldg(bx + 3), dy = __ldg(bx + 4), dz = __ldg(bx + 5);
+    const float zb = __fsub_rn(__ldg(bx + 2), __fmul_rn(dz, 0.5f));
+    const float ca = cosf(__ldg(bx + 6)), sa = sinf(__ldg(bx + 6));
+    const float fx[4] = {-0.5f, -0.5f, 0.5f, 0.5f}, fy[4] = {-0.5f, 0.5f, 0.5f, -0.5f};
+    float x0 = INFINITY, x1 = -INFINITY, y0 = INFINITY, y1 = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float sx = __fmul_rn(fx[k], dx), sy = __fmul_rn(fy[k], dy);
+      const float rx = __fadd_rn(__fadd_rn(__fmul_rn(sx, ca), __fmul_rn(sy, sa)), x);
+      const float ry = __fadd_rn(__fadd_rn(__fmul_rn(-sx, sa), __fmul_rn(sy, ca)), y);
+      x0 = fminf(x0, rx); x1 = fmaxf(x1, rx);
+      y0 = fminf(y0, ry); y1 = fmaxf(y1, ry);
+    }
+    const float z0 = __fadd_rn(zb, __fmul_rn(dz, 0.0f)), z1 = __fadd_rn(zb, __fmul_rn(dz, 1.0f));
+    float* o = minmax + e * 6;
+    o[0] = x0; o[1] = y0; o[2] = fminf(z0, z1);
+    o[3] = x1; o[4] = y1; o[5] = fmaxf(z0, z1);
+    const float* sp = sem + e * C;
+    int best = 0;
+    float bv = __ldg(sp);
+    for (int k = 1; k < C; ++k) {
+      const float v = __ldg(sp + k);
+      if (v > bv) { bv = v; best = k; }
+    }
+    classes[e] = best;
+    valid[e] = counts[e] > min_points;
+  }
+}
+
+// keep &= score > score_thr; per-scene number of selected boxes (for the single host read)
+__global__ void __launch_bounds__(256) nms_finish_kernel(const float* __restrict__ scores, float score_thr, int K,
+                                                         uint8_t* __restrict__ keep, int* __restrict__ nsel) {
+  __shared__ int s_cnt;
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  int c = 0;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const long e = (long)b * K + i;
+    const uint8_t k = keep[e] && scores[e] > score_thr;
+    keep[e] = k;
+    c += k;
+  }
+  if (c) atomicAdd(&s_cnt, c);
+  __syncthreads();
+  if (threadIdx.x == 0) nsel[b] = s_cnt;
+}
+
 }  // namespace
 }  // namespace demf
 
@@ -173,7 +236,7 @@ using namespace demf;
 extern "C" {
 
 int demf_box_point_count(const float* points, int point_stride, const float* boxes, int B, int N, int K,
-                         int32_t* counts, void* stream) {
+                         int gravity_centre, int32_t* counts, void* stream) {
   DEMF_REQUIRE_PTR(points);
   DEMF_REQUIRE_PTR(boxes);
   DEMF_REQUIRE_PTR(counts);
@@ -182,7 +245,8 @@ int demf_box_point_count(const float* points, int point_stride, const float* box
   if (B == 0 || K == 0) return 0;
   const int boxes_per_block = 8 * kBoxesPerWarp;
   dim3 grid((K + boxes_per_block - 1) / boxes_per_block, B);
-  box_point_count_kernel<<<grid, 256, 0, as_stream(stream)>>>(points, point_stride, boxes, N, K, counts);
+  box_point_count_kernel<<<grid, 256, 0, as_stream(stream)>>>(points, point_stride, boxes, N, K, gravity_centre,
+                                                             counts);
   return after_launch("box_point_count_kernel");
 }
 
@@ -208,6 +272,35 @@ int demf_aligned_3d_nms(const float* minmax, const float* scores, const int64_t*
   aligned_nms_kernel<<<B, kNmsThreads, smem, as_stream(stream)>>>(minmax, scores, classes, valid, K, Kpad,
                                                                 thresh, keep);
   return after_launch("aligned_nms_kernel");
+}
+
+int demf_nms_select(const float* boxes, const float* obj_scores, const float* sem_scores, const int32_t* counts,
+                    int B, int K, int C, int min_points, float nms_thresh, float score_thresh, float* minmax,
+                    int64_t* classes, uint8_t* valid, uint8_t* selected, int32_t* num_selected, void* stream) {
+  DEMF_REQUIRE_PTR(boxes);
+  DEMF_REQUIRE_PTR(obj_scores);
+  DEMF_REQUIRE_PTR(sem_scores);
+  DEMF_REQUIRE_PTR(counts);
+  DEMF_REQUIRE_PTR(minmax);
+  DEMF_REQUIRE_PTR(classes);
+  DEMF_REQUIRE_PTR(valid);
+  DEMF_REQUIRE_PTR(selected);
+  DEMF_REQUIRE_PTR(num_selected);
+  DEMF_REQUIRE(B >= 0 && K >= 0 && C >= 1, DEMF_E_SIZE);
+  DEMF_REQUIRE(K <= kNmsMaxBoxes, DEMF_E_UNSUPPORTED);
+  if (B == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  const long total = (long)B * K;
+  if (total > 0) {
+    long blocks = (total + 255) / 256;
+    if (blocks > (long)kNumSMs * 8) blocks = (long)kNumSMs * 8;
+    nms_prepare_kernel<<<(unsigned)blocks, 256, 0, st>>>(boxes, sem_scores, C, counts, min_points, total, minmax,
+                                                        classes, valid);
+    if (int rc = after_launch("nms_prepare_kernel")) return rc;
+    if (int rc = demf_aligned_3d_nms(minmax, obj_scores, classes, valid, B, K, nms_thresh, selected, stream)) return rc;
+  }
+  nms_finish_kernel<<<B, 256, 0, st>>>(obj_scores, score_thresh, K, selected, num_selected);
+  return after_launch("nms_finish_kernel");
 }
 
 }  // extern "C"

@@ -728,9 +728,9 @@ def bias_layer_norm_rows(x, gamma, beta, eps, bias=None, residual=None, out=None
     return out if out2 is None else (out, out2)
 
 
-def box_point_count(points, boxes):
-    """points (B,N,3+) rows, boxes (B,K,7) bottom-centre -> (B,K) int32 number of points inside each
-    box (column sums of mmdet3d `points_in_boxes`), one launch for the batch."""
+def box_point_count(points, boxes, gravity_centre=False):
+    """points (B,N,3+) rows, boxes (B,K,7) bottom-centre (or gravity-centre) -> (B,K) int32 number of
+    points inside each box (column sums of mmdet3d `points_in_boxes`), one launch for the batch."""
     _need_cuda(points, boxes)
     B, N = points.shape[:2]
     K = boxes.shape[1]
@@ -741,8 +741,9 @@ def box_point_count(points, boxes):
     if B == 0 or K == 0 or N == 0:
         return counts
     with torch.cuda.device_of(points):
-        _lib.check(_lib.load().demf_box_point_count(_p(points), points.stride(1), _p(boxes), B, N, K, _p(counts),
-                                                    _stream()), "demf_box_point_count")
+        _lib.check(_lib.load().demf_box_point_count(_p(points), points.stride(1), _p(boxes), B, N, K,
+                                                    int(bool(gravity_centre)), _p(counts), _stream()),
+                   "demf_box_point_count")
     return counts
 
 
@@ -867,3 +868,26 @@ def project_points(xyz, mats, affs):
         _lib.check(_lib.load().demf_project_points(_p(xyz), _p(mats), _p(affs), B, Q, _p(out), _stream()),
                    "demf_project_points")
     return out
+
+
+def nms_select(boxes, obj_scores, sem_scores, counts, min_points, nms_thr, score_thr):
+    """multiclass_nms_single up to the selection mask, for the batch: boxes (B,K,7) gravity-centre,
+    obj_scores (B,K), sem_scores (B,K,C), counts (B,K) i32 -> selected (B,K) bool, classes (B,K) i64,
+    num_selected (B,) i32 (device). Three launches (csrc/postprocess.cu)."""
+    _need_cuda(boxes, obj_scores, sem_scores, counts)
+    boxes, obj_scores, sem_scores = boxes.contiguous().float(), obj_scores.contiguous().float(), \
+        sem_scores.contiguous().float()
+    B, K, C = sem_scores.shape
+    dev = boxes.device
+    minmax = torch.empty(B, K, 6, dtype=torch.float32, device=dev)
+    classes = torch.empty(B, K, dtype=torch.int64, device=dev)
+    valid = torch.empty(B, K, dtype=torch.uint8, device=dev)
+    selected = torch.zeros(B, K, dtype=torch.uint8, device=dev)
+    nsel = torch.zeros(B, dtype=torch.int32, device=dev)
+    if B and K:
+        with torch.cuda.device_of(boxes):
+            _lib.check(_lib.load().demf_nms_select(
+                _p(boxes), _p(obj_scores), _p(sem_scores), _p(counts), B, K, C, int(min_points), float(nms_thr),
+                float(score_thr), _p(minmax), _p(classes), _p(valid), _p(selected), _p(nsel), _stream()),
+                "demf_nms_select")
+    return selected.bool(), classes, nsel

@@ -284,32 +284,35 @@ class DeMFVoteHead(BaseModule):
         axis-aligned hulls of the survivors by objectness; drop objectness <= score_thr; with
         per_class_proposal every kept box is emitted once per class with score obj * sem[k]."""
         cfg = self.test_cfg
-        boxes_bc = bbox.clone()
-        boxes_bc[..., 2] = boxes_bc[..., 2] - boxes_bc[..., 5] * 0.5      # origin (.5,.5,.5) -> (.5,.5,0)
-        counts = P.box_point_count(points, boxes_bc)
-        nonempty = counts > 5
-        minmax = geometry.box_corner_minmax(boxes_bc)
-        classes = torch.argmax(sem_scores, -1)
-        keep = P.aligned_3d_nms(minmax, obj_scores, classes, nonempty, cfg['nms_thr'])
-        selected = keep & (obj_scores > cfg['score_thr'])
-        rows = selected.nonzero(as_tuple=False)                           # the host sync
-        per_scene = torch.bincount(rows[:, 0], minlength=bbox.shape[0]).tolist()
-        box_sel = boxes_bc[rows[:, 0], rows[:, 1]]
-        obj_sel = obj_scores[rows[:, 0], rows[:, 1]]
-        sem_sel = sem_scores[rows[:, 0], rows[:, 1]]
-        cls_sel = classes[rows[:, 0], rows[:, 1]]
-        out, start = [], 0
+        counts = P.box_point_count(points, bbox, gravity_centre=True)
+        selected, classes, nsel = P.nms_select(bbox, obj_scores, sem_scores, counts, 5, cfg['nms_thr'],
+                                               cfg['score_thr'])
+        n_list = nsel.tolist()                                            # the ONE host sync
+        total = sum(n_list)
+        rows = torch.nonzero_static(selected, size=total)                 # (T,2), scene-major: no second sync
+        b_idx, r_idx = rows[:, 0], rows[:, 1]
+        box_sel = bbox[b_idx, r_idx]
+        box_sel[:, 2] = box_sel[:, 2] - box_sel[:, 5] * 0.5              # origin (.5,.5,.5) -> (.5,.5,0)
+        obj_sel = obj_scores[b_idx, r_idx]
+        cls_sel = classes[b_idx, r_idx]
+        starts = np.concatenate([[0], np.cumsum(n_list)]).astype(np.int64)
+        if not cfg['per_class_proposal']:
+            return [(box_sel[s:e], obj_sel[s:e], cls_sel[s:e]) for s, e in zip(starts[:-1], starts[1:])]
+        # every kept box once per class, class-major inside a scene (upstream: a Python loop over classes
+        # around boolean indexing, per scene). The gather indices are built on the host from the counts
+        # (<= B*R*C small integers, one copy); every scene's result is a slice of three batched gathers.
         C = sem_scores.shape[-1]
-        for n in per_scene:
-            sl = slice(start, start + n)
-            start += n
-            if cfg['per_class_proposal']:
-                out.append((box_sel[sl].repeat(C, 1),
-                            (obj_sel[sl, None] * sem_sel[sl]).t().reshape(-1),
-                            torch.arange(C, device=bbox.device, dtype=cls_sel.dtype).repeat_interleave(n)))
-            else:
-                out.append((box_sel[sl], obj_sel[sl], cls_sel[sl]))
-        return out
+        sem_sel = sem_scores[b_idx, r_idx]
+        src = np.concatenate([np.tile(np.arange(s, e), C) for s, e in zip(starts[:-1], starts[1:])]
+                             + [np.zeros(0, np.int64)])
+        cls = np.concatenate([np.repeat(np.arange(C, dtype=np.int64), e - s) for s, e in zip(starts[:-1], starts[1:])]
+                             + [np.zeros(0, np.int64)])
+        idx = torch.from_numpy(np.stack([src, cls])).to(bbox.device)
+        src_t, cls_t = idx[0], idx[1]
+        boxes_out = box_sel[src_t]
+        scores_out = obj_sel[src_t] * sem_sel[src_t, cls_t]
+        return [(boxes_out[C * s:C * e], scores_out[C * s:C * e], cls_t[C * s:C * e])
+                for s, e in zip(starts[:-1], starts[1:])]
 
     # --------------------------------------------------------------------- loss ---
     def loss(self, bbox_preds, *args, **kwargs):

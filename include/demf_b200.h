@@ -275,7 +275,16 @@ int demf_bn_rows_bwd(const float* grad_y, const float* y, const float* x, long R
  * boxes taking part; keep (B,K) u8 <- 1 for picked boxes. Greedy by descending score (ties: larger
  * index first), a box is dropped unless iou * (same class) <= thresh. K <= 4096. */
 int demf_box_point_count(const float* points, int point_stride, const float* boxes, int B, int N, int K,
-                         int32_t* counts, void* stream);
+                         int gravity_centre, int32_t* counts, void* stream);
+/* gravity_centre != 0: boxes carry the decoded gravity centre instead of the bottom centre.
+ * demf_nms_select: the rest of multiclass_nms_single up to the boolean selection, three launches for the batch:
+ * per box the axis-aligned hull of its corners (-> minmax (B,K,6)), argmax class (-> classes i64) and
+ * counts > min_points (-> valid u8); then demf_aligned_3d_nms; then selected &= obj_scores > score_thresh and
+ * num_selected (B) i32 = selected boxes per scene (the one number the host has to read).
+ * boxes (B,K,7) gravity-centre, sem_scores (B,K,C) probabilities. */
+int demf_nms_select(const float* boxes, const float* obj_scores, const float* sem_scores, const int32_t* counts,
+                    int B, int K, int C, int min_points, float nms_thresh, float score_thresh, float* minmax,
+                    int64_t* classes, uint8_t* valid, uint8_t* selected, int32_t* num_selected, void* stream);
 int demf_aligned_3d_nms(const float* minmax, const float* scores, const int64_t* classes, const uint8_t* valid,
                         int B, int K, float thresh, uint8_t* keep, void* stream);
 

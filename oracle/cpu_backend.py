@@ -80,8 +80,11 @@ def _three_interpolate(features, idx, weight):
     return _three_interpolate_rows(features.transpose(1, 2), idx, weight).transpose(1, 2)
 
 
-def _box_point_count(points, boxes):
+def _box_point_count(points, boxes, gravity_centre=False):
     from .postprocess import points_in_boxes_depth
+    if gravity_centre:
+        boxes = boxes.clone()
+        boxes[..., 2] = boxes[..., 2] - boxes[..., 5] * 0.5
     return torch.stack([points_in_boxes_depth(points[b, :, :3], boxes[b]).sum(0).to(torch.int32)
                         for b in range(points.shape[0])])
 
@@ -94,6 +97,18 @@ def _aligned_3d_nms(minmax, scores, classes, valid, thresh):
         picked = aligned_3d_nms(minmax[b][inds], scores[b][inds], classes[b][inds], thresh)
         keep[b, inds[picked]] = True
     return keep
+
+
+def _nms_select(boxes, obj_scores, sem_scores, counts, min_points, nms_thr, score_thr):
+    from .postprocess import box_corners_depth
+    bc = boxes.clone()
+    bc[..., 2] = bc[..., 2] - bc[..., 5] * 0.5
+    corners = torch.stack([box_corners_depth(b) for b in bc])
+    minmax = torch.cat([corners.min(2)[0], corners.max(2)[0]], -1)
+    classes = torch.argmax(sem_scores, -1)
+    keep = _aligned_3d_nms(minmax, obj_scores, classes, counts > min_points, nms_thr)
+    selected = keep & (obj_scores > score_thr)
+    return selected, classes, selected.sum(1).to(torch.int32)
 
 
 class _MsdaCpu:
@@ -116,7 +131,7 @@ def oracle_ops():
         "three_interpolate_rows": _three_interpolate_rows,
         "grouping_operation": _grouping_operation, "gather_points": _gather_points,
         "three_interpolate": _three_interpolate,
-        "box_point_count": _box_point_count, "aligned_3d_nms": _aligned_3d_nms,
+        "box_point_count": _box_point_count, "aligned_3d_nms": _aligned_3d_nms, "nms_select": _nms_select,
     }
     saved = {k: getattr(P, k) for k in patched}
     saved_fn = msda_mod.MultiScaleDeformableAttnFunction
