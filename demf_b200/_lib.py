@@ -65,6 +65,10 @@ _SIGNATURES = {
                          _ptr, _ptr, _ptr],
     "demf_bn_rows_bwd": [_ptr, _ptr, _ptr, ctypes.c_long, _c_int, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr,
                          _ptr, _ptr],
+    "demf_bn_max_rows_fwd": [_ptr, ctypes.c_long, _c_int, _c_int, _ptr, _ptr, _c_float, _c_float, _ptr, _ptr, _ptr,
+                             _ptr, _ptr, _ptr, _ptr, _ptr],
+    "demf_bn_max_rows_bwd": [_ptr, _ptr, _ptr, _ptr, ctypes.c_long, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr,
+                             _ptr, _ptr, _ptr, _ptr],
     "demf_box_point_count": [_ptr, _c_int, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
     "demf_nms_select": [_ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, _ptr, _ptr, _ptr,
                         _ptr, _ptr, _ptr],

@@ -211,6 +211,125 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
   }
 }
 
+// ---- last layer of a set-abstraction MLP in training: BatchNorm + ReLU + max over the ns rows of a centre ----
+// pooled[m,c] = max_r relu(bn(x[m*ns + r, c])), arg[m,c] = first r attaining it. The normalised (R,C) tensor is
+// never written: backward needs x, the pooled value (ReLU mask) and arg only.
+__global__ void __launch_bounds__(kBnThreads) bn_apply_max_kernel(const float* __restrict__ x, long M, int ns, int cq,
+                                                                  const float* __restrict__ mean,
+                                                                  const float* __restrict__ invstd,
+                                                                  const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta,
+                                                                  float* __restrict__ pooled,
+                                                                  uint8_t* __restrict__ arg) {
+  const long total = M * cq;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % cq);
+    const long m = e / cq;
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + c);
+    const float4 is = __ldg(reinterpret_cast<const float4*>(invstd) + c);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+    float4 best = make_float4(-1.f, -1.f, -1.f, -1.f);  // below every ReLU output
+    uchar4 at = make_uchar4(0, 0, 0, 0);
+    const float4* row = reinterpret_cast<const float4*>(x) + (m * ns) * cq + c;
+#pragma unroll 4
+    for (int r = 0; r < ns; ++r) {
+      const float4 v = __ldg(row + (long)r * cq);
+      const float ox = fmaxf((v.x - mu.x) * is.x * g.x + b.x, 0.f), oy = fmaxf((v.y - mu.y) * is.y * g.y + b.y, 0.f),
+                  oz = fmaxf((v.z - mu.z) * is.z * g.z + b.z, 0.f), ow = fmaxf((v.w - mu.w) * is.w * g.w + b.w, 0.f);
+      if (ox > best.x) { best.x = ox; at.x = (unsigned char)r; }
+      if (oy > best.y) { best.y = oy; at.y = (unsigned char)r; }
+      if (oz > best.z) { best.z = oz; at.z = (unsigned char)r; }
+      if (ow > best.w) { best.w = ow; at.w = (unsigned char)r; }
+    }
+    reinterpret_cast<float4*>(pooled)[e] = best;
+    reinterpret_cast<uchar4*>(arg)[e] = at;
+  }
+}
+
+// dy is nonzero only at (m*ns + arg[m,c], c) and only where pooled > 0: the two channel sums come from M*C
+// elements and as many gathered x values instead of two passes over (R,C).
+__global__ void __launch_bounds__(kBnThreads) bn_max_bwd_reduce_kernel(
+    const float* __restrict__ gp, const float* __restrict__ pooled, const uint8_t* __restrict__ arg,
+    const float* __restrict__ x, long M, int ns, int C, const float* __restrict__ mean,
+    const float* __restrict__ invstd, double* accum, unsigned* counter, float* __restrict__ grad_gamma,
+    float* __restrict__ grad_beta, float* __restrict__ coef) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* s_a = reinterpret_cast<float4*>(smem_raw);
+  float4* s_b = s_a + kBnThreads;
+  const int cq = C >> 2, lanes = kBnThreads / cq;
+  const int tx = threadIdx.x % cq, ty = threadIdx.x / cq;
+  const long per_block = (M + gridDim.x - 1) / gridDim.x;
+  const long m0 = (long)blockIdx.x * per_block, m1 = min(M, m0 + per_block);
+  const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + tx);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+  for (long m = m0 + ty; m < m1; m += lanes) {
+    float4 g = __ldg(reinterpret_cast<const float4*>(gp + m * C) + tx);
+    const float4 o = __ldg(reinterpret_cast<const float4*>(pooled + m * C) + tx);
+    const uchar4 at = __ldg(reinterpret_cast<const uchar4*>(arg + m * C) + tx);
+    g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
+    g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+    const float* xb = x + (m * ns) * C + tx * 4;
+    const float vx = __ldg(xb + (long)at.x * C), vy = __ldg(xb + (long)at.y * C + 1),
+                vz = __ldg(xb + (long)at.z * C + 2), vw = __ldg(xb + (long)at.w * C + 3);
+    s = f4_add(s, g);
+    q.x = fmaf(g.x, vx - mu.x, q.x); q.y = fmaf(g.y, vy - mu.y, q.y);
+    q.z = fmaf(g.z, vz - mu.z, q.z); q.w = fmaf(g.w, vw - mu.w, q.w);
+  }
+  block_reduce_rows(s, q, tx, ty, lanes, cq, s_a, s_b);
+  if (ty == 0) {
+    accumulate4(accum, tx * 4, s);
+    accumulate4(accum + C, tx * 4, q);
+  }
+  if (!last_block_ticket(counter)) return;
+  const double R = (double)M * ns;
+  for (int c = threadIdx.x; c < C; c += kBnThreads) {
+    const double ds = __ldcg(accum + c), dq = __ldcg(accum + C + c);
+    accum[c] = 0.0;
+    accum[C + c] = 0.0;
+    const float is = invstd[c];
+    grad_beta[c] = (float)ds;
+    grad_gamma[c] = (float)(dq * (double)is);
+    coef[c] = (float)(ds / R);
+    coef[C + c] = (float)(dq / R * (double)is * (double)is);
+  }
+}
+
+__global__ void __launch_bounds__(kBnThreads) bn_max_bwd_apply_kernel(
+    const float* __restrict__ gp, const float* __restrict__ pooled, const uint8_t* __restrict__ arg,
+    const float* __restrict__ x, long M, int ns, int cq, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ coef,
+    float* __restrict__ dx) {
+  const int C = cq * 4;
+  const long total = M * cq;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % cq);
+    const long m = e / cq;
+    float4 g = __ldg(reinterpret_cast<const float4*>(gp) + e);
+    const float4 o = __ldg(reinterpret_cast<const float4*>(pooled) + e);
+    const uchar4 at = __ldg(reinterpret_cast<const uchar4*>(arg) + e);
+    g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
+    g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + c);
+    const float4 is = __ldg(reinterpret_cast<const float4*>(invstd) + c);
+    const float4 w = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+    const float4 k1 = __ldg(reinterpret_cast<const float4*>(coef) + c);
+    const float4 k2 = __ldg(reinterpret_cast<const float4*>(coef + C) + c);
+    const float4* xr = reinterpret_cast<const float4*>(x) + (m * ns) * cq + c;
+    float4* dr = reinterpret_cast<float4*>(dx) + (m * ns) * cq + c;
+#pragma unroll 4
+    for (int r = 0; r < ns; ++r) {
+      const float4 v = __ldg(xr + (long)r * cq);
+      float4 d;
+      d.x = ((r == at.x ? g.x : 0.f) - k1.x - (v.x - mu.x) * k2.x) * is.x * w.x;
+      d.y = ((r == at.y ? g.y : 0.f) - k1.y - (v.y - mu.y) * k2.y) * is.y * w.y;
+      d.z = ((r == at.z ? g.z : 0.f) - k1.z - (v.z - mu.z) * k2.z) * is.z * w.z;
+      d.w = ((r == at.w ? g.w : 0.f) - k1.w - (v.w - mu.w) * k2.w) * is.w * w.w;
+      dr[(long)r * cq] = d;
+    }
+  }
+}
+
 inline bool bn_shape_ok(int C) {
   const int cq = C / 4;
   return C % 4 == 0 && cq >= 1 && cq <= kBnThreads && (cq & (cq - 1)) == 0;
@@ -303,6 +422,74 @@ int demf_bn_rows_bwd(const float* grad_y, const float* y, const float* x, long R
   bn_bwd_apply_kernel<<<(unsigned)ab, kBnThreads, 0, st>>>(grad_y, y, x, total4, C / 4, save_mean, save_invstd,
                                                           gamma, coef, relu, grad_x);
   return after_launch("bn_bwd_apply_kernel");
+}
+
+int demf_bn_max_rows_fwd(const float* x, long M, int ns, int C, const float* gamma, const float* beta, float eps,
+                         float momentum, float* running_mean, float* running_var, void* state, float* save_mean,
+                         float* save_invstd, float* pooled, uint8_t* arg, void* stream) {
+  DEMF_REQUIRE_PTR(x);
+  DEMF_REQUIRE_PTR(gamma);
+  DEMF_REQUIRE_PTR(beta);
+  DEMF_REQUIRE_PTR(state);
+  DEMF_REQUIRE_PTR(save_mean);
+  DEMF_REQUIRE_PTR(save_invstd);
+  DEMF_REQUIRE_PTR(pooled);
+  DEMF_REQUIRE_PTR(arg);
+  DEMF_REQUIRE(M > 0 && ns > 0 && ns <= 255 && C > 0, DEMF_E_SIZE);
+  DEMF_REQUIRE(bn_shape_ok(C), DEMF_E_UNSUPPORTED);
+  DEMF_REQUIRE((running_mean == nullptr) == (running_var == nullptr), DEMF_E_SIZE);
+  DEMF_REQUIRE(al16(x) && al16(pooled) && al16(gamma) && al16(beta) && al16(save_mean) && al16(save_invstd) &&
+                   al16(state) && (reinterpret_cast<uintptr_t>(arg) & 3u) == 0,
+               DEMF_E_UNSUPPORTED);
+  cudaStream_t st = as_stream(stream);
+  double* accum = static_cast<double*>(state);
+  unsigned* counter = reinterpret_cast<unsigned*>(accum + 2 * (long)C);
+  const long R = M * ns;
+  bn_stats_kernel<<<bn_blocks(R, C), kBnThreads, kBnThreads * 32, st>>>(x, R, C, eps, momentum, accum, counter,
+                                                                      save_mean, save_invstd, running_mean,
+                                                                      running_var);
+  if (int rc = after_launch("bn_stats_kernel")) return rc;
+  const long total = M * (C / 4);
+  long ab = (total + kBnThreads - 1) / kBnThreads;
+  if (ab > (long)kNumSMs * 16) ab = (long)kNumSMs * 16;
+  bn_apply_max_kernel<<<(unsigned)ab, kBnThreads, 0, st>>>(x, M, ns, C / 4, save_mean, save_invstd, gamma, beta,
+                                                          pooled, arg);
+  return after_launch("bn_apply_max_kernel");
+}
+
+int demf_bn_max_rows_bwd(const float* grad_pooled, const float* pooled, const uint8_t* arg, const float* x, long M,
+                         int ns, int C, const float* gamma, const float* save_mean, const float* save_invstd,
+                         void* state, float* coef, float* grad_x, float* grad_gamma, float* grad_beta,
+                         void* stream) {
+  DEMF_REQUIRE_PTR(grad_pooled);
+  DEMF_REQUIRE_PTR(pooled);
+  DEMF_REQUIRE_PTR(arg);
+  DEMF_REQUIRE_PTR(x);
+  DEMF_REQUIRE_PTR(gamma);
+  DEMF_REQUIRE_PTR(save_mean);
+  DEMF_REQUIRE_PTR(save_invstd);
+  DEMF_REQUIRE_PTR(state);
+  DEMF_REQUIRE_PTR(coef);
+  DEMF_REQUIRE_PTR(grad_x);
+  DEMF_REQUIRE_PTR(grad_gamma);
+  DEMF_REQUIRE_PTR(grad_beta);
+  DEMF_REQUIRE(M > 0 && ns > 0 && ns <= 255 && C > 0, DEMF_E_SIZE);
+  DEMF_REQUIRE(bn_shape_ok(C), DEMF_E_UNSUPPORTED);
+  DEMF_REQUIRE(al16(grad_pooled) && al16(pooled) && al16(x) && al16(grad_x) && al16(gamma) && al16(save_mean) &&
+                   al16(save_invstd) && al16(coef) && al16(state) && (reinterpret_cast<uintptr_t>(arg) & 3u) == 0,
+               DEMF_E_UNSUPPORTED);
+  cudaStream_t st = as_stream(stream);
+  double* accum = static_cast<double*>(state);
+  unsigned* counter = reinterpret_cast<unsigned*>(accum + 2 * (long)C);
+  bn_max_bwd_reduce_kernel<<<bn_blocks(M, C), kBnThreads, kBnThreads * 32, st>>>(
+      grad_pooled, pooled, arg, x, M, ns, C, save_mean, save_invstd, accum, counter, grad_gamma, grad_beta, coef);
+  if (int rc = after_launch("bn_max_bwd_reduce_kernel")) return rc;
+  const long total = M * (C / 4);
+  long ab = (total + kBnThreads - 1) / kBnThreads;
+  if (ab > (long)kNumSMs * 16) ab = (long)kNumSMs * 16;
+  bn_max_bwd_apply_kernel<<<(unsigned)ab, kBnThreads, 0, st>>>(grad_pooled, pooled, arg, x, M, ns, C / 4, save_mean,
+                                                              save_invstd, gamma, coef, grad_x);
+  return after_launch("bn_max_bwd_apply_kernel");
 }
 
 }  // extern "C"

@@ -550,6 +550,33 @@ def conv_module_rows(cm, x, cols=None):
 
 
 FUSED_BN_TRAIN = True
+FUSED_BN_MAX_TRAIN = True
+
+
+def conv_module_rows_max(cm, x, ns, cols=None):
+    """Training only: conv -> BN (batch statistics) -> ReLU -> max over every `ns` consecutive rows, for the
+    last layer of a set-abstraction MLP: (M*ns, Cin) -> (M, Cout) without materialising the normalised
+    (M*ns, Cout) tensor (csrc/bn_rows.cu). Returns None when the fused path does not apply."""
+    if not (FUSED_BN_MAX_TRAIN and torch.is_grad_enabled() and cm.with_norm and cm.with_activation
+            and x.is_cuda and ns <= 255 and x.shape[0] % ns == 0):
+        return None
+    w = cm.conv.weight.flatten(1)
+    if cols is not None:
+        y = torch.nn.functional.linear(x, permute_weight_columns(w, cols), cm.conv.bias)
+    else:
+        y = _linear_rows(cm, x, w)
+    if not _fused_bn_ok(cm, y):
+        return None
+    from . import point_ops as P
+    bn = cm.norm
+    if bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    state = bn.__dict__.get("_rows_state")
+    if state is None or state.device != y.device:
+        state = P.bn_rows_state(bn.num_features, y.device)
+        bn.__dict__["_rows_state"] = state
+    return P.batch_norm_relu_max_rows(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum,
+                                      bn.eps, ns, state)
 
 
 # ------------------------------------------------ weight gradients off the critical path --

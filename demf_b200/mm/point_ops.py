@@ -838,6 +838,52 @@ class _BatchNormReluRows(torch.autograd.Function):
         return grad_x, grads[0], grads[1], None, None, None, None, None, None
 
 
+class _BatchNormReluMaxRows(torch.autograd.Function):
+    """Training BatchNorm + ReLU + max over the ns rows of each centre (csrc/bn_rows.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, ns, state):
+        R, C = x.shape
+        M = R // ns
+        pooled = torch.empty(M, C, dtype=torch.float32, device=x.device)
+        arg = torch.empty(M, C, dtype=torch.uint8, device=x.device)
+        mean = torch.empty(C, dtype=torch.float32, device=x.device)
+        invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+        with torch.cuda.device_of(x):
+            _lib.check(_lib.load().demf_bn_max_rows_fwd(
+                _p(x), M, int(ns), C, _p(gamma), _p(beta), float(eps), float(momentum),
+                _p(running_mean) if running_mean is not None else None,
+                _p(running_var) if running_var is not None else None, _p(state), _p(mean), _p(invstd),
+                _p(pooled), _p(arg), _stream()), "demf_bn_max_rows_fwd")
+        ctx.save_for_backward(x, pooled, arg, gamma, mean, invstd, state)
+        ctx.ns = int(ns)
+        return pooled
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_pooled):
+        x, pooled, arg, gamma, mean, invstd, state = ctx.saved_tensors
+        R, C = x.shape
+        M = R // ctx.ns
+        grad_pooled = grad_pooled.contiguous()
+        grad_x = torch.empty_like(x)
+        grads = torch.empty(4, C, dtype=torch.float32, device=x.device)
+        with torch.cuda.device_of(x):
+            _lib.check(_lib.load().demf_bn_max_rows_bwd(
+                _p(grad_pooled), _p(pooled), _p(arg), _p(x), M, ctx.ns, C, _p(gamma), _p(mean), _p(invstd),
+                _p(state), _p(grads[2:]), _p(grad_x), _p(grads[0]), _p(grads[1]), _stream()),
+                "demf_bn_max_rows_bwd")
+        return grad_x, grads[0], grads[1], None, None, None, None, None, None
+
+
+def batch_norm_relu_max_rows(x, gamma, beta, running_mean, running_var, momentum, eps, ns, state):
+    """x (M*ns, C) rows -> (M, C) = max over each centre's ns rows of relu(batch_norm(x)); differentiable in
+    x, gamma, beta. The normalised tensor is never materialised."""
+    _need_cuda(x, gamma, beta)
+    assert x.dim() == 2 and x.is_contiguous() and x.dtype == torch.float32 and x.shape[0] % ns == 0 and ns <= 255
+    return _BatchNormReluMaxRows.apply(x, gamma, beta, running_mean, running_var, momentum, eps, ns, state)
+
+
 def bn_rows_supported(channels):
     return bool(_lib.load().demf_bn_rows_supported(int(channels)))
 

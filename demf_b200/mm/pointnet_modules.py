@@ -17,6 +17,7 @@ import torch.nn as nn
 
 from . import point_ops as P
 from .bricks import (BaseModule, ConvModule, _foldable, _folded_cached, as_rows, build_conv_layer,
+                     conv_module_rows_max,
                      conv_module_rows)
 from .registry import BACKBONES, SA_MODULES
 
@@ -195,8 +196,20 @@ class BasePointSAModule(nn.Module):
                     grouper.max_radius, grouper.sample_num, grouper.normalize_xyz, grid)
                 B, M, ns, K = rows.shape
                 x = rows.view(B * M * ns, K)
-                for j, layer in enumerate(mlp):
-                    x = conv_module_rows(layer, x, P.group_rows_columns(C) if j == 0 else None)
+                layers = list(mlp)
+                pooled = None
+                for j, layer in enumerate(layers):
+                    cols = P.group_rows_columns(C) if j == 0 else None
+                    if j == len(layers) - 1 and self.pool_mod == 'max':
+                        # training: the last layer's BatchNorm + ReLU and the max over the neighbourhood in
+                        # one pass (the (B*M*ns, C') activation is never written)
+                        pooled = conv_module_rows_max(layer, x, ns, cols)
+                        if pooled is not None:
+                            break
+                    x = conv_module_rows(layer, x, cols)
+                if pooled is not None:
+                    out.append(pooled.view(B, M, -1))
+                    continue
                 x = x.view(B, M, ns, -1)
                 if self.pool_mod == 'max':  # amax: no index tensor when nothing back-propagates
                     x = x.max(dim=2)[0] if torch.is_grad_enabled() else x.amax(dim=2)

@@ -264,6 +264,18 @@ int demf_bn_rows_bwd(const float* grad_y, const float* y, const float* x, long R
                      const float* save_mean, const float* save_invstd, int relu, void* state, float* coef,
                      float* grad_x, float* grad_gamma, float* grad_beta, void* stream);
 
+/* The LAST layer of a set-abstraction MLP in training, with the max over the neighbourhood folded in
+ * (mmdet3d PointSAModule: ... -> BN -> ReLU -> F.max_pool2d over nsample): x (M*ns, C) rows, ns consecutive rows per
+ * centre -> pooled (M,C) = max_r relu(bn(x)) and arg (M,C) u8 = the row attaining it. The normalised (M*ns,C)
+ * tensor is never written; backward takes grad_pooled (M,C) and returns the dense grad_x (M*ns,C). */
+int demf_bn_max_rows_fwd(const float* x, long M, int ns, int C, const float* gamma, const float* beta, float eps,
+                         float momentum, float* running_mean, float* running_var, void* state, float* save_mean,
+                         float* save_invstd, float* pooled, uint8_t* arg, void* stream);
+int demf_bn_max_rows_bwd(const float* grad_pooled, const float* pooled, const uint8_t* arg, const float* x, long M,
+                         int ns, int C, const float* gamma, const float* save_mean, const float* save_invstd,
+                         void* state, float* coef, float* grad_x, float* grad_gamma, float* grad_beta,
+                         void* stream);
+
 /* ------------------------------------------- inference post-processing --- */
 /* The two per-scene loops of mmdet3d 0.18.1 VoteHead.multiclass_nms_single, reached from
  * DeMFVoteHead.get_bboxes (demf/modeling/heads/class_agnostic_vote_head.py:739-743):

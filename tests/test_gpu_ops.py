@@ -537,6 +537,37 @@ def test_batch_norm_relu_rows_forward_backward(dev, R, C, relu):
         assert state.abs().sum().item() == 0.0
 
 
+@pytest.mark.parametrize("M,ns,C", [(500, 16, 128), (2048, 64, 128), (1024, 32, 256), (37, 16, 64), (3, 5, 8)])
+def test_batch_norm_relu_max_rows_forward_backward(dev, M, ns, C):
+    """BatchNorm + ReLU + max over each centre's ns rows in training (the normalised tensor is never
+    written) against torch batch_norm + relu + max evaluated in float64: pooled values, running
+    statistics and the gradients wrt x, gamma, beta."""
+    g = torch.Generator().manual_seed(M + ns + C)
+    x = torch.randn(M * ns, C, generator=g) * 1.5 + 0.3
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.5
+    gp = torch.randn(M, C, generator=g)
+    xd = x.double().requires_grad_(True)
+    gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    rm, rv = torch.zeros(C, dtype=torch.float64), torch.ones(C, dtype=torch.float64)
+    want = torch.relu(torch.nn.functional.batch_norm(xd, rm, rv, gd, bd, True, 0.1, 1e-5)).view(M, ns, C).max(1)[0]
+    want.backward(gp.double())
+    state = ops.bn_rows_state(C, dev)
+    for rep in range(2):
+        xg = x.to(dev).requires_grad_(True)
+        gg, bg = gamma.to(dev).requires_grad_(True), beta.to(dev).requires_grad_(True)
+        rmg, rvg = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+        got = ops.batch_norm_relu_max_rows(xg, gg, bg, rmg, rvg, 0.1, 1e-5, ns, state)
+        got.backward(gp.to(dev))
+        assert got.shape == (M, C)
+        assert (got.detach().cpu().double() - want.detach()).abs().max().item() <= 2e-5
+        assert (rmg.cpu().double() - rm).abs().max().item() <= 1e-6
+        assert (rvg.cpu().double() - rv).abs().max().item() <= 1e-5
+        for a, b in ((xg.grad, xd.grad), (gg.grad, gd.grad), (bg.grad, bd.grad)):
+            scale = b.abs().max().item() + 1e-12
+            assert (a.cpu().double() - b).abs().max().item() <= 5e-5 * scale + 2e-5
+        assert state.abs().sum().item() == 0.0
+
+
 def test_conv_module_rows_training_uses_fused_bn_and_matches_torch(dev):
     from demf_b200.mm import bricks
     torch.manual_seed(0)
