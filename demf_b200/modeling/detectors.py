@@ -156,7 +156,7 @@ class DeMFVoteNet(BaseModule):
         for meta in img_metas:
             meta['batch_input_shape'] = shape
 
-    def _forward_head(self, points, img, img_metas, sample_mod, projection=None, presampled=None):
+    def _forward_head(self, points, img, img_metas, sample_mod, projection=None, presampled=None, gt=None):
         self._batch_input_shape(img, img_metas)
         img_features = self.extract_img_feat(img, img_metas)
         points = torch.stack(list(points)) if not torch.is_tensor(points) else points
@@ -168,13 +168,16 @@ class DeMFVoteNet(BaseModule):
         img_dict = dict(img_features=img_features, img_metas=img_metas)
         if projection is not None:
             img_dict['projection'] = projection
+        if gt is not None:   # training: lets the head assign targets while its decoder still runs
+            img_dict['gt'] = (points,) + tuple(gt)
         return points, self.pts_bbox_head(feat_dict, sample_mod, img_dict)
 
     def forward_train(self, points=None, img=None, img_metas=None, gt_bboxes_ignore=None,
                       gt_bboxes_3d=None, gt_labels_3d=None, pts_semantic_mask=None,
                       pts_instance_mask=None, projection=None, presampled=None, **kwargs):
         points, bbox_preds = self._forward_head(points, img, img_metas,
-                                                self.train_cfg['pts']['sample_mod'], projection, presampled)
+                                                self.train_cfg['pts']['sample_mod'], projection, presampled,
+                                                gt=(gt_bboxes_3d, gt_labels_3d))
         loss_inputs = (points, gt_bboxes_3d, gt_labels_3d, pts_semantic_mask, pts_instance_mask,
                        img_metas)
         return self.pts_bbox_head.loss(bbox_preds, *loss_inputs, gt_bboxes_ignore=gt_bboxes_ignore)

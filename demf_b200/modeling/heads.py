@@ -130,6 +130,24 @@ class DeMFVoteHead(BaseModule):
             **aggregation_inputs)
         results['aggregated_points'] = aggregated_points
         results['aggregated_indices'] = aggregated_indices
+        if self.early_targets and img_dict.get('gt') is not None and aggregated_points.is_cuda \
+                and torch.is_tensor(img_dict['gt'][1]):
+            # Target assignment needs the proposals' positions but nothing the decoder computes: start it
+            # now on a second stream, under the decoder and prediction heads (~120 small kernels of latency).
+            dev = aggregated_points.device
+            cur = torch.cuda.current_stream(dev)
+            side = self._stage_stream(dev, 'targets')
+            side.wait_stream(cur)
+            common = {k: results[k].detach() for k in ('seed_points', 'seed_indices', 'aggregated_points',
+                                                       'vote_points')}
+            gt_points, gt_boxes, gt_labels = img_dict['gt']
+            for t in list(common.values()) + [gt_points, gt_boxes, gt_labels]:
+                t.record_stream(side)
+            with torch.cuda.stream(side), torch.no_grad():
+                targets = self.get_targets(gt_points, gt_boxes, gt_labels, bbox_preds=common)
+                done = torch.cuda.Event()
+                done.record(side)
+            results['_targets'] = (targets, done)
         results['decode_res_all'] = self.transformer_decoder(
             features, aggregated_points, img_features, img_metas,
             projection=img_dict.get('projection'))
@@ -322,7 +340,16 @@ class DeMFVoteHead(BaseModule):
         decode_res_all = bbox_preds.pop('decode_res_all')
         common = {k: bbox_preds[k] for k in ('seed_points', 'seed_indices', 'aggregated_points',
                                              'vote_points')}
-        targets = self.get_targets(args[0], args[1], args[2], bbox_preds=common)
+        early = bbox_preds.pop('_targets', None)
+        if early is not None:   # assigned on a second stream while the decoder ran (forward())
+            targets, done = early
+            cur = torch.cuda.current_stream(decode_res_all[0]['center'].device)
+            cur.wait_event(done)
+            for t in targets:
+                if torch.is_tensor(t):
+                    t.record_stream(cur)
+        else:
+            targets = self.get_targets(args[0], args[1], args[2], bbox_preds=common)
         assert self.num_fusion_layers + 1 == len(decode_res_all)
         first = decode_res_all[0]['center']
         if self.parallel_stage_loss and first.is_cuda and len(decode_res_all) > 1:
@@ -362,6 +389,7 @@ class DeMFVoteHead(BaseModule):
         return losses
 
     parallel_stage_loss = True
+    early_targets = True
     _stage_streams = {}
 
     @classmethod

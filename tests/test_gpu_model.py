@@ -357,3 +357,31 @@ def test_async_weight_gradients_equal_autograd(dev):
     a, b = grads
     assert b.abs().max().item() > 0
     assert ((a - b).norm() / b.norm()).item() <= 1e-3      # float atomics in the backward kernels reorder sums
+
+
+def test_early_targets_and_parallel_stage_losses_change_nothing(dev):
+    """Targets assigned on a second stream under the decoder, and stage losses on their own streams, against the
+    plain sequential loss: same loss terms and the same gradient (padded ground truth, as the trainer feeds it)."""
+    from demf_b200.modeling.heads import DeMFVoteHead
+    batch = engine.synthetic_batch(2, 20000, "S512", seed=41, device=dev)
+    box, lab = engine.pad_gt(batch["gt_bboxes_3d"], batch["gt_labels_3d"], 16, dev)
+    batch = dict(batch, gt_bboxes_3d=box, gt_labels_3d=lab)
+    runs = []
+    for fancy in (True, False):
+        torch.manual_seed(13)
+        model = engine.build_demf_votenet(num_points=4).to(dev).train()
+        _no_dropout(model)
+        DeMFVoteHead.early_targets = DeMFVoteHead.parallel_stage_loss = fancy
+        try:
+            losses = model.forward_train(**batch)
+            sum(losses.values()).backward()
+            torch.cuda.synchronize()
+        finally:
+            DeMFVoteHead.early_targets = DeMFVoteHead.parallel_stage_loss = True
+        grad = torch.cat([p.grad.flatten() for p in model.parameters() if p.grad is not None])
+        runs.append(({k: v.item() for k, v in losses.items()}, grad))
+    (la, ga), (lb, gb) = runs
+    assert la.keys() == lb.keys()
+    for k in la:
+        assert abs(la[k] - lb[k]) <= 1e-5 * max(1.0, abs(lb[k])), (k, la[k], lb[k])
+    assert ((ga - gb).norm() / gb.norm()).item() <= 1e-3
