@@ -160,6 +160,24 @@ def test_get_bboxes_host_logic_equals_per_scene_oracle(head, per_class):
     assert total > 0
 
 
+def test_nms_batch_with_empty_scenes(head):
+    """No box selected anywhere / in one scene: empty per-scene results of the right shapes, the other
+    scenes unaffected (the batched gathers are built from per-scene counts)."""
+    box, obj, sem = _scene_boxes(2, 32, 1)
+    pts = _scene_points(2, 500, box, 1)
+    with oracle_ops():
+        none = head.multiclass_nms_batch(obj * 0.0, sem, box, pts)
+        obj2 = obj.clone()
+        obj2[0] = 0
+        half = head.multiclass_nms_batch(obj2, sem, box, pts)
+        full = head.multiclass_nms_batch(obj, sem, box, pts)
+    for b, s, l in none:
+        assert b.shape == (0, 7) and s.shape == (0,) and l.shape == (0,)
+    assert half[0][0].shape == (0, 7) and len(half[1][2]) > 0
+    for a, b in zip(half[1], full[1]):
+        assert torch.equal(a, b)
+
+
 # -------------------------------------------------------------------- GPU tests ----
 @pytest.fixture(scope="module")
 def dev():
