@@ -252,3 +252,45 @@ def test_padded_gt_gives_the_same_targets(model):
     b = head.get_targets(pts, box, lab, bbox_preds=dict(aggregated_points=agg))
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+def test_async_weight_grads_is_a_noop_on_cpu_and_restores_its_flag():
+    from demf_b200.mm import bricks
+    assert not bricks._ASYNC_WGRAD["on"]
+    with bricks.async_weight_grads("cpu"):
+        assert not bricks._ASYNC_WGRAD["on"]          # CUDA only: the CPU path keeps autograd's own accumulation
+        cm = bricks.ConvModule(8, 16, 1, conv_cfg=dict(type="Conv1d"), norm_cfg=dict(type="BN1d"))
+        x = torch.randn(32, 8, requires_grad=True)
+        bricks.conv_module_rows(cm, x).sum().backward()
+        assert cm.conv.weight.grad is not None and x.grad is not None
+    assert not bricks._ASYNC_WGRAD["on"]
+
+
+def test_sampling_tensor_list_of_the_graphed_step_follows_the_chain_structure():
+    """GraphedTrainStep copies exactly these tensors from the sampler graph's outputs to the step graph's
+    inputs: (idx, xyz) per level, the seed indices, then every non-empty grid."""
+    lv = [(torch.zeros(2, 4, dtype=torch.int32), torch.zeros(2, 4, 3), None),
+          (torch.zeros(2, 2, dtype=torch.int32), torch.zeros(2, 2, 3), None)]
+    seed = (torch.zeros(2, 3, dtype=torch.int32), None)
+    grids = [torch.zeros(10, dtype=torch.uint8), None]
+    ts = engine.GraphedTrainStep._sampling_tensors((lv, seed, grids))
+    assert [tuple(t.shape) for t in ts] == [(2, 4), (2, 4, 3), (2, 2), (2, 2, 3), (2, 3), (10,)]
+    assert len(engine.GraphedTrainStep._sampling_tensors((lv, None, [None, None]))) == 4
+
+
+def test_vote_loss_is_stage_independent():
+    """DeMFVoteHead.loss computes the vote loss once on the GPU path because upstream's per-stage values are
+    identical (same inputs): check that claim on the CPU path, where it is still computed per stage."""
+    torch.manual_seed(3)
+    model = engine.build_demf_votenet(num_points=4).train()
+    batch = engine.synthetic_batch(1, 2048, "S512", seed=5)
+    with oracle_ops():
+        _, preds = model._forward_head(batch["points"], batch["img"], batch["img_metas"], "seed")
+        head = model.pts_bbox_head
+        common = {k: preds[k] for k in ("seed_points", "seed_indices", "aggregated_points", "vote_points")}
+        pts = torch.stack(list(batch["points"])) if not torch.is_tensor(batch["points"]) else batch["points"]
+        targets = head.get_targets(pts, batch["gt_bboxes_3d"], batch["gt_labels_3d"], bbox_preds=common)
+        per_stage = [head._loss(dict(common, **d), pts, batch["gt_bboxes_3d"], batch["gt_labels_3d"],
+                                targets=targets)["vote_loss"] for d in preds["decode_res_all"]]
+        shared = head._vote_loss(common, targets)
+    assert all(torch.equal(v, shared) for v in per_stage)
