@@ -294,3 +294,32 @@ def test_vote_loss_is_stage_independent():
                                 targets=targets)["vote_loss"] for d in preds["decode_res_all"]]
         shared = head._vote_loss(common, targets)
     assert all(torch.equal(v, shared) for v in per_stage)
+
+
+def test_simple_test_with_nms_on_cpu_matches_per_scene_oracle():
+    """Detector-level post-processing through the oracle backend: simple_test(nms=True) returns the
+    reference's per-scene dicts (demfnet.py:254-283) and they equal the literal per-scene NMS applied to the
+    decoded boxes of simple_test(nms=False)."""
+    from oracle import postprocess
+    torch.manual_seed(7)
+    model = engine.build_demf_votenet(num_points=4).eval()
+    # random weights give tiny objectness: lower the score threshold so that the selection is not empty
+    model.pts_bbox_head.test_cfg['score_thr'] = 0.0
+    with torch.no_grad():   # ... and give the boxes a size of about a metre so that they hold points
+        for pred in model.pts_bbox_head.conv_preds:
+            pred.conv_reg.bias[3:6] = 1.0
+    batch = engine.synthetic_batch(2, 2048, "S512", seed=9, with_gt=False)
+    kw = dict(points=batch["points"], img_metas=batch["img_metas"], img=batch["img"])
+    with torch.no_grad(), oracle_ops():
+        box, obj, sem = model.simple_test(**kw)
+        out = model.simple_test(nms=True, **kw)
+    pts = torch.stack(list(batch["points"])) if not torch.is_tensor(batch["points"]) else batch["points"]
+    assert len(out) == 2
+    total = 0
+    for b, res in enumerate(out):
+        wb, ws, wl = postprocess.multiclass_nms_single(obj[b], sem[b], box[b], pts[b, :, :3], 0.25, 0.0, True)
+        assert set(res) == {"boxes_3d", "scores_3d", "labels_3d"}
+        assert torch.equal(res["labels_3d"], wl) and torch.equal(res["boxes_3d"].tensor, wb)
+        assert torch.equal(res["scores_3d"], ws)
+        total += len(wl)
+    assert total > 0
