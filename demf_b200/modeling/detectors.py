@@ -2,12 +2,13 @@
 
 Point branch = PointNet2SASSG backbone + DeMFVoteHead; image branch (backbone, neck, deformable
 DETR encoder) is frozen in the reference and produces the 4-level feature pyramid the head
-samples. The image branch is outside this repository's scope (BASELINE
-configs feed synthetic pyramids); `img` may therefore be given directly as the list of
-(B,256,H_l,W_l) level features, which is what `extract_img_feat` returns upstream. When
-img_backbone / img_neck / img_encoder configs are present and their types are registered they are
-built and run exactly like the reference does; unregistered image modules are skipped with the
-pyramid passed through.
+samples. Its ResNet / ChannelMapper are outside this repository's scope (SURVEY.md section 8:
+BASELINE configs feed synthetic pyramids); `img` may therefore be given directly as the list of
+(B,256,H_l,W_l) level features, which is what `extract_img_feat` returns upstream. The encoder
+(`DeformableDetrEncoder`, modeling/encoder.py) is implemented: with a full `img_encoder` config the
+pyramids handed in are treated as the neck's output and run through it. When img_backbone /
+img_neck configs are present and their types are registered they are built and run exactly like
+the reference does; unregistered image modules are skipped with the pyramid passed through.
 """
 import torch
 import torch.nn as nn
@@ -37,7 +38,7 @@ class DeMFVoteNet(BaseModule):
             pts_bbox_head.update(train_cfg=train_cfg['pts'] if train_cfg is not None else None)
             pts_bbox_head.update(test_cfg=test_cfg['pts'] if test_cfg is not None else None)
             self.pts_bbox_head = build_head(pts_bbox_head)
-        # image branch: frozen feature extractor, out of scope here (see module docstring)
+        # image branch: frozen feature extractor (see module docstring)
         if _registered(img_backbone, BACKBONES):
             self.img_backbone = build_backbone(img_backbone)
         if _registered(img_neck, NECKS):
