@@ -155,6 +155,21 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint6
       : "memory");
 }
 
+// Same with the A operand in TENSOR MEMORY: lanes = the 128 rows, one 32-bit column per k (a K step of 8
+// tf32 = 8 consecutive columns starting at tmem_a); written by the row-owning threads with tmem_st32.
+// Verified on B200 by tools/umma_ts_probe.cu. Keeps an activation on chip between two layers: no store to
+// and no operand read from shared memory for it.
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // mbarrier arrive once every tcgen05.mma issued so far by this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
