@@ -223,6 +223,22 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------- CPU (oracle) arm ---
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def use_all_host_threads():
+    """Before torch / the OpenMP oracle are loaded: torchrun exports OMP_NUM_THREADS=1 to every rank, which
+    would time the CPU arm on ONE core. The reference arm uses every core the process may run on."""
+    n = host_cores()
+    for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[var] = str(n)
+    return n
+
+
 def cpu_forward_rate(scenes, steps, warmup, threads=None):
     """Scenes/s of the oracle CPU port of the same forward (oracle/cpu_backend.py)."""
     import torch
@@ -239,7 +255,7 @@ def cpu_forward_rate(scenes, steps, warmup, threads=None):
     with oracle_ops(), torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            model.simple_test(points=batch["points"], img=batch["img"], img_metas=batch["img_metas"])
+            model.simple_test(points=batch["points"], img=batch["img"], img_metas=batch["img_metas"], nms=False)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     total = sum(times)
@@ -251,7 +267,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    rate, ms, cores, omp = cpu_forward_rate(CPU_SAMPLE_SCENES, args.steps, args.warmup)
+    threads = use_all_host_threads()
+    rate, ms, cores, omp = cpu_forward_rate(CPU_SAMPLE_SCENES, args.steps, args.warmup, threads=threads)
     sample = (f"{CPU_SAMPLE_SCENES} scenes per step (same forward, same shapes; the GPU arm runs "
               f"{BATCH_PER_GPU} per GPU), torch threads={cores}, oracle OpenMP threads={omp}")
     line = {
@@ -327,7 +344,7 @@ def main():
     def forward(batch):
         with torch.no_grad():
             return model.simple_test(points=batch["points"], img=batch["img"],
-                                     img_metas=batch["img_metas"])
+                                     img_metas=batch["img_metas"], nms=False)
 
     for i in range(args.warmup):  # eager warm-up: fills every per-shape cache before capture
         forward(sets[i % ROTATE])

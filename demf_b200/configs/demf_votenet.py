@@ -1,12 +1,12 @@
 # Model section of the reference's configs/demf/demf_votenet.py:26-182 (DeMF on VoteNet, SUN RGB-D),
 # restated value for value so that the same `model = dict(type='DeMFVoteNet', ...)` builds here.
-# The frozen image branch (img_backbone / img_neck / img_encoder, inherited upstream from
-# configs/deformdetr/imvotenet_image.py) is outside this repository's scope: BASELINE.json feeds
-# synthetic 4-level pyramids in its place, so only its type names are kept for reference.
-# The encoder itself (demf/modeling/layers/deform_detr_encoder.py) IS implemented: `img_encoder_cfg`
-# below restates configs/demf/demf_votenet.py:28-47; put it in `model.img_encoder` (or call
-# demf_b200.engine.build_demf_votenet(img_encoder=True)) and the pyramids handed to the detector are
-# treated as the neck's output and run through it.
+# BASELINE.json's configs feed synthetic 4-level pyramids in place of the frozen image branch, so the
+# `model` below leaves img_backbone / img_neck / img_encoder out (the detector then takes `img` as the
+# pyramid itself). The branch IS implemented: `img_backbone_cfg` / `img_neck_cfg` restate
+# configs/deformdetr/imvotenet_image.py:3-20 and `img_encoder_cfg` configs/demf/demf_votenet.py:28-47;
+# demf_b200.engine.build_demf_votenet(img_encoder=True) adds the encoder (pyramids handed in are then
+# the neck's output), build_demf_votenet(img_branch=True) the whole branch (`img` = (B,3,H,W) images).
+# The reference's own config file builds unchanged (tests/test_model_cpu.py).
 # `num_points` of the deformable cross attention is 2 in the reference file (line 83); the
 # BASELINE.json configs quote 4 (the mmcv default) -- override with
 # Config.merge_from_dict({'model.pts_bbox_head.decoder.transformerlayers.attn_cfgs.1.num_points': 4})
@@ -42,11 +42,15 @@ img_encoder_cfg = dict(
     num_feature_levels=4,
     embed_dims=256)
 
+img_backbone_cfg = dict(
+    type='ResNet', depth=50, num_stages=4, out_indices=(1, 2, 3), frozen_stages=1,
+    norm_cfg=dict(type='BN', requires_grad=False), norm_eval=True, style='pytorch')
+img_neck_cfg = dict(
+    type='ChannelMapper', in_channels=[512, 1024, 2048], kernel_size=1, out_channels=256, act_cfg=None,
+    norm_cfg=dict(type='GN', num_groups=32), num_outs=4)
+
 model = dict(
     type='DeMFVoteNet',
-    img_backbone=dict(type='ResNet'),                 # frozen, not built here
-    img_neck=dict(type='ChannelMapper'),              # frozen, not built here
-    img_encoder=dict(type='DeformableDetrEncoder'),   # name only; see img_encoder_cfg
     pts_backbone=dict(
         type='PointNet2SASSG',
         in_channels=4,

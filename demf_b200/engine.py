@@ -22,15 +22,20 @@ from .mm.registry import build_model
 CONFIG = os.path.join(os.path.dirname(os.path.abspath(__file__)), "configs", "demf_votenet.py")
 
 
-def build_demf_votenet(num_points=4, cfg_options=None, init=True, img_encoder=False):
+def build_demf_votenet(num_points=4, cfg_options=None, init=True, img_encoder=False, img_branch=False):
     """DeMFVoteNet from demf_b200/configs/demf_votenet.py. `num_points` = sampling points per
     level and head of the deformable cross attention (2 in the reference config, 4 in
     BASELINE.json's configs). `img_encoder=True` also builds the frozen Deformable-DETR encoder of
-    the image branch; the pyramids given to the model are then the neck's output."""
+    the image branch; the pyramids given to the model are then the neck's output. `img_branch=True`
+    builds the whole frozen branch (ResNet-50 -> ChannelMapper -> encoder, demfnet.py:42-49): `img` is
+    then the (B,3,H,W) normalised image batch."""
     cfg = Config.fromfile(CONFIG)
     model_cfg = cfg.model.to_dict()
-    if img_encoder:
+    if img_encoder or img_branch:
         model_cfg["img_encoder"] = cfg.img_encoder_cfg.to_dict()
+    if img_branch:
+        model_cfg["img_backbone"] = cfg.img_backbone_cfg.to_dict()
+        model_cfg["img_neck"] = cfg.img_neck_cfg.to_dict()
     model_cfg["pts_bbox_head"]["decoder"]["transformerlayers"]["attn_cfgs"][1]["num_points"] = num_points
     if cfg_options:
         c = Config(dict(model=model_cfg))
@@ -167,7 +172,53 @@ def build_optimizer(model, cfg=None, capturable=False):
         groups[(lr, wd)]["names"].append(name)
     on_cuda = all(p.is_cuda for g in groups.values() for p in g["params"])
     extra = dict(fused=True, capturable=capturable) if on_cuda else dict(foreach=False)
-    return torch.optim.AdamW(list(groups.values()), **cfg, **extra)
+    groups = list(groups.values())
+    if on_cuda and capturable:
+        # a captured step reads the learning rate from DEVICE memory: `set_lr` / an LR schedule then
+        # takes effect on the next replay (a Python float would be baked into the graph)
+        dev = groups[0]["params"][0].device
+        for g in groups:
+            g["lr_mult"] = g["lr"] / base_lr if base_lr else 1.0
+            g["lr"] = torch.tensor(float(g["lr"]), dtype=torch.float32, device=dev)
+        cfg["lr"] = torch.tensor(float(base_lr), dtype=torch.float32, device=dev)
+    else:
+        for g in groups:
+            g["lr_mult"] = g["lr"] / base_lr if base_lr else 1.0
+    return torch.optim.AdamW(groups, **cfg, **extra)
+
+
+def set_lr(optimizer, base_lr):
+    """Set the base learning rate; every group keeps its paramwise `lr_mult` (configs/demf/
+    demf_votenet.py:17-24). Works for float and device-tensor rates (captured steps), in place."""
+    for g in optimizer.param_groups:
+        lr = float(base_lr) * g.get("lr_mult", 1.0)
+        if torch.is_tensor(g["lr"]):
+            g["lr"].fill_(lr)
+        else:
+            g["lr"] = lr
+
+
+def step_lr(base_lr, epoch, steps=(24, 32), gamma=0.1):
+    """configs/_base_/schedules/schedule_3x.py:5-9: lr_config = dict(policy='step', step=[24, 32])."""
+    return base_lr * gamma ** sum(epoch >= s for s in steps)
+
+
+def broadcast_module_state(model, src=0, group=None):
+    """Every parameter and buffer from rank `src` to all ranks (what MMDistributedDataParallel does at
+    construction); replicas then start identical whatever each rank's RNG did before."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    with torch.no_grad():
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, src=src, group=group)
+
+
+def module_state_checksum(model):
+    """float64 sum of squares over parameters and floating buffers (debug aid: equal across ranks)."""
+    acc = 0.0
+    for t in list(model.parameters()) + [b for b in model.buffers() if b.is_floating_point()]:
+        acc += float(t.detach().double().pow(2).sum())
+    return acc
 
 
 def pad_gt(gt_bboxes_3d, gt_labels_3d, max_gt=None, device=None):
@@ -198,12 +249,27 @@ class Trainer:
     """forward_train -> sum of losses -> backward into the flat buffer -> one all-reduce ->
     clip (max_norm 10, schedule_3x.py:6) -> AdamW."""
 
-    def __init__(self, model, grad_clip=10.0, group=None, capturable=False):
+    def __init__(self, model, grad_clip=10.0, group=None, capturable=False, sync_state=True):
         self.model = model
+        if sync_state:
+            broadcast_module_state(model, group=group)
         self.flat = FlatGradients(model.parameters())
         self.optimizer = build_optimizer(model, capturable=capturable)
+        self.base_lr = float(Config.fromfile(CONFIG).optimizer.lr)
         self.grad_clip = grad_clip
         self.group = group
+
+    def set_lr(self, base_lr):
+        """New base learning rate (every group keeps its lr_mult); takes effect on the next step, captured
+        or not."""
+        self.base_lr = float(base_lr)
+        set_lr(self.optimizer, base_lr)
+
+    def load_state_dict(self, state_dict, strict=True):
+        """Load model weights and re-synchronise the replicas (rank 0's copy wins)."""
+        out = self.model.load_state_dict(state_dict, strict=strict)
+        broadcast_module_state(self.model, group=self.group)
+        return out
 
     def step(self, batch, sync_collective=False):
         from .mm.bricks import async_weight_grads
@@ -238,6 +304,8 @@ class GraphedTrainStep:
         from .mm import geometry
         model = trainer.model
         assert model.training
+        assert trainer.optimizer.defaults.get("capturable"), \
+            "GraphedTrainStep needs Trainer(model, capturable=True): the captured AdamW reads step and lr from device memory"
         dev = example["points"].device
         self.trainer = trainer
         self.max_gt = max_gt
@@ -432,7 +500,7 @@ class GraphedForward:
 
     def _eager(self):
         return self.model.simple_test(points=self.points, img=self.levels, img_metas=self.metas,
-                                      projection=(self.mats, self.affs))
+                                      projection=(self.mats, self.affs), nms=False)
 
     def load(self, points, levels, img_metas=None):
         """Copy a new batch (host-pinned or device tensors, same shapes) into the static buffers."""

@@ -501,6 +501,14 @@ def _folded_cached(cm, cols):
     return cache[1], cache[2]
 
 
+def fold_key(cm):
+    """Identity of the folded (W', b') `_folded_cached` last built for `cm`: (storage, version) of every
+    source tensor. Callers that cache something derived from the folded weights key on this, not on the
+    folded tensors' addresses (a refold allocates new tensors and the allocator reuses freed addresses)."""
+    cache = cm.__dict__.get("_rows_fold")
+    return None if cache is None else cache[0]
+
+
 def _foldable(cm):
     if cm.with_norm:
         bn = cm.norm

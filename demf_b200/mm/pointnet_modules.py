@@ -17,8 +17,7 @@ import torch.nn as nn
 
 from . import point_ops as P
 from .bricks import (BaseModule, ConvModule, _foldable, _folded_cached, as_rows, build_conv_layer,
-                     conv_module_rows_max,
-                     conv_module_rows)
+                     conv_module_rows_max, conv_module_rows, fold_key)
 from .registry import BACKBONES, SA_MODULES
 
 
@@ -113,7 +112,7 @@ class BasePointSAModule(nn.Module):
         layers = list(mlp)
         folded = [_folded_cached(cm, P.group_rows_columns(C) if j == 0 else None)
                   for j, cm in enumerate(layers)]
-        key = tuple((w.data_ptr(), b.data_ptr()) for w, b in folded)
+        key = tuple(fold_key(cm) for cm in layers)     # (storage, version) of every source parameter
         cache = mlp.__dict__.get("_sa_pack")
         if cache is None or cache[0] != key:
             cache = (key,) + P.sa_pack_mlp([w for w, _ in folded], [b for _, b in folded])
@@ -130,7 +129,7 @@ class BasePointSAModule(nn.Module):
     def _fused_pack_pre(self, mlp):
         layers = list(mlp)
         folded = [_folded_cached(cm, None) for cm in layers]
-        key = tuple((w.data_ptr(), b.data_ptr()) for w, b in folded)
+        key = tuple(fold_key(cm) for cm in layers)
         cache = mlp.__dict__.get("_sa_pack_pre")
         if cache is None or cache[0] != key:
             cache = (key,) + P.sa_pack_mlp_pre(folded[0][0], [folded[1][0], folded[2][0]],

@@ -1,25 +1,21 @@
 """DeMFVoteNet detector (reference: demf/modeling/detectors/demfnet.py:12-283).
 
-Point branch = PointNet2SASSG backbone + DeMFVoteHead; image branch (backbone, neck, deformable
-DETR encoder) is frozen in the reference and produces the 4-level feature pyramid the head
-samples. Its ResNet / ChannelMapper are outside this repository's scope (SURVEY.md section 8:
-BASELINE configs feed synthetic pyramids); `img` may therefore be given directly as the list of
-(B,256,H_l,W_l) level features, which is what `extract_img_feat` returns upstream. The encoder
-(`DeformableDetrEncoder`, modeling/encoder.py) is implemented: with a full `img_encoder` config the
-pyramids handed in are treated as the neck's output and run through it. When img_backbone /
-img_neck configs are present and their types are registered they are built and run exactly like
-the reference does; unregistered image modules are skipped with the pyramid passed through.
+Point branch = PointNet2SASSG backbone + DeMFVoteHead; image branch (ResNet-50 backbone,
+ChannelMapper neck, Deformable-DETR encoder: mm/image_backbone.py, modeling/encoder.py) is frozen in
+the reference and produces the 4-level feature pyramid the head samples. Every image module named in
+the config is built through its registry exactly like the reference does (demfnet.py:42-49) -- an
+unknown `type` raises KeyError, nothing is skipped. BASELINE.json's configs feed synthetic pyramids in
+place of the branch: a model built WITHOUT an `img_backbone` accepts `img` as the list of
+(B,256,H_l,W_l) level features -- the encoder's output (what `extract_img_feat` returns upstream), or
+the neck's output when an `img_encoder` is built.
 """
 import torch
 import torch.nn as nn
 
 from ..mm.bricks import BaseModule
 from ..mm.geometry import bbox3d2result
-from ..mm.registry import BACKBONES, DETECTORS, HEADS, NECKS, build_backbone, build_head, build_neck
-
-
-def _registered(cfg, registry):
-    return cfg is not None and cfg.get('type') in registry
+from ..mm import image_backbone  # noqa: F401  (registers ResNet / ChannelMapper)
+from ..mm.registry import DETECTORS, build_backbone, build_head, build_neck
 
 
 @DETECTORS.register_module()
@@ -38,14 +34,12 @@ class DeMFVoteNet(BaseModule):
             pts_bbox_head.update(train_cfg=train_cfg['pts'] if train_cfg is not None else None)
             pts_bbox_head.update(test_cfg=test_cfg['pts'] if test_cfg is not None else None)
             self.pts_bbox_head = build_head(pts_bbox_head)
-        # image branch: frozen feature extractor (see module docstring)
-        if _registered(img_backbone, BACKBONES):
+        # image branch: frozen feature extractor; whatever the config names is built or raises
+        if img_backbone:
             self.img_backbone = build_backbone(img_backbone)
-        if _registered(img_neck, NECKS):
+        if img_neck is not None:
             self.img_neck = build_neck(img_neck)
-        # the shipped config keeps `img_encoder=dict(type='DeformableDetrEncoder')` as a name-only
-        # placeholder (BASELINE.json's pyramids are post-encoder); a full config builds it
-        if _registered(img_encoder, HEADS) and img_encoder.get('encoder') is not None:
+        if img_encoder is not None:
             self.img_encoder = build_head(img_encoder)
         self.freeze_img_branch = freeze_img_branch
         if freeze_img_branch:
@@ -188,11 +182,11 @@ class DeMFVoteNet(BaseModule):
         return self._forward_head(points, img, img_metas, self.test_cfg['pts']['sample_mod'])[1]
 
     def simple_test(self, points=None, img_metas=None, img=None, bboxes_2d=None, rescale=False,
-                    projection=None, nms=False, **kwargs):
-        """Forward + decoding of the ensemble layers. nms=False (what bench.py times, BASELINE.json's
-        scenes/s of the forward path): (boxes (B, len(ensemble)*Q, 7), objectness, semantic scores).
-        nms=True: the reference's return value (demfnet.py:254-283) -- per scene a dict of CPU
-        boxes_3d / scores_3d / labels_3d after DeMFVoteHead.get_bboxes."""
+                    projection=None, nms=True, **kwargs):
+        """Forward + decoding of the ensemble layers. nms=True (default): the reference's return value
+        (demfnet.py:254-283) -- per scene a dict of CPU boxes_3d / scores_3d / labels_3d after
+        DeMFVoteHead.get_bboxes. nms=False (what bench.py times, BASELINE.json's scenes/s of the
+        forward path): (boxes (B, len(ensemble)*Q, 7), objectness, semantic scores) on the device."""
         _, bbox_preds = self._forward_head(points, img, img_metas,
                                            self.test_cfg['pts']['sample_mod'], projection)
         head = self.pts_bbox_head

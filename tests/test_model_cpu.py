@@ -80,7 +80,7 @@ def test_forward_shapes_and_loss_keys(model):
             res = model.forward_dummy(points=batch["points"], img=batch["img"],
                                       img_metas=batch["img_metas"])
             boxes, obj, sem = model.simple_test(points=batch["points"], img=batch["img"],
-                                                img_metas=batch["img_metas"])
+                                                img_metas=batch["img_metas"], nms=False)
         model.train()
         losses = model.forward_train(**batch)
     assert tuple(res["seed_points"].shape) == (2, 1024, 3)
@@ -311,7 +311,7 @@ def test_simple_test_with_nms_on_cpu_matches_per_scene_oracle():
     batch = engine.synthetic_batch(2, 2048, "S512", seed=9, with_gt=False)
     kw = dict(points=batch["points"], img_metas=batch["img_metas"], img=batch["img"])
     with torch.no_grad(), oracle_ops():
-        box, obj, sem = model.simple_test(**kw)
+        box, obj, sem = model.simple_test(nms=False, **kw)
         out = model.simple_test(nms=True, **kw)
     pts = torch.stack(list(batch["points"])) if not torch.is_tensor(batch["points"]) else batch["points"]
     assert len(out) == 2

@@ -282,7 +282,7 @@ def test_simple_test_with_nms_end_to_end(dev):
     pyr = [f.to(dev) for f in synth.make_pyramid(B, "S512")]
     metas = synth.make_img_metas(B, "S512")
     with torch.no_grad():
-        box, obj, sem = model.simple_test(points=pts, img_metas=metas, img=pyr)
+        box, obj, sem = model.simple_test(points=pts, img_metas=metas, img=pyr, nms=False)
         out = model.simple_test(points=[p for p in pts], img_metas=metas, img=pyr, nms=True)
     assert len(out) == B
     for b in range(B):

@@ -13,6 +13,6 @@ model = engine.build_demf_votenet(num_points=4).to(dev).eval()
 batch = engine.synthetic_batch(B, 20000, "S512", seed=1234, device=dev, with_gt=False)
 with torch.no_grad():
     for _ in range(n):
-        model.simple_test(points=batch["points"], img=batch["img"], img_metas=batch["img_metas"])
+        model.simple_test(points=batch["points"], img=batch["img"], img_metas=batch["img_metas"], nms=False)
 torch.cuda.synchronize()
 print("done")

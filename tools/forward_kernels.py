@@ -97,7 +97,7 @@ def main():
         return train_step(args, dev)
     model = engine.build_demf_votenet(num_points=4).to(dev).eval()
     batch = engine.synthetic_batch(args.batch, 20000, "S512", seed=1, device=dev, with_gt=False)
-    kw = dict(points=batch["points"], img_metas=batch["img_metas"], img=batch["img"])
+    kw = dict(points=batch["points"], img_metas=batch["img_metas"], img=batch["img"], nms=False)
     with torch.no_grad():
         for _ in range(3):
             model.simple_test(**kw)

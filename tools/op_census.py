@@ -19,10 +19,10 @@ mats, affs = geometry.fold_projection(batch["img_metas"])
 proj = (mats.to(dev), affs.to(dev))
 with torch.no_grad():
     for _ in range(3):
-        model.simple_test(points=batch["points"], img=batch["img"], img_metas=batch["img_metas"], projection=proj)
+        model.simple_test(points=batch["points"], img=batch["img"], img_metas=batch["img_metas"], projection=proj, nms=False)
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
-        model.simple_test(points=batch["points"], img=batch["img"], img_metas=batch["img_metas"], projection=proj)
+        model.simple_test(points=batch["points"], img=batch["img"], img_metas=batch["img_metas"], projection=proj, nms=False)
         torch.cuda.synchronize()
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sites = Counter()

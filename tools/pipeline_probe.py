@@ -39,7 +39,7 @@ def run(lanes, steps=40, tag=""):
 
 with torch.no_grad():
     for _ in range(3):
-        model.simple_test(points=sets[0]["points"], img=sets[0]["img"], img_metas=sets[0]["img_metas"])
+        model.simple_test(points=sets[0]["points"], img=sets[0]["img"], img_metas=sets[0]["img_metas"], nms=False)
 if os.environ.get("PROBE_SERIAL_FPS"):
     model.pts_backbone.overlap_sampling = False
 quick = os.environ.get("PROBE_QUICK")
@@ -64,7 +64,7 @@ real_fps_grid = P.furthest_point_sample_grid
 P.furthest_point_sample_grid = lambda xyz, m, grid: cached_fps(xyz, m)
 P.furthest_point_sample = cached_fps
 with torch.no_grad():
-    model.simple_test(points=sets[0]["points"], img=sets[0]["img"], img_metas=sets[0]["img_metas"])
+    model.simple_test(points=sets[0]["points"], img=sets[0]["img"], img_metas=sets[0]["img_metas"], nms=False)
 for lanes in (1, 2, 4, 8):
     run(lanes, tag="cached FPS")
 # ... and without the fused set-abstraction kernels either (cached level outputs): what the
@@ -82,7 +82,7 @@ def cached_sa(xyz, center_xyz, feat_rows, *a, **k):
 
 P.sa_fused = cached_sa
 with torch.no_grad():
-    model.simple_test(points=sets[0]["points"], img=sets[0]["img"], img_metas=sets[0]["img_metas"])
+    model.simple_test(points=sets[0]["points"], img=sets[0]["img"], img_metas=sets[0]["img_metas"], nms=False)
 for lanes in (1, 4, 8):
     run(lanes, tag="cached FPS + cached SA")
 P.sa_fused = real_sa

@@ -17,7 +17,7 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 sets = [engine.synthetic_batch(8, 20000, "S512", seed=1234 + i, device=dev, with_gt=False) for i in range(max(lanes, 4))]
 with torch.no_grad():
     for _ in range(3):
-        model.simple_test(points=sets[0]["points"], img=sets[0]["img"], img_metas=sets[0]["img_metas"])
+        model.simple_test(points=sets[0]["points"], img=sets[0]["img"], img_metas=sets[0]["img_metas"], nms=False)
 pipe = engine.ForwardPipeline(model, sets, lanes=lanes)
 for _ in range(8):
     pipe.submit()
