@@ -24,7 +24,7 @@
 namespace demf {
 namespace {
 
-constexpr int kWarps = 8;
+constexpr int kWarps = 4;  // 128-thread CTAs: at Q=256, B=8 the grid is 1024 CTAs = 6.9 per SM (8 warps: 3.46 -> a 4-vs-3 imbalance)
 constexpr int kThreads = kWarps * 32;
 constexpr int kMaxLevels = 16;
 

@@ -93,6 +93,39 @@ def main():
                 report("msda_bwd", dict(pyramid=name, P=P, B=Bm), med, mn, 2 * nbytes)
                 del v, gv
 
+    if want("msda_hbm"):
+        # HBM-resident regime: XL pyramid at B=8 (2.85 GB of value, far beyond the 126 MB L2), the contract's
+        # Q=256 and larger query counts (>= 4 waves of CTAs); inputs generated on the device
+        name, Bm, H, D, L, P = "XL", B, 8, 32, 4, 4
+        shapes = synth.PYRAMIDS[name]
+        S = synth.pyramid_tokens(name)
+        g = torch.Generator(device=dev).manual_seed(11)
+        v = torch.randn(Bm, S, H, D, generator=g, device=dev)
+        sh = torch.tensor(shapes, dtype=torch.int64, device=dev)
+        lsi = torch.cat([sh.new_zeros(1), sh.prod(1).cumsum(0)[:-1]])
+        for Q in (256, 1024, 4096):
+            ref = torch.rand(Bm, Q, 1, 1, 1, 2, generator=g, device=dev)
+            loc = (ref + 0.05 * torch.randn(Bm, Q, H, L, P, 2, generator=g, device=dev)).contiguous()
+            at = torch.softmax(torch.randn(Bm, Q, H, L * P, generator=g, device=dev), -1).view(Bm, Q, H, L, P).contiguous()
+            nbytes = Bm * Q * H * L * P * (4 * D * 4 + 12) + Bm * Q * H * D * 4
+            med, mn = timeit(lambda: MSDA.apply(v, sh, lsi, loc, at, 64), args.reps, flush)
+            report("msda_fwd_hbm", dict(pyramid=name, P=P, B=Bm, Q=Q, value_GB=round(v.numel() * 4 / 1e9, 2)), med, mn, nbytes)
+        del v
+
+    if want("imgbranch"):
+        from demf_b200 import engine
+        torch.manual_seed(0)
+        engine.set_gemm_precision(args.gemm)
+        model = engine.build_demf_votenet(num_points=4, img_branch=True).to(dev).eval()
+        img = torch.randn(B, 3, 512, 512, device=dev)
+        metas = [dict(img_shape=(512, 512, 3), batch_input_shape=(512, 512)) for _ in range(B)]
+        with torch.no_grad():
+            for fn, nm in ((lambda: model.img_neck(model.img_backbone(img)), "resnet50+channelmapper"),
+                           (lambda: model.extract_img_feat(img, metas), "image branch (backbone+neck+encoder)")):
+                med, mn = timeit(fn, max(5, args.reps // 3), False)
+                report(nm, dict(B=B, image="512x512", gemm=args.gemm, images_per_s=round(B / med * 1e3, 1)), med, mn)
+        del model
+
     if want("msda_self"):
         # encoder regime (demf/modeling/layers/deform_detr_encoder.py): every pixel of the pyramid is a
         # query (Q = S) sampling around its own position. Compulsory HBM bytes = value + locations +
