@@ -69,6 +69,21 @@ _SIGNATURES = {
                              _ptr, _ptr, _ptr, _ptr, _ptr],
     "demf_bn_max_rows_bwd": [_ptr, _ptr, _ptr, _ptr, ctypes.c_long, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr,
                              _ptr, _ptr, _ptr, _ptr],
+    "demf_bn_rows_apply": [_ptr, ctypes.c_long, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr],
+    "demf_bn_max_rows_apply": [_ptr, ctypes.c_long, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "demf_bn_rows_bwd_apply": [_ptr, _ptr, ctypes.c_long, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "demf_gemm_rows_dgrad_bn": [_ptr, ctypes.c_long, _ptr, ctypes.c_long, ctypes.c_long, _c_int, _c_int, _ptr,
+                                ctypes.c_long, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, ctypes.c_long, _ptr],
+    "demf_bn_bwd_finalize": [_ptr, ctypes.c_long, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "demf_gemm_supported": [_c_int, _c_int],
+    "demf_gemm_error": [],
+    "demf_gemm_debug_mn": [_c_int, _c_int, _c_int],
+    "demf_gemm_rows_fwd": [_ptr, ctypes.c_long, _ptr, ctypes.c_long, _ptr, ctypes.c_long, _c_int, _c_int, _c_int, _ptr,
+                           _ptr, ctypes.c_long, _ptr],
+    "demf_gemm_rows_dgrad": [_ptr, ctypes.c_long, _ptr, ctypes.c_long, ctypes.c_long, _c_int, _c_int, _ptr,
+                             ctypes.c_long, _ptr],
+    "demf_gemm_wgrad": [_ptr, ctypes.c_long, _ptr, ctypes.c_long, ctypes.c_long, _c_int, _c_int, _ptr, _c_int, _ptr],
+    "demf_bn_finalize": [_ptr, ctypes.c_long, _c_int, _c_float, _c_float, _ptr, _ptr, _ptr, _ptr, _ptr],
     "demf_box_point_count": [_ptr, _c_int, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
     "demf_nms_select": [_ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, _ptr, _ptr, _ptr,
                         _ptr, _ptr, _ptr],

@@ -388,6 +388,72 @@ int demf_bn_rows_fwd(const float* x, long R, int C, const float* gamma, const fl
   return after_launch("bn_apply_kernel");
 }
 
+// The second half of demf_bn_rows_fwd / demf_bn_max_rows_fwd alone, for a layer whose statistics came out of the
+// producing GEMM's epilogue (demf_gemm_rows_fwd with bn_state, then demf_bn_finalize): one pass over x.
+int demf_bn_rows_apply(const float* x, long R, int C, const float* gamma, const float* beta, const float* mean,
+                       const float* invstd, int relu, float* y, void* stream) {
+  DEMF_REQUIRE_PTR(x);
+  DEMF_REQUIRE_PTR(gamma);
+  DEMF_REQUIRE_PTR(beta);
+  DEMF_REQUIRE_PTR(mean);
+  DEMF_REQUIRE_PTR(invstd);
+  DEMF_REQUIRE_PTR(y);
+  DEMF_REQUIRE(R > 0 && C > 0, DEMF_E_SIZE);
+  DEMF_REQUIRE(bn_shape_ok(C), DEMF_E_UNSUPPORTED);
+  DEMF_REQUIRE(al16(x) && al16(y) && al16(gamma) && al16(beta) && al16(mean) && al16(invstd), DEMF_E_UNSUPPORTED);
+  const long total4 = R * (C / 4);
+  long ab = (total4 + kBnThreads - 1) / kBnThreads;
+  if (ab > (long)kNumSMs * 16) ab = (long)kNumSMs * 16;
+  bn_apply_kernel<<<(unsigned)ab, kBnThreads, 0, as_stream(stream)>>>(x, total4, C / 4, mean, invstd, gamma, beta,
+                                                                     relu, y);
+  return after_launch("bn_apply_kernel");
+}
+
+// The input-gradient pass of demf_bn_rows_bwd alone: g = dL/dz with the ReLU mask already applied and the two
+// reductions already finalised into `coef` (demf_gemm_rows_dgrad_bn + demf_bn_bwd_finalize).
+int demf_bn_rows_bwd_apply(const float* g, const float* x, long R, int C, const float* gamma, const float* mean,
+                           const float* invstd, const float* coef, float* grad_x, void* stream) {
+  DEMF_REQUIRE_PTR(g);
+  DEMF_REQUIRE_PTR(x);
+  DEMF_REQUIRE_PTR(gamma);
+  DEMF_REQUIRE_PTR(mean);
+  DEMF_REQUIRE_PTR(invstd);
+  DEMF_REQUIRE_PTR(coef);
+  DEMF_REQUIRE_PTR(grad_x);
+  DEMF_REQUIRE(R > 0 && C > 0, DEMF_E_SIZE);
+  DEMF_REQUIRE(bn_shape_ok(C), DEMF_E_UNSUPPORTED);
+  DEMF_REQUIRE(al16(g) && al16(x) && al16(grad_x) && al16(gamma) && al16(mean) && al16(invstd) && al16(coef),
+               DEMF_E_UNSUPPORTED);
+  const long total4 = R * (C / 4);
+  long ab = (total4 + kBnThreads - 1) / kBnThreads;
+  if (ab > (long)kNumSMs * 16) ab = (long)kNumSMs * 16;
+  bn_bwd_apply_kernel<<<(unsigned)ab, kBnThreads, 0, as_stream(stream)>>>(g, nullptr, x, total4, C / 4, mean, invstd,
+                                                                         gamma, coef, 0, grad_x);
+  return after_launch("bn_bwd_apply_kernel");
+}
+
+int demf_bn_max_rows_apply(const float* x, long M, int ns, int C, const float* gamma, const float* beta,
+                           const float* mean, const float* invstd, float* pooled, uint8_t* arg, void* stream) {
+  DEMF_REQUIRE_PTR(x);
+  DEMF_REQUIRE_PTR(gamma);
+  DEMF_REQUIRE_PTR(beta);
+  DEMF_REQUIRE_PTR(mean);
+  DEMF_REQUIRE_PTR(invstd);
+  DEMF_REQUIRE_PTR(pooled);
+  DEMF_REQUIRE_PTR(arg);
+  DEMF_REQUIRE(M > 0 && ns > 0 && ns <= 255 && C > 0, DEMF_E_SIZE);
+  DEMF_REQUIRE(bn_shape_ok(C), DEMF_E_UNSUPPORTED);
+  DEMF_REQUIRE(al16(x) && al16(pooled) && al16(gamma) && al16(beta) && al16(mean) && al16(invstd) &&
+                   (reinterpret_cast<uintptr_t>(arg) & 3u) == 0,
+               DEMF_E_UNSUPPORTED);
+  const long total = M * (C / 4);
+  long ab = (total + kBnThreads - 1) / kBnThreads;
+  if (ab > (long)kNumSMs * 16) ab = (long)kNumSMs * 16;
+  bn_apply_max_kernel<<<(unsigned)ab, kBnThreads, 0, as_stream(stream)>>>(x, M, ns, C / 4, mean, invstd, gamma, beta,
+                                                                         pooled, arg);
+  return after_launch("bn_apply_max_kernel");
+}
+
 int demf_bn_rows_bwd(const float* grad_y, const float* y, const float* x, long R, int C, const float* gamma,
                      const float* save_mean, const float* save_invstd, int relu, void* state, float* coef,
                      float* grad_x, float* grad_gamma, float* grad_beta, void* stream) {

@@ -108,16 +108,19 @@ def synthetic_batch(B, num_points=20000, pyramid="S512", seed=0, device=None, cl
 class FlatGradients:
     """All trainable gradients in one contiguous fp32 buffer (params keep their own storage)."""
 
+    ALIGN = 4   # elements: every gradient starts on a 16-byte boundary (vector atomics of the wgrad kernel)
+
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
-        ref = self.params[0]
-        self.buffer = torch.zeros(total, dtype=torch.float32, device=ref.device)
-        off = 0
+        a = self.ALIGN
+        self.offsets, off = [], 0
         for p in self.params:
-            n = p.numel()
-            p.grad = self.buffer[off:off + n].view_as(p)
-            off += n
+            self.offsets.append(off)
+            off += (p.numel() + a - 1) // a * a
+        ref = self.params[0]
+        self.buffer = torch.zeros(off, dtype=torch.float32, device=ref.device)   # padding stays zero
+        for p, g in zip(self.params, self._views()):
+            p.grad = g
 
     def zero(self):
         self.buffer.zero_()
@@ -126,11 +129,8 @@ class FlatGradients:
                 p.grad = g  # re-attach if something replaced / dropped the view
 
     def _views(self):
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            yield self.buffer[off:off + n].view_as(p)
-            off += n
+        for p, off in zip(self.params, self.offsets):
+            yield self.buffer[off:off + p.numel()].view_as(p)
 
     def all_reduce_mean(self, group=None):
         """The step's only collective. Returns the async work handle (None when not distributed)."""

@@ -535,21 +535,17 @@ def conv_module_rows(cm, x, cols=None):
     w = cm.conv.weight.flatten(1)
     if cols is not None:
         w = permute_weight_columns(w, cols)
-        y = torch.nn.functional.linear(x, w, cm.conv.bias)
-    else:
-        y = _linear_rows(cm, x, w)
+    y, prestats = _linear_rows(cm, x, w, direct_wgrad=cols is None)
     if cm.with_norm and _fused_bn_ok(cm, y):
-        # training: batch statistics + normalise + ReLU in two launches (two more in backward)
+        # training: batch statistics (from the GEMM's epilogue when it ran on our tensor-core kernel) +
+        # normalise + ReLU
         from . import point_ops as P
         bn = cm.norm
         if bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
-        state = bn.__dict__.get("_rows_state")
-        if state is None or state.device != y.device:
-            state = P.bn_rows_state(bn.num_features, y.device)
-            bn.__dict__["_rows_state"] = state
         return P.batch_norm_relu_rows(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum,
-                                      bn.eps, cm.with_activation, state)
+                                      bn.eps, cm.with_activation, _bn_state(bn, y.device), prestats=prestats)
+    assert not prestats
     if cm.with_norm:
         y = batch_norm_rows(cm.norm, y)
     if cm.with_activation:
@@ -568,23 +564,18 @@ def conv_module_rows_max(cm, x, ns, cols=None):
     if not (FUSED_BN_MAX_TRAIN and torch.is_grad_enabled() and cm.with_norm and cm.with_activation
             and x.is_cuda and ns <= 255 and x.shape[0] % ns == 0):
         return None
+    if not _fused_bn_shape_ok(cm, x):
+        return None
     w = cm.conv.weight.flatten(1)
     if cols is not None:
-        y = torch.nn.functional.linear(x, permute_weight_columns(w, cols), cm.conv.bias)
-    else:
-        y = _linear_rows(cm, x, w)
-    if not _fused_bn_ok(cm, y):
-        return None
+        w = permute_weight_columns(w, cols)
+    y, prestats = _linear_rows(cm, x, w, direct_wgrad=cols is None)
     from . import point_ops as P
     bn = cm.norm
     if bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
-    state = bn.__dict__.get("_rows_state")
-    if state is None or state.device != y.device:
-        state = P.bn_rows_state(bn.num_features, y.device)
-        bn.__dict__["_rows_state"] = state
     return P.batch_norm_relu_max_rows(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum,
-                                      bn.eps, ns, state)
+                                      bn.eps, ns, _bn_state(bn, y.device), prestats=prestats)
 
 
 # ------------------------------------------------ weight gradients off the critical path --
@@ -649,26 +640,191 @@ class _LinearRowsAsyncWgrad(torch.autograd.Function):
         return gx, None, None, None
 
 
-def _linear_rows(cm, x, w):
-    """x @ w^T + bias for a ConvModule's 1x1 convolution; `w` is the flattened view of cm.conv.weight."""
+# Training GEMMs on the hand-written tcgen05 + TMA kernels (csrc/gemm_tf32.cu) instead of the library: forward
+# with the BatchNorm statistics in its epilogue, data gradient, split-K weight gradient. TF32 products, so only
+# in the 'tf32' arithmetic mode (engine.set_gemm_precision); the strict-fp32 mode keeps IEEE library GEMMs.
+NATIVE_TRAIN_GEMM = True
+
+
+def _tc_ok(x, w):
+    return (NATIVE_TRAIN_GEMM and x.is_cuda and torch.is_grad_enabled() and torch.backends.cuda.matmul.allow_tf32
+            and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] > 0 and x.stride(1) == 1
+            and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and w.dtype == torch.float32
+            and w.stride(1) == 1 and w.stride(0) % 4 == 0 and w.data_ptr() % 16 == 0
+            and x.shape[1] % 4 == 0 and w.shape[0] % 4 == 0 and x.shape[1] <= 512 and w.shape[0] <= 2048)
+
+
+class _LinearRowsTC(torch.autograd.Function):
+    """y = x @ w^T (+ bias) with all three GEMMs of the layer on csrc/gemm_tf32.cu. `bn_state`: the forward
+    epilogue also accumulates the per-channel sums of y for the BatchNorm behind the convolution. `conv`: the
+    weight gradient is accumulated straight into conv.weight.grad on the weight-gradient stream (inside an
+    `async_weight_grads` block); otherwise it is returned through autograd."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, conv, bn_state):
+        from . import point_ops as P
+        ctx.save_for_backward(x, w)
+        ctx.conv = conv
+        ctx.has_bias = bias is not None
+        return P.gemm_rows_fwd(x, w, bias=bias, bn_state=bn_state)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        from . import point_ops as P
+        x, w = ctx.saved_tensors
+        conv = ctx.conv
+        gy = gy.contiguous()
+        gx = P.gemm_rows_dgrad(gy, w) if ctx.needs_input_grad[0] else None
+        direct = (conv is not None and _ASYNC_WGRAD["on"] and conv.weight.grad is not None
+                  and (conv.bias is None or conv.bias.grad is not None))
+        if direct:
+            cur = torch.cuda.current_stream(gy.device)
+            side = _wgrad_stream(gy.device)
+            side.wait_stream(cur)
+            gy.record_stream(side)
+            x.record_stream(side)
+            with torch.cuda.stream(side):
+                P.gemm_wgrad_(conv.weight.grad.view(w.shape), gy, x)
+                if conv.bias is not None:
+                    conv.bias.grad.add_(gy.sum(0))
+            return gx, None, None, None, None
+        gw = gb = None
+        if ctx.needs_input_grad[1]:
+            gw = torch.zeros_like(w)
+            P.gemm_wgrad_(gw, gy, x)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum(0)
+        return gx, gw, gb, None, None
+
+
+class _BnReluConvRows(torch.autograd.Function):
+    """[BatchNorm (batch statistics) + ReLU of layer l] -> [1x1 convolution of layer l+1] on rows as ONE autograd
+    node, so that the backward of the pair can be fused across the layer boundary (csrc/gemm_tf32.cu):
+      forward   mean/invstd of y_l from the sums the previous GEMM's epilogue left in `state_prev`; z_l = relu(bn(y_l))
+                (one pass); y_{l+1} = z_l W^T with ITS BatchNorm's sums accumulated into `state_next` by the epilogue;
+      backward  g = (dy_{l+1} W) masked by the ReLU and the two BatchNorm-backward reductions come out of ONE GEMM
+                launch (gemm_rows_dgrad_bn) -- no pass over (dz, z, y) -- then one pass writes dL/dy_l; the weight
+                gradient dy_{l+1}^T z_l goes to the split-K tensor-core kernel (weight-gradient stream when the
+                trainer owns the gradient buffers).
+    Mirrors, for mmcv ConvModule stacks (conv -> BN -> ReLU -> conv ...), torch's batch_norm / threshold /
+    conv backward chain."""
+
+    @staticmethod
+    def forward(ctx, y_prev, gamma, beta, w, bn_prev, conv, state_prev, state_next, direct):
+        from . import point_ops as P
+        R, C = y_prev.shape
+        mean, invstd = P.bn_finalize(state_prev, R, C, bn_prev.eps, bn_prev.momentum, bn_prev.running_mean,
+                                     bn_prev.running_var)
+        z = P.bn_rows_apply(y_prev, gamma, beta, mean, invstd, True)
+        y = P.gemm_rows_fwd(z, w, bn_state=state_next)
+        ctx.save_for_backward(y_prev, z, w, gamma, beta, mean, invstd, state_prev)
+        ctx.conv = conv if direct else None
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        from . import point_ops as P
+        y_prev, z, w, gamma, beta, mean, invstd, state_prev = ctx.saved_tensors
+        conv = ctx.conv
+        gy = gy.contiguous()
+        g = P.gemm_rows_dgrad_bn(gy, w, y_prev, mean, invstd, gamma, beta, state_prev)
+        gyp, ggamma, gbeta = P.bn_bwd_from_masked(g, y_prev, gamma, mean, invstd, state_prev)
+        gw = None
+        if conv is not None and _ASYNC_WGRAD["on"] and conv.weight.grad is not None:
+            cur = torch.cuda.current_stream(gy.device)
+            side = _wgrad_stream(gy.device)
+            side.wait_stream(cur)
+            gy.record_stream(side)
+            z.record_stream(side)
+            with torch.cuda.stream(side):
+                P.gemm_wgrad_(conv.weight.grad.view(w.shape), gy, z)
+        elif ctx.needs_input_grad[3]:
+            gw = torch.zeros_like(w)
+            P.gemm_wgrad_(gw, gy, z)
+        return gyp, ggamma, gbeta, gw, None, None, None, None, None
+
+
+def sa_mlp_train_rows(mlp, x, ns, cols0=None):
+    """Training path of a set-abstraction shared MLP + max on grouped rows x (M*ns, K0): conv -> [BN+ReLU -> conv]*
+    -> BN+ReLU+max over every `ns` rows, every GEMM on the tcgen05 kernels, BatchNorm statistics out of the GEMM
+    epilogues, BatchNorm-backward reductions out of the data-gradient GEMMs. Returns pooled (M, C_last), or None
+    when the chain does not apply (then the caller runs layer by layer)."""
+    layers = list(mlp)
+    if not (NATIVE_TRAIN_GEMM and FUSED_BN_TRAIN and FUSED_BN_MAX_TRAIN and torch.is_grad_enabled() and len(layers) >= 2
+            and x.is_cuda and ns <= 255 and x.shape[0] % ns == 0):
+        return None
+    for cm in layers:
+        if not (isinstance(cm, ConvModule) and cm.with_norm and cm.with_activation and cm.conv.bias is None
+                and _fused_bn_shape_ok(cm, x) and cm.conv.out_channels <= 256 and cm.conv.out_channels % 4 == 0):
+            return None
+    w0 = layers[0].conv.weight.flatten(1)
+    if cols0 is not None:
+        w0 = permute_weight_columns(w0, cols0)
+    if not _tc_ok(x, w0):
+        return None
+    from . import point_ops as P
+    for cm in layers:
+        if cm.norm.num_batches_tracked is not None:
+            cm.norm.num_batches_tracked.add_(1)
+    y, prestats = _linear_rows(layers[0], x, w0, direct_wgrad=cols0 is None)
+    assert prestats
+    for prev, cm in zip(layers[:-1], layers[1:]):
+        bn, conv = prev.norm, cm.conv
+        direct = _ASYNC_WGRAD["on"] and conv.weight.requires_grad and conv.weight.grad is not None
+        y = _BnReluConvRows.apply(y, bn.weight, bn.bias, conv.weight.flatten(1), bn, conv, _bn_state(bn, y.device),
+                                  _bn_state(cm.norm, y.device), direct)
+    bn = layers[-1].norm
+    return P.batch_norm_relu_max_rows(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps,
+                                      ns, _bn_state(bn, y.device), prestats=True)
+
+
+def _bn_state(bn, device):
+    from . import point_ops as P
+    state = bn.__dict__.get("_rows_state")
+    if state is None or state.device != device:
+        state = P.bn_rows_state(bn.num_features, device)
+        bn.__dict__["_rows_state"] = state
+    return state
+
+
+def _linear_rows(cm, x, w, direct_wgrad=True):
+    """x @ w^T + bias for a ConvModule's 1x1 convolution; `w` is the flattened (possibly column-permuted) view
+    of cm.conv.weight. Returns (y, prestats): prestats = the BatchNorm statistics of y were accumulated into the
+    layer's state block by the GEMM epilogue. `direct_wgrad`: w IS the parameter (not a permuted copy), so its
+    gradient may be accumulated in place on the weight-gradient stream."""
     conv = cm.conv
-    if (_ASYNC_WGRAD["on"] and x.is_cuda and torch.is_grad_enabled() and conv.weight.requires_grad
-            and conv.weight.grad is not None and (conv.bias is None or conv.bias.grad is not None)):
-        return _LinearRowsAsyncWgrad.apply(x, w, conv.bias, conv)
-    return torch.nn.functional.linear(x, w, conv.bias)
+    direct = (direct_wgrad and _ASYNC_WGRAD["on"] and x.is_cuda and torch.is_grad_enabled()
+              and conv.weight.requires_grad and conv.weight.grad is not None
+              and (conv.bias is None or conv.bias.grad is not None))
+    if _tc_ok(x, w):
+        fuse = cm.with_norm and w.shape[0] <= 256 and _fused_bn_shape_ok(cm, x)
+        state = _bn_state(cm.norm, x.device) if fuse else None
+        return _LinearRowsTC.apply(x, w, conv.bias, conv if direct else None, state), fuse
+    if direct:
+        return _LinearRowsAsyncWgrad.apply(x, w, conv.bias, conv), False
+    return torch.nn.functional.linear(x, w, conv.bias), False
 
 
-def _fused_bn_ok(cm, y):
-    """Batch-statistics BatchNorm (+ ReLU or nothing) on contiguous fp32 CUDA rows of a supported width."""
+def _fused_bn_shape_ok(cm, x):
+    """_fused_bn_ok for the output of this module's convolution applied to rows x, before it exists."""
+    if not cm.with_norm:
+        return False
     bn = cm.norm
-    if not (FUSED_BN_TRAIN and y.is_cuda and y.dtype == torch.float32 and y.dim() == 2 and y.is_contiguous()
-            and y.shape[0] > 1 and isinstance(bn, nn.modules.batchnorm._BatchNorm) and bn.training
-            and bn.affine and bn.track_running_stats and bn.momentum is not None):
+    if not (FUSED_BN_TRAIN and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] > 1
+            and isinstance(bn, nn.modules.batchnorm._BatchNorm) and bn.training and bn.affine
+            and bn.track_running_stats and bn.momentum is not None):
         return False
     if cm.with_activation and type(cm.activate) is not nn.ReLU:
         return False
     from . import point_ops as P
     return P.bn_rows_supported(bn.num_features)
+
+
+def _fused_bn_ok(cm, y):
+    """Batch-statistics BatchNorm (+ ReLU or nothing) on contiguous fp32 CUDA rows of a supported width."""
+    return y.is_contiguous() and _fused_bn_shape_ok(cm, y)
 
 
 def as_rows(features):

@@ -808,17 +808,24 @@ class _BatchNormReluRows(torch.autograd.Function):
     """Training-mode BatchNorm (+ ReLU) on rows, two launches forward and two backward (csrc/bn_rows.cu)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, relu, state):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, relu, state, prestats=False):
         R, C = x.shape
         y = torch.empty_like(x)
-        mean = torch.empty(C, dtype=torch.float32, device=x.device)
-        invstd = torch.empty(C, dtype=torch.float32, device=x.device)
-        with torch.cuda.device_of(x):
-            _lib.check(_lib.load().demf_bn_rows_fwd(
-                _p(x), R, C, _p(gamma), _p(beta), float(eps), float(momentum), int(relu),
-                _p(running_mean) if running_mean is not None else None,
-                _p(running_var) if running_var is not None else None, _p(state), _p(mean), _p(invstd), _p(y),
-                _stream()), "demf_bn_rows_fwd")
+        if prestats:   # sums already in `state` (epilogue of the GEMM that produced x): finalise + one pass
+            mean, invstd = bn_finalize(state, R, C, eps, momentum, running_mean, running_var)
+            with torch.cuda.device_of(x):
+                _lib.check(_lib.load().demf_bn_rows_apply(
+                    _p(x), R, C, _p(gamma), _p(beta), _p(mean), _p(invstd), int(relu), _p(y), _stream()),
+                    "demf_bn_rows_apply")
+        else:
+            mean = torch.empty(C, dtype=torch.float32, device=x.device)
+            invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+            with torch.cuda.device_of(x):
+                _lib.check(_lib.load().demf_bn_rows_fwd(
+                    _p(x), R, C, _p(gamma), _p(beta), float(eps), float(momentum), int(relu),
+                    _p(running_mean) if running_mean is not None else None,
+                    _p(running_var) if running_var is not None else None, _p(state), _p(mean), _p(invstd), _p(y),
+                    _stream()), "demf_bn_rows_fwd")
         ctx.save_for_backward(x, y, gamma, mean, invstd, state)
         ctx.relu = bool(relu)
         return y
@@ -835,26 +842,33 @@ class _BatchNormReluRows(torch.autograd.Function):
             _lib.check(_lib.load().demf_bn_rows_bwd(
                 _p(grad_y), _p(y), _p(x), R, C, _p(gamma), _p(mean), _p(invstd), int(ctx.relu), _p(state),
                 _p(grads[2:]), _p(grad_x), _p(grads[0]), _p(grads[1]), _stream()), "demf_bn_rows_bwd")
-        return grad_x, grads[0], grads[1], None, None, None, None, None, None
+        return grad_x, grads[0], grads[1], None, None, None, None, None, None, None
 
 
 class _BatchNormReluMaxRows(torch.autograd.Function):
     """Training BatchNorm + ReLU + max over the ns rows of each centre (csrc/bn_rows.cu)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, ns, state):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, ns, state, prestats=False):
         R, C = x.shape
         M = R // ns
         pooled = torch.empty(M, C, dtype=torch.float32, device=x.device)
         arg = torch.empty(M, C, dtype=torch.uint8, device=x.device)
-        mean = torch.empty(C, dtype=torch.float32, device=x.device)
-        invstd = torch.empty(C, dtype=torch.float32, device=x.device)
-        with torch.cuda.device_of(x):
-            _lib.check(_lib.load().demf_bn_max_rows_fwd(
-                _p(x), M, int(ns), C, _p(gamma), _p(beta), float(eps), float(momentum),
-                _p(running_mean) if running_mean is not None else None,
-                _p(running_var) if running_var is not None else None, _p(state), _p(mean), _p(invstd),
-                _p(pooled), _p(arg), _stream()), "demf_bn_max_rows_fwd")
+        if prestats:
+            mean, invstd = bn_finalize(state, R, C, eps, momentum, running_mean, running_var)
+            with torch.cuda.device_of(x):
+                _lib.check(_lib.load().demf_bn_max_rows_apply(
+                    _p(x), M, int(ns), C, _p(gamma), _p(beta), _p(mean), _p(invstd), _p(pooled), _p(arg),
+                    _stream()), "demf_bn_max_rows_apply")
+        else:
+            mean = torch.empty(C, dtype=torch.float32, device=x.device)
+            invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+            with torch.cuda.device_of(x):
+                _lib.check(_lib.load().demf_bn_max_rows_fwd(
+                    _p(x), M, int(ns), C, _p(gamma), _p(beta), float(eps), float(momentum),
+                    _p(running_mean) if running_mean is not None else None,
+                    _p(running_var) if running_var is not None else None, _p(state), _p(mean), _p(invstd),
+                    _p(pooled), _p(arg), _stream()), "demf_bn_max_rows_fwd")
         ctx.save_for_backward(x, pooled, arg, gamma, mean, invstd, state)
         ctx.ns = int(ns)
         return pooled
@@ -873,15 +887,17 @@ class _BatchNormReluMaxRows(torch.autograd.Function):
                 _p(grad_pooled), _p(pooled), _p(arg), _p(x), M, ctx.ns, C, _p(gamma), _p(mean), _p(invstd),
                 _p(state), _p(grads[2:]), _p(grad_x), _p(grads[0]), _p(grads[1]), _stream()),
                 "demf_bn_max_rows_bwd")
-        return grad_x, grads[0], grads[1], None, None, None, None, None, None
+        return grad_x, grads[0], grads[1], None, None, None, None, None, None, None
 
 
-def batch_norm_relu_max_rows(x, gamma, beta, running_mean, running_var, momentum, eps, ns, state):
+def batch_norm_relu_max_rows(x, gamma, beta, running_mean, running_var, momentum, eps, ns, state, prestats=False):
     """x (M*ns, C) rows -> (M, C) = max over each centre's ns rows of relu(batch_norm(x)); differentiable in
-    x, gamma, beta. The normalised tensor is never materialised."""
+    x, gamma, beta. The normalised tensor is never materialised. `prestats`: the sums are already in `state`
+    (gemm_rows_fwd(..., bn_state=state) produced x)."""
     _need_cuda(x, gamma, beta)
     assert x.dim() == 2 and x.is_contiguous() and x.dtype == torch.float32 and x.shape[0] % ns == 0 and ns <= 255
-    return _BatchNormReluMaxRows.apply(x, gamma, beta, running_mean, running_var, momentum, eps, ns, state)
+    return _BatchNormReluMaxRows.apply(x, gamma, beta, running_mean, running_var, momentum, eps, ns, state,
+                                       bool(prestats))
 
 
 def bn_rows_supported(channels):
@@ -894,12 +910,14 @@ def bn_rows_state(channels, device):
     return torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=device)
 
 
-def batch_norm_relu_rows(x, gamma, beta, running_mean, running_var, momentum, eps, relu, state):
+def batch_norm_relu_rows(x, gamma, beta, running_mean, running_var, momentum, eps, relu, state, prestats=False):
     """y = [relu](batch_norm(x)) with batch statistics over the rows of x (R, C), differentiable in x,
-    gamma, beta; running statistics updated in place. `state` from bn_rows_state(C, device)."""
+    gamma, beta; running statistics updated in place. `state` from bn_rows_state(C, device). `prestats`: the
+    sums are already in `state` (gemm_rows_fwd(..., bn_state=state) produced x)."""
     _need_cuda(x, gamma, beta)
     assert x.dim() == 2 and x.is_contiguous() and x.dtype == torch.float32 and x.shape[0] > 0
-    return _BatchNormReluRows.apply(x, gamma, beta, running_mean, running_var, momentum, eps, relu, state)
+    return _BatchNormReluRows.apply(x, gamma, beta, running_mean, running_var, momentum, eps, relu, state,
+                                    bool(prestats))
 
 
 def project_points(xyz, mats, affs):
@@ -937,3 +955,117 @@ def nms_select(boxes, obj_scores, sem_scores, counts, min_points, nms_thr, score
                 float(score_thr), _p(minmax), _p(classes), _p(valid), _p(selected), _p(nsel), _stream()),
                 "demf_nms_select")
     return selected.bool(), classes, nsel
+
+
+# ------------------------------------------------------------ training GEMMs (csrc/gemm_tf32.cu) ---
+def gemm_supported(K, N):
+    """Shapes the TMA-fed tcgen05 GEMM kernels take: row strides multiples of 16 bytes, K <= 512."""
+    return bool(_lib.load().demf_gemm_supported(int(K), int(N)))
+
+
+def _rows2d(t):
+    assert t.dim() == 2 and t.dtype == torch.float32 and t.stride(1) == 1 and t.stride(0) % 4 == 0 \
+        and t.data_ptr() % 16 == 0, "fp32 rows with a 16-byte aligned base and row stride"
+    return t
+
+
+def gemm_rows_fwd(x, w, bias=None, relu=False, bn_state=None, out=None):
+    """y (R,N) = x (R,K) @ w (N,K)^T [+ bias] [ReLU] on the tcgen05 tensor cores (TF32 products, fp32
+    accumulation). `bn_state` (from bn_rows_state(N, device)): the per-channel sum / sum of squares of y are
+    added to the layer's accumulators by the kernel's epilogue (see bn_finalize)."""
+    _need_cuda(x, w, bias)
+    x, w = _rows2d(x), _rows2d(w)
+    R, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    y = torch.empty(R, N, dtype=torch.float32, device=x.device) if out is None else _rows2d(out)
+    with torch.cuda.device_of(x):
+        _lib.check(_lib.load().demf_gemm_rows_fwd(
+            _p(x), x.stride(0), _p(w), w.stride(0), _p(bias), R, K, N, int(bool(relu)), _p(bn_state), _p(y),
+            y.stride(0), _stream()), "demf_gemm_rows_fwd")
+    return y
+
+
+def gemm_rows_dgrad(dy, w, out=None):
+    """dx (R,K) = dy (R,N) @ w (N,K): the same weight matrix read as an MN-major tensor-core operand."""
+    _need_cuda(dy, w)
+    dy, w = _rows2d(dy), _rows2d(w)
+    R, N = dy.shape
+    K = w.shape[1]
+    assert w.shape[0] == N
+    dx = torch.empty(R, K, dtype=torch.float32, device=dy.device) if out is None else _rows2d(out)
+    with torch.cuda.device_of(dy):
+        _lib.check(_lib.load().demf_gemm_rows_dgrad(
+            _p(dy), dy.stride(0), _p(w), w.stride(0), R, N, K, _p(dx), dx.stride(0), _stream()),
+            "demf_gemm_rows_dgrad")
+    return dx
+
+
+def gemm_wgrad_(dw, dy, x):
+    """dw (N,K) += dy (R,N)^T @ x (R,K), split over row slabs (red.global.add); in place, returns dw."""
+    _need_cuda(dw, dy, x)
+    dy, x = _rows2d(dy), _rows2d(x)
+    R, N = dy.shape
+    K = x.shape[1]
+    assert x.shape[0] == R and dw.shape == (N, K) and dw.dtype == torch.float32 and dw.stride(1) == 1
+    with torch.cuda.device_of(dy):
+        _lib.check(_lib.load().demf_gemm_wgrad(
+            _p(dy), dy.stride(0), _p(x), x.stride(0), R, N, K, _p(dw), dw.stride(0), _stream()),
+            "demf_gemm_wgrad")
+    return dw
+
+
+def gemm_error():
+    return int(_lib.load().demf_gemm_error())
+
+
+def bn_finalize(state, R, C, eps, momentum, running_mean, running_var):
+    """(mean, invstd) of the batch from the sums a gemm_rows_fwd(..., bn_state=state) epilogue accumulated;
+    updates the running statistics and re-zeroes the accumulators."""
+    mean = torch.empty(C, dtype=torch.float32, device=state.device)
+    invstd = torch.empty(C, dtype=torch.float32, device=state.device)
+    with torch.cuda.device_of(state):
+        _lib.check(_lib.load().demf_bn_finalize(
+            _p(state), int(R), int(C), float(eps), float(momentum), _p(mean), _p(invstd), _p(running_mean),
+            _p(running_var), _stream()), "demf_bn_finalize")
+    return mean, invstd
+
+
+def gemm_rows_dgrad_bn(dy, w, y_prev, mean, invstd, gamma, beta, bn_state):
+    """g (R,K) = (dy (R,N) @ w (N,K)) zeroed where relu(bn(y_prev)) was inactive; the BatchNorm backward's two
+    reductions (sum g, sum g*y_prev) land in `bn_state`. Returns g."""
+    _need_cuda(dy, w, y_prev)
+    dy, w, y_prev = _rows2d(dy), _rows2d(w), _rows2d(y_prev)
+    R, N = dy.shape
+    K = w.shape[1]
+    assert w.shape[0] == N and y_prev.shape == (R, K)
+    g = torch.empty(R, K, dtype=torch.float32, device=dy.device)
+    with torch.cuda.device_of(dy):
+        _lib.check(_lib.load().demf_gemm_rows_dgrad_bn(
+            _p(dy), dy.stride(0), _p(w), w.stride(0), R, N, K, _p(y_prev), y_prev.stride(0), _p(mean), _p(invstd),
+            _p(gamma), _p(beta), _p(bn_state), _p(g), g.stride(0), _stream()), "demf_gemm_rows_dgrad_bn")
+    return g
+
+
+def bn_bwd_from_masked(g, y_prev, gamma, mean, invstd, bn_state):
+    """Finish the BatchNorm backward after gemm_rows_dgrad_bn: -> (grad of y_prev, grad_gamma, grad_beta)."""
+    R, C = g.shape
+    grads = torch.empty(4, C, dtype=torch.float32, device=g.device)     # grad_gamma, grad_beta, coef(2)
+    grad_x = torch.empty_like(g)
+    lib = _lib.load()
+    with torch.cuda.device_of(g):
+        _lib.check(lib.demf_bn_bwd_finalize(_p(bn_state), R, C, _p(mean), _p(invstd), _p(grads[0]), _p(grads[1]),
+                                            _p(grads[2:]), _stream()), "demf_bn_bwd_finalize")
+        _lib.check(lib.demf_bn_rows_bwd_apply(_p(g), _p(y_prev), R, C, _p(gamma), _p(mean), _p(invstd), _p(grads[2:]),
+                                              _p(grad_x), _stream()), "demf_bn_rows_bwd_apply")
+    return grad_x, grads[0], grads[1]
+
+
+def bn_rows_apply(y, gamma, beta, mean, invstd, relu=True):
+    """z = [relu]((y - mean) * invstd * gamma + beta) with given statistics (one pass)."""
+    R, C = y.shape
+    z = torch.empty_like(y)
+    with torch.cuda.device_of(y):
+        _lib.check(_lib.load().demf_bn_rows_apply(_p(y), R, C, _p(gamma), _p(beta), _p(mean), _p(invstd), int(relu),
+                                                  _p(z), _stream()), "demf_bn_rows_apply")
+    return z

@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from . import point_ops as P
 from .bricks import (BaseModule, ConvModule, _foldable, _folded_cached, as_rows, build_conv_layer,
-                     conv_module_rows_max, conv_module_rows, fold_key)
+                     conv_module_rows_max, conv_module_rows, fold_key, sa_mlp_train_rows)
 from .registry import BACKBONES, SA_MODULES
 
 
@@ -197,6 +197,12 @@ class BasePointSAModule(nn.Module):
                 x = rows.view(B * M * ns, K)
                 layers = list(mlp)
                 pooled = None
+                if self.pool_mod == 'max' and torch.is_grad_enabled():
+                    # training: the whole MLP + max as a chain of fused units on the tensor-core kernels
+                    pooled = sa_mlp_train_rows(mlp, x, ns, P.group_rows_columns(C))
+                    if pooled is not None:
+                        out.append(pooled.view(B, M, -1))
+                        continue
                 for j, layer in enumerate(layers):
                     cols = P.group_rows_columns(C) if j == 0 else None
                     if j == len(layers) - 1 and self.pool_mod == 'max':

@@ -276,6 +276,50 @@ int demf_bn_max_rows_bwd(const float* grad_pooled, const float* pooled, const ui
                          void* state, float* coef, float* grad_x, float* grad_gamma, float* grad_beta,
                          void* stream);
 
+/* The normalise(+ReLU)(+max) half alone, when mean / invstd came from demf_bn_finalize (statistics accumulated by
+ * the epilogue of the GEMM that produced x). */
+int demf_bn_rows_apply(const float* x, long R, int C, const float* gamma, const float* beta, const float* mean,
+                       const float* invstd, int relu, float* y, void* stream);
+int demf_bn_max_rows_apply(const float* x, long M, int ns, int C, const float* gamma, const float* beta,
+                           const float* mean, const float* invstd, float* pooled, uint8_t* arg, void* stream);
+int demf_bn_rows_bwd_apply(const float* g, const float* x, long R, int C, const float* gamma, const float* mean,
+                           const float* invstd, const float* coef, float* grad_x, void* stream);
+
+/* ------------------------------------------- training GEMMs (tcgen05 + TMA) --- */
+/* The 1x1 convolutions of mmcv ConvModule inside the shared MLPs in TRAINING (upstream: cuDNN / cuBLAS behind
+ * torch.nn.Conv1d/Conv2d forward and backward; mmdet3d ops/pointnet_modules/point_sa_module.py,
+ * point_fp_module.py, models/model_utils/vote_module.py, models/dense_heads/base_conv_bbox_head.py, built from
+ * configs/demf/demf_votenet.py:48-62,142-162). Row-major fp32 matrices with row strides (`ld*`, in floats,
+ * multiples of 4), TF32 products with fp32 accumulation on the tcgen05 tensor cores, operands and results moved
+ * by TMA tensor maps.
+ *   fwd   : y (R,N) = x (R,K) w(N,K)^T [+ bias] [ReLU]; bn_state != NULL (N <= 256): the per-column sum and sum
+ *           of squares of y are ADDED to the (2,N) double accumulators at the head of the BatchNorm layer's
+ *           state block (demf_bn_rows_state_bytes); demf_bn_finalize turns them into mean / invstd.
+ *   dgrad : dx (R,K) = dy (R,N) w(N,K)
+ *   wgrad : dw (N,K) += dy (R,N)^T x (R,K)   (accumulates: the caller zeroes or owns the running gradient)
+ * demf_gemm_error(): nonzero after an internal pipeline time-out (sticky; never expected). */
+int demf_gemm_supported(int K, int N);
+int demf_gemm_error(void);
+int demf_gemm_debug_mn(int sbo, int layout, int tma_swizzle); /* development: MN-major operand encoding */
+int demf_gemm_rows_fwd(const float* x, long ldx, const float* w, long ldw, const float* bias, long R, int K, int N,
+                       int relu, void* bn_state, float* y, long ldy, void* stream);
+int demf_gemm_rows_dgrad(const float* dy, long lddy, const float* w, long ldw, long R, int N, int K, float* dx,
+                         long lddx, void* stream);
+int demf_gemm_wgrad(const float* dy, long lddy, const float* x, long ldx, long R, int N, int K, float* dw, int ldw,
+                    void* stream);
+int demf_bn_finalize(void* state, long R, int C, float eps, float momentum, float* save_mean, float* save_invstd,
+                     float* running_mean, float* running_var, void* stream);
+/* Data gradient THROUGH the previous layer's BatchNorm + ReLU: g (R,K) = (dy (R,N) w(N,K)) masked where
+ * relu(bn(y_prev)) was inactive (y_prev (R,K) = that layer's pre-BN activations), and sum g / sum g*y_prev per
+ * channel ADDED to the (2,K) accumulators of `bn_state` -- the two reductions of the BatchNorm backward, for
+ * demf_bn_bwd_finalize (-> grad_gamma, grad_beta, coef (2,K)) and demf_bn_rows_bwd_apply (-> grad of y_prev).
+ * K <= 256. Replaces mmcv ConvModule's conv-backward-data + threshold_backward + batch_norm_backward_reduce. */
+int demf_gemm_rows_dgrad_bn(const float* dy, long lddy, const float* w, long ldw, long R, int N, int K,
+                            const float* y_prev, long ldy_prev, const float* mean, const float* invstd,
+                            const float* gamma, const float* beta, void* bn_state, float* g, long ldg, void* stream);
+int demf_bn_bwd_finalize(void* state, long R, int C, const float* mean, const float* invstd, float* grad_gamma,
+                         float* grad_beta, float* coef, void* stream);
+
 /* ------------------------------------------- inference post-processing --- */
 /* The two per-scene loops of mmdet3d 0.18.1 VoteHead.multiclass_nms_single, reached from
  * DeMFVoteHead.get_bboxes (demf/modeling/heads/class_agnostic_vote_head.py:739-743):

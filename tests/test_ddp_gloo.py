@@ -36,10 +36,13 @@ def _worker(rank, world, port, out):
     expect = torch.stack(gathered).mean(0)
     ok = torch.allclose(flat.buffer, expect, atol=1e-6)
     views_ok = all(p.grad.data_ptr() >= flat.buffer.data_ptr() for p in flat.params)
-    n_expected = sum(p.numel() for p in net.parameters() if p.requires_grad)
-    out[rank] = (ok, views_ok, flat.buffer.numel() == n_expected,
-                 torch.equal(net[2].weight.grad.flatten(),
-                             flat.buffer[-(15 + 3):-3]))
+    # every gradient starts on a 16-byte boundary of the buffer (padding elements stay zero)
+    n_expected = sum((p.numel() + 3) // 4 * 4 for p in net.parameters() if p.requires_grad)
+    off = flat.offsets[[id(p) for p in flat.params].index(id(net[2].weight))]
+    padding_zero = all(float(flat.buffer[o + p.numel():o + (p.numel() + 3) // 4 * 4].abs().sum()) == 0.0
+                       for p, o in zip(flat.params, flat.offsets))
+    out[rank] = (ok, views_ok, flat.buffer.numel() == n_expected and off % 4 == 0 and padding_zero,
+                 torch.equal(net[2].weight.grad.flatten(), flat.buffer[off:off + 15]))
     dist.destroy_process_group()
 
 

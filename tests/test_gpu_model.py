@@ -203,6 +203,68 @@ def test_training_step_gradients_match_cpu_oracle(dev):
     model.cpu()
 
 
+def _train_grads(model, batch):
+    model.zero_grad(set_to_none=True)
+    losses = model.forward_train(**batch)
+    sum(losses.values()).backward()
+    return ({k: v.item() for k, v in losses.items()},
+            {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None})
+
+
+def _rel_l2(a, b):
+    num = sum((a[n].double() - b[n].double()).pow(2).sum().item() for n in b)
+    den = sum(b[n].double().pow(2).sum().item() for n in b)
+    return (num / den) ** 0.5
+
+
+def test_training_step_tf32_native_gemms(dev):
+    """The 'tf32' arithmetic mode, where the shared MLPs' three GEMMs per layer run on the hand-written
+    tcgen05 + TMA kernels (csrc/gemm_tf32.cu: forward with the BatchNorm statistics in its epilogue, data
+    gradient, split-K weight gradient): losses and the whole gradient against (a) the same mode on the library's
+    TF32 GEMMs and (b) the strict-fp32 path. TF32 keeps 10 mantissa bits per operand: per-GEMM error ~1e-3 of
+    scale, accumulated over ~30 chained GEMMs and the BatchNorm statistics; a ball-query membership or a target
+    assignment that flips under the perturbation moves a loss term by more. The bar is therefore relative to
+    what the LIBRARY's TF32 path does on the same inputs: within 5e-2 of the gradient norm plus twice the
+    library-vs-fp32 distance (same for each loss term, 2e-2 + twice the library's deviation)."""
+    from demf_b200.mm import bricks
+    torch.manual_seed(2)
+    model = engine.build_demf_votenet(num_points=4).train().to(dev)
+    _no_dropout(model)
+    batch = engine.synthetic_batch(2, 20000, "S512", seed=8, device=dev)
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    try:
+        engine.set_gemm_precision("fp32")
+        loss32, g32 = _train_grads(model, batch)
+        model.load_state_dict(state)
+        engine.set_gemm_precision("tf32")
+        bricks.NATIVE_TRAIN_GEMM = False
+        loss_lib, g_lib = _train_grads(model, batch)
+        model.load_state_dict(state)
+        bricks.NATIVE_TRAIN_GEMM = True
+        n0 = _lib.launch_count()
+        loss_tc, g_tc = _train_grads(model, batch)
+        assert _lib.launch_count() - n0 > 100
+    finally:
+        bricks.NATIVE_TRAIN_GEMM = True
+        engine.set_gemm_precision("fp32")
+    assert ops.gemm_error() == 0
+    report = {k: (round(loss32[k], 5), round(loss_lib[k], 5), round(loss_tc[k], 5)) for k in loss32}
+    e32, elib = _rel_l2(g_tc, g32), _rel_l2(g_tc, g_lib)
+    print("losses (fp32, tf32 library, tf32 native):", report, "grad rel l2 vs fp32 / library:", e32, elib,
+          "library vs fp32:", _rel_l2(g_lib, g32))
+    for k in loss32:   # the library's TF32 path sets the scale of what TF32 arithmetic does to each loss term
+        tol = 2e-2 * max(1.0, abs(loss32[k])) + 2.0 * abs(loss_lib[k] - loss32[k])
+        assert abs(loss_tc[k] - loss32[k]) <= tol, (k, report[k])
+    assert set(g_tc) == set(g32)
+    assert e32 < 5e-2 + 2.0 * _rel_l2(g_lib, g32), (e32, _rel_l2(g_lib, g32))
+    assert elib < 5e-2 + 2.0 * _rel_l2(g_lib, g32), (elib, _rel_l2(g_lib, g32))
+    # running statistics were updated through the GEMM epilogue + finalize path
+    for (k, v), (_, v0) in zip(model.state_dict().items(), state.items()):
+        if k.endswith("running_mean") and "pts_backbone.SA_modules.0" in k:
+            assert not torch.equal(v, v0), k
+    model.cpu()
+
+
 def test_ops_refuse_cpu_tensors():
     with pytest.raises(RuntimeError):
         ops.furthest_point_sample(torch.zeros(1, 8, 3), 2)

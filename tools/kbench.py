@@ -126,6 +126,36 @@ def main():
                 report(nm, dict(B=B, image="512x512", gemm=args.gemm, images_per_s=round(B / med * 1e3, 1)), med, mn)
         del model
 
+    if want("gemm"):
+        # the training GEMMs at batch-4 shapes (configs[3]): own tcgen05/TMA kernels vs the library (TF32)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        shapes = [("SA1.l0", 524288, 8, 64), ("SA1.l1", 524288, 64, 64), ("SA1.l2", 524288, 64, 128),
+                  ("SA2.l0", 131072, 132, 128), ("SA2.l1", 131072, 128, 128), ("SA2.l2", 131072, 128, 256),
+                  ("SA3.l0", 32768, 260, 128), ("SA3.l2", 32768, 128, 256), ("agg.l0", 16384, 260, 256),
+                  ("agg.l1", 16384, 256, 256), ("FP.l0", 4096, 512, 256), ("vote.l0", 4096, 256, 256)]
+        only_layers = set(filter(None, os.environ.get("GEMM_LAYERS", "").split(",")))
+        for name, R, K, N in shapes:
+            if only_layers and name not in only_layers:
+                continue
+            x = torch.randn(R, K, device=dev)
+            w = torch.randn(N, K, device=dev) / K ** 0.5
+            dy = torch.randn(R, N, device=dev)
+            dw = torch.zeros(N, K, device=dev)
+            y = torch.empty(R, N, device=dev)
+            dx = torch.empty(R, K, device=dev)
+            st = ops.bn_rows_state(256, dev)
+            nb = R * (K + N) * 4
+            for label, fn in (("fwd", lambda: ops.gemm_rows_fwd(x, w, out=y)),
+                              ("fwd+stats", lambda: ops.gemm_rows_fwd(x, w, bn_state=st, out=y)),
+                              ("fwd torch", lambda: torch.mm(x, w.t(), out=y)),
+                              ("dgrad", lambda: ops.gemm_rows_dgrad(dy, w, out=dx)),
+                              ("dgrad torch", lambda: torch.mm(dy, w, out=dx)),
+                              ("wgrad", lambda: ops.gemm_wgrad_(dw, dy, x)),
+                              ("wgrad torch", lambda: dw.addmm_(dy.t(), x))):
+                med, mn = timeit(fn, args.reps, flush)
+                report("gemm " + label, dict(layer=name, R=R, K=K, N=N), med, mn, nb)
+        print(json.dumps(dict(gemm_error=ops.gemm_error())), flush=True)
+
     if want("msda_self"):
         # encoder regime (demf/modeling/layers/deform_detr_encoder.py): every pixel of the pyramid is a
         # query (Q = S) sampling around its own position. Compulsory HBM bytes = value + locations +
