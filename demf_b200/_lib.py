@@ -77,6 +77,7 @@ _SIGNATURES = {
     "demf_bn_bwd_finalize": [_ptr, ctypes.c_long, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "demf_gemm_supported": [_c_int, _c_int],
     "demf_gemm_error": [],
+    "demf_gemm_tune": [_c_int],
     "demf_gemm_debug_mn": [_c_int, _c_int, _c_int],
     "demf_gemm_rows_fwd": [_ptr, ctypes.c_long, _ptr, ctypes.c_long, _ptr, ctypes.c_long, _c_int, _c_int, _c_int, _ptr,
                            _ptr, ctypes.c_long, _ptr],

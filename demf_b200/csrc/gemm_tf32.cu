@@ -104,6 +104,7 @@ struct RowsGemmParams {
   const float* bias;   // (N) or null
   double* stats;       // (2, N) double accumulators of a BatchNorm layer's state block, or null
   MnTune mn;
+  int epi_groups;      // 1 or 2 epilogue warp groups in use
   int col_mode;        // 0 none; 1 forward: sum y, sum y^2; 2 data gradient through BN+ReLU: mask, sum g, sum g*y
   const float* bn_y;   // mode 2: pre-BN activations of the layer whose output gradient this kernel produces (R,N)
   long bn_ldy;
@@ -223,18 +224,29 @@ rows_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       __syncwarp();
     }
     uint32_t slab = 0;
-    for (uint32_t t_local = egrp; blockIdx.x + (long)t_local * gridDim.x < tiles; t_local += 2) {
+    const uint32_t t_step = (uint32_t)p.epi_groups;
+    for (uint32_t t_local = egrp; egrp < p.epi_groups && blockIdx.x + (long)t_local * gridDim.x < tiles;
+         t_local += t_step) {
       const long tile = blockIdx.x + (long)t_local * gridDim.x;
-      const uint32_t acc = egrp, aph = (t_local >> 1) & 1u;
+      const uint32_t acc = t_local & 1u, aph = (t_local >> 1) & 1u;
       wait_or_flag(tfull0 + 8u * acc, aph, 4);
       tc_fence_after_sync();
       const long row_base = tile * kTileRows + q * 32;
       const int nvalid = (int)max(0L, min(32L, p.R - row_base));
       for (int g = 0; g < groups; ++g, ++slab) {
+        const int col0 = n0 + g * 32;
+        // mode 2: this lane's column of the previous layer's pre-BN activations for the warp's 32 rows -- 32
+        // independent coalesced loads (one 128-byte row segment per instruction) issued before anything else
+        float yv[32];
+        if (p.col_mode == 2) {
+          const bool col_ok = col0 + (int)lane < p.N;
+          const float* ycol = p.bn_y + row_base * p.bn_ldy + col0 + (int)lane;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) yv[i] = (col_ok && i < nvalid) ? __ldg(ycol + (long)i * p.bn_ldy) : 0.f;
+        }
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)g * 32u, v);
         tmem_ld_wait();
-        const int col0 = n0 + g * 32;
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
@@ -275,20 +287,24 @@ rows_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             ga = __ldg(p.bn_gamma + col);
             be = __ldg(p.bn_beta + col);
           }
-          const float* ycol = p.bn_y + row_base * p.bn_ldy + col;
-#pragma unroll 4
-          for (int i = 0; i < nvalid; ++i) {
-            float* cell = reinterpret_cast<float*>(dst + sw128_offset((uint32_t)(q * 32 + i), lane >> 2) +
-                                                   ((lane & 3u) << 2));
-            float val = *cell;
-            if (p.col_mode == 2) {
-              const float yv = col_ok ? __ldg(ycol + (long)i * p.bn_ldy) : 0.f;
-              const float z = (yv - mu) * is * ga + be;
-              val = z > 0.f ? val : 0.f;
-              *cell = val;
-              sa += val;
-              sb = fmaf(val, yv, sb);
-            } else {
+          if (p.col_mode == 2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (i < nvalid) {
+                float* cell = reinterpret_cast<float*>(dst + sw128_offset((uint32_t)(q * 32 + i), lane >> 2) +
+                                                       ((lane & 3u) << 2));
+                const float z = (yv[i] - mu) * is * ga + be;
+                const float val = z > 0.f ? *cell : 0.f;
+                *cell = val;
+                sa += val;
+                sb = fmaf(val, yv[i], sb);
+              }
+            }
+          } else {
+#pragma unroll 8
+            for (int i = 0; i < nvalid; ++i) {
+              const float val = *reinterpret_cast<const float*>(
+                  dst + sw128_offset((uint32_t)(q * 32 + i), lane >> 2) + ((lane & 3u) << 2));
               sa += val;
               sb = fmaf(val, val, sb);
             }
@@ -312,7 +328,7 @@ rows_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
     if (leader) bulk_wait_all();
-    if (p.col_mode != 0) {
+    if (p.col_mode != 0 && egrp < p.epi_groups) {
       named_bar_sync(bar_a, 128);
       const float* gp = s_sum + (size_t)egrp * 2048;
       const int ncols = min(p.n_block, p.N - n0);
@@ -528,6 +544,7 @@ EncodeTiledFn encode_tiled() {
 
 // (rows, cols) fp32 matrix with row stride `ld` floats; boxes of 32 columns x box_rows rows, SWIZZLE_128B,
 // out-of-bounds elements read as zero / are not written.
+int g_epi_groups = 2;
 int g_mn_sbo = 512, g_mn_layout = 1, g_mn_tma = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;   // see demf_gemm_debug_mn
 
 int make_map(CUtensorMap* map, const float* base, long rows, int cols, long ld, int box_rows, bool mn_major = false) {
@@ -582,6 +599,7 @@ int launch_rows_gemm(const float* a, long lda, const float* w, long ldw, const f
   p.stats = stats;
   p.mn.sbo = g_mn_sbo;
   p.mn.layout = g_mn_layout;
+  p.epi_groups = g_epi_groups;
   p.col_mode = stats == nullptr ? 0 : (bn != nullptr ? 2 : 1);
   p.bn_y = bn ? bn->y : nullptr;
   p.bn_ldy = bn ? bn->ldy : 0;
@@ -629,8 +647,8 @@ using namespace demf;
 extern "C" {
 
 int demf_gemm_supported(int K, int N) {
-  // TMA row strides must be multiples of 16 bytes; the weight-gradient accumulator is at most 512 columns
-  return (K > 0 && N > 0 && K % 4 == 0 && N % 4 == 0 && K <= 512 && N <= 2048) ? 1 : 0;
+  // TMA row strides must be multiples of 16 bytes (the weight gradient takes 512 input channels per launch)
+  return (K > 0 && N > 0 && K % 4 == 0 && N % 4 == 0 && K <= 2048 && N <= 2048) ? 1 : 0;
 }
 
 /* development: the MN-major operand encoding (stride byte offset, UMMA layout type, CUtensorMapSwizzle) */
@@ -638,6 +656,11 @@ int demf_gemm_debug_mn(int sbo, int layout, int tma_swizzle) {
   g_mn_sbo = sbo;
   g_mn_layout = layout;
   g_mn_tma = tma_swizzle;
+  return 0;
+}
+
+int demf_gemm_tune(int epilogue_groups) {
+  g_epi_groups = epilogue_groups == 1 ? 1 : 2;
   return 0;
 }
 

@@ -132,6 +132,29 @@ class FlatGradients:
         for p, off in zip(self.params, self.offsets):
             yield self.buffer[off:off + p.numel()].view_as(p)
 
+    # Autograd ADDS into a `.grad` that already exists: with every `.grad` a view of the buffer, backward ends in
+    # one tiny `add_` launch per parameter (~200 per step). Parameters whose gradient our kernels accumulate in
+    # place (bricks marks them `_demf_direct_grad`: the rows convolutions' weights) keep their views; all others
+    # hand autograd an empty slot, keep the tensor it produces, and `collect()` moves those into the buffer with
+    # one multi-tensor copy.
+    def release(self):
+        """Before backward: drop the views of the parameters autograd itself accumulates."""
+        for p in self.params:
+            if not getattr(p, "_demf_direct_grad", False):
+                p.grad = None
+
+    def collect(self):
+        """After backward: every gradient back in the flat buffer, every `.grad` a view of it again."""
+        srcs, dsts = [], []
+        for p, v in zip(self.params, self._views()):
+            g = p.grad
+            if g is not None and g.data_ptr() != v.data_ptr():
+                srcs.append(g if g.is_contiguous() else g.contiguous())
+                dsts.append(v)
+            p.grad = v
+        if srcs:
+            torch._foreach_copy_(dsts, srcs)
+
     def all_reduce_mean(self, group=None):
         """The step's only collective. Returns the async work handle (None when not distributed)."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
@@ -274,10 +297,12 @@ class Trainer:
     def step(self, batch, sync_collective=False):
         from .mm.bricks import async_weight_grads
         self.flat.zero()
+        self.flat.release()
         with async_weight_grads(self.flat.buffer.device):   # dW GEMMs on a second stream, joined on exit
             losses = self.model.forward_train(**batch)
             total = sum(losses.values())
             total.backward()
+        self.flat.collect()
         work = self.flat.all_reduce_mean(self.group)
         if work is not None:
             work.wait()
@@ -390,12 +415,14 @@ class GraphedTrainStep:
         from .mm.bricks import async_weight_grads
         t = self.trainer
         t.flat.zero()
+        t.flat.release()
         with async_weight_grads(self.points.device):
             losses = t.model.forward_train(points=self.points, img=self.levels, img_metas=self.metas,
                                            gt_bboxes_3d=self.box, gt_labels_3d=self.label,
                                            projection=(self.mats, self.affs), presampled=self.presampled)
             total = sum(losses.values())
             total.backward()
+        t.flat.collect()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(t.group) > 1:
             t.flat.buffer.div_(dist.get_world_size(t.group))
             dist.all_reduce(t.flat.buffer, op=dist.ReduceOp.SUM, group=t.group)

@@ -222,8 +222,19 @@ class FFN(BaseModule):
         self.dropout_layer = build_dropout(dropout_layer) if dropout_layer else nn.Identity()
         self.add_identity = add_identity
 
+    def _layers(self, x):
+        if not (x.is_cuda and torch.is_grad_enabled()):
+            return self.layers(x)
+        for layer in self.layers:     # training: the Linear layers on our tensor-core GEMM kernels
+            if isinstance(layer, nn.Sequential):
+                for sub in layer:
+                    x = linear_nd(x, sub) if isinstance(sub, nn.Linear) else sub(x)
+            else:
+                x = linear_nd(x, layer) if isinstance(layer, nn.Linear) else layer(x)
+        return x
+
     def forward(self, x, identity=None):
-        out = self.layers(x)
+        out = self._layers(x)
         if not self.add_identity:
             return self.dropout_layer(out)
         if identity is None:
@@ -595,6 +606,13 @@ def _wgrad_stream(device):
     return _ASYNC_WGRAD["streams"][key]
 
 
+def _mark_direct(conv):
+    """These parameters' gradients are accumulated in place by our kernels (see engine.FlatGradients.release)."""
+    conv.weight._demf_direct_grad = True
+    if conv.bias is not None:
+        conv.bias._demf_direct_grad = True
+
+
 class async_weight_grads:
     """Context for forward + backward of one step: weight gradients of the rows convolutions are computed
     on a side stream into the pre-allocated `param.grad` buffers; leaving the block joins that stream."""
@@ -651,7 +669,7 @@ def _tc_ok(x, w):
             and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] > 0 and x.stride(1) == 1
             and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and w.dtype == torch.float32
             and w.stride(1) == 1 and w.stride(0) % 4 == 0 and w.data_ptr() % 16 == 0
-            and x.shape[1] % 4 == 0 and w.shape[0] % 4 == 0 and x.shape[1] <= 512 and w.shape[0] <= 2048)
+            and x.shape[1] % 4 == 0 and w.shape[0] % 4 == 0 and x.shape[1] <= 2048 and w.shape[0] <= 2048)
 
 
 class _LinearRowsTC(torch.autograd.Function):
@@ -772,12 +790,43 @@ def sa_mlp_train_rows(mlp, x, ns, cols0=None):
     assert prestats
     for prev, cm in zip(layers[:-1], layers[1:]):
         bn, conv = prev.norm, cm.conv
-        direct = _ASYNC_WGRAD["on"] and conv.weight.requires_grad and conv.weight.grad is not None
+        eligible = _ASYNC_WGRAD["on"] and conv.weight.requires_grad
+        if eligible:
+            _mark_direct(conv)      # from the next step on the trainer leaves this gradient's view in place
+        direct = eligible and conv.weight.grad is not None
         y = _BnReluConvRows.apply(y, bn.weight, bn.bias, conv.weight.flatten(1), bn, conv, _bn_state(bn, y.device),
                                   _bn_state(cm.norm, y.device), direct)
     bn = layers[-1].norm
     return P.batch_norm_relu_max_rows(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps,
                                       ns, _bn_state(bn, y.device), prestats=True)
+
+
+def linear_rows(x, w, bias=None):
+    """x (R,K) @ w (N,K)^T + bias for a plain Linear / kernel-size-1 convolution WITHOUT a BatchNorm behind it.
+    Training on CUDA in the TF32 mode: all three GEMMs on csrc/gemm_tf32.cu (an output width that is not a
+    multiple of 4 is zero-padded so that row strides stay 16-byte multiples, e.g. VoteModule.conv_out's 259 and
+    conv_reg's 30 channels -- upstream's unaligned shapes fall to the library's sm80 kernels); otherwise the
+    library."""
+    N = w.shape[0]
+    pad = (-N) % 4
+    if x.is_cuda and torch.is_grad_enabled() and x.dim() == 2 and x.shape[1] % 4 == 0:
+        wp, bp = w, bias
+        if pad:
+            wp = torch.nn.functional.pad(w, (0, 0, 0, pad))
+            bp = None if bias is None else torch.nn.functional.pad(bias, (0, pad))
+        xc = x if (x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0) else x.contiguous()
+        wp = wp if (wp.stride(1) == 1 and wp.stride(0) % 4 == 0 and wp.data_ptr() % 16 == 0) else wp.contiguous()
+        if _tc_ok(xc, wp):
+            y = _LinearRowsTC.apply(xc, wp, bp, None, None)
+            return y[:, :N] if pad else y
+    return torch.nn.functional.linear(x, w, bias)
+
+
+def linear_nd(x, lin):
+    """nn.Linear `lin` applied to x (..., K) through linear_rows."""
+    lead = x.shape[:-1]
+    y = linear_rows(x.reshape(-1, x.shape[-1]), lin.weight, lin.bias)
+    return y.reshape(*lead, y.shape[-1])
 
 
 def _bn_state(bn, device):
@@ -795,9 +844,11 @@ def _linear_rows(cm, x, w, direct_wgrad=True):
     layer's state block by the GEMM epilogue. `direct_wgrad`: w IS the parameter (not a permuted copy), so its
     gradient may be accumulated in place on the weight-gradient stream."""
     conv = cm.conv
-    direct = (direct_wgrad and _ASYNC_WGRAD["on"] and x.is_cuda and torch.is_grad_enabled()
-              and conv.weight.requires_grad and conv.weight.grad is not None
-              and (conv.bias is None or conv.bias.grad is not None))
+    eligible = (direct_wgrad and _ASYNC_WGRAD["on"] and x.is_cuda and torch.is_grad_enabled()
+                and conv.weight.requires_grad)
+    if eligible:
+        _mark_direct(conv)          # from the next step on the trainer leaves these gradients' views in place
+    direct = eligible and conv.weight.grad is not None and (conv.bias is None or conv.bias.grad is not None)
     if _tc_ok(x, w):
         fuse = cm.with_norm and w.shape[0] <= 256 and _fused_bn_shape_ok(cm, x)
         state = _bn_state(cm.norm, x.device) if fuse else None

@@ -15,7 +15,7 @@ import torch.nn as nn
 from torch.autograd.function import Function, once_differentiable
 
 from .. import _lib
-from .bricks import BaseModule
+from .bricks import BaseModule, linear_nd
 from .registry import ATTENTION
 
 
@@ -233,7 +233,7 @@ class MultiScaleDeformableAttention(BaseModule):
         bs, num_value, _ = value.shape
         _check_num_value(spatial_shapes, num_value)
 
-        value = self.value_proj(value)
+        value = linear_nd(value, self.value_proj)
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
         value = value.view(bs, num_value, self.num_heads, -1)
@@ -259,9 +259,9 @@ class MultiScaleDeformableAttention(BaseModule):
             attention_weights = proj[:, n_off:].view(
                 bs, num_query, self.num_heads, self.num_levels * self.num_points)
         else:
-            sampling_offsets = self.sampling_offsets(query).view(
+            sampling_offsets = linear_nd(query, self.sampling_offsets).view(
                 bs, num_query, self.num_heads, self.num_levels, self.num_points, 2)
-            attention_weights = self.attention_weights(query).view(
+            attention_weights = linear_nd(query, self.attention_weights).view(
                 bs, num_query, self.num_heads, self.num_levels * self.num_points)
         attention_weights = attention_weights.softmax(-1).view(
             bs, num_query, self.num_heads, self.num_levels, self.num_points)
@@ -279,7 +279,7 @@ class MultiScaleDeformableAttention(BaseModule):
             value.contiguous().float(), spatial_shapes, level_start_index,
             sampling_locations.contiguous().float(), attention_weights.contiguous().float(),
             self.im2col_step)
-        output = self.output_proj(output.to(query.dtype))
+        output = linear_nd(output.to(query.dtype), self.output_proj)
         if not self.batch_first:
             output = output.permute(1, 0, 2)
         return self.dropout(output) + identity

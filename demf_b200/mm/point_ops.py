@@ -1009,9 +1009,12 @@ def gemm_wgrad_(dw, dy, x):
     K = x.shape[1]
     assert x.shape[0] == R and dw.shape == (N, K) and dw.dtype == torch.float32 and dw.stride(1) == 1
     with torch.cuda.device_of(dy):
-        _lib.check(_lib.load().demf_gemm_wgrad(
-            _p(dy), dy.stride(0), _p(x), x.stride(0), R, N, K, _p(dw), dw.stride(0), _stream()),
-            "demf_gemm_wgrad")
+        for k0 in range(0, K, 512):     # the kernel's TMEM accumulator holds 512 input channels per launch
+            kw = min(512, K - k0)
+            xs, ds = x[:, k0:k0 + kw], dw[:, k0:k0 + kw]
+            _lib.check(_lib.load().demf_gemm_wgrad(
+                _p(dy), dy.stride(0), _p(xs), x.stride(0), R, N, kw, _p(ds), dw.stride(0), _stream()),
+                "demf_gemm_wgrad")
     return dw
 
 

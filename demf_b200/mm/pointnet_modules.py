@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from . import point_ops as P
 from .bricks import (BaseModule, ConvModule, _foldable, _folded_cached, as_rows, build_conv_layer,
-                     conv_module_rows_max, conv_module_rows, fold_key, sa_mlp_train_rows)
+                     conv_module_rows_max, conv_module_rows, fold_key, linear_rows, sa_mlp_train_rows)
 from .registry import BACKBONES, SA_MODULES
 
 
@@ -567,8 +567,8 @@ class VoteModule(nn.Module):
             vote_points, offset, vote_rows = P.vote_tail(votes, seed_xyz, seed_c, self.vote_xyz_range,
                                                          self.norm_feats)
             return vote_points, vote_rows.transpose(2, 1), offset.transpose(2, 1)
-        votes = torch.nn.functional.linear(x, self.conv_out.weight.flatten(1), self.conv_out.bias)
-        votes = votes.view(batch_size, num_seed, self.vote_per_seed, -1)
+        votes = linear_rows(x, self.conv_out.weight.flatten(1), self.conv_out.bias)
+        votes = votes.reshape(batch_size, num_seed, self.vote_per_seed, -1)
         offset = votes[:, :, :, 0:3]
         if self.vote_xyz_range is not None:
             limited = []
@@ -686,11 +686,9 @@ class BaseConvBboxHead(BaseModule):
         if len(self.cls_conv_channels) > 0:
             for layer in self.cls_convs:
                 x_cls = conv_module_rows(layer, x_cls)
-        cls_score = torch.nn.functional.linear(x_cls, self.conv_cls.weight.flatten(1),
-                                               self.conv_cls.bias)
+        cls_score = linear_rows(x_cls, self.conv_cls.weight.flatten(1), self.conv_cls.bias)
         if len(self.reg_conv_channels) > 0:
             for layer in self.reg_convs:
                 x_reg = conv_module_rows(layer, x_reg)
-        bbox_pred = torch.nn.functional.linear(x_reg, self.conv_reg.weight.flatten(1),
-                                               self.conv_reg.bias)
-        return cls_score.view(B, N, -1).transpose(1, 2), bbox_pred.view(B, N, -1).transpose(1, 2)
+        bbox_pred = linear_rows(x_reg, self.conv_reg.weight.flatten(1), self.conv_reg.bias)
+        return cls_score.reshape(B, N, -1).transpose(1, 2), bbox_pred.reshape(B, N, -1).transpose(1, 2)

@@ -300,6 +300,7 @@ int demf_bn_rows_bwd_apply(const float* g, const float* x, long R, int C, const 
  * demf_gemm_error(): nonzero after an internal pipeline time-out (sticky; never expected). */
 int demf_gemm_supported(int K, int N);
 int demf_gemm_error(void);
+int demf_gemm_tune(int epilogue_groups); /* development: 1 or 2 epilogue warp groups (default 2) */
 int demf_gemm_debug_mn(int sbo, int layout, int tma_swizzle); /* development: MN-major operand encoding */
 int demf_gemm_rows_fwd(const float* x, long ldx, const float* w, long ldw, const float* bias, long R, int K, int N,
                        int relu, void* bn_state, float* y, long ldy, void* stream);

@@ -52,7 +52,7 @@ def test_rows_gemm_dgrad(dev, R, K, N):
     assert P.gemm_error() == 0
 
 
-@pytest.mark.parametrize("R,K,N", SHAPES + [(100000, 64, 128), (33, 128, 128)])
+@pytest.mark.parametrize("R,K,N", SHAPES + [(100000, 64, 128), (33, 128, 128), (1024, 1024, 256)])
 def test_wgrad(dev, R, K, N):
     g = torch.Generator(device=dev).manual_seed(R + K + N + 2)
     dy = torch.randn(R, N, generator=g, device=dev)
@@ -121,4 +121,31 @@ def test_dgrad_through_batchnorm_relu(dev, R, N, K):
     assert _rel(gm, (dy.double() @ w.double()) * mask) < TOL
     assert _rel(gyp, yd.grad) < 2 * TOL
     assert _rel(ggamma, gd.grad) < 2 * TOL and _rel(gbeta, bd.grad) < 2 * TOL
+    assert P.gemm_error() == 0
+
+
+@pytest.mark.parametrize("R,K,N", [(1024, 256, 259), (2048, 128, 30), (1024, 1024, 256), (1024, 256, 1024)])
+def test_linear_rows_autograd(dev, R, K, N):
+    """bricks.linear_rows (padded output widths, K up to 2048) forward and all three gradients vs fp64 autograd."""
+    from demf_b200.mm import bricks
+    g = torch.Generator(device=dev).manual_seed(R + K + N)
+    x = torch.randn(R, K, generator=g, device=dev, requires_grad=True)
+    w = (torch.randn(N, K, generator=g, device=dev) / K ** 0.5).requires_grad_(True)
+    b = torch.randn(N, generator=g, device=dev, requires_grad=True)
+    gy = torch.randn(R, N, generator=g, device=dev)
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n0 = _lib.launch_count()
+        y = bricks.linear_rows(x, w, b)
+        y.backward(gy)
+        assert _lib.launch_count() - n0 >= 3          # our kernels, not the library
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    yd = torch.nn.functional.linear(xd, wd, bd)
+    yd.backward(gy.double())
+    assert y.shape == (R, N)
+    assert _rel(y.detach(), yd.detach()) < TOL and _rel(x.grad, xd.grad) < TOL
+    assert _rel(w.grad, wd.grad) < TOL and _rel(b.grad, bd.grad) < TOL
     assert P.gemm_error() == 0

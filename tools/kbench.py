@@ -134,6 +134,7 @@ def main():
                   ("SA3.l0", 32768, 260, 128), ("SA3.l2", 32768, 128, 256), ("agg.l0", 16384, 260, 256),
                   ("agg.l1", 16384, 256, 256), ("FP.l0", 4096, 512, 256), ("vote.l0", 4096, 256, 256)]
         only_layers = set(filter(None, os.environ.get("GEMM_LAYERS", "").split(",")))
+        _lib.load().demf_gemm_tune(int(os.environ.get("GEMM_EPI", "2")))
         for name, R, K, N in shapes:
             if only_layers and name not in only_layers:
                 continue
@@ -144,14 +145,21 @@ def main():
             y = torch.empty(R, N, device=dev)
             dx = torch.empty(R, K, device=dev)
             st = ops.bn_rows_state(256, dev)
+            st2 = ops.bn_rows_state(256, dev)
+            bn_m, bn_i = torch.zeros(K, device=dev), torch.ones(K, device=dev)
+            bn_g, bn_b = torch.ones(K, device=dev), torch.zeros(K, device=dev)
             nb = R * (K + N) * 4
             for label, fn in (("fwd", lambda: ops.gemm_rows_fwd(x, w, out=y)),
                               ("fwd+stats", lambda: ops.gemm_rows_fwd(x, w, bn_state=st, out=y)),
                               ("fwd torch", lambda: torch.mm(x, w.t(), out=y)),
                               ("dgrad", lambda: ops.gemm_rows_dgrad(dy, w, out=dx)),
+                              ("dgrad+bn", (lambda: ops.gemm_rows_dgrad_bn(dy, w, x, bn_m, bn_i, bn_g, bn_b, st2))
+                               if K in (64, 128, 256) else None),
                               ("dgrad torch", lambda: torch.mm(dy, w, out=dx)),
                               ("wgrad", lambda: ops.gemm_wgrad_(dw, dy, x)),
                               ("wgrad torch", lambda: dw.addmm_(dy.t(), x))):
+                if fn is None:
+                    continue
                 med, mn = timeit(fn, args.reps, flush)
                 report("gemm " + label, dict(layer=name, R=R, K=K, N=N), med, mn, nb)
         print(json.dumps(dict(gemm_error=ops.gemm_error())), flush=True)
