@@ -117,7 +117,8 @@ template <int kThreads, int kPPT>
 __global__ void __launch_bounds__(kThreads, 1) fps_cluster_kernel(const float* __restrict__ xyz,
                                                                   int N, int m, int log2T,
                                                                   int32_t* __restrict__ idx,
-                                                                  float* __restrict__ new_xyz) {
+                                                                  float* __restrict__ new_xyz,
+                                                                  const int32_t* __restrict__ unique_prefix) {
   constexpr int kWarps = kThreads / 32;
   __shared__ FpsSmem<kThreads> sm;
   const unsigned long long trace_t0 = trace_begin();
@@ -131,6 +132,24 @@ __global__ void __launch_bounds__(kThreads, 1) fps_cluster_kernel(const float* _
   const int warp = tid >> 5;
   const float* cloud = xyz + (long)b * N * 3;
   int32_t* out = idx + (long)b * m;
+
+  // ---- sampling a cloud that IS the pick sequence of an earlier furthest point sampling ----------------
+  // If xyz[b] = (p_0, p_1, ...) are the picks, in order, of FPS on a superset, and each of the first m picks
+  // was the UNIQUE arg-max of its iteration (no second point at the same running distance: certified by the
+  // kernel that produced them, see fps_grid_kernel), then p_k is also the unique arg-max of iteration k of
+  // FPS on this cloud -- the running distances are the same fp32 values, taken over a subset that contains
+  // the maximum -- whatever the tie rule. The result is idx = 0..m-1 without a single iteration.
+  if (unique_prefix != nullptr && __ldg(unique_prefix + b) >= m && m <= N) {
+    if (rank == 0) {
+      for (int i = tid; i < m; i += kThreads) out[i] = i;
+      if (new_xyz) {
+        float* o = new_xyz + (long)b * m * 3;
+        for (int i = tid; i < m * 3; i += kThreads) o[i] = __ldg(cloud + i);
+      }
+    }
+    trace_end(1, trace_t0);
+    return;   // every CTA of the cluster takes this branch: nobody waits for anybody
+  }
 
   // ---- load this thread's points into registers (coalesced: consecutive tid = consecutive k)
   float px[kPPT], py[kPPT], pz[kPPT], pd[kPPT];
@@ -280,7 +299,8 @@ constexpr int kGridFpsWarps = kGridFpsThreads / 32;
 __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const float* __restrict__ xyz,
                                                                       const void* __restrict__ grid, int N, int m,
                                                                       int log2T, int cap, int32_t* __restrict__ idx,
-                                                                      float* __restrict__ new_xyz) {
+                                                                      float* __restrict__ new_xyz,
+                                                                      int32_t* __restrict__ unique_prefix) {
   extern __shared__ __align__(16) unsigned char gsm[];
   __shared__ FpsSmem<kGridFpsThreads> sm;
   __shared__ __align__(16) Packet flat_inbox[2][32];  // [iteration parity][source CTA * 16 + warp]
@@ -319,6 +339,11 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
   float lox = 0.f, loy = 0.f, loz = 0.f, hix = 0.f, hiy = 0.f, hiz = 0.f;
   uint32_t bmax = 0u, bkd = 0u, bkp = 0u;
   int bli = 0;
+  // Uniqueness certificate for the sampling chain (see fps_cluster_kernel): `btie` = this block's best running
+  // distance is attained by more than one of its points; first_tie = first iteration whose global arg-max was
+  // not provably unique (m if none). Conservative: any doubt counts as a tie.
+  bool btie = true;     // all distances start equal (1e10)
+  int first_tie = m;
   if (has_blk) {
     lox = loy = loz = 3.0e38f;
     hix = hiy = hiz = -3.0e38f;
@@ -346,7 +371,7 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
   }
 
   const bool flat = C * kGridFpsWarps <= 32;
-  const unsigned tx_bytes = flat ? 20u * C * kGridFpsWarps : 20u * C;
+  const unsigned tx_bytes = flat ? 24u * C * kGridFpsWarps : 20u * C;
   if (tid == 0) {
     mbar_init(&sm.bar[0], 1);
     mbar_init(&sm.bar[1], 1);
@@ -388,11 +413,13 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
       const uint32_t wd = __reduce_max_sync(0xffffffffu, tb);
       const uint32_t wp = __reduce_max_sync(0xffffffffu, tb == wd ? pr : 0u);
       const int who = __ffs(__ballot_sync(0xffffffffu, tb == wd && pr == wp)) - 1;
+      const bool multi = __popc(__ballot_sync(0xffffffffu, tb == wd)) > 1;
       if ((int)lane == j) {
         bmax = wd;
         bkd = wd;
         bkp = wp;
         bli = who;
+        btie = multi;
       }
     }
     // c. this warp's candidate = best key over its blocks
@@ -401,6 +428,9 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
     const uint32_t wp = __reduce_max_sync(0xffffffffu, kd == wd ? kp : 0u);
     const unsigned owners = __ballot_sync(0xffffffffu, has_blk && kd == wd && kp == wp);
     const int src = owners ? __ffs(owners) - 1 : 0;
+    // tie inside this warp: two of its blocks at the best distance, or several points inside the best block
+    const bool wtie = __popc(__ballot_sync(0xffffffffu, has_blk && kd == wd)) > 1 ||
+                      __shfl_sync(0xffffffffu, btie ? 1 : 0, src) != 0 || wd == 0u;
     float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
     if ((int)lane == src && owners) c = pts[my_blk * 32 + bli];
     c.x = __shfl_sync(0xffffffffu, c.x, src);
@@ -416,23 +446,32 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
         const uint32_t dbar = map_to_cta(smem_u32(&sm.bar[par]), lane);
         st_async_v4(dst, owners ? wd : 0u, owners ? wp : 0u, __float_as_uint(c.x), __float_as_uint(c.y), dbar);
         st_async_b32(dst + 16, __float_as_uint(c.z), dbar);
+        st_async_b32(dst + 20, wtie ? 1u : 0u, dbar);
       }
       mbar_wait(&sm.bar[par], (unsigned)(((it - 1) >> 1) & 1));
       if (tid == 0) mbar_arrive_expect_tx(&sm.bar[par], tx_bytes);
-      uint32_t pd = 0u, pp = 0u;
+      uint32_t pd = 0u, pp = 0u, ptie = 0u;
       if (lane < C * kGridFpsWarps) {
         const uint2 q2 = *reinterpret_cast<const uint2*>(&flat_inbox[par][lane]);
         pd = q2.x;
         pp = q2.y;
+        ptie = flat_inbox[par][lane].pad[0];
       }
       const uint32_t gd = __reduce_max_sync(0xffffffffu, pd);
       gp = __reduce_max_sync(0xffffffffu, pd == gd ? pp : 0u);
+      {
+        const unsigned at_max = __ballot_sync(0xffffffffu, lane < C * kGridFpsWarps && pd == gd);
+        const bool gtie = __popc(at_max) > 1 || __ballot_sync(0xffffffffu, (at_max >> lane) & 1u && ptie != 0u) != 0u ||
+                          gd == 0u;
+        if (gtie && first_tie == m) first_tie = it;
+      }
       const unsigned srcc = __ffs(__ballot_sync(0xffffffffu, lane < C * kGridFpsWarps && pd == gd && pp == gp)) - 1;
       const Packet* w = &flat_inbox[par][srcc];
       ox = w->x;
       oy = w->y;
       oz = w->z;
     } else {
+      if (first_tie == m) first_tie = it;   // the two-stage exchange carries no uniqueness information
       if (lane == 0) {
         sm.warp_xyz[par][warp] = make_float4(c.x, c.y, c.z, 0.f);
         sm.warp_key[par][warp] = make_uint2(owners ? wd : 0u, owners ? wp : 0u);
@@ -479,6 +518,7 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
       }
     }
   }
+  if (unique_prefix != nullptr && rank == 0 && tid == 0) unique_prefix[b] = first_tie;
   cluster.sync();  // nobody may exit while peers can still write into its inbox
   trace_end(1, trace_t0);
 }
@@ -558,6 +598,9 @@ int env_int(const char* name, int dflt) {
   return v ? std::atoi(v) : dflt;
 }
 
+// set by demf_fps_prefix for the launch it is about to make (host-side call state of this thread)
+thread_local const int32_t* t_unique_prefix = nullptr;
+
 template <int kThreads, int kPPT>
 int launch_cluster(const float* xyz, int B, int N, int m, int C, int log2T, int32_t* idx, float* new_xyz,
                    cudaStream_t st, bool probe_only, int* max_clusters) {
@@ -596,7 +639,7 @@ int launch_cluster(const float* xyz, int B, int N, int m, int C, int log2T, int3
     *max_clusters = cached[C] - 1;
     return 0;
   }
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, xyz, N, m, log2T, idx, new_xyz);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, xyz, N, m, log2T, idx, new_xyz, t_unique_prefix);
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
     set_error("fps_cluster_kernel<%d,%d> C=%d: %s", kThreads, kPPT, C, cudaGetErrorString(e));
@@ -684,6 +727,14 @@ size_t demf_fps_workspace_bytes(int B, int N, int m) {
   return (size_t)B * N * sizeof(float);
 }
 
+int demf_fps_prefix(const float* xyz, int B, int N, int m, void* workspace, int32_t* idx, float* new_xyz,
+                    const int32_t* unique_prefix, void* stream) {
+  t_unique_prefix = unique_prefix;
+  const int rc = demf_fps(xyz, B, N, m, workspace, idx, new_xyz, stream);
+  t_unique_prefix = nullptr;
+  return rc;
+}
+
 int demf_fps(const float* xyz, int B, int N, int m, void* workspace, int32_t* idx, float* new_xyz,
              void* stream) {
   DEMF_REQUIRE_PTR(xyz);
@@ -731,6 +782,11 @@ unsigned long long demf_fps_stat(int i) {
  * (any radius). The cloud sits in the shared memory of a 2-, 4- or 8-CTA cluster per scene. */
 int demf_fps_grid(const float* xyz, const void* grid, int B, int N, int m, int32_t* idx, float* new_xyz,
                   void* stream) {
+  return demf_fps_grid_prefix(xyz, grid, B, N, m, idx, new_xyz, nullptr, stream);
+}
+
+int demf_fps_grid_prefix(const float* xyz, const void* grid, int B, int N, int m, int32_t* idx, float* new_xyz,
+                         int32_t* unique_prefix, void* stream) {
   DEMF_REQUIRE_PTR(xyz);
   DEMF_REQUIRE_PTR(grid);
   DEMF_REQUIRE_PTR(idx);
@@ -772,7 +828,7 @@ int demf_fps_grid(const float* xyz, const void* grid, int B, int N, int m, int32
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, fps_grid_kernel, xyz, grid, N, m, log2T, cap, idx, new_xyz);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, fps_grid_kernel, xyz, grid, N, m, log2T, cap, idx, new_xyz, unique_prefix);
   if (e != cudaSuccess) {
     set_error("demf_fps_grid: launch failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();

@@ -58,28 +58,40 @@ class FurthestPointSampling(Function):
 furthest_point_sample = FurthestPointSampling.apply
 
 
-def furthest_point_sample_xyz(points_xyz, num_points, grid=None):
+def furthest_point_sample_xyz(points_xyz, num_points, grid=None, unique_prefix=None, return_prefix=False):
     """furthest_point_sample that also returns the picked points' coordinates (B,m,3): the kernel
     has them in registers when it writes an index, so the separate gather launch (and the int64
     index copy in front of it) disappears. `grid` = ball_grid workspace: grid-pruned kernel.
-    Sampling is not differentiable; use gather on the indices when gradients must flow to xyz."""
+    Sampling is not differentiable; use gather on the indices when gradients must flow to xyz.
+
+    The sampling chain: with `return_prefix` (grid kernel) a third result (B,) i32 certifies, per scene, how many
+    leading picks were the unique arg-max of their iteration; handed back as `unique_prefix` when the cloud to
+    sample IS that pick sequence, scenes whose certificate covers `num_points` get idx = 0..m-1 without
+    iterating (identical to the ordinary result; see include/demf_b200.h)."""
     assert points_xyz.is_contiguous()
-    _need_cuda(points_xyz, grid)
+    _need_cuda(points_xyz, grid, unique_prefix)
     B, N = points_xyz.shape[:2]
     lib = _lib.load()
+    prefix = None
     with torch.cuda.device_of(points_xyz):
         idx = torch.empty(B, num_points, dtype=torch.int32, device=points_xyz.device)
         new_xyz = torch.empty(B, num_points, 3, dtype=torch.float32, device=points_xyz.device)
+        if return_prefix:
+            prefix = torch.zeros(B, dtype=torch.int32, device=points_xyz.device)
         if idx.numel():
             if grid is not None:
-                _lib.check(lib.demf_fps_grid(_p(points_xyz), _p(grid), B, N, int(num_points), _p(idx),
-                                             _p(new_xyz), _stream()), "demf_fps_grid")
+                _lib.check(lib.demf_fps_grid_prefix(_p(points_xyz), _p(grid), B, N, int(num_points), _p(idx),
+                                                    _p(new_xyz), _p(prefix), _stream()), "demf_fps_grid")
             else:
                 ws_bytes = lib.demf_fps_workspace_bytes(B, N, num_points)
                 ws = (torch.empty(ws_bytes // 4, dtype=torch.float32, device=points_xyz.device)
                       if ws_bytes else None)
-                _lib.check(lib.demf_fps(_p(points_xyz), B, N, int(num_points), _p(ws), _p(idx),
-                                        _p(new_xyz), _stream()), "demf_fps")
+                if unique_prefix is not None:
+                    assert unique_prefix.dtype == torch.int32 and unique_prefix.numel() == B
+                _lib.check(lib.demf_fps_prefix(_p(points_xyz), B, N, int(num_points), _p(ws), _p(idx),
+                                               _p(new_xyz), _p(unique_prefix), _stream()), "demf_fps")
+    if return_prefix:
+        return idx, new_xyz, prefix
     return idx, new_xyz
 
 

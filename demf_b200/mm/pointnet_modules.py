@@ -380,6 +380,7 @@ class PointNet2SASSG(BaseModule):
     # FPS iterations of levels > i. Each level publishes an event the main stream waits on.
     prefetch_seed_fps = None   # set by the detector: (fp level whose xyz are the seeds, m)
     grid_fps = True            # first-level FPS through the ball-query grid (identical indices)
+    chain_shortcut = True      # levels > 0: certified pick sequences are sampled without iterating
     overlap_sampling = True    # False: run the sampling chain on the current stream
 
     def _side_stream(self, device):
@@ -417,10 +418,18 @@ class PointNet2SASSG(BaseModule):
             # level's ball query and its (grid-pruned) furthest point sampling
             grid0 = self.SA_modules[0].ball_grid(xyz)
             grids.append(grid0)
+            prefix = None     # uniqueness certificate of the first level's picks (chain shortcut)
             for i, sa in enumerate(self.SA_modules):
                 if cur.is_cuda:   # the kernel writes the picked coordinates next to the indices
-                    idx, new_xyz = P.furthest_point_sample_xyz(
-                        cur, sa.num_point[0], grid0 if (i == 0 and self.grid_fps) else None)
+                    if i == 0 and grid0 is not None and self.grid_fps and self.chain_shortcut:
+                        idx, new_xyz, prefix = P.furthest_point_sample_xyz(cur, sa.num_point[0], grid0,
+                                                                           return_prefix=True)
+                    else:
+                        # levels > 0 sample the previous level's pick sequence: scenes whose certificate
+                        # covers this level's count get idx = 0..m-1 without iterating (same result)
+                        idx, new_xyz = P.furthest_point_sample_xyz(
+                            cur, sa.num_point[0], grid0 if (i == 0 and self.grid_fps) else None,
+                            unique_prefix=prefix if i > 0 else None)
                 else:
                     idx = P.furthest_point_sample(cur, sa.num_point[0])
                     new_xyz = P.gather_rows(cur, idx).contiguous()
@@ -436,8 +445,12 @@ class PointNet2SASSG(BaseModule):
                     grids.append(self.SA_modules[i + 1].ball_grid(cur))
                 levels.append((idx, new_xyz, ev))
                 if self.prefetch_seed_fps is not None and self.prefetch_seed_fps[0] == i + 1:
-                    seed_fps = (P.furthest_point_sample(cur, self.prefetch_seed_fps[1]),
-                                torch.cuda.Event() if overlap else None)
+                    if cur.is_cuda and prefix is not None:   # the seeds are a pick sequence too
+                        seed_idx = P.furthest_point_sample_xyz(cur, self.prefetch_seed_fps[1],
+                                                               unique_prefix=prefix)[0]
+                    else:
+                        seed_idx = P.furthest_point_sample(cur, self.prefetch_seed_fps[1])
+                    seed_fps = (seed_idx, torch.cuda.Event() if overlap else None)
                     if overlap:
                         seed_fps[1].record(side)
         return levels, seed_fps, grids

@@ -889,3 +889,51 @@ def test_sa_fused_cta_pairs_match_oracle(dev, B, N, M, C, ns, radius, widths):
     scale = ref.abs().max().item()
     assert (paired.cpu().transpose(1, 2) - ref).abs().max().item() <= 1e-3 * scale
     assert (paired - single).abs().max().item() <= 1e-4 * scale    # same operands, other summation order
+
+
+# ------------------------------------------------------- FPS chain shortcut (certified pick sequences) ---
+def _chain(xyz_gpu, counts, shortcut):
+    """The backbone's sampling chain on one cloud: level 0 through the grid kernel, later levels on the picks."""
+    grid = ops.ball_grid(xyz_gpu, 0.2)
+    out = []
+    if shortcut:
+        idx, cur, prefix = ops.furthest_point_sample_xyz(xyz_gpu, counts[0], grid, return_prefix=True)
+    else:
+        idx, cur = ops.furthest_point_sample_xyz(xyz_gpu, counts[0], grid)
+        prefix = None
+    out.append(idx)
+    for m in counts[1:]:
+        idx, cur = ops.furthest_point_sample_xyz(cur, m, None, unique_prefix=prefix)
+        out.append(idx)
+    return out, prefix
+
+
+@pytest.mark.parametrize("kind", ["uniform", "clustered", "lattice", "duplicates"])
+def test_fps_chain_shortcut_identical(dev, kind):
+    """Levels > 0 of the sampling chain sample the previous level's pick sequence: where the first level
+    certified its picks unique they are returned as 0..m-1 without iterating; the indices must equal the
+    ordinary kernels' (and the oracle's) in every case, including clouds full of exact ties (integer lattice,
+    duplicated points), where the certificate is short and the ordinary kernel runs."""
+    B, N = 3, 20000
+    if kind in ("uniform", "clustered"):
+        xyz = _xyz(B, N, 11, clustered=kind == "clustered")
+    elif kind == "lattice":
+        g = torch.Generator().manual_seed(3)
+        xyz = torch.randint(0, 24, (B, N, 3), generator=g).float() * 0.25
+    else:
+        xyz = _xyz(B, N, 12)
+        xyz[:, 5000:10000] = xyz[:, :5000]
+    counts = (2048, 1024, 512, 256)
+    fast, prefix = _chain(xyz.to(dev), counts, True)
+    slow, _ = _chain(xyz.to(dev), counts, False)
+    for a, b in zip(fast, slow):
+        assert torch.equal(a, b)
+    assert torch.equal(fast[0].cpu(), cref.furthest_point_sample(xyz, counts[0]))
+    c1 = torch.gather(xyz, 1, fast[0].cpu().long()[..., None].expand(-1, -1, 3)).contiguous()
+    assert torch.equal(fast[1].cpu(), cref.furthest_point_sample(c1, counts[1]))
+    p = prefix.cpu()
+    if kind in ("uniform", "clustered"):
+        assert int(p.min()) == counts[0], p          # generic clouds: no exact tie anywhere
+        assert torch.equal(fast[1].cpu(), torch.arange(counts[1], dtype=torch.int32).expand(B, -1))
+    if kind == "lattice":
+        assert int(p.max()) < counts[1], p           # ties from the first iterations on: ordinary kernel
