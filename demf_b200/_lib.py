@@ -87,6 +87,8 @@ _SIGNATURES = {
                              ctypes.c_long, _ptr],
     "demf_gemm_wgrad": [_ptr, ctypes.c_long, _ptr, ctypes.c_long, ctypes.c_long, _c_int, _c_int, _ptr, _c_int, _ptr],
     "demf_bn_finalize": [_ptr, ctypes.c_long, _c_int, _c_float, _c_float, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "demf_stage_loss_fwd": [_ptr] * 14 + [ctypes.c_long, _c_int, _c_int, _ptr, _ptr, _ptr],
+    "demf_stage_loss_bwd": [_ptr] * 14 + [ctypes.c_long, _c_int, _c_int, _ptr, _ptr] + [_ptr] * 6 + [_ptr],
     "demf_box_point_count": [_ptr, _c_int, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
     "demf_nms_select": [_ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, _ptr, _ptr, _ptr,
                         _ptr, _ptr, _ptr],

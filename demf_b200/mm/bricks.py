@@ -801,8 +801,10 @@ def sa_mlp_train_rows(mlp, x, ns, cols0=None):
                                       ns, _bn_state(bn, y.device), prestats=True)
 
 
-def linear_rows(x, w, bias=None):
+def linear_rows(x, w, bias=None, owner=None):
     """x (R,K) @ w (N,K)^T + bias for a plain Linear / kernel-size-1 convolution WITHOUT a BatchNorm behind it.
+    `owner`: the nn.Linear / conv module whose `.weight` / `.bias` ARE (views of) w and bias -- inside an
+    `async_weight_grads` block its gradients are then accumulated in place on the weight-gradient stream.
     Training on CUDA in the TF32 mode: all three GEMMs on csrc/gemm_tf32.cu (an output width that is not a
     multiple of 4 is zero-padded so that row strides stay 16-byte multiples, e.g. VoteModule.conv_out's 259 and
     conv_reg's 30 channels -- upstream's unaligned shapes fall to the library's sm80 kernels); otherwise the
@@ -817,7 +819,13 @@ def linear_rows(x, w, bias=None):
         xc = x if (x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0) else x.contiguous()
         wp = wp if (wp.stride(1) == 1 and wp.stride(0) % 4 == 0 and wp.data_ptr() % 16 == 0) else wp.contiguous()
         if _tc_ok(xc, wp):
-            y = _LinearRowsTC.apply(xc, wp, bp, None, None)
+            direct = None
+            if owner is not None and not pad and _ASYNC_WGRAD["on"] and owner.weight.requires_grad \
+                    and (owner.bias is None or owner.bias.requires_grad):
+                _mark_direct(owner)
+                if owner.weight.grad is not None and (owner.bias is None or owner.bias.grad is not None):
+                    direct = owner
+            y = _LinearRowsTC.apply(xc, wp, bp, direct, None)
             return y[:, :N] if pad else y
     return torch.nn.functional.linear(x, w, bias)
 
@@ -825,7 +833,7 @@ def linear_rows(x, w, bias=None):
 def linear_nd(x, lin):
     """nn.Linear `lin` applied to x (..., K) through linear_rows."""
     lead = x.shape[:-1]
-    y = linear_rows(x.reshape(-1, x.shape[-1]), lin.weight, lin.bias)
+    y = linear_rows(x.reshape(-1, x.shape[-1]), lin.weight, lin.bias, owner=lin)
     return y.reshape(*lead, y.shape[-1])
 
 

@@ -7,6 +7,8 @@ gather_points, interpolate}). Semantics follow upstream: float32 / int32 contigu
 tensors, `assert`-style contiguity checks (no silent .contiguous()), index outputs
 non-differentiable. CUDA only -- there is deliberately no CPU implementation.
 """
+import ctypes
+
 import torch
 from torch.autograd import Function
 
@@ -1084,3 +1086,68 @@ def bn_rows_apply(y, gamma, beta, mean, invstd, relu=True):
         _lib.check(_lib.load().demf_bn_rows_apply(_p(y), R, C, _p(gamma), _p(beta), _p(mean), _p(invstd), int(relu),
                                                   _p(z), _stream()), "demf_bn_rows_apply")
     return z
+
+
+# ------------------------------------------------------------ per-stage detection loss (csrc/loss.cu) ---
+class _StageLoss(torch.autograd.Function):
+    """(7,) = weighted sums (objectness, dir_class, dir_res, size, center, semantic, iou) of one prediction stage;
+    one launch forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, center, size, dir_class, dir_res_norm, obj, sem, targets, cfg):
+        obj_t, obj_w, box_w, size_t, center_t, dir_class_t, dir_res_t, sem_t = targets
+        rows = center.shape[0] * center.shape[1]
+        nb = dir_class.shape[-1]
+        ns = 0 if sem is None else sem.shape[-1]
+        cfg_c = (ctypes.c_float * 12)(*cfg)
+        out = torch.zeros(7, dtype=torch.float32, device=center.device)
+        with torch.cuda.device_of(center):
+            _lib.check(_lib.load().demf_stage_loss_fwd(
+                _p(center), _p(size), _p(dir_class), _p(dir_res_norm), _p(obj), _p(sem), _p(obj_t), _p(obj_w),
+                _p(box_w), _p(size_t), _p(center_t), _p(dir_class_t), _p(dir_res_t), _p(sem_t), rows, nb, ns,
+                ctypes.cast(cfg_c, ctypes.c_void_p), _p(out), _stream()), "demf_stage_loss_fwd")
+        ctx.save_for_backward(center, size, dir_class, dir_res_norm, obj, *( [sem] if sem is not None else []),
+                              obj_t, obj_w, box_w, size_t, center_t, dir_class_t, dir_res_t,
+                              *([sem_t] if sem is not None else []))
+        ctx.has_sem = sem is not None
+        ctx.cfg = tuple(cfg)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, up):
+        t = list(ctx.saved_tensors)
+        center, size, dir_class, dir_res_norm, obj = t[:5]
+        k = 5
+        sem = None
+        if ctx.has_sem:
+            sem = t[k]
+            k += 1
+        obj_t, obj_w, box_w, size_t, center_t, dir_class_t, dir_res_t = t[k:k + 7]
+        sem_t = t[k + 7] if ctx.has_sem else None
+        rows = center.shape[0] * center.shape[1]
+        nb = dir_class.shape[-1]
+        ns = 0 if sem is None else sem.shape[-1]
+        cfg_c = (ctypes.c_float * 12)(*ctx.cfg)
+        up = up.contiguous().float()
+        gs = [torch.empty_like(x) for x in (center, size, dir_class, dir_res_norm, obj)]
+        g_sem = torch.empty_like(sem) if sem is not None else None
+        with torch.cuda.device_of(center):
+            _lib.check(_lib.load().demf_stage_loss_bwd(
+                _p(center), _p(size), _p(dir_class), _p(dir_res_norm), _p(obj), _p(sem), _p(obj_t), _p(obj_w),
+                _p(box_w), _p(size_t), _p(center_t), _p(dir_class_t), _p(dir_res_t), _p(sem_t), rows, nb, ns,
+                ctypes.cast(cfg_c, ctypes.c_void_p), _p(up), _p(gs[0]), _p(gs[1]), _p(gs[2]), _p(gs[3]), _p(gs[4]),
+                _p(g_sem), _stream()), "demf_stage_loss_bwd")
+        return gs[0], gs[1], gs[2], gs[3], gs[4], g_sem, None, None
+
+
+def stage_loss(center, size, dir_class, dir_res_norm, obj, sem, targets, cfg):
+    """Predictions (B,Q,C) fp32 contiguous CUDA tensors; targets = (objectness_targets i64, objectness_weights,
+    box_loss_weights, size_targets, center_targets, dir_class_targets i64, dir_res_targets, mask_targets i64 | None);
+    cfg = 12 floats (see include/demf_b200.h). -> (7,) losses, differentiable in the predictions."""
+    _need_cuda(center, size, dir_class, dir_res_norm, obj, sem)
+    for x in (center, size, dir_class, dir_res_norm, obj) + ((sem,) if sem is not None else ()):
+        assert x.is_contiguous() and x.dtype == torch.float32
+    targets = tuple(None if t is None else t.contiguous() for t in targets)
+    assert targets[0].dtype == torch.int64 and targets[5].dtype == torch.int64
+    return _StageLoss.apply(center, size, dir_class, dir_res_norm, obj, sem, targets, tuple(float(c) for c in cfg))

@@ -415,6 +415,12 @@ class DeMFVoteHead(BaseModule):
 
         if vote_loss is None:
             vote_loss = self._vote_loss(bbox_preds, targets)
+        fused = self._fused_stage_loss(bbox_preds, targets)
+        if fused is not None:
+            losses = dict(vote_loss=vote_loss, **fused)
+            if ret_target:
+                losses['targets'] = targets
+            return losses
         objectness_loss = self.objectness_loss(bbox_preds['obj_scores'].transpose(2, 1),
                                                objectness_targets, weight=objectness_weights)
         w3 = box_loss_weights.unsqueeze(-1).expand(-1, -1, 3)
@@ -438,6 +444,47 @@ class DeMFVoteHead(BaseModule):
                                                weight=box_loss_weights)
         if ret_target:
             losses['targets'] = targets
+        return losses
+
+    fused_stage_loss = True
+
+    def _fused_stage_loss(self, bbox_preds, targets):
+        """The seven per-proposal loss sums of one stage in one launch (csrc/loss.cu) when every term is configured
+        the way the reference config does (softmax CE / SmoothL1 / AxisAlignedIoU, reduction='sum'); None otherwise."""
+        from ..mm.losses import AxisAlignedIoULoss, CrossEntropyLoss, SmoothL1Loss
+        center = bbox_preds['center']
+        if not (self.fused_stage_loss and center.is_cuda and center.dtype == torch.float32):
+            return None
+        ce = [self.objectness_loss, self.dir_class_loss] + ([self.semantic_loss] if hasattr(self, 'semantic_loss') else [])
+        sl1 = [self.dir_res_loss, self.size_res_loss, self.center_loss]
+        if not (all(type(m) is CrossEntropyLoss and m.reduction == 'sum' for m in ce)
+                and all(type(m) is SmoothL1Loss and m.reduction == 'sum' for m in sl1)
+                and (self.iou_loss is None or (type(self.iou_loss) is AxisAlignedIoULoss
+                                               and self.iou_loss.reduction == 'sum'))
+                and self.dir_class_loss.class_weight is None
+                and (not hasattr(self, 'semantic_loss') or self.semantic_loss.class_weight is None)
+                and bbox_preds['dir_class'].shape[-1] <= 16):
+            return None
+        cw = self.objectness_loss.class_weight or [1.0, 1.0]
+        has_sem = hasattr(self, 'semantic_loss')
+        cfg = [cw[0], cw[1], self.objectness_loss.loss_weight, self.dir_class_loss.loss_weight,
+               self.dir_res_loss.loss_weight, self.size_res_loss.loss_weight, self.center_loss.loss_weight,
+               self.semantic_loss.loss_weight if has_sem else 0.0,
+               self.iou_loss.loss_weight if self.iou_loss is not None else 0.0,
+               self.dir_res_loss.beta, self.size_res_loss.beta, self.center_loss.beta]
+        (_, _, dir_class_targets, dir_res_targets, mask_targets, objectness_targets, objectness_weights,
+         box_loss_weights, _, _, size_targets, center_targets) = targets
+        sem = bbox_preds['sem_scores'].contiguous() if has_sem else None
+        out = P.stage_loss(center.contiguous(), bbox_preds['size'].contiguous(), bbox_preds['dir_class'].contiguous(),
+                           bbox_preds['dir_res_norm'].contiguous(), bbox_preds['obj_scores'].contiguous(), sem,
+                           (objectness_targets, objectness_weights.float(), box_loss_weights.float(), size_targets,
+                            center_targets, dir_class_targets, dir_res_targets, mask_targets if has_sem else None), cfg)
+        losses = dict(objectness_loss=out[0], dir_class_loss=out[1], dir_res_loss=out[2], size_res_loss=out[3],
+                      center_loss=out[4])
+        if has_sem:
+            losses['semantic_loss'] = out[5]
+        if self.iou_loss is not None:
+            losses['iou_loss'] = out[6]
         return losses
 
     # ------------------------------------------------------------------ targets ---

@@ -333,6 +333,28 @@ int demf_gemm_rows_dgrad_bn(const float* dy, long lddy, const float* w, long ldw
 int demf_bn_bwd_finalize(void* state, long R, int C, const float* mean, const float* invstd, float* grad_gamma,
                          float* grad_beta, float* coef, void* stream);
 
+/* ------------------------------------------- training: per-stage detection loss --- */
+/* The seven weighted sums of DeMFVoteHead._loss (demf/modeling/heads/class_agnostic_vote_head.py:622-712;
+ * mmdet CrossEntropyLoss / SmoothL1Loss, mmdet3d AxisAlignedIoULoss with reduction='sum', loss weights and betas of
+ * configs/demf/demf_votenet.py:113-141) over `rows` = B*Q proposals in one launch, and their gradient with respect
+ * to every prediction tensor in one more. Predictions (rows, C) fp32 contiguous; targets as the head assigns them
+ * (int64 class targets, fp32 weights). sem / sem_t / g_sem may be NULL together (no semantic loss).
+ * cfg (HOST, 12 floats): objectness class weights (2); loss_weight of objectness, dir_class, dir_res, size, center,
+ * semantic, iou (7; iou 0 = no IoU loss); SmoothL1 beta of dir_res, size, center (3).
+ * fwd: losses (7 device floats, ZERO on entry) += weighted sums in the order objectness, dir_class, dir_res, size,
+ * center, semantic, iou. bwd: upstream (7 device floats) = dL/dloss_i; g_* get d(sum_i upstream_i loss_i)/d(pred). */
+int demf_stage_loss_fwd(const float* center, const float* size, const float* dir_class, const float* dir_res_norm,
+                        const float* obj, const float* sem, const int64_t* obj_t, const float* obj_w,
+                        const float* box_w, const float* size_t_, const float* center_t, const int64_t* dir_class_t,
+                        const float* dir_res_t, const int64_t* sem_t, long rows, int num_dir_bins, int num_sem,
+                        const float* cfg, float* losses, void* stream);
+int demf_stage_loss_bwd(const float* center, const float* size, const float* dir_class, const float* dir_res_norm,
+                        const float* obj, const float* sem, const int64_t* obj_t, const float* obj_w,
+                        const float* box_w, const float* size_t_, const float* center_t, const int64_t* dir_class_t,
+                        const float* dir_res_t, const int64_t* sem_t, long rows, int num_dir_bins, int num_sem,
+                        const float* cfg, const float* upstream, float* g_center, float* g_size, float* g_dir_class,
+                        float* g_dir_res_norm, float* g_obj, float* g_sem, void* stream);
+
 /* ------------------------------------------- inference post-processing --- */
 /* The two per-scene loops of mmdet3d 0.18.1 VoteHead.multiclass_nms_single, reached from
  * DeMFVoteHead.get_bboxes (demf/modeling/heads/class_agnostic_vote_head.py:739-743):

@@ -516,3 +516,51 @@ def test_early_targets_and_parallel_stage_losses_change_nothing(dev):
     for k in la:
         assert abs(la[k] - lb[k]) <= 1e-5 * max(1.0, abs(lb[k])), (k, la[k], lb[k])
     assert ((ga - gb).norm() / gb.norm()).item() <= 1e-3
+
+
+def test_fused_stage_loss_matches_torch_modules(dev):
+    """csrc/loss.cu (one launch per stage and direction) against the loss modules it replaces on the same
+    predictions and targets: every loss value to 1e-5 relative, every prediction gradient to 1e-4 of its norm
+    (only the order of the fp32 sums differs)."""
+    torch.manual_seed(5)
+    model = engine.build_demf_votenet(num_points=4).to(dev).train()
+    head = model.pts_bbox_head
+    B, Q = 4, 256
+    g = torch.Generator(device=dev).manual_seed(1)
+
+    def rnd(*shape, scale=1.0):
+        return (torch.randn(*shape, generator=g, device=dev) * scale).requires_grad_(True)
+    agg = torch.randn(B, Q, 3, generator=g, device=dev)
+    preds = dict(center=rnd(B, Q, 3, scale=0.3), size=rnd(B, Q, 3, scale=0.5), dir_class=rnd(B, Q, 12),
+                 dir_res_norm=rnd(B, Q, 12), obj_scores=rnd(B, Q, 2), sem_scores=rnd(B, Q, 10))
+    with torch.no_grad():
+        preds['center'].add_(agg)
+        preds['size'].add_(1.0)
+    obj_t = (torch.rand(B, Q, generator=g, device=dev) < 0.3).long()
+    obj_mask = (torch.rand(B, Q, generator=g, device=dev) < 0.8).float()
+    targets = (None, None, torch.randint(0, 12, (B, Q), generator=g, device=dev),
+               torch.randn(B, Q, generator=g, device=dev) * 0.3, torch.randint(0, 10, (B, Q), generator=g, device=dev),
+               obj_t, obj_mask / (obj_mask.sum() + 1e-6), obj_t.float() / (obj_t.sum().float() + 1e-6), None, None,
+               torch.rand(B, Q, 3, generator=g, device=dev) + 0.5, agg + 0.1 * torch.randn(B, Q, 3, generator=g, device=dev))
+    zero = torch.zeros((), device=dev)
+    keys = ("objectness_loss", "dir_class_loss", "dir_res_loss", "size_res_loss", "center_loss", "semantic_loss",
+            "iou_loss")
+    up = {k: float(i + 1) / 3 for i, k in enumerate(keys)}        # distinct upstream gradients per term
+    results = {}
+    for fused in (True, False):
+        head.fused_stage_loss = fused
+        for p in preds.values():
+            p.grad = None
+        n0 = _lib.launch_count()
+        losses = head._loss(dict(preds), None, None, None, targets=targets, vote_loss=zero)
+        sum(up[k] * losses[k] for k in keys).backward()
+        launched = _lib.launch_count() - n0
+        results[fused] = ({k: losses[k].item() for k in keys}, {k: p.grad.clone() for k, p in preds.items()}, launched)
+    head.fused_stage_loss = True
+    assert results[True][2] == 2 and results[False][2] == 0       # one launch forward, one backward
+    for k in keys:
+        a, b = results[True][0][k], results[False][0][k]
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(b)), (k, a, b)
+    for k in preds:
+        a, b = results[True][1][k], results[False][1][k]
+        assert (a - b).norm() <= 1e-4 * b.norm() + 1e-9, (k, (a - b).norm().item(), b.norm().item())
