@@ -22,7 +22,7 @@ _SIGNATURES = {
     "demf_fps_workspace_bytes": [_c_int, _c_int, _c_int],
     "demf_fps": [_ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr],
     "demf_fps_grid": [_ptr, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr],
-    "demf_fps_grid_prefix": [_ptr, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr],
+    "demf_fps_grid_prefix": [_ptr, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _ptr],
     "demf_fps_prefix": [_ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr],
     "demf_chain_indices": [_c_int, _c_int] + [_ptr, _c_int] * 4 + [_ptr] * 4 + [_ptr],
     "demf_interp_cat_rows_fwd": [_ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],

@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
                                                                       const void* __restrict__ grid, int N, int m,
                                                                       int log2T, int cap, int32_t* __restrict__ idx,
                                                                       float* __restrict__ new_xyz,
-                                                                      int32_t* __restrict__ unique_prefix) {
+                                                                      int32_t* __restrict__ unique_prefix, int cert) {
   extern __shared__ __align__(16) unsigned char gsm[];
   __shared__ FpsSmem<kGridFpsThreads> sm;
   __shared__ __align__(16) Packet flat_inbox[2][32];  // [iteration parity][source CTA * 16 + warp]
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
   }
 
   const bool flat = C * kGridFpsWarps <= 32;
-  const unsigned tx_bytes = flat ? 24u * C * kGridFpsWarps : 20u * C;
+  const unsigned tx_bytes = flat ? 20u * C * kGridFpsWarps : 20u * C;
   if (tid == 0) {
     mbar_init(&sm.bar[0], 1);
     mbar_init(&sm.bar[1], 1);
@@ -412,8 +412,9 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
       const uint32_t tb = __float_as_uint(t), pr = __float_as_uint(p.w);
       const uint32_t wd = __reduce_max_sync(0xffffffffu, tb);
       const uint32_t wp = __reduce_max_sync(0xffffffffu, tb == wd ? pr : 0u);
-      const int who = __ffs(__ballot_sync(0xffffffffu, tb == wd && pr == wp)) - 1;
-      const bool multi = __popc(__ballot_sync(0xffffffffu, tb == wd)) > 1;
+      const unsigned at = __ballot_sync(0xffffffffu, tb == wd);
+      const bool multi = (at & (at - 1u)) != 0u;            // more than one point at the block's best distance
+      const int who = (multi ? __ffs(__ballot_sync(0xffffffffu, tb == wd && pr == wp)) : __ffs(at)) - 1;
       if ((int)lane == j) {
         bmax = wd;
         bkd = wd;
@@ -426,11 +427,16 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
     const uint32_t kd = has_blk ? bkd : 0u, kp = has_blk ? bkp : 0u;
     const uint32_t wd = __reduce_max_sync(0xffffffffu, kd);
     const uint32_t wp = __reduce_max_sync(0xffffffffu, kd == wd ? kp : 0u);
-    const unsigned owners = __ballot_sync(0xffffffffu, has_blk && kd == wd && kp == wp);
+    // blocks of this warp at its best distance; the tie flag of each rides along in bit 0 of a second mask
+    const unsigned same = __ballot_sync(0xffffffffu, has_blk && kd == wd);
+    const bool several = (same & (same - 1u)) != 0u;
+    const unsigned owners = several ? __ballot_sync(0xffffffffu, has_blk && kd == wd && kp == wp) : same;
     const int src = owners ? __ffs(owners) - 1 : 0;
     // tie inside this warp: two of its blocks at the best distance, or several points inside the best block
-    const bool wtie = __popc(__ballot_sync(0xffffffffu, has_blk && kd == wd)) > 1 ||
-                      __shfl_sync(0xffffffffu, btie ? 1 : 0, src) != 0 || wd == 0u;
+    // (only the first `cert` iterations are certified: that is all the later sampling levels ask for)
+    const bool track = it < cert;
+    bool wtie = false;
+    if (track) wtie = several || __ballot_sync(0xffffffffu, has_blk && kd == wd && btie) != 0u || wd == 0u;
     float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
     if ((int)lane == src && owners) c = pts[my_blk * 32 + bli];
     c.x = __shfl_sync(0xffffffffu, c.x, src);
@@ -444,9 +450,11 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
       if (lane < C) {
         const uint32_t dst = map_to_cta(smem_u32(&flat_inbox[par][rank * kGridFpsWarps + warp]), lane);
         const uint32_t dbar = map_to_cta(smem_u32(&sm.bar[par]), lane);
-        st_async_v4(dst, owners ? wd : 0u, owners ? wp : 0u, __float_as_uint(c.x), __float_as_uint(c.y), dbar);
+        // the tie flag rides in bit 30 of the priority word, which is 1 in every real inverse priority
+        // (inv_priority >= 0xC0000000): cleared = "this warp's best distance is not unique"; the receiver restores it
+        st_async_v4(dst, owners ? wd : 0u, owners ? (wtie ? (wp & ~0x40000000u) : wp) : 0u, __float_as_uint(c.x),
+                    __float_as_uint(c.y), dbar);
         st_async_b32(dst + 16, __float_as_uint(c.z), dbar);
-        st_async_b32(dst + 20, wtie ? 1u : 0u, dbar);
       }
       mbar_wait(&sm.bar[par], (unsigned)(((it - 1) >> 1) & 1));
       if (tid == 0) mbar_arrive_expect_tx(&sm.bar[par], tx_bytes);
@@ -455,11 +463,12 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
         const uint2 q2 = *reinterpret_cast<const uint2*>(&flat_inbox[par][lane]);
         pd = q2.x;
         pp = q2.y;
-        ptie = flat_inbox[par][lane].pad[0];
+        ptie = (pp != 0u && (pp & 0x40000000u) == 0u) ? 1u : 0u;
+        pp = pp != 0u ? (pp | 0x40000000u) : 0u;
       }
       const uint32_t gd = __reduce_max_sync(0xffffffffu, pd);
       gp = __reduce_max_sync(0xffffffffu, pd == gd ? pp : 0u);
-      {
+      if (track) {
         const unsigned at_max = __ballot_sync(0xffffffffu, lane < C * kGridFpsWarps && pd == gd);
         const bool gtie = __popc(at_max) > 1 || __ballot_sync(0xffffffffu, (at_max >> lane) & 1u && ptie != 0u) != 0u ||
                           gd == 0u;
@@ -471,7 +480,7 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
       oy = w->y;
       oz = w->z;
     } else {
-      if (first_tie == m) first_tie = it;   // the two-stage exchange carries no uniqueness information
+      if (track && first_tie == m) first_tie = it;   // the two-stage exchange carries no uniqueness information
       if (lane == 0) {
         sm.warp_xyz[par][warp] = make_float4(c.x, c.y, c.z, 0.f);
         sm.warp_key[par][warp] = make_uint2(owners ? wd : 0u, owners ? wp : 0u);
@@ -518,7 +527,7 @@ __global__ void __launch_bounds__(kGridFpsThreads, 1) fps_grid_kernel(const floa
       }
     }
   }
-  if (unique_prefix != nullptr && rank == 0 && tid == 0) unique_prefix[b] = first_tie;
+  if (unique_prefix != nullptr && rank == 0 && tid == 0) unique_prefix[b] = min(first_tie, max(cert, 1));
   cluster.sync();  // nobody may exit while peers can still write into its inbox
   trace_end(1, trace_t0);
 }
@@ -782,11 +791,11 @@ unsigned long long demf_fps_stat(int i) {
  * (any radius). The cloud sits in the shared memory of a 2-, 4- or 8-CTA cluster per scene. */
 int demf_fps_grid(const float* xyz, const void* grid, int B, int N, int m, int32_t* idx, float* new_xyz,
                   void* stream) {
-  return demf_fps_grid_prefix(xyz, grid, B, N, m, idx, new_xyz, nullptr, stream);
+  return demf_fps_grid_prefix(xyz, grid, B, N, m, idx, new_xyz, nullptr, 0, stream);
 }
 
 int demf_fps_grid_prefix(const float* xyz, const void* grid, int B, int N, int m, int32_t* idx, float* new_xyz,
-                         int32_t* unique_prefix, void* stream) {
+                         int32_t* unique_prefix, int certify, void* stream) {
   DEMF_REQUIRE_PTR(xyz);
   DEMF_REQUIRE_PTR(grid);
   DEMF_REQUIRE_PTR(idx);
@@ -828,7 +837,8 @@ int demf_fps_grid_prefix(const float* xyz, const void* grid, int B, int N, int m
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, fps_grid_kernel, xyz, grid, N, m, log2T, cap, idx, new_xyz, unique_prefix);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, fps_grid_kernel, xyz, grid, N, m, log2T, cap, idx, new_xyz, unique_prefix,
+                                           unique_prefix ? (certify < m ? certify : m) : 0);
   if (e != cudaSuccess) {
     set_error("demf_fps_grid: launch failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();

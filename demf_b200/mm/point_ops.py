@@ -60,7 +60,8 @@ class FurthestPointSampling(Function):
 furthest_point_sample = FurthestPointSampling.apply
 
 
-def furthest_point_sample_xyz(points_xyz, num_points, grid=None, unique_prefix=None, return_prefix=False):
+def furthest_point_sample_xyz(points_xyz, num_points, grid=None, unique_prefix=None, return_prefix=False,
+                              certify=None):
     """furthest_point_sample that also returns the picked points' coordinates (B,m,3): the kernel
     has them in registers when it writes an index, so the separate gather launch (and the int64
     index copy in front of it) disappears. `grid` = ball_grid workspace: grid-pruned kernel.
@@ -69,7 +70,8 @@ def furthest_point_sample_xyz(points_xyz, num_points, grid=None, unique_prefix=N
     The sampling chain: with `return_prefix` (grid kernel) a third result (B,) i32 certifies, per scene, how many
     leading picks were the unique arg-max of their iteration; handed back as `unique_prefix` when the cloud to
     sample IS that pick sequence, scenes whose certificate covers `num_points` get idx = 0..m-1 without
-    iterating (identical to the ordinary result; see include/demf_b200.h)."""
+    iterating (identical to the ordinary result; see include/demf_b200.h). `certify`: how many leading picks the
+    caller will ask about (default all): only those iterations pay for the bookkeeping."""
     assert points_xyz.is_contiguous()
     _need_cuda(points_xyz, grid, unique_prefix)
     B, N = points_xyz.shape[:2]
@@ -82,8 +84,9 @@ def furthest_point_sample_xyz(points_xyz, num_points, grid=None, unique_prefix=N
             prefix = torch.zeros(B, dtype=torch.int32, device=points_xyz.device)
         if idx.numel():
             if grid is not None:
-                _lib.check(lib.demf_fps_grid_prefix(_p(points_xyz), _p(grid), B, N, int(num_points), _p(idx),
-                                                    _p(new_xyz), _p(prefix), _stream()), "demf_fps_grid")
+                _lib.check(lib.demf_fps_grid_prefix(
+                    _p(points_xyz), _p(grid), B, N, int(num_points), _p(idx), _p(new_xyz), _p(prefix),
+                    int(num_points if certify is None else min(certify, num_points)), _stream()), "demf_fps_grid")
             else:
                 ws_bytes = lib.demf_fps_workspace_bytes(B, N, num_points)
                 ws = (torch.empty(ws_bytes // 4, dtype=torch.float32, device=points_xyz.device)

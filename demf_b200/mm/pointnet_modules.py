@@ -422,8 +422,11 @@ class PointNet2SASSG(BaseModule):
             for i, sa in enumerate(self.SA_modules):
                 if cur.is_cuda:   # the kernel writes the picked coordinates next to the indices
                     if i == 0 and grid0 is not None and self.grid_fps and self.chain_shortcut:
-                        idx, new_xyz, prefix = P.furthest_point_sample_xyz(cur, sa.num_point[0], grid0,
-                                                                           return_prefix=True)
+                        later = [s.num_point[0] for s in self.SA_modules[1:]]
+                        if self.prefetch_seed_fps is not None:
+                            later.append(self.prefetch_seed_fps[1])
+                        idx, new_xyz, prefix = P.furthest_point_sample_xyz(
+                            cur, sa.num_point[0], grid0, return_prefix=True, certify=max(later) if later else 1)
                     else:
                         # levels > 0 sample the previous level's pick sequence: scenes whose certificate
                         # covers this level's count get idx = 0..m-1 without iterating (same result)

@@ -176,13 +176,14 @@ int demf_fps_grid(const float* xyz, const void* grid, int B, int N, int m, int32
 /* The sampling CHAIN of PointNet2SASSG (configs/demf/demf_votenet.py:51: 20000 -> 2048 -> 1024 -> 512 -> 256, and
  * the head's 1024 -> 256 seed sampling, class_agnostic_vote_head.py:429-430): every level after the first samples
  * a cloud that is the previous level's pick sequence. demf_fps_grid_prefix also writes, per scene,
- * unique_prefix[b] = the first iteration whose arg-max was not provably unique (m if none). demf_fps_prefix, given
+ * unique_prefix[b] = the first iteration whose arg-max was not provably unique (`certify` if none of the first
+ * `certify` iterations -- only those are tracked). demf_fps_prefix, given
  * that certificate for a cloud that is such a pick sequence, returns idx = 0..m-1 (and the first m points) without
  * iterating whenever unique_prefix[b] >= m -- the greedy pick of iteration k on the full cloud is then also the
  * unique greedy pick on the subset -- and runs the ordinary kernel for the other scenes. Results are identical to
  * demf_fps in every case. */
 int demf_fps_grid_prefix(const float* xyz, const void* grid, int B, int N, int m, int32_t* idx, float* new_xyz,
-                         int32_t* unique_prefix, void* stream);
+                         int32_t* unique_prefix, int certify /* iterations to certify, <= m */, void* stream);
 int demf_fps_prefix(const float* xyz, int B, int N, int m, void* workspace, int32_t* idx, float* new_xyz,
                     const int32_t* unique_prefix, void* stream);
 
