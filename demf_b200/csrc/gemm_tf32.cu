@@ -53,6 +53,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int
                "r"(c0), "r"(c1), "r"(src)
                : "memory");
 }
+// bring one box into L2 ahead of ordinary loads of it (no shared memory, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_map(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -120,7 +126,8 @@ struct RowsGemmParams {
 template <bool kBMN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 rows_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_y, const RowsGemmParams p) {
+                 const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_p,
+                 const RowsGemmParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms: 1 KB aligned
   const int warp = threadIdx.x >> 5;
@@ -164,6 +171,12 @@ rows_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (lane == 0) {
       uint32_t it = 0;
       for (long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        if (p.col_mode == 2) {
+          // the epilogue of this tile will read the previous layer's pre-BN activations (map_p): start pulling
+          // them into L2 now, a whole operand pipeline ahead of their use
+          for (int g = 0; n0 + g * 32 < min(p.N, n0 + p.n_block); ++g)
+            tma_prefetch_l2_2d(&map_p, n0 + g * 32, (int)(tile * kTileRows));
+        }
         for (int kc = 0; kc < kc_total; ++kc, ++it) {
           const uint32_t s = it % p.stages, ph = (it / p.stages) & 1u;
           wait_or_flag(empty0 + 8u * s, ph ^ 1u, 1);
@@ -241,8 +254,13 @@ rows_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (p.col_mode == 2) {
           const bool col_ok = col0 + (int)lane < p.N;
           const float* ycol = p.bn_y + row_base * p.bn_ldy + col0 + (int)lane;
+          if (col_ok && nvalid == 32) {       // full tile (all but the last one): no per-row predicate
 #pragma unroll
-          for (int i = 0; i < 32; ++i) yv[i] = (col_ok && i < nvalid) ? __ldg(ycol + (long)i * p.bn_ldy) : 0.f;
+            for (int i = 0; i < 32; ++i) yv[i] = __ldg(ycol + (long)i * p.bn_ldy);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) yv[i] = (col_ok && i < nvalid) ? __ldg(ycol + (long)i * p.bn_ldy) : 0.f;
+          }
         }
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)g * 32u, v);
@@ -288,25 +306,56 @@ rows_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             be = __ldg(p.bn_beta + col);
           }
           if (p.col_mode == 2) {
+            // (row & 7) == (i & 7): the swizzled position of this lane's cell in row i is a compile-time
+            // function of i once the lane's slot is known
+            unsigned char* base = dst + (uint32_t)(q * 32) * 128u + ((lane & 3u) << 2);
+            const uint32_t slot = lane >> 2;
+            if (nvalid == 32) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (i < nvalid) {
-                float* cell = reinterpret_cast<float*>(dst + sw128_offset((uint32_t)(q * 32 + i), lane >> 2) +
-                                                       ((lane & 3u) << 2));
+              for (int i = 0; i < 32; ++i) {
+                float* cell = reinterpret_cast<float*>(base + i * 128 + ((slot ^ (uint32_t)(i & 7)) << 4));
                 const float z = (yv[i] - mu) * is * ga + be;
                 const float val = z > 0.f ? *cell : 0.f;
                 *cell = val;
                 sa += val;
                 sb = fmaf(val, yv[i], sb);
               }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (i < nvalid) {
+                  float* cell = reinterpret_cast<float*>(base + i * 128 + ((slot ^ (uint32_t)(i & 7)) << 4));
+                  const float z = (yv[i] - mu) * is * ga + be;
+                  const float val = z > 0.f ? *cell : 0.f;
+                  *cell = val;
+                  sa += val;
+                  sb = fmaf(val, yv[i], sb);
+                }
+              }
             }
           } else {
-#pragma unroll 8
-            for (int i = 0; i < nvalid; ++i) {
-              const float val = *reinterpret_cast<const float*>(
-                  dst + sw128_offset((uint32_t)(q * 32 + i), lane >> 2) + ((lane & 3u) << 2));
-              sa += val;
-              sb = fmaf(val, val, sb);
+            const unsigned char* base = dst + (uint32_t)(q * 32) * 128u + ((lane & 3u) << 2);
+            const uint32_t slot = lane >> 2;
+            if (nvalid == 32) {
+              float sa2 = 0.f, sb2 = 0.f;      // two chains: the 32 dependent adds are the pass's latency
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float v0 = *reinterpret_cast<const float*>(base + i * 128 + ((slot ^ (uint32_t)(i & 7)) << 4));
+                const float v1 =
+                    *reinterpret_cast<const float*>(base + (i + 1) * 128 + ((slot ^ (uint32_t)((i + 1) & 7)) << 4));
+                sa += v0;
+                sb = fmaf(v0, v0, sb);
+                sa2 += v1;
+                sb2 = fmaf(v1, v1, sb2);
+              }
+              sa += sa2;
+              sb += sb2;
+            } else {
+              for (int i = 0; i < nvalid; ++i) {
+                const float val = *reinterpret_cast<const float*>(base + i * 128 + ((slot ^ (uint32_t)(i & 7)) << 4));
+                sa += val;
+                sb = fmaf(val, val, sb);
+              }
             }
           }
           if (g < 8) {
@@ -635,7 +684,11 @@ int launch_rows_gemm(const float* a, long lda, const float* w, long ldw, const f
     cudaFuncSetAttribute(rows_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  rows_gemm_kernel<kBMN><<<dim3(gx, nb), kGemmThreads, smem, st>>>(ma, mb, my, p);
+  CUtensorMap mp = my;
+  if (bn != nullptr) {
+    if (int rc = make_map(&mp, bn->y, R, N, bn->ldy, kTileRows)) return rc;
+  }
+  rows_gemm_kernel<kBMN><<<dim3(gx, nb), kGemmThreads, smem, st>>>(ma, mb, my, mp, p);
   return after_launch(kBMN ? "rows_gemm_kernel<dgrad>" : "rows_gemm_kernel<fwd>");
 }
 
@@ -758,9 +811,10 @@ int demf_gemm_rows_dgrad_bn(const float* dy, long lddy, const float* w, long ldw
   DEMF_REQUIRE_PTR(g);
   DEMF_REQUIRE(R > 0 && K > 0 && N > 0, DEMF_E_SIZE);
   DEMF_REQUIRE(K <= 256, DEMF_E_UNSUPPORTED);
-  DEMF_REQUIRE(lddy % 4 == 0 && ldw % 4 == 0 && ldg % 4 == 0 && lddy >= N && ldw >= K && ldg >= K && ldy_prev >= K,
+  DEMF_REQUIRE(lddy % 4 == 0 && ldw % 4 == 0 && ldg % 4 == 0 && ldy_prev % 4 == 0 && lddy >= N && ldw >= K &&
+                   ldg >= K && ldy_prev >= K,
                DEMF_E_UNSUPPORTED);
-  DEMF_REQUIRE(al16(dy) && al16(w) && al16(g), DEMF_E_UNSUPPORTED);
+  DEMF_REQUIRE(al16(dy) && al16(w) && al16(g) && al16(y_prev), DEMF_E_UNSUPPORTED);
   BnMask bn;
   bn.y = y_prev;
   bn.ldy = ldy_prev;
