@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(PKG, "libdemf_b200.so")
-SOURCES = ["capi.cu", "msda.cu", "fps.cu", "ball_query.cu", "point_ops.cu", "rows.cu", "sa_fused.cu", "ball_grid.cu", "glue.cu", "postprocess.cu", "bn_rows.cu", "gemm_tf32.cu", "loss.cu"]
+SOURCES = ["capi.cu", "msda.cu", "fps.cu", "ball_query.cu", "point_ops.cu", "rows.cu", "sa_fused.cu", "ball_grid.cu", "glue.cu", "postprocess.cu", "bn_rows.cu", "gemm_tf32.cu", "loss.cu", "sa_pipe.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "umma.cuh"), os.path.join(CSRC, "ball_grid.cuh"), os.path.join(PKG, "..", "include", "demf_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
@@ -41,7 +41,7 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     env = dict(os.environ)
     env.pop("CC", None)
-    flags = list(NVCC_FLAGS)
+    flags = list(NVCC_FLAGS) + os.environ.get("DEMF_NVCC_EXTRA", "").split()   # e.g. -DDEMF_SAP_PROF (diagnostic builds)
     jobs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)

@@ -1154,3 +1154,29 @@ def stage_loss(center, size, dir_class, dir_res_norm, obj, sem, targets, cfg):
     targets = tuple(None if t is None else t.contiguous() for t in targets)
     assert targets[0].dtype == torch.int64 and targets[5].dtype == torch.int64
     return _StageLoss.apply(center, size, dir_class, dir_res_norm, obj, sem, targets, tuple(float(c) for c in cfg))
+
+
+# ------------------------------------------------- pipelined first-level set abstraction (csrc/sa_pipe.cu) ---
+def sa_pipe_supported(C, sample_num, widths, M):
+    return bool(_lib.load().demf_sa_pipe_supported(int(C), int(sample_num), int(widths[0]), int(widths[1]),
+                                                   int(widths[2]), int(M)))
+
+
+def sa_pipe(xyz, center_xyz, feat_rows, max_radius, sample_num, normalize_xyz, wpack, bias, idx):
+    """sa_fused for the first backbone level (one feature channel, widths 64/64/128) as a warp-specialised
+    pipeline over 128-row tiles; `idx` = the ball-query rows (B,M,ns) i32. -> (B,M,128) rows. Inference only."""
+    assert xyz.is_contiguous() and center_xyz.is_contiguous() and feat_rows.is_contiguous() and idx.is_contiguous()
+    _need_cuda(xyz, center_xyz, feat_rows, wpack, bias, idx)
+    B, N, _ = xyz.shape
+    M = center_xyz.size(1)
+    assert feat_rows.shape == (B, N, 1) and idx.shape == (B, M, sample_num) and idx.dtype == torch.int32
+    with torch.cuda.device_of(xyz):
+        out = torch.empty(B, M, 128, dtype=torch.float32, device=xyz.device)
+        _lib.check(_lib.load().demf_sa_pipe_fwd(_p(xyz), _p(feat_rows), _p(center_xyz), _p(idx), B, N, M,
+                                                int(sample_num), float(max_radius), int(bool(normalize_xyz)),
+                                                _p(wpack), _p(bias), _p(out), _stream()), "demf_sa_pipe_fwd")
+    return out
+
+
+def sa_pipe_error():
+    return int(_lib.load().demf_sa_pipe_error())

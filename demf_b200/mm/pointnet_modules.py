@@ -106,6 +106,7 @@ class BasePointSAModule(nn.Module):
     # grouped tensor nor any activation reaches HBM. `fused_eval = False` keeps the layer-by-layer
     # path (group rows kernel + library GEMMs), which is also what training uses.
     fused_eval = True
+    pipe_eval = True      # first level: warp-specialised tile pipeline (csrc/sa_pipe.cu) instead of sa_fused.cu
 
     def _fused_pack(self, mlp, C):
         """(wpack, bias, widths) of this MLP for P.sa_fused, rebuilt when a parameter changes."""
@@ -182,6 +183,19 @@ class BasePointSAModule(nn.Module):
                     out.append(P.sa_fused_pre(points_xyz, new_xyz.contiguous(), proj, grouper.min_radius,
                                               grouper.max_radius, grouper.sample_num,
                                               grouper.normalize_xyz, wpack, bias, widths, grid=grid))
+                    continue
+                if self._fused_ok(grouper, mlp, points_xyz, C) and self.pipe_eval and grouper.min_radius == 0 \
+                        and P.sa_pipe_supported(C, grouper.sample_num, [cm.conv.out_channels for cm in mlp],
+                                                new_xyz.size(1)):
+                    # first backbone level: the pipelined kernel (csrc/sa_pipe.cu) behind the exact grid query
+                    wpack, bias, widths = self._fused_pack(mlp, C)
+                    centres = new_xyz.contiguous()
+                    if grid is not None:
+                        nbr = P.ball_query_grid(0.0, grouper.max_radius, grouper.sample_num, points_xyz, centres, grid)
+                    else:
+                        nbr = P.ball_query(0.0, grouper.max_radius, grouper.sample_num, points_xyz, centres)
+                    out.append(P.sa_pipe(points_xyz, centres, feat_rows, grouper.max_radius, grouper.sample_num,
+                                         grouper.normalize_xyz, wpack, bias, nbr))
                     continue
                 if self._fused_ok(grouper, mlp, points_xyz, C):
                     wpack, bias, widths = self._fused_pack(mlp, C)

@@ -937,3 +937,37 @@ def test_fps_chain_shortcut_identical(dev, kind):
         assert torch.equal(fast[1].cpu(), torch.arange(counts[1], dtype=torch.int32).expand(B, -1))
     if kind == "lattice":
         assert int(p.max()) < counts[1], p           # ties from the first iterations on: ordinary kernel
+
+
+# ------------------------------------------------- pipelined first-level set abstraction (csrc/sa_pipe.cu) ---
+@pytest.mark.parametrize("B,N,M,r,ns", [(2, 20000, 2048, 0.2, 64), (3, 4096, 256, 0.3, 32), (1, 3000, 64, 0.4, 16),
+                                        (8, 20000, 2048, 0.2, 64)])
+def test_sa_pipe_matches_sa_fused_and_oracle(dev, B, N, M, r, ns):
+    """The pipelined kernel against (a) sa_fused on the same rows -- same TF32 operands, same MMA K order: equal to
+    accumulation-order noise (<= 1e-5 of scale) -- and (b) the TF32-emulating CPU oracle (<= 1e-3 of scale, the
+    fused kernel's own bar)."""
+    from demf_b200.mm.bricks import permute_weight_columns
+    from oracle import sa_module
+    xyz = _xyz(B, N, 21, clustered=True)
+    g = torch.Generator().manual_seed(4)
+    feats = torch.randn(B, 1, N, generator=g)
+    ws = [torch.randn(co, ci, generator=g) / ci ** 0.5 for co, ci in ((64, 4), (64, 64), (128, 64))]
+    bs = [torch.randn(co, generator=g) * 0.1 for co in (64, 64, 128)]
+    gx = xyz.to(dev)
+    centres = ops.gather_rows(gx, ops.furthest_point_sample(gx, M)).contiguous()
+    w0 = permute_weight_columns(ws[0].to(dev), ops.group_rows_columns(1))
+    wpack, bias, widths = ops.sa_pack_mlp([w0, ws[1].to(dev), ws[2].to(dev)], [b.to(dev) for b in bs])
+    frows = feats.transpose(1, 2).contiguous().to(dev)
+    grid = ops.ball_grid(gx, r) if N >= 2048 else None
+    nbr = ops.ball_query_grid(0.0, r, ns, gx, centres, grid) if grid is not None else ops.ball_query(0.0, r, ns, gx, centres)
+    assert ops.sa_pipe_supported(1, ns, widths, M)
+    got = ops.sa_pipe(gx, centres, frows, r, ns, True, wpack, bias, nbr)
+    want = ops.sa_fused(gx, centres, frows, 0.0, r, ns, True, wpack, bias, widths, idx=nbr)
+    torch.cuda.synchronize()
+    assert ops.sa_pipe_error() == 0
+    scale = want.abs().max().item()
+    assert (got - want).abs().max().item() <= 1e-5 * scale
+    if B <= 3:
+        ref_idx, ref_out = sa_module.sa_forward(xyz, centres.cpu(), feats, 0.0, r, ns, True, ws, bs, tf32=True)
+        assert torch.equal(nbr.cpu(), ref_idx)
+        assert (got.cpu().transpose(1, 2) - ref_out).abs().max().item() <= 1e-3 * ref_out.abs().max().item()
