@@ -70,7 +70,23 @@ __device__ __forceinline__ void wait_flag(uint32_t bar, uint32_t parity, int cod
 #ifdef DEMF_SAP_PROF
   const long long t0 = clock64();
 #endif
-  if (!mbar_wait(bar, parity)) atomicCAS(&g_sap_error, 0, code);
+#if SAP_X == 7
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+  }
+#elif SAP_X == 8
+  while (!mbar_try_wait(bar, parity)) __nanosleep(500);
+#else
+  // try_wait with a suspend-time hint: the warp sleeps in hardware instead of polling (the polling loops of 20+
+  // waiting warps were ~40 % of all issued instructions); bounded, a protocol bug must not hang the GPU
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok && spin < (1u << 20); ++spin)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000u) : "memory");
+  if (!ok) atomicCAS(&g_sap_error, 0, code);
+#endif
 #ifdef DEMF_SAP_PROF
   if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && ((1u << (threadIdx.x >> 5)) & 0x01010117u)) atomicAdd((unsigned long long*)&g_sap_prof[code], (unsigned long long)(clock64() - t0));
 #endif
@@ -78,7 +94,30 @@ __device__ __forceinline__ void wait_flag(uint32_t bar, uint32_t parity, int cod
 __device__ __forceinline__ void arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// bar.sync over one role's warps: orders their shared-memory stores (it drains them) before the single thread that
+// then crosses to the async proxy and signals the MMA issuer -- one fence per tile instead of one per warp
+__device__ __forceinline__ void role_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 __device__ __forceinline__ float tf32_op(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+// tf32_op(max(x, 0)) in one instruction (VIADDMNMX): as signed integers the non-negative floats order like the
+// floats and every negative float is a negative integer, so max(bits + 0x1000, 0x1000) is the rounded ReLU
+__device__ __forceinline__ float relu_tf32_op(float x) {
+  return __int_as_float(__viaddmax_s32(__float_as_int(x), 0x1000, 0x1000));
+}
+// two IEEE fp32 additions in one instruction (FADD2): acc pair + bias pair
+__device__ __forceinline__ void add_pair(uint32_t a0, uint32_t a1, float b0, float b1, float& r0, float& r1) {
+  uint64_t pa, pb, pr;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "r"(a0), "r"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pb) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(pa), "l"(pb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(pr));
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 
 __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -97,17 +136,17 @@ __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams
 
   if (threadIdx.x == 0) {
     for (int sl = 0; sl < 8; ++sl) {
-      mbar_init(bar(0, sl), 4);  // four gather warps
+      mbar_init(bar(0, sl), 1);  // one gather thread, after the role's bar.sync
       mbar_init(bar(1, sl), 1);  // tcgen05.commit
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(2, b), 1);
       mbar_init(bar(3, b), 8);   // eight epilogue-0 warps
-      mbar_init(bar(4, b), 8);
+      mbar_init(bar(4, b), 1);   // one epilogue-0 thread, after the role's bar.sync
       mbar_init(bar(5, b), 1);
       mbar_init(bar(6, b), 1);
       mbar_init(bar(7, b), 8);   // eight epilogue-1 warps
-      mbar_init(bar(8, b), 8);
+      mbar_init(bar(8, b), 1);
       mbar_init(bar(9, b), 1);
       mbar_init(bar(10, b), 1);
       mbar_init(bar(11, b), 8);  // eight max warps
@@ -129,7 +168,10 @@ __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const float* bias_s = reinterpret_cast<const float*>(smem + kBias);
-  const int nt = p.tiles > (int)blockIdx.x ? (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;   // tiles of this CTA
+  // this CTA's tiles: the contiguous range [t_first, t_first + nt)
+  const int t_base = p.tiles / (int)gridDim.x, t_rem = p.tiles % (int)gridDim.x;
+  const int nt = t_base + ((int)blockIdx.x < t_rem ? 1 : 0);
+  const int t_first = (int)blockIdx.x * t_base + min((int)blockIdx.x, t_rem);
   const int cpt = kRows / p.ns;
   const int tps = p.M / cpt;                    // tiles per scene
 
@@ -201,58 +243,92 @@ __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams
     }
   } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------------------ gather
-    // Each thread owns one grouped row of every tile and runs ahead of itself: the neighbour index of tile j+2
-    // and the point / centre loads of tile j+1 are in flight while tile j is written, so neither dependent
-    // global-memory latency is exposed; the eight-slot operand ring lets the warps run ahead of the MMA.
+    // Each thread owns one grouped row of every tile and runs ahead of itself (see the register ring below), so
+    // neither dependent global-memory latency is exposed; the eight-slot operand ring lets the warps run ahead
+    // of the MMA.
     const int row = (warp - 4) * 32 + (int)lane;
-    const int rc = row / p.ns, rs = row % p.ns;
+    const int rc = row / p.ns;
     struct Pt { float x, y, z, f, cx, cy, cz; };
+    // tile T = grouped rows [128 T, 128 T + 128) = centres [T cpt, (T + 1) cpt) of scene T / tps
     auto nbr_of = [&](int j) -> int {
-      const int T = (int)blockIdx.x + j * (int)gridDim.x;
-      const int scene = T / tps;
-      const int m = (T - scene * tps) * cpt + rc;
-      return __ldg(p.nbr + ((long)scene * p.M + m) * p.ns + rs);
+#if SAP_X == 3
+      return row + j;
+#else
+      return __ldg(p.nbr + (long)(t_first + j) * kRows + row);
+#endif
     };
+    int pt_scene = t_first / tps, pt_t = t_first - pt_scene * tps;   // the tile whose points are loaded next
     auto load_pt = [&](int j, int k) -> Pt {
-      const int T = (int)blockIdx.x + j * (int)gridDim.x;
-      const int scene = T / tps;
-      const int m = (T - scene * tps) * cpt + rc;
-      const float* c = p.centres + ((long)scene * p.M + m) * 3;
-      const float* pt = p.xyz + ((long)scene * p.N + k) * 3;
+      const float* c = p.centres + ((long)(t_first + j) * cpt + rc) * 3;
+      const float* pt = p.xyz + ((long)pt_scene * p.N + k) * 3;
       Pt r;
+#if SAP_X == 3
+      r.x = r.y = r.z = r.f = r.cx = r.cy = r.cz = (float)(k + j) + (float)(c - pt);
+#else
       r.x = __ldg(pt);
       r.y = __ldg(pt + 1);
       r.z = __ldg(pt + 2);
-      r.f = __ldg(p.feat + (long)scene * p.N + k);
+      r.f = __ldg(p.feat + (long)pt_scene * p.N + k);
       r.cx = __ldg(c);
       r.cy = __ldg(c + 1);
       r.cz = __ldg(c + 2);
+#endif
+      if (++pt_t == tps) {
+        pt_t = 0;
+        ++pt_scene;
+      }
       return r;
     };
-    Pt cur = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int k_next = 0;
-    if (nt > 0) cur = load_pt(0, nbr_of(0));
-    if (nt > 1) k_next = nbr_of(1);
-    for (int j = 0; j < nt; ++j) {
-      const int k_next2 = (j + 2 < nt) ? nbr_of(j + 2) : 0;
-      Pt nxt = cur;
-      if (j + 1 < nt) nxt = load_pt(j + 1, k_next);
-      const float dx = __fmul_rn(__fsub_rn(cur.x, cur.cx), p.scale);
-      const float dy = __fmul_rn(__fsub_rn(cur.y, cur.cy), p.scale);
-      const float dz = __fmul_rn(__fsub_rn(cur.z, cur.cz), p.scale);
-      const int sl = j & 7;
-      wait_flag(bar(1, sl), (uint32_t)(((j >> 3) & 1) ^ 1), 7);   // layer-0 MMA of the tile that last used the slot
-      unsigned char* a0 = smem + kA0 + (sl >> 2) * 16384;
-      const uint32_t u = (uint32_t)(sl & 3) * 2u;
-      *reinterpret_cast<float4*>(a0 + sw128_offset((uint32_t)row, u)) =
-          make_float4(tf32_op(cur.f), tf32_op(0.f), tf32_op(0.f), tf32_op(0.f));
-      *reinterpret_cast<float4*>(a0 + sw128_offset((uint32_t)row, u + 1u)) =
-          make_float4(tf32_op(dx), tf32_op(dy), tf32_op(dz), tf32_op(0.f));
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) arrive(bar(0, sl));
-      cur = nxt;
-      k_next = k_next2;
+    // Batches of kBatch tiles. fence.proxy.async is a full memory barrier for the thread (MEMBAR.ALL.CTA): it
+    // also waits for global loads in flight, so the loads of the next batch are issued AFTER the fence of this one,
+    // and one exposed load latency is shared by kBatch tiles (the eight-slot operand ring holds two batches, so
+    // the MMA never waits for it).
+    constexpr int kBatch = 4;
+    Pt ring[kBatch];
+    int knext[kBatch];
+#pragma unroll
+    for (int d = 0; d < kBatch; ++d) {
+      ring[d] = Pt{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      knext[d] = 0;
+      if (d < nt) knext[d] = nbr_of(d);
+    }
+#pragma unroll
+    for (int d = 0; d < kBatch; ++d) {
+      if (d < nt) ring[d] = load_pt(d, knext[d]);
+      if (d + kBatch < nt) knext[d] = nbr_of(d + kBatch);
+    }
+    for (int j0 = 0; j0 < nt; j0 += kBatch) {
+#pragma unroll
+      for (int d = 0; d < kBatch; ++d) {
+        const int j = j0 + d;
+        if (j < nt) {
+          const Pt cur = ring[d];
+          const float dx = __fmul_rn(__fsub_rn(cur.x, cur.cx), p.scale);
+          const float dy = __fmul_rn(__fsub_rn(cur.y, cur.cy), p.scale);
+          const float dz = __fmul_rn(__fsub_rn(cur.z, cur.cz), p.scale);
+          const int sl = j & 7;
+          wait_flag(bar(1, sl), (uint32_t)(((j >> 3) & 1) ^ 1), 7);   // layer-0 MMA of the tile that last used the slot
+          unsigned char* a0 = smem + kA0 + (sl >> 2) * 16384;
+          const uint32_t u = (uint32_t)(sl & 3) * 2u;
+          *reinterpret_cast<float4*>(a0 + sw128_offset((uint32_t)row, u)) =
+              make_float4(tf32_op(cur.f), tf32_op(0.f), tf32_op(0.f), tf32_op(0.f));
+          *reinterpret_cast<float4*>(a0 + sw128_offset((uint32_t)row, u + 1u)) =
+              make_float4(tf32_op(dx), tf32_op(dy), tf32_op(dz), tf32_op(0.f));
+        }
+      }
+      role_sync(1, 128);
+      if (warp == 4 && lane == 0) {
+        fence_proxy_async();
+#pragma unroll
+        for (int d = 0; d < kBatch; ++d)
+          if (j0 + d < nt) arrive(bar(0, (j0 + d) & 7));
+      }
+#pragma unroll
+      for (int d = 0; d < kBatch; ++d)
+        if (j0 + d + kBatch < nt) ring[d] = load_pt(j0 + d + kBatch, knext[d]);
+#pragma unroll
+      for (int d = 0; d < kBatch; ++d)
+        if (j0 + d + 2 * kBatch < nt) knext[d] = nbr_of(j0 + d + 2 * kBatch);
     }
   } else if (warp >= 8 && warp < 24) {
     // ------------------------------------------------------------------------------ epilogues 0 and 1
@@ -270,7 +346,12 @@ __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams
       tc_fence_after_sync();
       SAP_T0();
       uint32_t u0[32];
+#if SAP_X == 6
+#pragma unroll
+      for (int i = 0; i < 32; ++i) u0[i] = (uint32_t)(j + i);
+#else
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (e ? kD1 : kD0) + b * 64u + h * 32u, u0);
+#endif
       const float4* bs4 = reinterpret_cast<const float4*>(bs);
       float4 bb[4];                                   // bias of the first 16 columns; the rest follows in the loop
 #pragma unroll
@@ -288,10 +369,12 @@ __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
           const int c = 16 * half + 4 * s;
-          v[s].x = tf32_op(fmaxf(__uint_as_float(u0[c + 0]) + bb[s].x, 0.f));
-          v[s].y = tf32_op(fmaxf(__uint_as_float(u0[c + 1]) + bb[s].y, 0.f));
-          v[s].z = tf32_op(fmaxf(__uint_as_float(u0[c + 2]) + bb[s].z, 0.f));
-          v[s].w = tf32_op(fmaxf(__uint_as_float(u0[c + 3]) + bb[s].w, 0.f));
+          add_pair(u0[c + 0], u0[c + 1], bb[s].x, bb[s].y, v[s].x, v[s].y);
+          add_pair(u0[c + 2], u0[c + 3], bb[s].z, bb[s].w, v[s].z, v[s].w);
+          v[s].x = relu_tf32_op(v[s].x);
+          v[s].y = relu_tf32_op(v[s].y);
+          v[s].z = relu_tf32_op(v[s].z);
+          v[s].w = relu_tf32_op(v[s].w);
         }
         if (half == 0) {
 #pragma unroll
@@ -299,12 +382,17 @@ __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams
         }
 #pragma unroll
         for (int s = 0; s < 4; ++s)
+#if SAP_X == 4
+          if (p.ns == 7 || v[s].x == 123.f)
+#endif
           *reinterpret_cast<float4*>(dst + sw128_offset((uint32_t)row, (uint32_t)(4 * half + s))) = v[s];
       }
       SAP_T(1, threadIdx.x == 256);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) arrive(bar(k_afull, b));
+      role_sync(2 + e, 256);
+      if (((warp - 8) & 7) == 0 && lane == 0) {
+        fence_proxy_async();
+        arrive(bar(k_afull, b));
+      }
       SAP_T(2, threadIdx.x == 256);
     }
   } else if (warp >= 24) {
@@ -316,10 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams
     for (int j = 0; j < nt; ++j) {
       const int b = j & 1;
       const uint32_t ph = (uint32_t)((j >> 1) & 1);
-      const int T = (int)blockIdx.x + j * (int)gridDim.x;
-      const int scene = T / tps;
-      const int m0 = (T - scene * tps) * cpt;
-      float* o = p.out + ((long)scene * p.M + m0) * kC3 + ch;
+      float* o = p.out + ((long)(t_first + j) * cpt) * kC3 + ch;   // centre (scene, m) is row T cpt + .. of (B*M, 128)
       wait_flag(bar(10, b), ph, 12);
       tc_fence_after_sync();
       float run = -3.0e38f;
@@ -333,19 +418,25 @@ __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams
         if (p.ns == 16) {
           float ma = __uint_as_float(u[0]), mb = __uint_as_float(u[16]);
 #pragma unroll
-          for (int i = 1; i < 16; ++i) {
-            ma = fmaxf(ma, __uint_as_float(u[i]));
-            mb = fmaxf(mb, __uint_as_float(u[16 + i]));
+          for (int i = 1; i < 15; i += 2) {
+            ma = max3(ma, __uint_as_float(u[i]), __uint_as_float(u[i + 1]));
+            mb = max3(mb, __uint_as_float(u[16 + i]), __uint_as_float(u[17 + i]));
           }
+          ma = fmaxf(ma, __uint_as_float(u[15]));
+          mb = fmaxf(mb, __uint_as_float(u[31]));
           o[(long)(2 * blk) * kC3] = fmaxf(ma + b2, 0.f);
           o[(long)(2 * blk + 1) * kC3] = fmaxf(mb + b2, 0.f);
         } else {
           float mx = __uint_as_float(u[0]);
 #pragma unroll
-          for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(u[i]));
+          for (int i = 1; i < 31; i += 2) mx = max3(mx, __uint_as_float(u[i]), __uint_as_float(u[i + 1]));
+          mx = fmaxf(mx, __uint_as_float(u[31]));
           run = fmaxf(run, mx);
           const int per = p.ns >> 5;                   // 32-row blocks per centre (1 or 2)
           if ((blk + 1) % per == 0) {
+#if SAP_X == 5
+            if (run == 123.f)
+#endif
             o[(long)(blk / per) * kC3] = fmaxf(run + b2, 0.f);
             run = -3.0e38f;
           }
