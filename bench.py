@@ -64,9 +64,10 @@ def msda_algorithmic_bytes(B, Q=256, H=8, D=32, L=4, P=P_POINTS):
 
 
 def time_sa_levels(model, batch, reps=20):
-    """The fused set-abstraction kernel (csrc/sa_fused.cu: ball query + grouping + 3-layer TF32
-    tcgen05 MLP + max), one level at a time on the model's own tensors: CUDA events around the
-    module call (grid build + query + fused kernel), L2 flushed between repetitions."""
+    """The fused set-abstraction kernels (SA1: grid ball query + csrc/sa_pipe.cu, the warp-specialised tile
+    pipeline; SA2-4: csrc/sa_fused.cu, ball query + grouping + 3-layer TF32 tcgen05 MLP + max in one launch),
+    one level at a time on the model's own tensors: CUDA events around the module call (grid build + query +
+    kernel), L2 flushed between repetitions."""
     import torch
     bb = model.pts_backbone
     dev = batch["points"].device
@@ -77,8 +78,9 @@ def time_sa_levels(model, batch, reps=20):
         for i, sa in enumerate(bb.SA_modules):
             xyz, feats, new_xyz = out["sa_xyz"][i], out["sa_features"][i], out["sa_xyz"][i + 1]
             idx = out["sa_indices"][i + 1]
-            call = lambda sa=sa, xyz=xyz, feats=feats, idx=idx, new_xyz=new_xyz: sa(  # noqa: E731
-                xyz, feats, indices=idx, target_xyz=new_xyz)
+            packed = batch["points"] if (i == 0 and batch["points"].size(-1) == 4) else None   # as the backbone does
+            call = lambda sa=sa, xyz=xyz, feats=feats, idx=idx, new_xyz=new_xyz, packed=packed: sa(  # noqa: E731
+                xyz, feats, indices=idx, target_xyz=new_xyz, packed=packed)
             for _ in range(3):
                 call()
             ts = []
@@ -274,7 +276,7 @@ def host_link_probe(dev, nbytes, reps=20, barrier=None):
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     best = 0.0
-    for _ in range(3):                # best of three bursts, every rank in step
+    for _ in range(5):                # best of five bursts, every rank in step
         if barrier is not None:
             barrier()
         a.record()
@@ -650,8 +652,12 @@ def main():
     e2e_value = BATCH_PER_GPU * n_gpus * args.steps / (e2e_ms * 1e-3)
     clock_info = clocks.stop() if clocks is not None else None
 
+    e2e_copy_gbs = (h2d + d2h) * args.steps / (e2e_ms * 1e-3) / 1e9      # per rank, achieved inside the e2e leg
     # ---- what the host link gives this rank while all ranks copy: bare pinned H2D copies of one step's bytes
-    link_gbs = host_link_probe(dev, h2d, reps=20, barrier=barrier)
+    probe_gbs = host_link_probe(dev, h2d, reps=20, barrier=barrier)
+    # the link gives at least what the timed end-to-end copies themselves sustained: a probe burst that lands on a
+    # slower moment (fresh pinned pages, link power state) must not read as "more than the link"
+    link_gbs = max(probe_gbs, e2e_copy_gbs)
     if world > 1:
         t = torch.tensor([link_gbs], dtype=torch.float64, device=dev)
         gathered = [torch.zeros_like(t) for _ in range(world)]
@@ -659,7 +665,6 @@ def main():
         link_all = [float(x) for x in gathered]
     else:
         link_all = [link_gbs]
-    e2e_copy_gbs = (h2d + d2h) * args.steps / (e2e_ms * 1e-3) / 1e9      # per rank, achieved inside the e2e leg
 
     # ---- end to end from raw inputs (points + uint8 images): the image branch runs on the device
     e2e_img = time_e2e_images(dev, max(10, args.steps // 4), barrier, max_over_ranks, rank, n_gpus)
@@ -791,9 +796,10 @@ def main():
                 "wall_ms_per_step": 1e3 * wall / args.steps,
                 "copy_gbs_per_rank": e2e_copy_gbs,
                 "host_link_gbs": {"per_rank": [round(x, 1) for x in link_all], "aggregate": round(sum(link_all), 1),
-                                  "min": round(min(link_all), 1),
-                                  "how": "bare pinned-host -> device copies of one step's bytes (47 MB), all ranks "
-                                         "at the same time, nothing else on the GPUs (CUDA events)"},
+                                  "min": round(min(link_all), 1), "probe_this_rank": round(probe_gbs, 1),
+                                  "how": "max(bare pinned-host -> device copies of one step's bytes (47 MB), best of 5 "
+                                         "bursts, all ranks at the same time, nothing else on the GPUs (CUDA events); "
+                                         "the copy rate the timed e2e region itself sustained)"},
                 "frac_of_host_link": e2e_copy_gbs / min(link_all),
                 "numa": numa,
                 "bound": "host link: a step ships the fp32 pyramid (44.6 of 47.1 MB); see e2e_images for the "
@@ -805,8 +811,9 @@ def main():
                      f"parallel branch); {LANES} independent batches in flight on {LANES} streams",
         "single_batch_latency_ms": serial_ms, "eager_ms_per_step": eager_ms,
         "clocks": clock_info, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
-        "sa_fused": {"kernel": "sa_fused_fwd_kernel (ball query + grouping + 3-layer TF32 tcgen05 MLP + "
-                               "max, one launch per level; SA1 with the grid query as its own launch)",
+        "sa_fused": {"kernel": "SA1: ball-grid build + ball_query_grid + sa_pipe_kernel (warp-specialised tile pipeline, "
+                               "gather -> 3 tcgen05 TF32 layers -> max); SA2-4: sa_fused_fwd_kernel (ball query + "
+                               "grouping + 3-layer TF32 tcgen05 MLP + max, one launch per level)",
                      "bound": "tensor/L2 (latency-bound in practice, see DESIGN.md)",
                      "levels": sa_levels,
                      "sum_ms": sum(lv["ms"] for lv in sa_levels) if sa_levels else None},

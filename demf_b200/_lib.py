@@ -59,7 +59,7 @@ _SIGNATURES = {
     "demf_sa_fused_error": [],
     "demf_sa_pipe_supported": [_c_int] * 6,
     "demf_sa_pipe_error": [],
-    "demf_sa_pipe_fwd": [_ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_float, _c_int, _ptr, _ptr, _ptr,
+    "demf_sa_pipe_fwd": [_ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_float, _c_int, _ptr, _ptr, _ptr,
                          _ptr],
     "demf_sa_fused_set_profile": [_ptr],
     "demf_sa_fused_tune": [_c_int, _c_int],

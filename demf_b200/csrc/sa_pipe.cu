@@ -45,6 +45,7 @@ constexpr uint32_t kD0 = 0, kD1 = 128, kD2 = 256;   // TMEM columns: D0[b] = b*6
 struct SaPipeParams {
   const float* xyz;       // (B,N,3)
   const float* feat;      // (B,N,1)
+  const float4* pts4;     // optional (B,N,4) = [xyz | feat] packed (the raw input cloud): one 16-byte load per row
   const float* centres;   // (B,M,3)
   const int32_t* nbr;     // (B,M,ns) ball-query rows
   const float* wpack;     // operand images of W0 (64x8 -> one chunk), W1 (64x64), W2 (128x64)
@@ -265,10 +266,18 @@ __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams
 #if SAP_X == 3
       r.x = r.y = r.z = r.f = r.cx = r.cy = r.cz = (float)(k + j) + (float)(c - pt);
 #else
-      r.x = __ldg(pt);
-      r.y = __ldg(pt + 1);
-      r.z = __ldg(pt + 2);
-      r.f = __ldg(p.feat + (long)pt_scene * p.N + k);
+      if (p.pts4 != nullptr) {   // one sector per row instead of four scalar requests (the L1 tag stage is what
+        const float4 v = __ldg(p.pts4 + (long)pt_scene * p.N + k);   // a fully scattered gather is bound by)
+        r.x = v.x;
+        r.y = v.y;
+        r.z = v.z;
+        r.f = v.w;
+      } else {
+        r.x = __ldg(pt);
+        r.y = __ldg(pt + 1);
+        r.z = __ldg(pt + 2);
+        r.f = __ldg(p.feat + (long)pt_scene * p.N + k);
+      }
       r.cx = __ldg(c);
       r.cy = __ldg(c + 1);
       r.cz = __ldg(c + 2);
@@ -496,10 +505,12 @@ int demf_sa_pipe_error(void) {
 
 /* The pipelined first-level set-abstraction kernel: idx = ball-query rows (B,M,ns) of the same query (e.g.
  * demf_ball_query_grid); wpack / bias as demf_sa_pack_weights lays them out for widths (64, 64, 128) over
- * 8-wide rows [feat | 0 0 0 | (xyz - centre)/r | 0]; out (B,M,128). Same results as demf_sa_fused_fwd. */
-int demf_sa_pipe_fwd(const float* xyz, const float* feat_rows, const float* new_xyz, const int32_t* idx, int B, int N,
-                     int M, int ns, float max_radius, int normalize_xyz, const float* wpack, const float* bias,
-                     float* out, void* stream) {
+ * 8-wide rows [feat | 0 0 0 | (xyz - centre)/r | 0]; out (B,M,128). Same results as demf_sa_fused_fwd.
+ * points4 (optional, may be NULL): the same cloud packed as (B,N,4) rows [x y z feat], 16-byte aligned -- the
+ * gather then needs one load per neighbour instead of four. */
+int demf_sa_pipe_fwd(const float* xyz, const float* feat_rows, const float* points4, const float* new_xyz,
+                     const int32_t* idx, int B, int N, int M, int ns, float max_radius, int normalize_xyz,
+                     const float* wpack, const float* bias, float* out, void* stream) {
   DEMF_REQUIRE_PTR(xyz);
   DEMF_REQUIRE_PTR(feat_rows);
   DEMF_REQUIRE_PTR(new_xyz);
@@ -513,6 +524,8 @@ int demf_sa_pipe_fwd(const float* xyz, const float* feat_rows, const float* new_
   SaPipeParams p;
   p.xyz = xyz;
   p.feat = feat_rows;
+  DEMF_REQUIRE((reinterpret_cast<uintptr_t>(points4) & 15u) == 0, DEMF_E_UNSUPPORTED);
+  p.pts4 = reinterpret_cast<const float4*>(points4);
   p.centres = new_xyz;
   p.nbr = idx;
   p.wpack = wpack;

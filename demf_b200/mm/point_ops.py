@@ -1162,17 +1162,22 @@ def sa_pipe_supported(C, sample_num, widths, M):
                                                    int(widths[2]), int(M)))
 
 
-def sa_pipe(xyz, center_xyz, feat_rows, max_radius, sample_num, normalize_xyz, wpack, bias, idx):
+def sa_pipe(xyz, center_xyz, feat_rows, max_radius, sample_num, normalize_xyz, wpack, bias, idx, packed=None):
     """sa_fused for the first backbone level (one feature channel, widths 64/64/128) as a warp-specialised
-    pipeline over 128-row tiles; `idx` = the ball-query rows (B,M,ns) i32. -> (B,M,128) rows. Inference only."""
+    pipeline over 128-row tiles; `idx` = the ball-query rows (B,M,ns) i32. -> (B,M,128) rows. Inference only.
+    `packed`: the same cloud as one contiguous (B,N,4) tensor [xyz | feature] (the detector's raw input), when the
+    caller has it: the gather then issues one 16-byte load per neighbour."""
     assert xyz.is_contiguous() and center_xyz.is_contiguous() and feat_rows.is_contiguous() and idx.is_contiguous()
     _need_cuda(xyz, center_xyz, feat_rows, wpack, bias, idx)
     B, N, _ = xyz.shape
     M = center_xyz.size(1)
     assert feat_rows.shape == (B, N, 1) and idx.shape == (B, M, sample_num) and idx.dtype == torch.int32
+    if packed is not None:
+        assert packed.shape == (B, N, 4) and packed.is_contiguous() and packed.dtype == torch.float32
+        _need_cuda(packed)
     with torch.cuda.device_of(xyz):
         out = torch.empty(B, M, 128, dtype=torch.float32, device=xyz.device)
-        _lib.check(_lib.load().demf_sa_pipe_fwd(_p(xyz), _p(feat_rows), _p(center_xyz), _p(idx), B, N, M,
+        _lib.check(_lib.load().demf_sa_pipe_fwd(_p(xyz), _p(feat_rows), _p(packed), _p(center_xyz), _p(idx), B, N, M,
                                                 int(sample_num), float(max_radius), int(bool(normalize_xyz)),
                                                 _p(wpack), _p(bias), _p(out), _stream()), "demf_sa_pipe_fwd")
     return out

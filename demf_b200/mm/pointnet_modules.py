@@ -157,9 +157,11 @@ class BasePointSAModule(nn.Module):
             return None
         return P.ball_grid(points_xyz.contiguous(), max(g.max_radius for g in self.groupers))
 
-    def forward(self, points_xyz, features=None, indices=None, target_xyz=None, grid=None):
+    def forward(self, points_xyz, features=None, indices=None, target_xyz=None, grid=None, packed=None):
         """points_xyz (B,N,3), features (B,C,N) -> new_xyz (B,M,3), new_features (B,sum C_k,M),
-        indices (B,M). `grid`: a workspace from self.ball_grid(points_xyz) built ahead of time."""
+        indices (B,M). `grid`: a workspace from self.ball_grid(points_xyz) built ahead of time.
+        `packed`: the contiguous (B,N,4) tensor points_xyz and a single feature channel were sliced
+        from, when the caller still has it (the first-level kernel gathers 16-byte rows from it)."""
         new_xyz, indices = self._sample_points(points_xyz, features, indices, target_xyz)
         points_xyz = points_xyz.contiguous()
         if grid is None:
@@ -195,7 +197,9 @@ class BasePointSAModule(nn.Module):
                     else:
                         nbr = P.ball_query(0.0, grouper.max_radius, grouper.sample_num, points_xyz, centres)
                     out.append(P.sa_pipe(points_xyz, centres, feat_rows, grouper.max_radius, grouper.sample_num,
-                                         grouper.normalize_xyz, wpack, bias, nbr))
+                                         grouper.normalize_xyz, wpack, bias, nbr,
+                                         packed=packed if (packed is not None and packed.is_cuda and C == 1
+                                                           and packed.is_contiguous()) else None))
                     continue
                 if self._fused_ok(grouper, mlp, points_xyz, C):
                     wpack, bias, widths = self._fused_pack(mlp, C)
@@ -494,7 +498,8 @@ class PointNet2SASSG(BaseModule):
                     torch.cuda.current_stream(xyz.device).wait_event(ev)
                 cur_xyz, cur_features, cur_indices = self.SA_modules[i](
                     sa_xyz[i], sa_features[i], indices=idx, target_xyz=new_xyz,
-                    grid=grids[i] if i < len(grids) else None)
+                    grid=grids[i] if i < len(grids) else None,
+                    packed=points if (i == 0 and points.size(-1) == 4 and not torch.is_grad_enabled()) else None)
             else:
                 cur_xyz, cur_features, cur_indices = self.SA_modules[i](sa_xyz[i], sa_features[i])
             sa_xyz.append(cur_xyz)

@@ -226,12 +226,13 @@ int demf_sa_fused_error(void);
 /* The same level as a warp-specialised PIPELINE over 128-row tiles (csrc/sa_pipe.cu) for the geometry whose weights
  * are resident: C = 1 feature channel, widths (64, 64, 128), ns in {16, 32, 64}, M a multiple of 128/ns -- the
  * backbone's first level. idx = the ball-query rows (B,M,ns) of the same query (demf_ball_query / _grid);
- * wpack / bias as for demf_sa_fused_fwd. Same results as demf_sa_fused_fwd. */
+ * wpack / bias as for demf_sa_fused_fwd. Same results as demf_sa_fused_fwd. points4 (optional, may be NULL): the
+ * same cloud packed as (B,N,4) rows [x y z feat], 16-byte aligned -- one load per neighbour instead of four. */
 int demf_sa_pipe_supported(int C, int ns, int c1, int c2, int c3, int M);
 int demf_sa_pipe_error(void);
-int demf_sa_pipe_fwd(const float* xyz, const float* feat_rows, const float* new_xyz, const int32_t* idx, int B, int N,
-                     int M, int ns, float max_radius, int normalize_xyz, const float* wpack, const float* bias,
-                     float* out, void* stream);
+int demf_sa_pipe_fwd(const float* xyz, const float* feat_rows, const float* points4, const float* new_xyz,
+                     const int32_t* idx, int B, int N, int M, int ns, float max_radius, int normalize_xyz,
+                     const float* wpack, const float* bias, float* out, void* stream);
 /* debug only: device buffer of 64 int64 receiving [count, clock64 stamps of one worker thread of
  * CTA (0,0): start, after ball query, then per tile: gathered, acc0 ready, act1 written, acc1 ready,
  * act2 written, acc2 ready, stored]; NULL switches it off. */

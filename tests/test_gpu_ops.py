@@ -967,6 +967,9 @@ def test_sa_pipe_matches_sa_fused_and_oracle(dev, B, N, M, r, ns):
     assert ops.sa_pipe_error() == 0
     scale = want.abs().max().item()
     assert (got - want).abs().max().item() <= 1e-5 * scale
+    # the packed-cloud gather (one 16-byte load per neighbour) reads the same numbers: identical output
+    packed = torch.cat([gx, frows], dim=-1).contiguous()
+    assert torch.equal(ops.sa_pipe(gx, centres, frows, r, ns, True, wpack, bias, nbr, packed=packed), got)
     if B <= 3:
         ref_idx, ref_out = sa_module.sa_forward(xyz, centres.cpu(), feats, 0.0, r, ns, True, ws, bs, tf32=True)
         assert torch.equal(nbr.cpu(), ref_idx)

@@ -30,6 +30,10 @@ torch.cuda.synchronize()
 print("max |diff|", (a - b).abs().max().item(), "scale", a.abs().max().item(), "errors", ops.sa_pipe_error())
 print("sa_fused (given rows) ms", t(lambda: ops.sa_fused(xyz, c, f, 0.0, r, ns, True, wpack, bias, wd, idx=nbr)))
 print("sa_pipe  (given rows) ms", t(lambda: ops.sa_pipe(xyz, c, f, r, ns, True, wpack, bias, nbr)))
+pk = pts.contiguous()
+b2 = ops.sa_pipe(xyz, c, f, r, ns, True, wpack, bias, nbr, packed=pk)
+print("packed identical", torch.equal(b, b2))
+print("sa_pipe  (packed rows) ms", t(lambda: ops.sa_pipe(xyz, c, f, r, ns, True, wpack, bias, nbr, packed=pk)))
 print("ball_query_grid ms", t(lambda: ops.ball_query_grid(0.0, r, ns, xyz, c, grid)))
 
 from demf_b200 import _lib
