@@ -755,10 +755,10 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float4 v;
-              v.x = tf32_operand(fmaxf(__uint_as_float(u[4 * j + 0]), 0.f));
-              v.y = tf32_operand(fmaxf(__uint_as_float(u[4 * j + 1]), 0.f));
-              v.z = tf32_operand(fmaxf(__uint_as_float(u[4 * j + 2]), 0.f));
-              v.w = tf32_operand(fmaxf(__uint_as_float(u[4 * j + 3]), 0.f));
+              v.x = relu_tf32_op(__uint_as_float(u[4 * j + 0]));
+              v.y = relu_tf32_op(__uint_as_float(u[4 * j + 1]));
+              v.z = relu_tf32_op(__uint_as_float(u[4 * j + 2]));
+              v.w = relu_tf32_op(__uint_as_float(u[4 * j + 3]));
               *reinterpret_cast<float4*>(dst + sw128_offset(r_epi, j)) = v;
             }
           }
@@ -774,10 +774,13 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
           for (int j = 0; j < 8; ++j) {
             const float4 bj = bl4[j];
             float4 v;
-            v.x = tf32_operand(fmaxf(__uint_as_float(u[4 * j + 0]) + bj.x, 0.f));
-            v.y = tf32_operand(fmaxf(__uint_as_float(u[4 * j + 1]) + bj.y, 0.f));
-            v.z = tf32_operand(fmaxf(__uint_as_float(u[4 * j + 2]) + bj.z, 0.f));
-            v.w = tf32_operand(fmaxf(__uint_as_float(u[4 * j + 3]) + bj.w, 0.f));
+            // FADD2 + VIADDMNMX: 1.5 issue slots per element instead of 3 (same bits as fmaxf + rounding add)
+            add_pair(u[4 * j + 0], u[4 * j + 1], bj.x, bj.y, v.x, v.y);
+            add_pair(u[4 * j + 2], u[4 * j + 3], bj.z, bj.w, v.z, v.w);
+            v.x = relu_tf32_op(v.x);
+            v.y = relu_tf32_op(v.y);
+            v.z = relu_tf32_op(v.z);
+            v.w = relu_tf32_op(v.w);
             *reinterpret_cast<float4*>(dst + sw128_offset(r_epi, j)) = v;
           }
         }
@@ -811,10 +814,12 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
           tmem_ld_wait();
           float m0 = __uint_as_float(u[0]), m1 = __uint_as_float(u[16]);
 #pragma unroll
-          for (int i = 1; i < 16; ++i) {
-            m0 = fmaxf(m0, __uint_as_float(u[i]));
-            m1 = fmaxf(m1, __uint_as_float(u[16 + i]));
+          for (int i = 1; i < 15; i += 2) {            // FMNMX3: two elements per issue slot
+            m0 = max3(m0, __uint_as_float(u[i]), __uint_as_float(u[i + 1]));
+            m1 = max3(m1, __uint_as_float(u[16 + i]), __uint_as_float(u[17 + i]));
           }
+          m0 = fmaxf(m0, __uint_as_float(u[15]));
+          m1 = fmaxf(m1, __uint_as_float(u[31]));
           if (ns == 16) {
             const int m = mt + blk0 * 2;
             if (m < p.M) p.out[((long)b * p.M + m) * c3 + ch] = fmaxf(m0 + bias_c, 0.f);
@@ -825,7 +830,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
               tmem_ld32(tmem + lane_base + p.acc_col[2] + h * 128 + (blk0 + 1) * 32, u);
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) m0 = fmaxf(m0, __uint_as_float(u[i]));
+              for (int i = 0; i < 32; i += 2) m0 = max3(m0, __uint_as_float(u[i]), __uint_as_float(u[i + 1]));
             }
             const int m = mt + blk0 / upb;
             if (m < p.M) p.out[((long)b * p.M + m) * c3 + ch] = fmaxf(m0 + bias_c, 0.f);

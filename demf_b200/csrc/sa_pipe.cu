@@ -101,25 +101,6 @@ __device__ __forceinline__ void role_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 __device__ __forceinline__ float tf32_op(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
-// tf32_op(max(x, 0)) in one instruction (VIADDMNMX): as signed integers the non-negative floats order like the
-// floats and every negative float is a negative integer, so max(bits + 0x1000, 0x1000) is the rounded ReLU
-__device__ __forceinline__ float relu_tf32_op(float x) {
-  return __int_as_float(__viaddmax_s32(__float_as_int(x), 0x1000, 0x1000));
-}
-// two IEEE fp32 additions in one instruction (FADD2): acc pair + bias pair
-__device__ __forceinline__ void add_pair(uint32_t a0, uint32_t a1, float b0, float b1, float& r0, float& r1) {
-  uint64_t pa, pb, pr;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "r"(a0), "r"(a1));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(pb) : "f"(b0), "f"(b1));
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(pa), "l"(pb));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(pr));
-}
-__device__ __forceinline__ float max3(float a, float b, float c) {
-  float r;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-  return r;
-}
-
 __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);

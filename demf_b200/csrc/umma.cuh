@@ -53,6 +53,26 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   return false;
 }
 
+// ---- epilogue arithmetic: fewer issue slots per accumulator element -----------------------------
+// (bits of max(x, 0)) + 0x1000, the TF32 operand rounding of a ReLU output, in one instruction (VIADDMNMX): as signed integers the non-negative floats order like the
+// floats and every negative float is a negative integer, so max(bits + 0x1000, 0x1000) is the rounded ReLU
+__device__ __forceinline__ float relu_tf32_op(float x) {
+  return __int_as_float(__viaddmax_s32(__float_as_int(x), 0x1000, 0x1000));
+}
+// two IEEE fp32 additions in one instruction (FADD2): acc pair + bias pair
+__device__ __forceinline__ void add_pair(uint32_t a0, uint32_t a1, float b0, float b1, float& r0, float& r1) {
+  uint64_t pa, pb, pr;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "r"(a0), "r"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pb) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(pa), "l"(pb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(pr));
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 // ---- proxies / fences -----------------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_proxy_async() {
