@@ -295,12 +295,15 @@ class Trainer:
         return out
 
     def step(self, batch, sync_collective=False):
-        from .mm.bricks import async_weight_grads
+        from .mm.bricks import async_weight_grads, deferred_batch_counters
         self.flat.zero()
         self.flat.release()
-        with async_weight_grads(self.flat.buffer.device):   # dW GEMMs on a second stream, joined on exit
+        # dW GEMMs on a second stream, joined on exit; BatchNorm step counters bumped by one launch on exit
+        with async_weight_grads(self.flat.buffer.device), deferred_batch_counters():
             losses = self.model.forward_train(**batch)
-            total = sum(losses.values())
+            total = getattr(losses, "total", None)     # the head's own reduction when it has one
+            if total is None:
+                total = sum(losses.values())
             total.backward()
         self.flat.collect()
         work = self.flat.all_reduce_mean(self.group)
@@ -412,15 +415,17 @@ class GraphedTrainStep:
             self.sample_graph.replay()
 
     def _eager(self):
-        from .mm.bricks import async_weight_grads
+        from .mm.bricks import async_weight_grads, deferred_batch_counters
         t = self.trainer
         t.flat.zero()
         t.flat.release()
-        with async_weight_grads(self.points.device):
+        with async_weight_grads(self.points.device), deferred_batch_counters():
             losses = t.model.forward_train(points=self.points, img=self.levels, img_metas=self.metas,
                                            gt_bboxes_3d=self.box, gt_labels_3d=self.label,
                                            projection=(self.mats, self.affs), presampled=self.presampled)
-            total = sum(losses.values())
+            total = getattr(losses, "total", None)     # the head's own reduction when it has one
+            if total is None:
+                total = sum(losses.values())
             total.backward()
         t.flat.collect()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(t.group) > 1:

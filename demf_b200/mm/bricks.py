@@ -468,8 +468,53 @@ def batch_norm_rows(bn, x):
 _column_index_cache = {}
 
 
-def permute_weight_columns(w, cols):
+# BatchNorm's num_batches_tracked += 1 is one tiny kernel per layer and step (25 in the DeMF training step). Inside a
+# `deferred_batch_counters()` block (engine.Trainer.step) the counters are collected and bumped by ONE foreach launch
+# when the block exits; outside it they are bumped on the spot, as nn.BatchNorm does.
+_NBT = {"pending": None}
+
+
+def bump_batches_tracked(bn):
+    t = bn.num_batches_tracked
+    if t is None:
+        return
+    if _NBT["pending"] is not None:
+        _NBT["pending"].append(t)
+    else:
+        t.add_(1)
+
+
+class deferred_batch_counters:
+    def __enter__(self):
+        self.prev = _NBT["pending"]
+        _NBT["pending"] = []
+        return self
+
+    def __exit__(self, *exc):
+        pending, _NBT["pending"] = _NBT["pending"], self.prev
+        if pending and exc[0] is None:
+            uniq = list({id(t): t for t in pending}.values())
+            counts = [sum(1 for q in pending if q is t) for t in uniq]
+            if all(c == 1 for c in counts):
+                torch._foreach_add_(uniq, 1)
+            else:
+                for t, c in zip(uniq, counts):
+                    t.add_(c)
+        return False
+
+
+def permute_weight_columns(w, cols, zero_pad=True):
     """w (Cout, Cin) -> (Cout, len(cols)); cols[j] = source column or -1 for a zero column."""
+    if not zero_pad:
+        # training: the padding columns of the ROWS are exact zeros, so a padding column of the weight may hold
+        # anything finite -- it is given a copy of column 0 (one index_select, no pad kernel; the gradient that
+        # flows back into column 0 through the copy is a sum of products with those zeros: exactly 0)
+        key = (tuple(cols), w.size(1), str(w.device), "dup")
+        idx = _column_index_cache.get(key)
+        if idx is None:
+            idx = torch.as_tensor([c if c >= 0 else 0 for c in cols]).to(w.device)
+            _column_index_cache[key] = idx
+        return w.index_select(1, idx)
     key = (tuple(cols), w.size(1), str(w.device))
     idx = _column_index_cache.get(key)
     if idx is None:  # built once per layout and device: no host->device copy in the step
@@ -545,15 +590,14 @@ def conv_module_rows(cm, x, cols=None):
         return torch.addmm(b, x, w.t())
     w = cm.conv.weight.flatten(1)
     if cols is not None:
-        w = permute_weight_columns(w, cols)
+        w = permute_weight_columns(w, cols, zero_pad=False)   # x's padding columns are exact zeros (csrc/rows.cu)
     y, prestats = _linear_rows(cm, x, w, direct_wgrad=cols is None)
     if cm.with_norm and _fused_bn_ok(cm, y):
         # training: batch statistics (from the GEMM's epilogue when it ran on our tensor-core kernel) +
         # normalise + ReLU
         from . import point_ops as P
         bn = cm.norm
-        if bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+        bump_batches_tracked(bn)
         return P.batch_norm_relu_rows(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum,
                                       bn.eps, cm.with_activation, _bn_state(bn, y.device), prestats=prestats)
     assert not prestats
@@ -579,12 +623,11 @@ def conv_module_rows_max(cm, x, ns, cols=None):
         return None
     w = cm.conv.weight.flatten(1)
     if cols is not None:
-        w = permute_weight_columns(w, cols)
+        w = permute_weight_columns(w, cols, zero_pad=False)   # x's padding columns are exact zeros (csrc/rows.cu)
     y, prestats = _linear_rows(cm, x, w, direct_wgrad=cols is None)
     from . import point_ops as P
     bn = cm.norm
-    if bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
+    bump_batches_tracked(bn)
     return P.batch_norm_relu_max_rows(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum,
                                       bn.eps, ns, _bn_state(bn, y.device), prestats=prestats)
 
@@ -705,7 +748,7 @@ class _LinearRowsTC(torch.autograd.Function):
             with torch.cuda.stream(side):
                 P.gemm_wgrad_(conv.weight.grad.view(w.shape), gy, x)
                 if conv.bias is not None:
-                    conv.bias.grad.add_(gy.sum(0))
+                    P.col_sum_add_(conv.bias.grad, gy)
             return gx, None, None, None, None
         gw = gb = None
         if ctx.needs_input_grad[1]:
@@ -779,13 +822,12 @@ def sa_mlp_train_rows(mlp, x, ns, cols0=None):
             return None
     w0 = layers[0].conv.weight.flatten(1)
     if cols0 is not None:
-        w0 = permute_weight_columns(w0, cols0)
+        w0 = permute_weight_columns(w0, cols0, zero_pad=False)   # x's padding columns are exact zeros (csrc/rows.cu)
     if not _tc_ok(x, w0):
         return None
     from . import point_ops as P
     for cm in layers:
-        if cm.norm.num_batches_tracked is not None:
-            cm.norm.num_batches_tracked.add_(1)
+        bump_batches_tracked(cm.norm)
     y, prestats = _linear_rows(layers[0], x, w0, direct_wgrad=cols0 is None)
     assert prestats
     for prev, cm in zip(layers[:-1], layers[1:]):

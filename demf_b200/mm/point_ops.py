@@ -1144,6 +1144,17 @@ class _StageLoss(torch.autograd.Function):
         return gs[0], gs[1], gs[2], gs[3], gs[4], g_sem, None, None
 
 
+def col_sum_add_(out, x):
+    """out (N,) += x (R,N).sum(0) in one launch (csrc/bn_rows.cu): the bias gradient of a Linear layer."""
+    _need_cuda(out, x)
+    assert x.dim() == 2 and x.stride(1) == 1 and out.is_contiguous() and out.numel() == x.shape[1]
+    assert x.dtype == torch.float32 and out.dtype == torch.float32
+    with torch.cuda.device_of(x):
+        _lib.check(_lib.load().demf_col_sum_add(_p(x), x.shape[0], x.shape[1], x.stride(0), _p(out), _stream()),
+                   "demf_col_sum_add")
+    return out
+
+
 def stage_loss(center, size, dir_class, dir_res_norm, obj, sem, targets, cfg):
     """Predictions (B,Q,C) fp32 contiguous CUDA tensors; targets = (objectness_targets i64, objectness_weights,
     box_loss_weights, size_targets, center_targets, dir_class_targets i64, dir_res_targets, mask_targets i64 | None);

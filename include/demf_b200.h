@@ -299,6 +299,9 @@ int demf_bn_max_rows_bwd(const float* grad_pooled, const float* pooled, const ui
                          void* state, float* coef, float* grad_x, float* grad_gamma, float* grad_beta,
                          void* stream);
 
+/* out[c] += sum over the R rows of x (R, N), row stride ld floats: the bias gradient of a Linear / 1x1 convolution
+ * accumulated in place (autograd's grad.sum(0) + accumulate in one launch). */
+int demf_col_sum_add(const float* x, long R, int N, long ld, float* out, void* stream);
 /* The normalise(+ReLU)(+max) half alone, when mean / invstd came from demf_bn_finalize (statistics accumulated by
  * the epilogue of the GEMM that produced x). */
 int demf_bn_rows_apply(const float* x, long R, int C, const float* gamma, const float* beta, const float* mean,

@@ -149,3 +149,19 @@ def test_linear_rows_autograd(dev, R, K, N):
     assert _rel(y.detach(), yd.detach()) < TOL and _rel(x.grad, xd.grad) < TOL
     assert _rel(w.grad, wd.grad) < TOL and _rel(b.grad, bd.grad) < TOL
     assert P.gemm_error() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R,N", [(1, 3), (1024, 259), (21760, 256), (37, 30), (100000, 8)])
+def test_col_sum_add_matches_torch(R, N):
+    """Bias gradient in one launch: out += x.sum(0) (csrc/bn_rows.cu col_sum_add_kernel), also on a strided view."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(R + N)
+    base = torch.randn(R, N + 4, generator=g, device=dev)
+    x = base[:, :N]                              # row stride N + 4
+    out = torch.randn(N, generator=g, device=dev)
+    want = out.double() + x.double().sum(0)
+    P.col_sum_add_(out, x)
+    torch.cuda.synchronize()
+    scale = x.abs().double().sum(0).max().item() + 1.0
+    assert (out.double() - want).abs().max().item() <= 1e-6 * scale

@@ -299,6 +299,10 @@ def test_sa_mlp_training_chain_matches_fp64_autograd(dev, M, ns, C, widths):
         engine.set_gemm_precision("fp32")
     assert ops.gemm_error() == 0
     got = {"x": x.grad.clone()}
+    # the layout's zero columns: the training path gives their weight columns a copy of column 0 instead of zeros
+    # (bricks.permute_weight_columns(zero_pad=False)), so dL/dx there is not zero -- and is never read
+    # (group_rows_bwd scatters the feature and xyz columns only)
+    got["x"][:, [j for j, c in enumerate(cols) if c < 0]] = 0
     for j, cm in enumerate(mlp):
         got[f"w{j}"], got[f"g{j}"], got[f"b{j}"] = cm.conv.weight.grad.flatten(1).clone(), cm.norm.weight.grad.clone(), \
             cm.norm.bias.grad.clone()
@@ -564,3 +568,40 @@ def test_fused_stage_loss_matches_torch_modules(dev):
     for k in preds:
         a, b = results[True][1][k], results[False][1][k]
         assert (a - b).norm() <= 1e-4 * b.norm() + 1e-9, (k, (a - b).norm().item(), b.norm().item())
+
+
+@pytest.mark.gpu
+def test_loss_dict_total_equals_sum_of_entries(dev):
+    """The head's own reduction (`LossDict.total`: stage vectors averaged as vectors, one sum) against adding the
+    entries one by one, and against the unfused per-term path: same value to fp32 sum-order noise, same gradients."""
+    from demf_b200.modeling.heads import LossDict
+    torch.manual_seed(11)
+    model = engine.build_demf_votenet(num_points=4).to(dev).train()
+    batch = engine.synthetic_batch(2, 20000, "S512", seed=31, device=dev)
+    engine.set_gemm_precision("fp32")
+    try:
+        out = {}
+        for fused in (True, False):
+            model.pts_bbox_head.fused_stage_loss = fused
+            model.zero_grad(set_to_none=True)
+            torch.manual_seed(3)                       # dropout masks
+            losses = model.forward_train(**batch)
+            if fused:
+                assert isinstance(losses, LossDict) and losses.total is not None
+                by_entry = sum(losses.values())
+                assert abs(losses.total.item() - by_entry.item()) <= 1e-5 * abs(by_entry.item())
+                total = losses.total
+            else:
+                assert getattr(losses, "total", None) is None
+                total = sum(losses.values())
+            total.backward()
+            out[fused] = (total.item(), {k: v.item() for k, v in losses.items()},
+                          torch.cat([p.grad.flatten() for p in model.parameters() if p.grad is not None]))
+    finally:
+        model.pts_bbox_head.fused_stage_loss = True
+        engine.set_gemm_precision("tf32")
+    assert abs(out[True][0] - out[False][0]) <= 1e-4 * abs(out[False][0])
+    for k, v in out[False][1].items():
+        assert abs(out[True][1][k] - v) <= 1e-4 * max(1.0, abs(v)), k
+    a, b = out[True][2], out[False][2]
+    assert a.shape == b.shape and (a - b).norm() <= 2e-3 * b.norm()
