@@ -602,6 +602,16 @@ int make_map(CUtensorMap* map, const float* base, long rows, int cols, long ld, 
     set_error("cuTensorMapEncodeTiled is not available from this driver");
     return DEMF_E_UNSUPPORTED;
   }
+  // The driver entry point needs a current context in THIS thread. A thread whose first CUDA call is this one
+  // (an autograd worker running our backward before any runtime call) has none yet: binding the device's
+  // primary context is what the runtime would do on its first call.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    int d = 0;
+    if (cudaGetDevice(&d) == cudaSuccess) cudaSetDevice(d);
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
   const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};

@@ -191,13 +191,79 @@ class MultiheadAttention(BaseModule):
             value = value.contiguous()
         if self.batch_first:
             query, key, value = (t.transpose(0, 1) for t in (query, key, value))
-        # the attention map itself is never used: without it PyTorch takes its fused
-        # scaled-dot-product path instead of mul + bmm + softmax + bmm + mean
-        out = self.attn(query=query, key=key, value=value, attn_mask=attn_mask,
-                        key_padding_mask=key_padding_mask, need_weights=False)[0]
+        out = self._attn_train_rows(query, key, value, attn_mask, key_padding_mask, shared_qk)
+        if out is None:
+            # the attention map itself is never used: without it PyTorch takes its fused
+            # scaled-dot-product path instead of mul + bmm + softmax + bmm + mean
+            out = self.attn(query=query, key=key, value=value, attn_mask=attn_mask,
+                            key_padding_mask=key_padding_mask, need_weights=False)[0]
         if self.batch_first:
             out = out.transpose(0, 1)
         return identity + self.dropout_layer(self.proj_drop(out))
+
+
+class _ParamRows:
+    """Rows [lo, hi) of a packed parameter, with what `linear_rows(owner=...)` reads of a parameter."""
+    __slots__ = ("par", "lo", "hi", "requires_grad")
+
+    def __init__(self, par, lo, hi):
+        self.par, self.lo, self.hi, self.requires_grad = par, lo, hi, par.requires_grad
+
+    @property
+    def grad(self):
+        return None if self.par.grad is None else self.par.grad[self.lo:self.hi]
+
+
+class _SliceOwner:
+    __slots__ = ("weight", "bias", "params")
+
+
+def _slice_owner(weight, bias, lo, hi):
+    """What `linear_rows(owner=...)` needs of a module, for rows [lo, hi) of a packed projection: `.weight` /
+    `.bias` objects whose `.grad` is the matching view of the packed parameter's gradient (None until it exists)."""
+    o = _SliceOwner()
+    o.weight = _ParamRows(weight, lo, hi)
+    o.bias = None if bias is None else _ParamRows(bias, lo, hi)
+    o.params = [weight] + ([] if bias is None else [bias])
+    return o
+
+
+def _mha_train_rows(self, query, key, value, attn_mask, key_padding_mask, shared_qk):
+    """nn.MultiheadAttention.forward (need_weights=False) for TRAINING on CUDA in the TF32 mode with the four
+    projections on our tensor-core GEMMs (`linear_rows`; the library picks sm80 kernels for these 1024-row
+    products) and the attention itself through F.scaled_dot_product_attention, exactly what the module's own
+    fast path composes. (L,B,E) in, (L,B,E) out; None when the case is not this plain one."""
+    attn = self.attn
+    if not (torch.is_grad_enabled() and query.is_cuda and NATIVE_TRAIN_GEMM and torch.backends.cuda.matmul.allow_tf32
+            and attn_mask is None and key_padding_mask is None and attn._qkv_same_embed_dim
+            and attn.in_proj_weight is not None and attn.bias_k is None and not attn.add_zero_attn
+            and query.dim() == 3 and attn.embed_dim % 4 == 0):
+        return None
+    E, H = attn.embed_dim, attn.num_heads
+    Lq, B, _ = query.shape
+    Lk = key.shape[0]
+    w, b = attn.in_proj_weight, attn.in_proj_bias
+
+    def proj(x, lo, hi):
+        rows = x.reshape(-1, E)
+        return linear_rows(rows, w[lo:hi], None if b is None else b[lo:hi], owner=_slice_owner(w, b, lo, hi))
+    if shared_qk:
+        qk = proj(query, 0, 2 * E)                      # one GEMM for both: (L*B, 2E)
+        q, k = qk[:, :E], qk[:, E:]
+    else:
+        q, k = proj(query, 0, E), proj(key, E, 2 * E)
+    v = proj(value, 2 * E, 3 * E)
+    # (L*B, E) -> (B, H, L, E/H), as nn.functional.multi_head_attention_forward lays heads out
+    q = q.reshape(Lq, B * H, E // H).transpose(0, 1).reshape(B, H, Lq, E // H)
+    k = k.reshape(Lk, B * H, E // H).transpose(0, 1).reshape(B, H, Lk, E // H)
+    v = v.reshape(Lk, B * H, E // H).transpose(0, 1).reshape(B, H, Lk, E // H)
+    o = torch.nn.functional.scaled_dot_product_attention(q, k, v, None, attn.dropout if attn.training else 0.0)
+    o = o.permute(2, 0, 1, 3).reshape(Lq * B, E)
+    o = linear_rows(o, attn.out_proj.weight, attn.out_proj.bias, owner=attn.out_proj)
+    return o.view(Lq, B, E)
+
+
+MultiheadAttention._attn_train_rows = _mha_train_rows
 
 
 @FEEDFORWARD_NETWORK.register_module()
@@ -651,6 +717,10 @@ def _wgrad_stream(device):
 
 def _mark_direct(conv):
     """These parameters' gradients are accumulated in place by our kernels (see engine.FlatGradients.release)."""
+    if hasattr(conv, "params"):          # a view of a packed parameter (bricks._slice_owner)
+        for par in conv.params:
+            par._demf_direct_grad = True
+        return
     conv.weight._demf_direct_grad = True
     if conv.bias is not None:
         conv.bias._demf_direct_grad = True

@@ -605,3 +605,41 @@ def test_loss_dict_total_equals_sum_of_entries(dev):
         assert abs(out[True][1][k] - v) <= 1e-4 * max(1.0, abs(v)), k
     a, b = out[True][2], out[False][2]
     assert a.shape == b.shape and (a - b).norm() <= 2e-3 * b.norm()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shared_qk", [True, False])
+def test_mha_training_path_matches_nn_multihead_attention(dev, shared_qk):
+    """bricks.MultiheadAttention in training (projections on csrc/gemm_tf32.cu, attention through SDPA) against the
+    nn.MultiheadAttention it wraps, same parameters: output and every gradient (inputs, packed in_proj weight / bias,
+    out_proj) to TF32 accuracy: 1e-2 of the norm (observed <= 4e-3 -- three chained TF32 GEMMs around a softmax; a
+    wrong head layout, slice or scale is O(1))."""
+    from demf_b200.mm.bricks import MultiheadAttention
+    torch.manual_seed(3)
+    E, H, L, B = 288, 8, 256, 4
+    mha = MultiheadAttention(E, H, attn_drop=0.0, proj_drop=0.0).to(dev).train()
+    with torch.no_grad():
+        mha.attn.in_proj_bias.normal_(0, 0.1)
+        mha.attn.out_proj.bias.normal_(0, 0.1)
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = torch.randn(L, B, E, generator=g, device=dev, requires_grad=True)
+    pos = torch.randn(L, B, E, generator=g, device=dev)
+    mem = x if shared_qk else torch.randn(L + 64, B, E, generator=g, device=dev, requires_grad=True)
+    up = torch.randn(L, B, E, generator=g, device=dev)
+    res = {}
+    for mode in ("tf32", "fp32"):                   # fp32 mode -> the module's own path
+        engine.set_gemm_precision(mode)
+        for t in (x, mem):
+            t.grad = None
+        mha.zero_grad(set_to_none=True)
+        if shared_qk:
+            out = mha(x, query_pos=pos)
+        else:
+            out = mha(x, key=mem, value=mem, query_pos=pos)
+        out.backward(up)
+        res[mode] = [out.detach().clone(), x.grad.clone(), mem.grad.clone()] + [p.grad.clone() for p in mha.parameters()]
+    engine.set_gemm_precision("tf32")
+    assert ops.gemm_error() == 0
+    for a, b in zip(res["tf32"], res["fp32"]):
+        assert a.shape == b.shape
+        assert (a - b).norm() <= 1e-2 * b.norm() + 1e-7, ((a - b).norm().item(), b.norm().item())
