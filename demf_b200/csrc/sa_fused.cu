@@ -31,6 +31,7 @@
 //
 // Roofline: tensor pipe / L2 (weights re-streamed per tile unless resident). HBM bytes per scene =
 // N*12 + N*C*4 + M*12 + M*C3*4 (+ weights once).
+#include <cstdlib>
 #include "ball_grid.cuh"
 #include "common.cuh"
 #include "umma.cuh"
@@ -985,10 +986,16 @@ bool configure(SaParams& p, int B) {
       const int top = p.acc_col[2] + c3 > a1 + c2 ? p.acc_col[2] + c3 : a1 + c2;
       const int used = (lanes - 1) * lane_cols + top;
       p.tmem_cols = used <= 32 ? 32 : used <= 64 ? 64 : used <= 128 ? 128 : used <= 256 ? 256 : 512;
-      // fewer tiles per CTA when the grid would not fill the GPU (but keep every lane busy)
+      // fewer tiles per CTA when the grid would not fill the GPU (but keep every lane busy) -- unless halving
+      // costs a whole extra wave of CTAs for the same number of tile rounds per CTA (the vote-aggregation level:
+      // 128 CTAs x 2 overlapped tiles beat 256 CTAs x 1 tile, 58 vs 66 us)
       int tiles = max_tiles;
+      auto cost = [&](int t) {
+        const long ctas = (long)B * ((p.M + t * cpt - 1) / (t * cpt));
+        return ((ctas + kNumSMs - 1) / kNumSMs) * ((t + lanes - 1) / lanes);
+      };
       while (tiles > 1 && tiles / 2 >= lanes &&
-             (long)B * ((p.M + tiles * cpt - 1) / (tiles * cpt)) < kNumSMs)
+             (long)B * ((p.M + tiles * cpt - 1) / (tiles * cpt)) < kNumSMs && cost(tiles / 2) < cost(tiles))
         tiles >>= 1;
       p.tiles = tiles;
       p.G = tiles * cpt;
