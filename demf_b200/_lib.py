@@ -54,8 +54,6 @@ _SIGNATURES = {
     "demf_sa_fused_supported": [_c_int] * 5,
     "demf_sa_fused_fwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, _c_int,
                           _c_int, _c_int, _ptr, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr],
-    "demf_sa_fused_pre_fwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_float, _c_float, _c_int,
-                              _c_int, _c_int, _ptr, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr],
     "demf_sa_fused_error": [],
     "demf_sa_pipe_supported": [_c_int] * 6,
     "demf_sa_pipe_error": [],
@@ -63,8 +61,6 @@ _SIGNATURES = {
                          _ptr],
     "demf_sa_fused_set_profile": [_ptr],
     "demf_sa_fused_tune": [_c_int, _c_int],
-    "demf_sa_fused_tune_pair": [_c_int],
-    "demf_sa_fused_tune_bias_init": [_c_int],
     "demf_msda_fwd": [_ptr, _ptr, _ptr, _ptr, _ptr] + [_c_int] * 7 + [_ptr, _ptr],
     "demf_bn_rows_supported": [_c_int],
     "demf_bn_rows_state_bytes": [_c_int],

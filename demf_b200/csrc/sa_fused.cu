@@ -54,8 +54,6 @@ __device__ int g_sa_error = 0;  // sticky: first protocol time-out (never expect
 long long* g_sa_prof = nullptr;
 int g_sa_max_lanes = kMaxLanes;  // tuning knobs (demf_sa_fused_tune)
 int g_sa_sleep_ns = 0;
-int g_sa_bias_init = 0;  // layers 0/1: bias stored into the TMEM accumulator instead of added in the epilogue (no faster)
-int g_sa_pair = 0;       // CTA pairs for streamed weights (demf_sa_fused_tune_pair): correct, not yet faster  // host copy of the debug stamp buffer pointer (demf_sa_fused_set_profile)
 
 struct SaParams {
   const float* xyz;
@@ -76,13 +74,10 @@ struct SaParams {
   int tmem_cols, lane_cols, acc_col[3];
   int sleep_ns;  // back-off between mbarrier polls of the worker warps (0 = spin)
   int t2;        // layer 2 runs transposed (D^T = W3 * act2^T): lanes = channels, columns = rows
-  int pair;      // CTA pairs (cta_group::2): one MMA covers the tiles of two CTAs, each CTA streams half the weights
-  int pre0;      // layer 0 pre-projected per POINT: feat = (B,N,c0) rows of W1_feat * feat_j, bias carries W1_xyz
-  int bias_init; // layers 0/1: the workers store the bias into the TMEM accumulator before the MMAs accumulate onto it
 };
 
 struct SmemLayout {
-  int ring, rows, centres, bias, part, drow, bars, total;
+  int ring, rows, centres, bias, part, bars, total;
 };
 
 __host__ __device__ inline SmemLayout smem_layout(const SaParams& p) {
@@ -91,9 +86,8 @@ __host__ __device__ inline SmemLayout smem_layout(const SaParams& p) {
   L.rows = L.ring + p.slots * p.slot_bytes;
   L.centres = L.rows + p.G * p.ns * 4;
   L.bias = L.centres + p.G * 16;
-  L.part = L.bias + (p.c[0] + p.c[1] + p.c[2] + (p.pre0 ? 3 * p.c[0] : 0)) * 4;
-  L.drow = (L.part + (p.ns == 64 ? p.lanes * 2 * p.c[2] * 4 : 0) + 15) & ~15;
-  L.bars = (L.drow + (p.pre0 ? p.lanes * kTileRows * 16 : 0) + 15) & ~15;
+  L.part = L.bias + (p.c[0] + p.c[1] + p.c[2]) * 4;
+  L.bars = (L.part + (p.ns == 64 ? p.lanes * 2 * p.c[2] * 4 : 0) + 15) & ~15;
   L.total = L.bars + (3 * kMaxSlots + 2 * kMaxLanes) * 8 + 16 + 1024;  // + alignment slack
   return L;
 }
@@ -219,7 +213,6 @@ __device__ __forceinline__ bool issue_group(const SaParams& p, const IssueCtx& c
     // resident weights arrive once: after a lane's first tile their barriers need no second look
     if (check_w && !wait_or_fail(c.wfull0 + 8 * s, p.resident ? 0u : wph, c.failed, 2)) return false;
     const int ksteps = layer == 0 ? (min(32, p.K0 - 32 * (ch0 + ch)) >> 3) : 4;
-    const uint32_t acc0 = layer < 2 ? (uint32_t)p.bias_init : 0u;  // accumulate from the first K step on
     // a K step of 8 tf32 = +32 bytes = +2 in the descriptor's (address >> 4) field
     const uint64_t da = smem_desc_sw128(a0 + ch * kChunkBytes), dw = smem_desc_sw128(c.ring_u32 + s * p.slot_bytes);
     if (layer == 2 && p.t2) {
@@ -233,11 +226,10 @@ __device__ __forceinline__ bool issue_group(const SaParams& p, const IssueCtx& c
         for (int k = 0; k < 4; ++k) mma_tf32(d + h * 128, dwh + 2 * k, da + 2 * k, it, (ch | k) != 0);
       }
     } else if (ksteps == 4) {
-      // layers 0 and 1 accumulate onto columns the workers initialised with the bias (p.bias_init)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) mma_tf32(d, da + 2 * k, dw + 2 * k, idesc, acc0 | ch0 | ch | k);
+      for (int k = 0; k < 4; ++k) mma_tf32(d, da + 2 * k, dw + 2 * k, idesc, ch0 | ch | k);
     } else {
-      for (int k = 0; k < ksteps; ++k) mma_tf32(d, da + 2 * k, dw + 2 * k, idesc, acc0 | ch0 | ch | k);
+      for (int k = 0; k < ksteps; ++k) mma_tf32(d, da + 2 * k, dw + 2 * k, idesc, ch0 | ch | k);
     }
     if (!p.resident) {
       mma_commit(c.wempty0 + 8 * slot);
@@ -251,43 +243,6 @@ __device__ __forceinline__ bool issue_group(const SaParams& p, const IssueCtx& c
   return true;
 }
 
-// CTA-pair version (leader CTA only): every instruction covers the lane-`ln` tiles of BOTH CTAs
-// (M = 256); each CTA's ring slot holds its half of the weight chunk (layers 0/1: half of the output
-// channels = N split; transposed layer 2: its 128 channels = M split, the two activation tiles are
-// the N halves). A slot is ready when the local copy landed (wfull) and the peer forwarded its own
-// (pfull); commits are multicast to the barriers of both CTAs.
-__device__ __forceinline__ bool issue_group_pair(const SaParams& p, const IssueCtx& c, uint32_t pfull0, int ln,
-                                                 int g, uint32_t& slot, uint32_t& wph) {
-  int layer, ch0, nch;
-  group_span(p, c.nch0, g, layer, ch0, nch);
-  const uint32_t idesc = layer == 2 ? instr_desc_tf32(256, 2 * kTileRows) : instr_desc_tf32(256, p.c[layer]);
-  const uint32_t d = c.tmem + ln * p.lane_cols + p.acc_col[layer];
-  const uint32_t a0 = c.act_u32 + ln * p.lane_act_bytes;
-  tc_fence_after_sync();
-  for (int ch = 0; ch < nch; ++ch) {
-    if (!wait_or_fail(c.wfull0 + 8 * slot, wph, c.failed, 2)) return false;
-    if (!wait_or_fail(pfull0 + 8 * slot, wph, c.failed, 7)) return false;
-    tc_fence_after_sync();
-    const int ksteps = layer == 0 ? (min(32, p.K0 - 32 * (ch0 + ch)) >> 3) : 4;
-    const uint64_t da = smem_desc_sw128(a0 + ch * kChunkBytes), dw = smem_desc_sw128(c.ring_u32 + slot * p.slot_bytes);
-    if (layer == 2) {
-      for (int k = 0; k < 4; ++k) mma2_tf32(d, dw + 2 * k, da + 2 * k, idesc, (ch | k) != 0);
-    } else {
-      for (int k = 0; k < ksteps; ++k) mma2_tf32(d, da + 2 * k, dw + 2 * k, idesc, (ch0 | ch | k) != 0);
-    }
-    mma2_commit(c.wempty0 + 8 * slot);
-    if (++slot == (uint32_t)p.slots) {
-      slot = 0;
-      wph ^= 1;
-    }
-  }
-  mma2_commit(c.acc_full0 + 8 * ln);
-  return true;
-}
-
-// kPair: the CTA-pair variant. A kernel that contains cta_group::2 instructions can only be launched
-// with an even cluster size, so the unpaired variant is compiled without them.
-template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParams p) {
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned chunks: align the carve-up by hand
@@ -301,9 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
   const int b = blockIdx.y;
   const int m_base = blockIdx.x * p.G;
   const int cpt = kTileRows / p.ns;  // centres per tile
-  const uint32_t crank = kPair ? cluster_ctarank() : 0u;  // CTA pairs: both CTAs run the leader's tile count
-  const int m_lead = m_base - (int)crank * p.G;
-  const int ntiles = min(p.tiles, (min(p.G, p.M - m_lead) + cpt - 1) / cpt);
+  const int ntiles = min(p.tiles, (min(p.G, p.M - m_base) + cpt - 1) / cpt);
   const int nrounds = (ntiles + p.lanes - 1) / p.lanes;
   const int ngroups = p.npass + 2;
 
@@ -316,7 +269,6 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
   volatile int* failed = reinterpret_cast<volatile int*>(tmem_slot + 1);
   const uint32_t wfull0 = smem_u32(&bars[0]), wempty0 = smem_u32(&bars[kMaxSlots]);
   const uint32_t op_ready0 = smem_u32(&bars[2 * kMaxSlots]), acc_full0 = smem_u32(&bars[2 * kMaxSlots + kMaxLanes]);
-  const uint32_t pfull0 = smem_u32(&bars[2 * kMaxSlots + 2 * kMaxLanes]);  // CTA pairs: the peer's copy landed
   const uint32_t act_u32 = smem_u32(smem), ring_u32 = smem_u32(ring);
   const int wpl = kWorkerWarps / p.lanes;  // worker warps per lane
 
@@ -325,24 +277,21 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
     for (int s = 0; s < kMaxSlots; ++s) {
       mbar_init(wfull0 + 8 * s, 1);
       mbar_init(wempty0 + 8 * s, 1);
-      mbar_init(pfull0 + 8 * s, 1);
     }
     for (int l = 0; l < kMaxLanes; ++l) {
-      mbar_init(op_ready0 + 8 * l, p.pair ? 2 * wpl : wpl);  // pairs: the leader hears both CTAs' lanes
+      mbar_init(op_ready0 + 8 * l, wpl);
       mbar_init(acc_full0 + 8 * l, 1);
     }
     mbar_fence_init();
   }
   if (warp == 0) {
     __syncwarp();
-    if constexpr (kPair) tmem_alloc2(smem_u32(tmem_slot), p.tmem_cols);
-    else tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+    tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
   }
-  for (int i = tid; i < p.c[0] + p.c[1] + p.c[2] + (p.pre0 ? 3 * p.c[0] : 0); i += kThreads)
+  for (int i = tid; i < p.c[0] + p.c[1] + p.c[2]; i += kThreads)
     bias_s[i] = __ldg(p.bias + i);
   tc_fence_before_sync();
-  if constexpr (kPair) cluster_sync_all();  // the peer's barriers exist before anything arrives on them
-  else __syncthreads();
+  __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const int nch0 = (p.K0 + 31) >> 5;
@@ -353,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
     // Streamed weights only: MMA groups are issued in the fixed order the producer warp mirrors.
     // (With resident weights every lane issues its own MMAs, see publish() in the worker code.)
     // The k-th group of a lane waits for the k-th completion of that lane's op_ready barrier.
-    if (lane == 0 && !p.resident && crank == 0) {
+    if (lane == 0 && !p.resident) {
       uint32_t slot = 0, wph = 0;
       bool ok = true;
       for (int r = 0; r < nrounds && ok; ++r) {
@@ -361,30 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
           for (int ln = 0; ln < p.lanes && ok; ++ln) {
             if (r * p.lanes + ln >= ntiles) break;
             ok = wait_or_fail(op_ready0 + 8 * ln, (uint32_t)(r * ngroups + g) & 1u, failed, 1);
-            if constexpr (kPair) ok = ok && issue_group_pair(p, ictx, pfull0, ln, g, slot, wph);
-            else ok = ok && issue_group(p, ictx, ln, g, slot, wph);
-          }
-        }
-      }
-    } else if (kPair && lane == 0 && crank == 1) {
-      // peer CTA of a pair: tell the leader when each of OUR weight copies has landed
-      uint32_t slot = 0, wph = 0;
-      bool ok = true;
-      for (int r = 0; r < nrounds && ok; ++r) {
-        for (int g = 0; g < ngroups && ok; ++g) {
-          int layer, ch0, nch;
-          group_span(p, nch0, g, layer, ch0, nch);
-          for (int ln = 0; ln < p.lanes && ok; ++ln) {
-            if (r * p.lanes + ln >= ntiles) break;
-            for (int ch = 0; ch < nch; ++ch) {
-              ok = wait_or_fail(wfull0 + 8 * slot, wph, failed, 8);
-              if (!ok) break;
-              mbar_arrive_remote(map_to_rank(pfull0 + 8 * slot, 0));
-              if (++slot == (uint32_t)p.slots) {
-                slot = 0;
-                wph ^= 1;
-              }
-            }
+            ok = ok && issue_group(p, ictx, ln, g, slot, wph);
           }
         }
       }
@@ -412,9 +338,6 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
             int layer, ch0, nch;
             group_span(p, nch0, g, layer, ch0, nch);
             const uint32_t bytes = p.c[layer] * 128;
-            // CTA pairs: this CTA's half of every chunk (half of the rows = output channels)
-            const uint32_t ld_bytes = p.pair ? bytes >> 1 : bytes;
-            const uint32_t ld_off = p.pair ? crank * (ld_bytes >> 2) : 0u;
             // chunk offsets in wpack: layer 0 at 0, layer 1 after nch0 chunks of c0 rows, ...
             const float* base = p.wpack;
             if (layer >= 1) base += (size_t)nch0 * p.c[0] * 32;
@@ -424,9 +347,9 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
               for (int ch = 0; ch < nch; ++ch) {
                 ok = wait_or_fail(wempty0 + 8 * slot, ph ^ 1, failed, 3);
                 if (!ok) break;
-                mbar_expect_tx(wfull0 + 8 * slot, ld_bytes);
-                bulk_g2s(ring_u32 + slot * p.slot_bytes, base + (size_t)(ch0 + ch) * (bytes >> 2) + ld_off,
-                         ld_bytes, wfull0 + 8 * slot);
+                mbar_expect_tx(wfull0 + 8 * slot, bytes);
+                bulk_g2s(ring_u32 + slot * p.slot_bytes, base + (size_t)(ch0 + ch) * (bytes >> 2), bytes,
+                         wfull0 + 8 * slot);
                 if (++slot == (uint32_t)p.slots) {
                   slot = 0;
                   ph ^= 1;
@@ -564,29 +487,8 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
         }
       } else {
         __syncwarp();
-        if (lane == 0) {
-          if (!kPair || crank == 0) mbar_arrive(op_ready);
-          else mbar_arrive_remote(map_to_rank(op_ready, 0));  // the leader CTA issues for both
-        }
+        if (lane == 0) mbar_arrive(op_ready);
       }
-    };
-
-    // Bias of layer l into this warp's part of the lane's accumulator (every row gets the same vector):
-    // the MMAs then accumulate onto it and the epilogue has no bias add left (32 FADD + 8 LDS per 32
-    // columns per thread, a quarter of its instructions). Exact: the bias never passes through TF32.
-    auto init_acc = [&](int l) {
-      const float* bl = bias_s + (l == 0 ? 0 : p.c[0]);
-      for (int blk = cg; blk < (p.c[l] >> 5); blk += ncg) {
-        uint32_t u[32];
-        const uint4* bl4 = reinterpret_cast<const uint4*>(bl + blk * 32);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint4 b = bl4[j];
-          u[4 * j + 0] = b.x; u[4 * j + 1] = b.y; u[4 * j + 2] = b.z; u[4 * j + 3] = b.w;
-        }
-        tmem_st32(tmem + lane_base + p.acc_col[l] + blk * 32, u);
-      }
-      tmem_st_wait();
     };
 
     // two tail elements (unaligned feature slot / xyz slot / zero slot) of tile t for this thread
@@ -627,7 +529,6 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
     };
     for (int t = ln; t < ntiles && ok; t += p.lanes) {
       const int32_t* trow = rows + t * kTileRows;  // rows of centre g are contiguous: g*ns
-      if (p.bias_init && !p.pre0) init_acc(0);      // (the previous tile's last epilogue has read these columns)
       // ---- layer 0: gather the 128 grouped rows (one pass = `cpp` chunks = 8*cpp slots per row)
       for (int pass = 0; pass < p.npass && ok; ++pass) {
         const int s_lo = pass * p.cpp * 8, s_hi = min(S4, s_lo + p.cpp * 8);
@@ -679,92 +580,11 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
 
       // ---- layers 0 and 1: accumulator -> bias, ReLU, tf32 -> next layer's A operand
       for (int l = 0; l < 2 && ok; ++l) {
-        if (l == 0 && p.pre0) {
-          // Layer 0 is linear in its input [feat_j | (xyz_j - c_i)/r]: the feature half W1f * feat_j does
-          // not depend on the centre and was computed once per POINT (N rows) instead of once per grouped
-          // row (M*ns rows) -- p.feat holds those c0-wide rows. What is left per grouped row is a K = 3
-          // product, done here in fp32 FMAs on TF32-rounded operands while the row is gathered:
-          //   act1[r, c] = relu(P[idx_r, c] + W1x[c] . d_r + b0[c])
-          // written straight into layer 1's A operand. No layer-0 MMA, no W1 stream, no epilogue 0.
-          float4* drow = reinterpret_cast<float4*>(smem + L.drow) + ln * kTileRows;
-          for (int r = lt; r < kTileRows; r += lthreads) {
-            const float4 c = centres[t * cpt + r / ns];
-            const float* pt = cloud + (long)trow[r] * 3;
-            float dx = __fsub_rn(__ldg(pt + 0), c.x), dy = __fsub_rn(__ldg(pt + 1), c.y),
-                  dz = __fsub_rn(__ldg(pt + 2), c.z);
-            if (p.normalize_xyz) {
-              dx = __fmul_rn(dx, scale);
-              dy = __fmul_rn(dy, scale);
-              dz = __fmul_rn(dz, scale);
-            }
-            drow[r] = make_float4(tf32_rna(dx), tf32_rna(dy), tf32_rna(dz), 0.f);
-          }
-          named_sync(2 + ln, lthreads);
-          const int c0 = p.c[0], w = c0 >> 2, total = kTileRows * w;
-          const int w_shift = 31 - __clz(w);  // c0 is a multiple of 32 ...
-          const bool pow2 = (w & (w - 1)) == 0;
-          const float4* b0v = reinterpret_cast<const float4*>(bias_s);
-          const float4* wxv = reinterpret_cast<const float4*>(bias_s + p.c[0] + p.c[1] + p.c[2]);
-          const float4* wyv = wxv + w;
-          const float4* wzv = wyv + w;
-          constexpr int U = 2;
-          for (int e0 = lt; e0 < total; e0 += lthreads * U) {
-            float4 v[U];
-            int rr[U], jj[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const int e = e0 + u * lthreads;
-              rr[u] = -1;
-              if (e < total) {
-                const int r = pow2 ? (e >> w_shift) : (e / w);
-                const int j = e - r * w;
-                v[u] = __ldg(reinterpret_cast<const float4*>(fb + (long)trow[r] * c0) + j);
-                rr[u] = r;
-                jj[u] = j;
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              if (rr[u] < 0) continue;
-              const float4 d = drow[rr[u]];
-              const float4 wx = wxv[jj[u]], wy = wyv[jj[u]], wz = wzv[jj[u]], bb = b0v[jj[u]];
-              float4 o;
-              o.x = fmaxf(v[u].x + fmaf(wz.x, d.z, fmaf(wy.x, d.y, wx.x * d.x)) + bb.x, 0.f);
-              o.y = fmaxf(v[u].y + fmaf(wz.y, d.z, fmaf(wy.y, d.y, wx.y * d.x)) + bb.y, 0.f);
-              o.z = fmaxf(v[u].z + fmaf(wz.z, d.z, fmaf(wy.z, d.y, wx.z * d.x)) + bb.z, 0.f);
-              o.w = fmaxf(v[u].w + fmaf(wz.w, d.z, fmaf(wy.w, d.y, wx.w * d.x)) + bb.w, 0.f);
-              *reinterpret_cast<float4*>(act + (jj[u] >> 3) * kChunkBytes + sw128_offset(rr[u], jj[u] & 7)) =
-                  tf32_operand4(o);
-            }
-          }
-          if (p.bias_init) init_acc(1);
-          publish(p.npass + l, t == ln);
-          SA_STAMP();
-          continue;
-        }
         ok = wait_or_fail(acc_full, accp, failed, 4, p.sleep_ns);
         accp ^= 1;
         tc_fence_after_sync();
         SA_STAMP();
         const float* bl = bias_s + (l == 0 ? 0 : p.c[0]);
-        if (p.bias_init) {
-          for (int blk = cg; blk < (p.c[l] >> 5); blk += ncg) {
-            uint32_t u[32];
-            tmem_ld32(tmem + lane_base + p.acc_col[l] + blk * 32, u);
-            tmem_ld_wait();
-            unsigned char* dst = act + blk * kChunkBytes;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 v;
-              v.x = relu_tf32_op(__uint_as_float(u[4 * j + 0]));
-              v.y = relu_tf32_op(__uint_as_float(u[4 * j + 1]));
-              v.z = relu_tf32_op(__uint_as_float(u[4 * j + 2]));
-              v.w = relu_tf32_op(__uint_as_float(u[4 * j + 3]));
-              *reinterpret_cast<float4*>(dst + sw128_offset(r_epi, j)) = v;
-            }
-          }
-          if (l == 0) init_acc(1);  // layer 1's columns are free: its previous epilogue is long done
-        } else
         for (int blk = cg; blk < (p.c[l] >> 5); blk += ncg) {
           uint32_t u[32];
           tmem_ld32(tmem + lane_base + p.acc_col[l] + blk * 32, u);
@@ -805,10 +625,8 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
         const int nunits = (c3 >> 7) * (4 / upb);
         for (int uidx = cg; uidx < nunits; uidx += ncg) {
           const int h = uidx / (4 / upb), blk0 = (uidx - h * (4 / upb)) * upb;
-          // CTA pairs: this CTA's TMEM holds ITS 128 channels for the tile rows of both CTAs
-          // (columns [0,128) = the leader's tile, [128,256) = the peer's)
-          const int ch = (p.pair ? (int)crank : h) * 128 + q * 32 + (int)lane;
-          const int mt = p.pair ? m_lead + h * p.G + t * cpt : m_tile;
+          const int ch = h * 128 + q * 32 + (int)lane;
+          const int mt = m_tile;
           const float bias_c = b2[ch];
           uint32_t u[32];
           tmem_ld32(tmem + lane_base + p.acc_col[2] + h * 128 + blk0 * 32, u);
@@ -899,12 +717,10 @@ __global__ void __launch_bounds__(kThreads, 1) sa_fused_fwd_kernel(const SaParam
 
   // ---- teardown
   tc_fence_before_sync();
-  if constexpr (kPair) cluster_sync_all();  // the peer may still be reading this CTA's operands / TMEM pair
-  else __syncthreads();
+  __syncthreads();
   if (warp == 0) {
     __syncwarp();
-    if constexpr (kPair) tmem_free2(tmem, p.tmem_cols);
-    else tmem_free(tmem, p.tmem_cols);
+    tmem_free(tmem, p.tmem_cols);
   }
   trace_end(2, trace_t0);
 }
@@ -931,7 +747,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 bool configure(SaParams& p, int B) {
   const int c1 = p.c[0], c2 = p.c[1], c3 = p.c[2];
   const int cpt = kTileRows / p.ns;
-  const int nch0 = (p.K0 + 31) / 32, nch1 = c1 / 32, nch2 = c2 / 32;   // K0 = 0 with a pre-projected layer 0
+  const int nch0 = (p.K0 + 31) / 32, nch1 = c1 / 32, nch2 = c2 / 32;
   const int total_chunks = nch0 + nch1 + nch2;
   const int cmax = c1 > c2 ? (c1 > c3 ? c1 : c3) : (c2 > c3 ? c2 : c3);
   const int act_chunks = nch1 > nch2 ? nch1 : nch2;
@@ -943,14 +759,14 @@ bool configure(SaParams& p, int B) {
   for (int lanes = kMaxLanes; lanes >= 1; lanes >>= 1) {
     if (lanes > max_tiles || lanes > g_sa_max_lanes) continue;
     const int lane_cols = 512 / lanes;
-    if ((p.pre0 ? c2 : c1 + c2) > lane_cols || c3 > lane_cols) continue;
+    if (c1 + c2 > lane_cols || c3 > lane_cols) continue;
     // layer-0 passes of `cpp` chunks: fewer passes first; a pass shorter than the activation
     // region would not shrink the lane's operand region any further
     const int cpp_min = nch0 < act_chunks ? nch0 : act_chunks;
     for (int cpp = nch0; cpp >= cpp_min; --cpp) {
       p.lanes = lanes;
       p.cpp = cpp;
-      p.npass = cpp > 0 ? (nch0 + cpp - 1) / cpp : 0;  // pre-projected layer 0: no layer-0 MMA passes
+      p.npass = (nch0 + cpp - 1) / cpp;
       int region = (cpp > act_chunks ? cpp : act_chunks) * kChunkBytes;
       while (lanes * region < scratch) region += kChunkBytes;
       p.lane_act_bytes = region;
@@ -958,18 +774,10 @@ bool configure(SaParams& p, int B) {
       p.G = max_tiles * cpt;
       // resident weights if they fit, else the deepest ring (>= 2 slots) that does
       p.resident = 1;
-      p.pair = 0;
       p.slots = total_chunks;
       p.slot_bytes = cmax * 128;
       if (total_chunks > kMaxSlots || smem_layout(p).total > budget) {
         p.resident = 0;
-        // streamed weights: CTA pairs when the shapes allow (each CTA then streams half of every
-        // chunk -- 16 KB ring entries -- for twice the rows per byte that crosses L2 -> SM)
-        p.pair = (g_sa_pair && !p.pre0 && c3 == 256 && c1 % 16 == 0 && c2 % 16 == 0 && c1 <= 256 && c2 <= 256) ? 1 : 0;
-        if (p.pair) {
-          const int h1 = c1 / 2, h2 = c2 / 2;
-          p.slot_bytes = (h1 > h2 ? (h1 > 128 ? h1 : 128) : (h2 > 128 ? h2 : 128)) * 128;
-        }
         p.slots = 0;
         for (int sl = kMaxSlots; sl >= 2; --sl) {
           p.slots = sl;
@@ -979,7 +787,7 @@ bool configure(SaParams& p, int B) {
       }
       if (p.slots == 0) continue;
       p.lane_cols = lane_cols;
-      const int a1 = p.pre0 ? 0 : c1;   // no layer-0 accumulator when layer 0 is pre-projected
+      const int a1 = c1;
       p.acc_col[0] = 0;
       p.acc_col[1] = a1;
       p.acc_col[2] = (a1 + c2 + c3 <= lane_cols) ? a1 + c2 : 0;
@@ -1045,16 +853,6 @@ int demf_sa_fused_set_profile(long long* device_buffer) {
 
 /* tuning knobs (development): most tile pipelines per CTA (1, 2 or 4) and the worker warps'
  * back-off between mbarrier polls in ns (0 = spin) */
-int demf_sa_fused_tune_bias_init(int enable) {
-  g_sa_bias_init = enable ? 1 : 0;
-  return 0;
-}
-
-int demf_sa_fused_tune_pair(int enable) {
-  g_sa_pair = enable ? 1 : 0;
-  return 0;
-}
-
 int demf_sa_fused_tune(int max_lanes, int sleep_ns) {
   g_sa_max_lanes = max_lanes < 1 ? 1 : max_lanes;
   g_sa_sleep_ns = sleep_ns < 0 ? 0 : sleep_ns;
@@ -1070,7 +868,7 @@ int demf_sa_fused_error(void) {
 static int sa_fused_launch(const float* xyz, const float* feat_rows, const float* new_xyz, int B, int N, int M,
                            int C, float min_radius, float max_radius, int ns, int normalize_xyz, int query,
                            const float* wpack, const float* bias, int c1, int c2, int c3, const void* grid,
-                           int32_t* idx, float* out, void* stream, int pre0) {
+                           int32_t* idx, float* out, void* stream) {
   DEMF_REQUIRE_PTR(xyz);
   DEMF_REQUIRE_PTR(new_xyz);
   DEMF_REQUIRE_PTR(wpack);
@@ -1096,9 +894,7 @@ static int sa_fused_launch(const float* xyz, const float* feat_rows, const float
   p.M = M;
   p.C = C;
   p.ns = ns;
-  p.pre0 = pre0;
-  p.bias_init = g_sa_bias_init;
-  p.K0 = pre0 ? 0 : ((((C + 3) / 4) * 4 + 4) + 7) / 8 * 8;
+  p.K0 = ((((C + 3) / 4) * 4 + 4) + 7) / 8 * 8;
   p.c[0] = c1;
   p.c[1] = c2;
   p.c[2] = c3;
@@ -1122,41 +918,29 @@ static int sa_fused_launch(const float* xyz, const float* feat_rows, const float
   }
   static_assert(kWorkerWarps * (kGridCap + kGridHist) * 4 <= kCloudTile * 12, "grid scratch fits the tile");
   DEMF_REQUIRE(configure(p, B), DEMF_E_UNSUPPORTED);
-  if (p.pair) p.bias_init = 0;
   const SmemLayout L = smem_layout(p);
 
-  auto kernel = p.pair ? sa_fused_fwd_kernel<true> : sa_fused_fwd_kernel<false>;
-  static int configured_smem[2] = {0, 0};
-  if (L.total > configured_smem[p.pair]) {
+  auto kernel = sa_fused_fwd_kernel;
+  static int configured_smem = 0;
+  if (L.total > configured_smem) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
     if (e != cudaSuccess) {
       set_error("demf_sa_fused_fwd: cannot reserve %d bytes of shared memory: %s", L.total,
                 cudaGetErrorString(e));
       return static_cast<int>(e);
     }
-    configured_smem[p.pair] = L.total;
+    configured_smem = L.total;
   }
   dim3 grid_dim((M + p.G - 1) / p.G, B);
-  // CTA pairs: clusters of two CTAs along x (an odd tail gets a CTA without centres: it still feeds
-  // its pair). The kernel contains cluster instructions, so it is always launched with an explicit
-  // cluster dimension (1 when unpaired).
-  if (p.pair) grid_dim.x = (grid_dim.x + 1) & ~1u;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid_dim;
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = L.total;
   cfg.stream = as_stream(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = p.pair ? 2 : 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
   if (e != cudaSuccess) {
-    set_error("demf_sa_fused_fwd: launch failed: %s (grid %u x %u, cluster %d, %d B smem, lanes %d, slots %d, resident %d)",
-              cudaGetErrorString(e), grid_dim.x, grid_dim.y, p.pair ? 2 : 1, L.total, p.lanes, p.slots, p.resident);
+    set_error("demf_sa_fused_fwd: launch failed: %s (grid %u x %u, %d B smem, lanes %d, slots %d, resident %d)",
+              cudaGetErrorString(e), grid_dim.x, grid_dim.y, L.total, p.lanes, p.slots, p.resident);
     (void)cudaGetLastError();
     return static_cast<int>(e);
   }
@@ -1168,18 +952,7 @@ int demf_sa_fused_fwd(const float* xyz, const float* feat_rows, const float* new
                       const float* wpack, const float* bias, int c1, int c2, int c3, const void* grid,
                       int32_t* idx, float* out, void* stream) {
   return sa_fused_launch(xyz, feat_rows, new_xyz, B, N, M, C, min_radius, max_radius, ns, normalize_xyz, query,
-                         wpack, bias, c1, c2, c3, grid, idx, out, stream, 0);
-}
-
-/* Layer 0 pre-projected per point: proj_rows (B,N,c1) = feat_rows * W1_feat^T (no bias), wpack = the packed
- * images of W2 and W3 only, bias = [b1(c1) | b2(c2) | b3(c3) | W1_xyz^T (3 x c1, TF32-rounded)]. */
-int demf_sa_fused_pre_fwd(const float* xyz, const float* proj_rows, const float* new_xyz, int B, int N, int M,
-                          float min_radius, float max_radius, int ns, int normalize_xyz, int query,
-                          const float* wpack, const float* bias, int c1, int c2, int c3, const void* grid,
-                          int32_t* idx, float* out, void* stream) {
-  DEMF_REQUIRE_PTR(proj_rows);
-  return sa_fused_launch(xyz, proj_rows, new_xyz, B, N, M, c1, min_radius, max_radius, ns, normalize_xyz, query,
-                         wpack, bias, c1, c2, c3, grid, idx, out, stream, 1);
+                         wpack, bias, c1, c2, c3, grid, idx, out, stream);
 }
 
 }  // extern "C"

@@ -615,57 +615,6 @@ def sa_fused(xyz, center_xyz, feat_rows, min_radius, max_radius, sample_num, nor
     return (out, idx) if return_idx else out
 
 
-def sa_pack_mlp_pre(w0, weights, biases):
-    """Packing for `sa_fused_pre`: w0 = the BN-folded first layer (c1, 3+C) in upstream's column order
-    [xyz(3) | feat(C)]; weights = [W2, W3]; biases = [b1, b2, b3].
-    -> (w_feat_t (C,c1) for the per-point projection GEMM, wpack of W2/W3, bias block, widths)."""
-    assert len(weights) == 2 and len(biases) == 3
-    _need_cuda(w0, *weights)
-    lib = _lib.load()
-    dev = w0.device
-    sizes = [int(lib.demf_sa_pack_floats(w.size(0), w.size(1))) for w in weights]
-    with torch.cuda.device_of(w0):
-        wpack = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
-        off = 0
-        for w, n in zip(weights, sizes):
-            w = w.detach().float().contiguous()
-            _lib.check(lib.demf_sa_pack_weights(_p(w), w.size(0), w.size(1),
-                                                wpack.data_ptr() + 4 * off, _stream()),
-                       "demf_sa_pack_weights")
-            off += n
-    w0 = w0.detach().float()
-    w_xyz = w0[:, :3].t().contiguous()                                   # (3, c1)
-    # TF32 operand rounding (nearest, ties away) of the coordinate columns, as the packed matrices get
-    w_xyz = ((w_xyz.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
-    bias = torch.cat([b.detach().float().flatten() for b in biases] + [w_xyz.flatten()]).contiguous()
-    w_feat_t = w0[:, 3:].t().contiguous()                                # (C, c1)
-    return w_feat_t, wpack, bias, (int(w0.size(0)), int(weights[0].size(0)), int(weights[1].size(0)))
-
-
-def sa_fused_pre(xyz, center_xyz, proj_rows, min_radius, max_radius, sample_num, normalize_xyz, wpack,
-                 bias, widths, idx=None, return_idx=False, grid=None):
-    """`sa_fused` with the first layer's feature half already applied per point: proj_rows (B,N,c1)
-    = feat_rows @ W1_feat^T. Inference only."""
-    assert xyz.is_contiguous() and center_xyz.is_contiguous() and proj_rows.is_contiguous()
-    _need_cuda(xyz, center_xyz, proj_rows, wpack, bias)
-    B, N, _ = xyz.shape
-    M = center_xyz.size(1)
-    assert proj_rows.shape == (B, N, widths[0])
-    query = idx is None
-    with torch.cuda.device_of(xyz):
-        out = torch.empty(B, M, widths[2], dtype=torch.float32, device=xyz.device)
-        if query and (return_idx or grid is not None):
-            idx = torch.empty(B, M, sample_num, dtype=torch.int32, device=xyz.device)
-        elif not query:
-            assert idx.is_contiguous() and idx.dtype == torch.int32
-        if out.numel():
-            _lib.check(_lib.load().demf_sa_fused_pre_fwd(
-                _p(xyz), _p(proj_rows), _p(center_xyz), B, N, M, float(min_radius), float(max_radius),
-                int(sample_num), int(bool(normalize_xyz)), int(query), _p(wpack), _p(bias), widths[0],
-                widths[1], widths[2], _p(grid), _p(idx), _p(out), _stream()), "demf_sa_fused_pre_fwd")
-    return (out, idx) if return_idx else out
-
-
 # --------------------------------------------------- fused glue kernels (inference) --
 def chain_indices(level_indices):
     """[idx_0 (B,M0) i32, idx_1 (B,M1) i32, ...] (each indexing the previous level's points) ->

@@ -120,24 +120,6 @@ class BasePointSAModule(nn.Module):
             mlp.__dict__["_sa_pack"] = cache
         return cache[1:]
 
-    # Optional: levels with at least this many input feature channels project them through the first
-    # layer once per POINT (one small GEMM) and hand the kernel the projected rows (P.sa_fused_pre): the
-    # first layer's tensor-core pass, its weight stream and its epilogue disappear from the grouped rows.
-    # Parity-tested, off by default.
-    pre_project_min_channels = 32
-    pre_project = False   # measured on B200: no faster (the kernel is bound by its worker warps' issue slots)
-
-    def _fused_pack_pre(self, mlp):
-        layers = list(mlp)
-        folded = [_folded_cached(cm, None) for cm in layers]
-        key = tuple(fold_key(cm) for cm in layers)
-        cache = mlp.__dict__.get("_sa_pack_pre")
-        if cache is None or cache[0] != key:
-            cache = (key,) + P.sa_pack_mlp_pre(folded[0][0], [folded[1][0], folded[2][0]],
-                                               [b for _, b in folded])
-            mlp.__dict__["_sa_pack_pre"] = cache
-        return cache[1:]
-
     def _fused_ok(self, grouper, mlp, points_xyz, C):
         return (self.fused_eval and self.pool_mod == 'max' and points_xyz.is_cuda
                 and not torch.is_grad_enabled() and len(mlp) == 3
@@ -171,21 +153,6 @@ class BasePointSAModule(nn.Module):
             if self._rows_ok(grouper):
                 feat_rows = None if features is None else as_rows(features)
                 C = 0 if feat_rows is None else feat_rows.size(-1)
-                if self._fused_ok(grouper, mlp, points_xyz, C) and C >= self.pre_project_min_channels \
-                        and self.pre_project:
-                    w_feat_t, wpack, bias, widths = self._fused_pack_pre(mlp)
-                    B, N = feat_rows.shape[:2]
-                    # exact fp32 products for the per-point half (the grouped-row half rounds to TF32)
-                    tf32 = torch.backends.cuda.matmul.allow_tf32
-                    torch.backends.cuda.matmul.allow_tf32 = False
-                    try:
-                        proj = torch.mm(feat_rows.reshape(B * N, C), w_feat_t).view(B, N, -1)
-                    finally:
-                        torch.backends.cuda.matmul.allow_tf32 = tf32
-                    out.append(P.sa_fused_pre(points_xyz, new_xyz.contiguous(), proj, grouper.min_radius,
-                                              grouper.max_radius, grouper.sample_num,
-                                              grouper.normalize_xyz, wpack, bias, widths, grid=grid))
-                    continue
                 if self._fused_ok(grouper, mlp, points_xyz, C) and self.pipe_eval and grouper.min_radius == 0 \
                         and P.sa_pipe_supported(C, grouper.sample_num, [cm.conv.out_channels for cm in mlp],
                                                 new_xyz.size(1)):

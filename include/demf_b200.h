@@ -210,18 +210,6 @@ int demf_sa_fused_fwd(const float* xyz, const float* feat_rows, const float* new
                       const float* wpack, const float* bias, int c1, int c2, int c3,
                       const void* grid /* demf_ball_grid_build workspace of xyz, or NULL */,
                       int32_t* idx, float* out, void* stream);
-/* Same level with its first layer PRE-PROJECTED per point. Layer 0 of the shared MLP is linear in
- * [feat_j | (xyz_j - c_i)/r], so its feature half W1_feat * feat_j is computed once per point (N rows, one
- * library GEMM by the caller) instead of once per grouped row (M*ns rows, 16x more at every level):
- *   proj_rows (B,N,c1) f32 = feat_rows * W1_feat^T (no bias);
- *   wpack = demf_sa_pack_weights images of W2 then W3 only;
- *   bias  = [b1 (c1) | b2 (c2) | b3 (c3) | W1_xyz^T (3 x c1)] (the xyz columns of the folded first layer).
- * The kernel adds the K = 3 coordinate product and the bias while it gathers the row and writes layer 1's
- * operand directly: no layer-0 MMA, no W1 stream, no first epilogue. Other arguments as demf_sa_fused_fwd. */
-int demf_sa_fused_pre_fwd(const float* xyz, const float* proj_rows, const float* new_xyz, int B, int N, int M,
-                          float min_radius, float max_radius, int ns, int normalize_xyz, int query,
-                          const float* wpack, const float* bias, int c1, int c2, int c3, const void* grid,
-                          int32_t* idx, float* out, void* stream);
 int demf_sa_fused_error(void);
 /* The same level as a warp-specialised PIPELINE over 128-row tiles (csrc/sa_pipe.cu) for the geometry whose weights
  * are resident: C = 1 feature channel, widths (64, 64, 128), ns in {16, 32, 64}, M a multiple of 128/ns -- the
@@ -240,8 +228,6 @@ int demf_sa_fused_set_profile(long long* device_buffer);
 /* development knobs: most tile pipelines ("lanes") per CTA (1, 2 or 4; default 4) and the worker
  * warps' back-off between mbarrier polls in ns (default 0 = spin). */
 int demf_sa_fused_tune(int max_lanes, int sleep_ns);
-int demf_sa_fused_tune_pair(int enable); /* CTA pairs (cta_group::2) for streamed weights; default off */
-int demf_sa_fused_tune_bias_init(int enable); /* layers 1-2: bias stored into the TMEM accumulator; default off */
 
 /* ----------------------------------------------------- fused glue (inference) --- */
 /* Each replaces a chain of tiny library launches in the upstream Python modules:

@@ -674,45 +674,6 @@ def test_sa_fused_matches_oracle(dev, B, N, M, C, ns, radius, widths):
     assert torch.equal(out2, out)
 
 
-@pytest.mark.parametrize("B,N,M,C,ns,radius,widths", [
-    (2, 2048, 1024, 128, 32, 0.4, (128, 128, 256)),   # SA2
-    (2, 1024, 512, 256, 16, 0.8, (128, 128, 256)),    # SA3
-    (2, 512, 256, 256, 16, 1.2, (128, 128, 256)),     # SA4
-    (2, 1024, 256, 256, 16, 0.3, (256, 256, 256)),    # vote aggregation (streamed 256-wide layers)
-    (1, 700, 101, 40, 64, 0.5, (32, 64, 96)),         # ragged M, ns = 64, odd widths (butterfly last layer)
-    (3, 300, 37, 8, 32, 0.6, (64, 32, 128)),
-])
-def test_sa_fused_pre_projected_matches_oracle(dev, B, N, M, C, ns, radius, widths):
-    """First layer's feature half applied per point by a GEMM, the K = 3 coordinate half inside the kernel:
-    same index rows, same result class as the fully fused kernel (TF32 oracle 1e-3, fp32 oracle 1e-2)."""
-    sa_module, xyz, centres, feats, weights, biases = _sa_case(B, N, M, C, ns, radius, widths, seed=N + M + 1)
-    w_feat_t, wpack, bias, wd = ops.sa_pack_mlp_pre(weights[0].to(dev), [weights[1].to(dev), weights[2].to(dev)],
-                                                    [b.to(dev) for b in biases])
-    assert wd == tuple(widths) and w_feat_t.shape == (C, widths[0])
-    feat_rows = feats.transpose(1, 2).contiguous().to(dev)
-    torch.backends.cuda.matmul.allow_tf32 = False
-    proj = (feat_rows.reshape(B * N, C) @ w_feat_t).view(B, N, -1)
-    out, idx = ops.sa_fused_pre(xyz.to(dev), centres.to(dev), proj, 0.0, radius, ns, True, wpack, bias, wd,
-                                return_idx=True)
-    torch.cuda.synchronize()
-    assert _lib.load().demf_sa_fused_error() == 0
-    ref_idx, ref_tf32 = sa_module.sa_forward(xyz, centres, feats, 0.0, radius, ns, True, weights, biases, tf32=True)
-    _, ref_fp32 = sa_module.sa_forward(xyz, centres, feats, 0.0, radius, ns, True, weights, biases, tf32=False)
-    assert torch.equal(idx.cpu(), ref_idx)
-    got = out.cpu().transpose(1, 2)
-    scale = ref_fp32.abs().max().item()
-    assert (got - ref_tf32).abs().max().item() <= 1e-3 * scale
-    assert (got - ref_fp32).abs().max().item() <= 1e-2 * scale
-    out2 = ops.sa_fused_pre(xyz.to(dev), centres.to(dev), proj, 0.0, radius, ns, True, wpack, bias, wd, idx=idx)
-    assert torch.equal(out2, out)
-    # and against the fully fused kernel on the same inputs
-    from demf_b200.mm.bricks import permute_weight_columns
-    w0 = permute_weight_columns(weights[0].to(dev), ops.group_rows_columns(C))
-    wp3, b3, wd3 = ops.sa_pack_mlp([w0, weights[1].to(dev), weights[2].to(dev)], [b.to(dev) for b in biases])
-    full = ops.sa_fused(xyz.to(dev), centres.to(dev), feat_rows, 0.0, radius, ns, True, wp3, b3, wd3)
-    assert (full - out).abs().max().item() <= 1e-3 * scale
-
-
 # ----------------------------------------------------------- exact grid ball query --
 @pytest.mark.parametrize("B,N,M,r,ns,min_r,kind", [
     (2, 20000, 2048, 0.2, 64, 0.0, "clustered"),   # SA1
@@ -865,30 +826,22 @@ def test_decode_boxes_matches_coder(dev):
     (2, 1024, 250, 256, 16, 0.3, (256, 256, 256)),    # vote aggregation, ragged: a pair with a centre-less CTA
     (1, 512, 100, 256, 16, 1.2, (128, 128, 256)),     # odd number of CTAs along x
 ])
-def test_sa_fused_cta_pairs_match_oracle(dev, B, N, M, C, ns, radius, widths):
-    """The cta_group::2 variant (two CTAs per MMA, each streaming half of every weight chunk;
-    off by default, demf_sa_fused_tune_pair) gives the same rows and features."""
+def test_sa_fused_streamed_levels_match_oracle(dev, B, N, M, C, ns, radius, widths):
+    """The levels whose weights are streamed through the ring (SA2, SA3, vote aggregation), including ragged centre
+    counts (a last CTA with fewer centres, an odd number of CTAs): rows identical, features to 1e-3 of scale."""
     sa_module, xyz, centres, feats, weights, biases = _sa_case(B, N, M, C, ns, radius, widths, seed=N + M + 1)
     from demf_b200.mm.bricks import permute_weight_columns
     w0 = permute_weight_columns(weights[0].to(dev), ops.group_rows_columns(C))
     wpack, bias, wd = ops.sa_pack_mlp([w0, weights[1].to(dev), weights[2].to(dev)], [b.to(dev) for b in biases])
     rows = feats.transpose(1, 2).contiguous().to(dev)
-    lib = _lib.load()
-    single, idx1 = ops.sa_fused(xyz.to(dev), centres.to(dev), rows, 0.0, radius, ns, True, wpack, bias, wd,
-                                return_idx=True)
-    try:
-        lib.demf_sa_fused_tune_pair(1)
-        paired, idx2 = ops.sa_fused(xyz.to(dev), centres.to(dev), rows, 0.0, radius, ns, True, wpack, bias, wd,
-                                    return_idx=True)
-        torch.cuda.synchronize()
-    finally:
-        lib.demf_sa_fused_tune_pair(0)
-    assert lib.demf_sa_fused_error() == 0
+    out, idx = ops.sa_fused(xyz.to(dev), centres.to(dev), rows, 0.0, radius, ns, True, wpack, bias, wd,
+                            return_idx=True)
+    torch.cuda.synchronize()
+    assert _lib.load().demf_sa_fused_error() == 0
     ref_idx, ref = sa_module.sa_forward(xyz, centres, feats, 0.0, radius, ns, True, weights, biases, tf32=True)
-    assert torch.equal(idx2.cpu(), ref_idx) and torch.equal(idx1, idx2)
+    assert torch.equal(idx.cpu(), ref_idx)
     scale = ref.abs().max().item()
-    assert (paired.cpu().transpose(1, 2) - ref).abs().max().item() <= 1e-3 * scale
-    assert (paired - single).abs().max().item() <= 1e-4 * scale    # same operands, other summation order
+    assert (out.cpu().transpose(1, 2) - ref).abs().max().item() <= 1e-3 * scale
 
 
 # ------------------------------------------------------- FPS chain shortcut (certified pick sequences) ---

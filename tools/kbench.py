@@ -56,8 +56,6 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--sa-lanes", type=int, default=4)
     ap.add_argument("--sa-sleep", type=int, default=0)
-    ap.add_argument("--sa-pair", type=int, default=0)
-    ap.add_argument("--sa-bias-init", type=int, default=0)
     ap.add_argument("--gemm", default="tf32", choices=("tf32", "fp32"), help="library GEMM arithmetic (encoder)")
     ap.add_argument("--profile", action="store_true", help="encoder: print the per-kernel time table")
     args = ap.parse_args()
@@ -65,8 +63,6 @@ def main():
     want = lambda k: not only or k in only  # noqa: E731
     dev = torch.device("cuda:0")
     _lib.load().demf_sa_fused_tune(args.sa_lanes, args.sa_sleep)
-    _lib.load().demf_sa_fused_tune_pair(args.sa_pair)
-    _lib.load().demf_sa_fused_tune_bias_init(args.sa_bias_init)
     B, flush = args.B, not args.hot
     print(json.dumps(dict(device=torch.cuda.get_device_name(0), B=B, flush_l2=flush)), flush=True)
 
@@ -271,19 +267,6 @@ def main():
                              args.reps, flush)
             report("sa_fused", dict(B=B, N=N, M=M, ns=ns, C=C, widths=widths,
                                     TFLOPs_median=round(flops / med / 1e9, 1)), med, mn, hbm)
-            if C >= 32:
-                # first layer pre-projected per point (one GEMM over N rows) + the kernel without layer 0
-                w0 = torch.cat([ws[0][:, K - 4:K - 1], ws[0][:, :C]], 1)      # upstream order [xyz | feat]
-                w_feat_t, wpack2, bias2, wd2 = ops.sa_pack_mlp_pre(w0, [ws[1], ws[2]], bs)
-
-                def pre():
-                    torch.backends.cuda.matmul.allow_tf32 = False
-                    proj = (f.view(B * N, C) @ w_feat_t).view(B, N, -1)
-                    torch.backends.cuda.matmul.allow_tf32 = True
-                    return ops.sa_fused_pre(x, c, proj, 0.0, r, ns, True, wpack2, bias2, wd2)
-                med, mn = timeit(pre, args.reps, flush)
-                report("sa_fused_pre", dict(B=B, N=N, M=M, ns=ns, C=C, widths=widths,
-                                            TFLOPs_median=round(flops / med / 1e9, 1)), med, mn, hbm)
             if N >= 2048:
                 med, mn = timeit(lambda: ops.ball_grid(x, r), args.reps, flush)
                 report("ball_grid_build", dict(B=B, N=N, r=r), med, mn, B * N * 28)
