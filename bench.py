@@ -390,7 +390,7 @@ def time_e2e_images(dev, steps, barrier, max_over_ranks, rank, n_gpus):
     out = {"value": B * n_gpus * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
            "workload": "points + uint8 512x512 image per scene from pinned host memory; pyramid produced on the "
-                       "device by the frozen image branch (ResNet-50 + ChannelMapper as library convolutions, "
+                       "device by the frozen image branch (ResNet-50 + ChannelMapper as fused cuDNN conv+bias+ReLU, BatchNorm folded; "
                        "encoder + forward on demf kernels), TF32"}
     del lanes, model
     torch.cuda.empty_cache()

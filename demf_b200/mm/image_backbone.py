@@ -6,15 +6,48 @@ them under `torch.no_grad()` in `extract_img_feat` (demfnet.py:124-132).
 Same registry names, constructor arguments and state-dict keys as upstream (`conv1`, `bn1`,
 `layerN.M.{conv1,bn1,conv2,bn2,conv3,bn3,downsample.0,downsample.1}`; `convs.N.{conv,gn}`,
 `extra_convs.N.{conv,gn}`), so released checkpoints load. The branch is frozen and its arithmetic is
-plain dense convolution: the convolutions are library kernels (cuDNN, channels-last when on CUDA) --
-SURVEY.md section 8(f) row 2 names them "cuDNN"; the sm_100a kernels of this repository start at the
-encoder's deformable attention.
+plain dense convolution: the convolutions are library kernels (cuDNN, channels-last when on CUDA; in frozen
+inference every conv -> BN -> (add) -> ReLU group is ONE fused cuDNN convolution with the BatchNorm folded into
+its weight and bias) -- SURVEY.md section 8(f) row 2 names them "cuDNN"; the sm_100a kernels of this repository
+start at the encoder's deformable attention.
 """
 import torch
 import torch.nn as nn
 
 from .bricks import BaseModule, ConvModule, build_norm_layer
 from .registry import BACKBONES, NECKS
+
+
+def _fold_bn(conv, bn):
+    """(W', b') with bn(conv(x)) == conv(x; W') + b' for a BatchNorm in eval mode; cached on the modules until one
+    of the five source tensors changes (the branch is frozen: computed once)."""
+    src = (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    key = tuple((t.data_ptr(), t._version) for t in src)
+    hit = conv.__dict__.get('_demf_folded')
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+            w = (conv.weight * scale.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
+            b = (bn.bias - bn.running_mean * scale).contiguous()
+        hit = (key, w, b)
+        conv.__dict__['_demf_folded'] = hit
+    return hit[1], hit[2]
+
+
+def _frozen_inference(x, *bns):
+    """The fused library path applies: CUDA, no autograd, every BatchNorm using its running statistics."""
+    return x.is_cuda and not torch.is_grad_enabled() and all(
+        isinstance(bn, nn.modules.batchnorm._BatchNorm) and not bn.training and bn.track_running_stats for bn in bns)
+
+
+def _conv_bias_relu(x, conv, bn, residual=None):
+    """relu(bn(conv(x)) [+ residual]) as ONE cuDNN fused convolution (BatchNorm folded into weight and bias):
+    the activation tensor is written once instead of conv -> BN -> (add) -> ReLU, each a full pass."""
+    w, b = _fold_bn(conv, bn)
+    if residual is None:
+        return torch.cudnn_convolution_relu(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+    return torch.cudnn_convolution_add_relu(x, w, residual, 1.0, b, conv.stride, conv.padding, conv.dilation,
+                                            conv.groups)
 
 
 class Bottleneck(nn.Module):
@@ -36,7 +69,19 @@ class Bottleneck(nn.Module):
         self.relu = nn.ReLU(inplace=True)
         self.downsample = downsample
 
+    fused_inference = True
+
     def forward(self, x):
+        if self.fused_inference and _frozen_inference(x, self.bn1, self.bn2, self.bn3) and (
+                self.downsample is None or _frozen_inference(x, self.downsample[1])):
+            if self.downsample is None:
+                identity = x
+            else:
+                wd, bd = _fold_bn(self.downsample[0], self.downsample[1])
+                identity = nn.functional.conv2d(x, wd, bd, self.downsample[0].stride)
+            out = _conv_bias_relu(x, self.conv1, self.bn1)
+            out = _conv_bias_relu(out, self.conv2, self.bn2)
+            return _conv_bias_relu(out, self.conv3, self.bn3, residual=identity)
         identity = x if self.downsample is None else self.downsample(x)
         out = self.relu(self.bn1(self.conv1(x)))
         out = self.relu(self.bn2(self.conv2(out)))
@@ -123,7 +168,10 @@ class ResNet(BaseModule):
     def forward(self, x):
         if x.is_cuda and x.dim() == 4:   # NHWC is what the library's tensor-core convolutions want
             x = x.contiguous(memory_format=torch.channels_last)
-        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        if Bottleneck.fused_inference and _frozen_inference(x, self.bn1):
+            x = self.maxpool(_conv_bias_relu(x, self.conv1, self.bn1))
+        else:
+            x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
         outs = []
         for i, name in enumerate(self.res_layers):
             x = getattr(self, name)(x)

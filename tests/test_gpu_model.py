@@ -643,3 +643,42 @@ def test_mha_training_path_matches_nn_multihead_attention(dev, shared_qk):
     for a, b in zip(res["tf32"], res["fp32"]):
         assert a.shape == b.shape
         assert (a - b).norm() <= 1e-2 * b.norm() + 1e-7, ((a - b).norm().item(), b.norm().item())
+
+
+@pytest.mark.gpu
+def test_resnet_fused_inference_matches_plain_path(dev):
+    """Frozen ResNet-50 in inference: every conv -> BN -> (add) -> ReLU group as one fused cuDNN convolution with the
+    BatchNorm folded in (mm/image_backbone.py) against the module-by-module path, strict fp32: all four stage outputs
+    to 1e-4 of their scale; and the folded weights are refreshed when a source tensor changes."""
+    from demf_b200.mm.image_backbone import Bottleneck, ResNet
+    torch.manual_seed(2)
+    net = ResNet(depth=50, frozen_stages=4, norm_eval=True).to(dev).eval()
+    g = torch.Generator(device=dev).manual_seed(9)
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5, generator=g)
+                m.bias.normal_(0, 0.1, generator=g)
+                m.running_mean.normal_(0, 0.1, generator=g)
+                m.running_var.uniform_(0.5, 1.5, generator=g)
+    x = torch.randn(2, 3, 256, 320, generator=g, device=dev)
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            fused = net(x)
+            Bottleneck.fused_inference = False
+            plain = net(x)
+            Bottleneck.fused_inference = True
+            net.layer1[0].bn1.weight.mul_(2.0)          # a source tensor changes -> the fold is rebuilt
+            fused2 = net(x)
+            Bottleneck.fused_inference = False
+            plain2 = net(x)
+    finally:
+        Bottleneck.fused_inference = True
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    for a, b in list(zip(fused, plain)) + list(zip(fused2, plain2)):
+        assert a.shape == b.shape
+        assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item()
+    assert not torch.allclose(fused[0], fused2[0])
