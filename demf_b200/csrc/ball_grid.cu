@@ -129,23 +129,31 @@ __global__ void __launch_bounds__(kBuildThreads) ball_grid_build_kernel(const fl
 
 constexpr int kQueryWarps = 8;
 
+// kBitmap: selection through a per-warp bitmap over the index range (ball_grid_query_bitmap_warp) when N / 8 bytes
+// per warp fit; otherwise the hit-buffer form.
+template <bool kBitmap>
 __global__ void __launch_bounds__(kQueryWarps * 32) ball_query_grid_kernel(
     const float* __restrict__ xyz, const float* __restrict__ new_xyz, const void* __restrict__ grid, int N, int M,
     float min_r2, float max_r2, int ns, int32_t* __restrict__ idx) {
-  extern __shared__ int smem_i[];
+  extern __shared__ __align__(16) int smem_i[];
   const unsigned long long trace_t0 = trace_begin();
   const unsigned lane = lane_id();
   const int warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int m = blockIdx.x * kQueryWarps + warp;
   if (m >= M) return;
-  int* buf = smem_i + warp * (kGridCap + kGridHist);
-  int* hist = buf + kGridCap;
-  int32_t* row = smem_i + kQueryWarps * (kGridCap + kGridHist) + warp * ns;
+  const int scratch = kBitmap ? ball_bitmap_words(N) : kGridCap + kGridHist;
+  int* buf = smem_i + warp * scratch;
+  int32_t* row = smem_i + kQueryWarps * scratch + warp * ns;
   const float* c = new_xyz + ((long)b * M + m) * 3;
   const BallGridView g = ball_grid_view(grid, b, N);
-  ball_query_warp(g, xyz + (long)b * N * 3, N, __ldg(c), __ldg(c + 1), __ldg(c + 2), min_r2, max_r2, ns, row,
-                  buf, hist, lane);
+  const float cx = __ldg(c), cy = __ldg(c + 1), cz = __ldg(c + 2);
+  if (kBitmap && max_r2 <= g.h.radius * g.h.radius)
+    ball_grid_query_bitmap_warp(g, N, cx, cy, cz, min_r2, max_r2, ns, row, reinterpret_cast<unsigned*>(buf), lane);
+  else if (kBitmap)
+    ball_scan_warp(xyz + (long)b * N * 3, N, cx, cy, cz, min_r2, max_r2, ns, row, lane);
+  else
+    ball_query_warp(g, xyz + (long)b * N * 3, N, cx, cy, cz, min_r2, max_r2, ns, row, buf, buf + kGridCap, lane);
   int32_t* out = idx + ((long)b * M + m) * ns;
   for (int l = lane; l < ns; l += 32) out[l] = row[l];
   trace_end(3, trace_t0);
@@ -155,15 +163,18 @@ __global__ void __launch_bounds__(kQueryWarps * 32) ball_query_grid_kernel(
 
 int launch_ball_query_grid(const float* xyz, const float* new_xyz, const void* grid, int B, int N, int M,
                            float min_radius, float max_radius, int ns, int32_t* idx, cudaStream_t stream) {
-  const size_t smem = (size_t)kQueryWarps * (kGridCap + kGridHist + ns) * 4;
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    cudaFuncSetAttribute(ball_query_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
+  // the bitmap form wants N/8 bytes per warp: up to 8 KB (N = 65 536) keeps 3 CTAs of 8 warps on an SM
+  const bool bitmap = ball_bitmap_words(N) * 4 <= 8 * 1024;
+  const size_t smem = (size_t)kQueryWarps * ((bitmap ? ball_bitmap_words(N) : kGridCap + kGridHist) + ns) * 4;
+  auto kernel = bitmap ? ball_query_grid_kernel<true> : ball_query_grid_kernel<false>;
+  static size_t configured[2] = {48 * 1024, 48 * 1024};
+  if (smem > configured[bitmap]) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured[bitmap] = smem;
   }
   dim3 grid_dim((M + kQueryWarps - 1) / kQueryWarps, B);
-  ball_query_grid_kernel<<<grid_dim, kQueryWarps * 32, smem, stream>>>(
-      xyz, new_xyz, grid, N, M, min_radius * min_radius, max_radius * max_radius, ns, idx);
+  kernel<<<grid_dim, kQueryWarps * 32, smem, stream>>>(xyz, new_xyz, grid, N, M, min_radius * min_radius,
+                                                      max_radius * max_radius, ns, idx);
   return after_launch("ball_query_grid_kernel");
 }
 

@@ -212,6 +212,95 @@ __device__ __forceinline__ int ball_grid_query_warp(const BallGridView& g, int N
   return -1;
 }
 
+// The same query with the selection done through a BITMAP over the index range (the stand-alone launch, where a
+// warp can afford N/8 bytes of shared memory): every hit sets bit k of `bm`; the row -- the ns smallest hit indices in
+// ascending order -- is then read off the bitmap with a popcount prefix over the lanes' word ranges. One pass over
+// the candidates, no hit buffer, no histogram, no O(hits^2) ranking (31 % of the instructions of the buffer form at
+// the first level), and no overflow case: any number of hits is handled. `bm`: `ball_bitmap_words(N)` words.
+__host__ __device__ inline int ball_bitmap_lane_words(int N) { return ((((N + 31) >> 5) + 31) / 32 + 3) & ~3; }
+__host__ __device__ inline int ball_bitmap_words(int N) { return 32 * ball_bitmap_lane_words(N); }
+
+__device__ __forceinline__ int ball_grid_query_bitmap_warp(const BallGridView& g, int N, float cx, float cy, float cz,
+                                                           float min_r2, float max_r2, int ns, int32_t* row,
+                                                           unsigned* bm, unsigned lane) {
+  const int ix = ball_grid_coord(cx, g.h.x0, g.h.inv_h);
+  const int iy = ball_grid_coord(cy, g.h.y0, g.h.inv_h);
+  const int iz = ball_grid_coord(cz, g.h.z0, g.h.inv_h);
+  const int zlo = max(iz - 1, 0), zhi = min(iz + 1, g.h.nz - 1);
+  const int per = ball_bitmap_lane_words(N);          // words per lane, a multiple of 4
+  uint4* mine = reinterpret_cast<uint4*>(bm + lane * per);
+  for (int i = 0; i < per / 4; ++i) mine[i] = make_uint4(0u, 0u, 0u, 0u);
+  // the 3x3 cell columns as one flat candidate range (see ball_grid_query_warp)
+  int cbeg = 0, clen = 0;
+  if (lane < 9 && zlo <= zhi) {
+    const int x = ix - 1 + (int)lane / 3, y = iy - 1 + (int)lane % 3;
+    if (x >= 0 && x < g.h.nx && y >= 0 && y < g.h.ny) {
+      const int c0 = (x * kGridY + y) * kGridZ;
+      cbeg = __ldg(g.cell_start + c0 + zlo);
+      clen = __ldg(g.cell_start + c0 + zhi + 1) - cbeg;
+    }
+  }
+  int incl = clen;
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((int)lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 8);
+  int coff[9], cb[9];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) {
+    coff[c] = __shfl_sync(0xffffffffu, incl - clen, c);
+    cb[c] = __shfl_sync(0xffffffffu, cbeg, c) - coff[c];   // candidate t of column c is sorted[cb[c] + t]
+  }
+  __syncwarp();
+  for (int t0 = 0; t0 < total; t0 += 32) {
+    const int t = t0 + (int)lane;
+    if (t < total) {
+      int base = cb[0];
+#pragma unroll
+      for (int c = 1; c < 9; ++c)
+        if (t >= coff[c]) base = cb[c];
+      const float4 p = __ldg(g.sorted + base + t);
+      const int k = __float_as_int(p.w);
+      const float d2 = sqdist(cx, cy, cz, p.x, p.y, p.z);
+      if ((d2 == 0.f) || (d2 >= min_r2 && d2 < max_r2)) atomicOr(bm + (k >> 5), 1u << (k & 31));
+    }
+  }
+  __syncwarp();
+  // popcount prefix over the lanes' word ranges, then every lane writes the indices of its set bits
+  int mycount = 0;
+  for (int i = 0; i < per / 4; ++i) {
+    const uint4 v = mine[i];
+    mycount += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+  }
+  int upto = mycount;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, upto, o);
+    if ((int)lane >= o) upto += t;
+  }
+  const int cnt = __shfl_sync(0xffffffffu, upto, 31);
+  int pos = upto - mycount;
+  if (mycount > 0 && pos < ns) {
+    const unsigned* w = bm + lane * per;
+    for (int i = 0; i < per && pos < ns; ++i) {
+      unsigned v = w[i];
+      while (v != 0u && pos < ns) {
+        const int bit = __ffs(v) - 1;
+        v &= v - 1u;
+        row[pos++] = ((int)lane * per + i) * 32 + bit;
+      }
+    }
+  }
+  __syncwarp();
+  const int kept = min(cnt, ns);
+  const int first = cnt > 0 ? row[0] : 0;
+  for (int l = kept + lane; l < ns; l += 32) row[l] = first;
+  __syncwarp();
+  return kept;
+}
+
 // Full scan of the cloud by one warp straight from global memory (rare fallback of the grid path).
 __device__ __forceinline__ int ball_scan_warp(const float* __restrict__ cloud, int N, float cx, float cy,
                                               float cz, float min_r2, float max_r2, int ns, int32_t* row,
