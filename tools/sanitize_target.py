@@ -1,6 +1,6 @@
 """Small invocations of the protocol-heavy kernels (mbarrier / TMEM / DSMEM / TMA) for compute-sanitizer:
-fps_cluster_kernel, fps_grid_kernel, sa_fused_fwd_kernel, rows_gemm_kernel (fwd + statistics, dgrad through
-BatchNorm), wgrad_kernel, msda fwd/bwd. Results are checked so that a tool-induced failure is visible.
+fps_cluster_kernel, fps_grid_kernel, sa_fused_fwd_kernel, sa_pipe_kernel, ball_query_grid_kernel (bitmap selection),
+rows_gemm_kernel (fwd + statistics, dgrad through BatchNorm), wgrad_kernel, col_sum_add_kernel, msda fwd/bwd. Results are checked so that a tool-induced failure is visible.
 
     compute-sanitizer --tool memcheck  python tools/sanitize_target.py
     compute-sanitizer --tool racecheck python tools/sanitize_target.py
@@ -38,6 +38,23 @@ if want("sa"):
     torch.cuda.synchronize()
     assert torch.isfinite(out).all() and int(_lib.load().demf_sa_fused_error()) == 0
     print("sa_fused ok", float(out.abs().mean()))
+if want("pipe"):
+    g = torch.Generator().manual_seed(2)
+    f1 = torch.randn(2, 4096, 1, generator=g).to(dev)
+    centres = ops.gather_rows(pts, ops.furthest_point_sample(pts, 64)).contiguous()
+    ws = [torch.randn(co, ci, generator=g).to(dev) / ci ** 0.5 for co, ci in ((64, 4), (64, 64), (128, 64))]
+    bs = [torch.randn(co, generator=g).to(dev) * 0.1 for co in (64, 64, 128)]
+    w0 = permute_weight_columns(ws[0], ops.group_rows_columns(1))
+    wpack, bias, widths = ops.sa_pack_mlp([w0, ws[1], ws[2]], bs)
+    grid = ops.ball_grid(pts, 0.4)
+    nbr = ops.ball_query_grid(0.0, 0.4, 32, pts, centres, grid)
+    assert torch.equal(nbr, ops.ball_query(0.0, 0.4, 32, pts, centres)), "bitmap grid query != scan"
+    packed = torch.cat([pts, f1], -1).contiguous()
+    a = ops.sa_pipe(pts, centres, f1, 0.4, 32, True, wpack, bias, nbr, packed=packed)
+    b = ops.sa_fused(pts, centres, f1, 0.0, 0.4, 32, True, wpack, bias, widths, idx=nbr)
+    torch.cuda.synchronize()
+    assert ops.sa_pipe_error() == 0 and (a - b).abs().max() <= 1e-5 * b.abs().max()
+    print("sa_pipe + ball_query_grid ok", float(a.abs().mean()))
 if want("gemm"):
     g = torch.Generator(device=dev).manual_seed(1)
     R, K, N = 640, 64, 128
@@ -49,7 +66,9 @@ if want("gemm"):
     st2 = ops.bn_rows_state(K, dev)
     gm = ops.gemm_rows_dgrad_bn(dy, w, x, x.mean(0), 1.0 / x.std(0), torch.ones(K, device=dev), torch.zeros(K, device=dev), st2)
     dw = torch.zeros(N, K, device=dev); ops.gemm_wgrad_(dw, dy, x)
+    db = torch.zeros(N, device=dev); ops.col_sum_add_(db, dy)
     torch.cuda.synchronize()
+    assert (db - dy.sum(0)).abs().max() < 1e-3
     assert (y - x @ w.t()).abs().max() < 2e-2 and (dw - dy.t() @ x).abs().max() < 0.2 and ops.gemm_error() == 0
     assert torch.allclose(mean, y.mean(0), atol=1e-4)
     print("gemm ok", float(gm.abs().mean()))
