@@ -95,8 +95,9 @@ __device__ __forceinline__ void wait_flag(uint32_t bar, uint32_t parity, int cod
 __device__ __forceinline__ void arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// bar.sync over one role's warps: orders their shared-memory stores (it drains them) before the single thread that
-// then crosses to the async proxy and signals the MMA issuer -- one fence per tile instead of one per warp
+// bar.sync over one role's warps. The canonical hand-off of operands written with ordinary stores to the tensor
+// core (async proxy): every WRITER executes fence.proxy.async, the role meets at this barrier, ONE thread arrives on
+// the mbarrier the MMA issuer waits for (one arrive per tile instead of one per warp).
 __device__ __forceinline__ void role_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -306,9 +307,9 @@ __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams
               make_float4(tf32_op(dx), tf32_op(dy), tf32_op(dz), tf32_op(0.f));
         }
       }
+      fence_proxy_async();
       role_sync(1, 128);
       if (warp == 4 && lane == 0) {
-        fence_proxy_async();
 #pragma unroll
         for (int d = 0; d < kBatch; ++d)
           if (j0 + d < nt) arrive(bar(0, (j0 + d) & 7));
@@ -378,11 +379,9 @@ __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams
           *reinterpret_cast<float4*>(dst + sw128_offset((uint32_t)row, (uint32_t)(4 * half + s))) = v[s];
       }
       SAP_T(1, threadIdx.x == 256);
+      fence_proxy_async();
       role_sync(2 + e, 256);
-      if (((warp - 8) & 7) == 0 && lane == 0) {
-        fence_proxy_async();
-        arrive(bar(k_afull, b));
-      }
+      if (((warp - 8) & 7) == 0 && lane == 0) arrive(bar(k_afull, b));
       SAP_T(2, threadIdx.x == 256);
     }
   } else if (warp >= 24) {
