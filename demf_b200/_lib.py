@@ -74,6 +74,9 @@ _SIGNATURES = {
                              _ptr, _ptr, _ptr, _ptr],
     "demf_bn_rows_apply": [_ptr, ctypes.c_long, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr],
     "demf_bn_max_rows_apply": [_ptr, ctypes.c_long, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "demf_mha_supported": [_c_int],
+    "demf_mha_fwd": [_ptr, ctypes.c_long, _ptr, ctypes.c_long, _ptr, ctypes.c_long, _ptr, ctypes.c_long, _c_int, _c_int,
+                     _c_int, _c_int, _c_int, _c_float, _c_int, _ptr],
     "demf_col_sum_add": [_ptr, ctypes.c_long, _c_int, ctypes.c_long, _ptr, _ptr],
     "demf_bn_rows_bwd_apply": [_ptr, _ptr, ctypes.c_long, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "demf_gemm_rows_dgrad_bn": [_ptr, ctypes.c_long, _ptr, ctypes.c_long, ctypes.c_long, _c_int, _c_int, _ptr,

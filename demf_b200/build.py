@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(PKG, "libdemf_b200.so")
-SOURCES = ["capi.cu", "msda.cu", "fps.cu", "ball_query.cu", "point_ops.cu", "rows.cu", "sa_fused.cu", "ball_grid.cu", "glue.cu", "postprocess.cu", "bn_rows.cu", "gemm_tf32.cu", "loss.cu", "sa_pipe.cu"]
+SOURCES = ["capi.cu", "msda.cu", "fps.cu", "ball_query.cu", "point_ops.cu", "rows.cu", "sa_fused.cu", "ball_grid.cu", "glue.cu", "postprocess.cu", "bn_rows.cu", "gemm_tf32.cu", "loss.cu", "sa_pipe.cu", "mha.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "umma.cuh"), os.path.join(CSRC, "ball_grid.cuh"), os.path.join(PKG, "..", "include", "demf_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]

@@ -193,6 +193,8 @@ class MultiheadAttention(BaseModule):
             query, key, value = (t.transpose(0, 1) for t in (query, key, value))
         out = self._attn_train_rows(query, key, value, attn_mask, key_padding_mask, shared_qk)
         if out is None:
+            out = self._attn_eval_rows(query, key, value, attn_mask, key_padding_mask, shared_qk)
+        if out is None:
             # the attention map itself is never used: without it PyTorch takes its fused
             # scaled-dot-product path instead of mul + bmm + softmax + bmm + mean
             out = self.attn(query=query, key=key, value=value, attn_mask=attn_mask,
@@ -263,7 +265,38 @@ def _mha_train_rows(self, query, key, value, attn_mask, key_padding_mask, shared
     return o.view(Lq, B, E)
 
 
+def _mha_eval_rows(self, query, key, value, attn_mask, key_padding_mask, shared_qk):
+    """nn.MultiheadAttention.forward (need_weights=False) in INFERENCE on CUDA: the projections are the library's
+    bias GEMMs (one for q and k together when they are the same tensor), the attention itself our exact-fp32 kernel
+    (csrc/mha.cu) instead of torch's sm80 memory-efficient attention. (L,B,E) in, (L,B,E) out; None when the case is
+    not this plain one."""
+    from . import point_ops as P
+    attn = self.attn
+    if not (not torch.is_grad_enabled() and not attn.training and query.is_cuda and query.dtype == torch.float32
+            and attn_mask is None and key_padding_mask is None and attn._qkv_same_embed_dim
+            and attn.in_proj_weight is not None and attn.in_proj_bias is not None and attn.bias_k is None
+            and not attn.add_zero_attn and query.dim() == 3 and attn.embed_dim % attn.num_heads == 0
+            and attn.out_proj.bias is not None and self.fused_eval_attention
+            and P.mha_supported(attn.embed_dim // attn.num_heads)):
+        return None
+    E, H = attn.embed_dim, attn.num_heads
+    Lq, B, _ = query.shape
+    w, b = attn.in_proj_weight, attn.in_proj_bias
+    q2, k2, v2 = query.reshape(-1, E), key.reshape(-1, E), value.reshape(-1, E)
+    if shared_qk:
+        qk = torch.addmm(b[:2 * E], q2, w[:2 * E].t())          # (L*B, 2E): q | k
+        q, k = qk[:, :E], qk[:, E:]
+    else:
+        q, k = torch.addmm(b[:E], q2, w[:E].t()), torch.addmm(b[E:2 * E], k2, w[E:2 * E].t())
+    v = torch.addmm(b[2 * E:], v2, w[2 * E:].t())
+    o = P.mha_rows(q, k, v, B, H)
+    o = torch.addmm(attn.out_proj.bias, o, attn.out_proj.weight.t())
+    return o.view(Lq, B, E)
+
+
 MultiheadAttention._attn_train_rows = _mha_train_rows
+MultiheadAttention._attn_eval_rows = _mha_eval_rows
+MultiheadAttention.fused_eval_attention = True   # False: nn.MultiheadAttention's own scaled_dot_product_attention
 
 
 @FEEDFORWARD_NETWORK.register_module()

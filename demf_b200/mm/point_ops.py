@@ -1093,6 +1093,31 @@ class _StageLoss(torch.autograd.Function):
         return gs[0], gs[1], gs[2], gs[3], gs[4], g_sem, None, None
 
 
+def mha_supported(head_dim):
+    return bool(_lib.load().demf_mha_supported(int(head_dim)))
+
+
+def mha_rows(q, k, v, B, H, scale=None, batch_first=False):
+    """softmax(q k^T * scale) v per (scene, head) in exact fp32 (csrc/mha.cu), inference only. q (Lq*B, E) rows of a
+    (Lq, B, E) tensor (a column slice of a wider projection is fine: unit column stride, 16-byte aligned rows), k / v
+    (Lk*B, E); heads are the H column groups of width E / H. `batch_first`: the rows are those of (B, L, E) tensors
+    instead. -> (Lq*B, E) in the same row order."""
+    _need_cuda(q, k, v)
+    E = q.shape[1]
+    D = E // H
+    Lq, Lk = q.shape[0] // B, k.shape[0] // B
+    for t in (q, k, v):
+        assert t.dim() == 2 and t.stride(1) == 1 and t.dtype == torch.float32 and t.shape[1] == E
+    assert k.shape[0] == v.shape[0] and q.shape[0] == Lq * B and k.shape[0] == Lk * B and D * H == E
+    out = torch.empty(Lq * B, E, dtype=torch.float32, device=q.device)
+    with torch.cuda.device_of(q):
+        _lib.check(_lib.load().demf_mha_fwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out),
+                                            out.stride(0), Lq, Lk, B, H, D,
+                                            float(D ** -0.5 if scale is None else scale), int(bool(batch_first)),
+                                            _stream()), "demf_mha_fwd")
+    return out
+
+
 def col_sum_add_(out, x):
     """out (N,) += x (R,N).sum(0) in one launch (csrc/bn_rows.cu): the bias gradient of a Linear layer."""
     _need_cuda(out, x)

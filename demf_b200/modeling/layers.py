@@ -119,11 +119,16 @@ class DeMFTransformerDecoderLayer(nn.Module):
         H = mha.num_heads
         xp = x + pos
         w_in, b_in = mha.in_proj_weight, mha.in_proj_bias
-        qk = torch.addmm(b_in[:2 * C], xp, w_in[:2 * C].t()).view(B, Q, 2, H, C // H)
-        v = torch.addmm(b_in[2 * C:], x, w_in[2 * C:].t()).view(B, Q, H, C // H)
-        att = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2),
-                                             v.transpose(1, 2))     # (B,H,Q,d)
-        att = att.transpose(1, 2).reshape(B * Q, C)
+        qk = torch.addmm(b_in[:2 * C], xp, w_in[:2 * C].t())       # (B*Q, 2C): q | k
+        v = torch.addmm(b_in[2 * C:], x, w_in[2 * C:].t())
+        if P.mha_supported(C // H):
+            # exact-fp32 attention among the proposals (csrc/mha.cu) instead of torch's sm80 memory-efficient kernel
+            att = P.mha_rows(qk[:, :C], qk[:, C:], v, B, H, batch_first=True)
+        else:
+            qk5 = qk.view(B, Q, 2, H, C // H)
+            att = F.scaled_dot_product_attention(qk5[:, :, 0].transpose(1, 2), qk5[:, :, 1].transpose(1, 2),
+                                                 v.view(B, Q, H, C // H).transpose(1, 2))     # (B,H,Q,d)
+            att = att.transpose(1, 2).reshape(B * Q, C)
         t = torch.mm(att, mha.out_proj.weight.t())
         x, xp = P.bias_layer_norm_rows(t, n1.weight, n1.bias, n1.eps, bias=mha.out_proj.bias, residual=x,
                                        out=t, post_add=pos)

@@ -285,6 +285,16 @@ int demf_bn_max_rows_bwd(const float* grad_pooled, const float* pooled, const ui
                          void* state, float* coef, float* grad_x, float* grad_gamma, float* grad_beta,
                          void* stream);
 
+/* Scaled-dot-product attention of one nn.MultiheadAttention call in inference (csrc/mha.cu), exact fp32: q (Lq*B, .)
+ * rows with stride ldq floats -- token l of scene b is row l*B + b (b*L + l when batch_first), head h occupies columns
+ * [h*D, h*D + D) -- k / v
+ * (Lk*B, .) likewise; o (Lq*B, .) = softmax(q k^T * scale) v per (scene, head). D in {32, 36, 64}; row starts and
+ * strides 16-byte aligned; K and V of one head (Lk * D * 8 bytes) must fit 200 KB of shared memory. Replaces torch's
+ * scaled_dot_product_attention (an sm80 memory-efficient kernel) under the decoder layer's self-attention among the
+ * proposals (demf/modeling/layers/transformer.py:55-80; configs/demf/demf_votenet.py:76-78). */
+int demf_mha_supported(int D);
+int demf_mha_fwd(const float* q, long ldq, const float* k, long ldk, const float* v, long ldv, float* o, long ldo,
+                 int Lq, int Lk, int B, int H, int D, float scale, int batch_first, void* stream);
 /* out[c] += sum over the R rows of x (R, N), row stride ld floats: the bias gradient of a Linear / 1x1 convolution
  * accumulated in place (autograd's grad.sum(0) + accumulate in one launch). */
 int demf_col_sum_add(const float* x, long R, int N, long ld, float* out, void* stream);

@@ -927,3 +927,56 @@ def test_sa_pipe_matches_sa_fused_and_oracle(dev, B, N, M, r, ns):
         ref_idx, ref_out = sa_module.sa_forward(xyz, centres.cpu(), feats, 0.0, r, ns, True, ws, bs, tf32=True)
         assert torch.equal(nbr.cpu(), ref_idx)
         assert (got.cpu().transpose(1, 2) - ref_out).abs().max().item() <= 1e-3 * ref_out.abs().max().item()
+
+
+# ------------------------------------------------- attention among the proposals (csrc/mha.cu) ---
+@pytest.mark.parametrize("Lq,Lk,B,H,D", [(256, 256, 8, 8, 36), (100, 77, 3, 4, 32), (64, 300, 2, 2, 64),
+                                         (1, 1, 1, 1, 36), (130, 16, 2, 8, 36)])
+def test_mha_rows_matches_torch_sdpa(dev, Lq, Lk, B, H, D):
+    """The exact-fp32 attention kernel against torch's math scaled_dot_product_attention in fp64 on the same rows,
+    incl. ragged query / key counts and q, k taken as column slices of one packed projection: 2e-5 of scale."""
+    g = torch.Generator(device=dev).manual_seed(Lq + Lk + D)
+    E = H * D
+    qk = torch.randn(Lq * B, 2 * E, generator=g, device=dev) if Lq == Lk else None
+    q = qk[:, :E] if qk is not None else torch.randn(Lq * B, E, generator=g, device=dev)
+    k = qk[:, E:] if qk is not None else torch.randn(Lk * B, E, generator=g, device=dev)
+    v = torch.randn(Lk * B, E, generator=g, device=dev)
+    got = ops.mha_rows(q, k, v, B, H)
+
+    def heads(t, L):
+        return t.double().reshape(L, B, H, D).permute(1, 2, 0, 3)
+    want = torch.softmax(heads(q, Lq) @ heads(k, Lk).transpose(-1, -2) * D ** -0.5, -1) @ heads(v, Lk)
+    want = want.permute(2, 0, 1, 3).reshape(Lq * B, E)
+    torch.cuda.synchronize()
+    assert (got.double() - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+    # the same problem with (B, L, E) rows: same numbers in the other row order
+    def bf(t, L):
+        return t.reshape(L, B, E).transpose(0, 1).reshape(B * L, E).contiguous()
+    got_bf = ops.mha_rows(bf(q, Lq), bf(k, Lk), bf(v, Lk), B, H, batch_first=True)
+    assert torch.equal(got_bf.reshape(B, Lq, E).transpose(0, 1).reshape(Lq * B, E), got)
+
+
+def test_multihead_attention_eval_matches_torch_module(dev):
+    """bricks.MultiheadAttention in inference (library projections + csrc/mha.cu) against the nn.MultiheadAttention it
+    wraps, strict fp32, self-attention with positional encodings as the decoder layer calls it."""
+    from demf_b200 import engine
+    from demf_b200.mm.bricks import MultiheadAttention
+    torch.manual_seed(7)
+    mha = MultiheadAttention(288, 8, attn_drop=0.1, proj_drop=0.0).to(dev).eval()
+    g = torch.Generator(device=dev).manual_seed(8)
+    x = torch.randn(256, 4, 288, generator=g, device=dev)
+    pos = torch.randn(256, 4, 288, generator=g, device=dev)
+    mem = torch.randn(300, 4, 288, generator=g, device=dev)
+    engine.set_gemm_precision("fp32")
+    try:
+        with torch.no_grad():
+            n0 = _lib.launch_count()
+            a1, a2 = mha(x, query_pos=pos), mha(x, key=mem, value=mem, query_pos=pos)
+            assert _lib.launch_count() - n0 == 2
+            MultiheadAttention.fused_eval_attention = False
+            b1, b2 = mha(x, query_pos=pos), mha(x, key=mem, value=mem, query_pos=pos)
+    finally:
+        MultiheadAttention.fused_eval_attention = True
+        engine.set_gemm_precision("tf32")
+    for a, b in ((a1, b1), (a2, b2)):
+        assert (a - b).abs().max().item() <= 2e-5 * b.abs().max().item()
