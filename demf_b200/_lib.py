@@ -7,8 +7,7 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-# DEMF_B200_LIB: a diagnostic build of the same library (tools/sap_variants.sh); never a different backend
-LIB_PATH = os.environ.get("DEMF_B200_LIB") or os.path.join(_PKG, "libdemf_b200.so")
+LIB_PATH = os.path.join(_PKG, "libdemf_b200.so")
 
 _c_int = ctypes.c_int
 _c_float = ctypes.c_float

@@ -5,25 +5,29 @@
 // `PointSAModule.forward` in eval mode -- configs/demf/demf_votenet.py:48-62 -- group_points + cuDNN convs +
 // max_pool2d), for the geometry whose three weight matrices fit shared memory together: C = 1 input feature
 // (+ xyz: 8-wide rows), widths 64 / 64 / 128 -- the backbone's first level, the largest of the five (131 072
-// grouped rows per scene, 0.20 of the 0.57 ms the fused kernels take per step).
+// grouped rows per scene, 0.20 of the 0.57 ms the fused kernels took per step in round 1).
 //
 // sa_fused.cu gives each 128-row tile to a "lane" of four warps that walks gather -> MMA 0 -> epilogue 0 ->
 // MMA 1 -> epilogue 1 -> MMA 2 -> max strictly in sequence; four lanes per SM overlap four such chains, and a
 // tile costs the SUM of its phases' latencies (16 k cycles per lane, 4 k per SM). Here every phase has its own
 // warps and the tiles flow through them:
 //
-//   warps 2-9    gather     neighbour indices (coalesced) -> point + feature -> (xyz - centre) / r -> the layer-0
-//                           operand A0 (K-major SWIZZLE_128B rows, 8 floats used), two tiles in flight
-//   warp 0       MMA        tcgen05.mma kind::tf32, one thread, software-pipelined over tiles:
-//                           L0(t+2): D0 = A0 W0^T (K 8)   L1(t+1): D1 = A1 W1^T (K 64)   L2(t): D2^T = W2 A2^T (K 64)
-//   warps 10-13  epilogue 0 D0 (TMEM) -> + b0, ReLU, tf32 -> A1 (shared memory)
-//   warps 14-17  epilogue 1 D1 -> + b1, ReLU, tf32 -> A2
-//   warps 18-21  max        D2^T: TMEM lanes = the 128 output channels, columns = the tile's rows, so the max over
-//                           a centre's ns rows is an in-thread fmax chain; + b2, ReLU, coalesced store
+//   warps 4-7    gather     neighbour indices (coalesced) -> point + feature (one 16-byte load from the packed
+//                           (B,N,4) cloud when the caller has it) -> (xyz - centre) / r -> the layer-0 operand A0
+//                           (K-major SWIZZLE_128B rows, 8 floats used); batches of four tiles, eight-slot ring
+//   warps 0-2    MMA        tcgen05.mma kind::tf32, ONE issuing thread per layer, each in its own loop over tiles
+//                           (tcgen05.commit tracks the committing thread's instructions only):
+//                           L0: D0 = A0 W0^T (K 8)   L1: D1 = A1 W1^T (K 64)   L2: D2^T = W2 A2^T (K 64)
+//   warps 8-15   epilogue 0 D0 (TMEM, 32 columns per warp) -> + b0, ReLU, tf32 -> A1 (shared memory)
+//   warps 16-23  epilogue 1 D1 -> + b1, ReLU, tf32 -> A2
+//   warps 24-31  max        D2^T: TMEM lanes = the 128 output channels, columns = the tile's rows, so the max over
+//                           a centre's ns rows is an in-thread max chain; + b2, ReLU, coalesced store
 //
-// Every buffer (A0, A1, A2, the three accumulators) exists twice and is handed over through mbarrier pairs; the
-// weights (56 KB, host-packed operand images of sa_pack_weights) are resident. A tile then costs the SLOWEST
-// phase -- the 17 MMA issues (~1.2 k cycles) -- instead of the sum.
+// Every buffer (A1, A2, the three accumulators) exists twice -- A0 eight times -- and is handed over through mbarrier
+// pairs; the weights (56 KB, host-packed operand images of sa_pack_weights) are resident. A CTA takes a contiguous
+// range of tiles. A tile then costs the SLOWEST phase instead of the sum: measured (DEMF_SAP_PROF build, ncu source
+// counters) that is the issue slots of the epilogue / max warps, which is why their instruction streams are pared
+// down (FADD2 bias, VIADDMNMX ReLU + rounding, FMNMX3) and the roles are eight warps wide.
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -71,15 +75,6 @@ __device__ __forceinline__ void wait_flag(uint32_t bar, uint32_t parity, int cod
 #ifdef DEMF_SAP_PROF
   const long long t0 = clock64();
 #endif
-#if SAP_X == 7
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
-  }
-#elif SAP_X == 8
-  while (!mbar_try_wait(bar, parity)) __nanosleep(500);
-#else
   // try_wait with a suspend-time hint: the warp sleeps in hardware instead of polling (the polling loops of 20+
   // waiting warps were ~40 % of all issued instructions); bounded, a protocol bug must not hang the GPU
   uint32_t ok = 0;
@@ -87,7 +82,6 @@ __device__ __forceinline__ void wait_flag(uint32_t bar, uint32_t parity, int cod
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000u) : "memory");
   if (!ok) atomicCAS(&g_sap_error, 0, code);
-#endif
 #ifdef DEMF_SAP_PROF
   if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && ((1u << (threadIdx.x >> 5)) & 0x01010117u)) atomicAdd((unsigned long long*)&g_sap_prof[code], (unsigned long long)(clock64() - t0));
 #endif
@@ -193,9 +187,6 @@ __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams
           for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-#if SAP_X == 2
-              if ((kc | ks) == 0)
-#endif
               mma_tf32(tmem + kD1 + b * 64u, smem_desc_sw128(a + kc * 16384 + ks * 32),
                        smem_desc_sw128(w1 + kc * 8192 + ks * 32), id64, (kc | ks) ? 1u : 0u);
           mma_commit(bar(5, b));
@@ -214,9 +205,6 @@ __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams
           for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-#if SAP_X == 2
-              if ((kc | ks) == 0)
-#endif
               mma_tf32(tmem + kD2 + b * 128u, smem_desc_sw128(w2 + kc * 16384 + ks * 32),
                        smem_desc_sw128(a + kc * 16384 + ks * 32), id128, (kc | ks) ? 1u : 0u);
           mma_commit(bar(9, b));
@@ -234,20 +222,13 @@ __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams
     struct Pt { float x, y, z, f, cx, cy, cz; };
     // tile T = grouped rows [128 T, 128 T + 128) = centres [T cpt, (T + 1) cpt) of scene T / tps
     auto nbr_of = [&](int j) -> int {
-#if SAP_X == 3
-      return row + j;
-#else
       return __ldg(p.nbr + (long)(t_first + j) * kRows + row);
-#endif
     };
     int pt_scene = t_first / tps, pt_t = t_first - pt_scene * tps;   // the tile whose points are loaded next
     auto load_pt = [&](int j, int k) -> Pt {
       const float* c = p.centres + ((long)(t_first + j) * cpt + rc) * 3;
       const float* pt = p.xyz + ((long)pt_scene * p.N + k) * 3;
       Pt r;
-#if SAP_X == 3
-      r.x = r.y = r.z = r.f = r.cx = r.cy = r.cz = (float)(k + j) + (float)(c - pt);
-#else
       if (p.pts4 != nullptr) {   // one sector per row instead of four scalar requests (the L1 tag stage is what
         const float4 v = __ldg(p.pts4 + (long)pt_scene * p.N + k);   // a fully scattered gather is bound by)
         r.x = v.x;
@@ -263,7 +244,6 @@ __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams
       r.cx = __ldg(c);
       r.cy = __ldg(c + 1);
       r.cz = __ldg(c + 2);
-#endif
       if (++pt_t == tps) {
         pt_t = 0;
         ++pt_scene;
@@ -337,12 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams
       tc_fence_after_sync();
       SAP_T0();
       uint32_t u0[32];
-#if SAP_X == 6
-#pragma unroll
-      for (int i = 0; i < 32; ++i) u0[i] = (uint32_t)(j + i);
-#else
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (e ? kD1 : kD0) + b * 64u + h * 32u, u0);
-#endif
       const float4* bs4 = reinterpret_cast<const float4*>(bs);
       float4 bb[4];                                   // bias of the first 16 columns; the rest follows in the loop
 #pragma unroll
@@ -373,9 +348,6 @@ __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams
         }
 #pragma unroll
         for (int s = 0; s < 4; ++s)
-#if SAP_X == 4
-          if (p.ns == 7 || v[s].x == 123.f)
-#endif
           *reinterpret_cast<float4*>(dst + sw128_offset((uint32_t)row, (uint32_t)(4 * half + s))) = v[s];
       }
       SAP_T(1, threadIdx.x == 256);
@@ -423,9 +395,6 @@ __global__ void __launch_bounds__(kThreads, 1) sa_pipe_kernel(const SaPipeParams
           run = fmaxf(run, mx);
           const int per = p.ns >> 5;                   // 32-row blocks per centre (1 or 2)
           if ((blk + 1) % per == 0) {
-#if SAP_X == 5
-            if (run == 123.f)
-#endif
             o[(long)(blk / per) * kC3] = fmaxf(run + b2, 0.f);
             run = -3.0e38f;
           }
