@@ -39,9 +39,9 @@ TRAIN_BATCH_PER_GPU = 4
 NUM_POINTS = 20000
 PYRAMID = "S512"
 P_POINTS = 4
-ROTATE = 8  # resident input sets, rotated so that a step never finds its inputs in L2
+LANES = int(os.environ.get("DEMF_BENCH_LANES", "10"))   # forward graphs in flight (engine.ForwardPipeline); measured on B200: 4: 7.8 k, 6: 7.9 k, 8: 10.1 k, 10: 10.5 k, 12: 10.4 k, 16: 10.5 k scenes/s
+ROTATE = max(8, LANES)  # resident input sets (one per lane at least), rotated so that a step never finds its inputs in L2
 CPU_SAMPLE_SCENES = 2
-LANES = 8   # forward graphs in flight (engine.ForwardPipeline)
 
 
 def workload_config(n_gpus):
