@@ -325,7 +325,7 @@ def time_e2e_images(dev, steps, barrier, max_over_ranks, rank, n_gpus):
     THE DEVICE by the frozen image branch (ResNet-50 -> ChannelMapper -> 6-layer Deformable-DETR encoder,
     demfnet.py:124-132) instead of being copied in as 5.6 MB of fp32 features per scene. Host -> device per
     step: 8 x (786 KB image + 320 KB points); one CUDA graph per step (normalise, image branch, forward,
-    decode), two steps in flight on two streams."""
+    decode), four steps in flight on four streams."""
     import torch
     from demf_b200 import engine, synth
     torch.manual_seed(4321)
@@ -337,8 +337,9 @@ def time_e2e_images(dev, steps, barrier, max_over_ranks, rank, n_gpus):
     from demf_b200.mm import geometry
     mats, affs = geometry.fold_projection(metas)
     mats, affs = mats.to(dev), affs.to(dev)
+    n_lanes = int(os.environ.get("DEMF_BENCH_IMG_LANES", "4"))   # measured: 2 lanes 1.34 k scenes/s, 3: 1.48 k, 4: 1.57 k, 8: 1.59 k
     lanes = []
-    for lane in range(2):
+    for lane in range(n_lanes):
         st = torch.cuda.Stream(device=dev)
         pts = torch.empty(B, NUM_POINTS, 4, device=dev)
         img8 = torch.empty(B, H, W, 3, dtype=torch.uint8, device=dev)
@@ -360,18 +361,18 @@ def time_e2e_images(dev, steps, barrier, max_over_ranks, rank, n_gpus):
     g = torch.Generator().manual_seed(77 + rank)
     host = [(synth.make_points(B, NUM_POINTS, seed=900 + rank * 10 + i, clustered=True).pin_memory(),
              torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=g).pin_memory()) for i in range(4)]
-    host_out = [[torch.empty(tuple(t.shape), dtype=t.dtype).pin_memory() for t in lanes[0][4]] for _ in range(2)]
+    host_out = [[torch.empty(tuple(t.shape), dtype=t.dtype).pin_memory() for t in lanes[0][4]] for _ in range(n_lanes)]
     h2d = host[0][0].numel() * 4 + host[0][1].numel()
     d2h = sum(t.numel() * t.element_size() for t in host_out[0])
 
     def step(i):
-        st, pts, img8, graph, outs = lanes[i % 2]
+        st, pts, img8, graph, outs = lanes[i % n_lanes]
         hp, hi = host[i % 4]
         with torch.cuda.stream(st):
             pts.copy_(hp, non_blocking=True)
             img8.copy_(hi, non_blocking=True)
             graph.replay()
-            for dst, src in zip(host_out[i % 2], outs):
+            for dst, src in zip(host_out[i % n_lanes], outs):
                 dst.copy_(src, non_blocking=True)
 
     for i in range(4):
