@@ -1,6 +1,6 @@
 """Small invocations of the protocol-heavy kernels (mbarrier / TMEM / DSMEM / TMA) for compute-sanitizer:
 fps_cluster_kernel, fps_grid_kernel, sa_fused_fwd_kernel, sa_pipe_kernel, ball_query_grid_kernel (bitmap selection),
-rows_gemm_kernel (fwd + statistics, dgrad through BatchNorm), wgrad_kernel, col_sum_add_kernel, msda fwd/bwd. Results are checked so that a tool-induced failure is visible.
+rows_gemm_kernel (fwd + statistics, dgrad through BatchNorm), wgrad_kernel, col_sum_add_kernel, mha_fwd_kernel, msda fwd/bwd. Results are checked so that a tool-induced failure is visible.
 
     compute-sanitizer --tool memcheck  python tools/sanitize_target.py
     compute-sanitizer --tool racecheck python tools/sanitize_target.py
@@ -72,6 +72,18 @@ if want("gemm"):
     assert (y - x @ w.t()).abs().max() < 2e-2 and (dw - dy.t() @ x).abs().max() < 0.2 and ops.gemm_error() == 0
     assert torch.allclose(mean, y.mean(0), atol=1e-4)
     print("gemm ok", float(gm.abs().mean()))
+if want("mha"):
+    g = torch.Generator(device=dev).manual_seed(3)
+    Lq, Lk, B, H, D = 100, 77, 2, 4, 36
+    q = torch.randn(Lq * B, H * D, generator=g, device=dev)
+    k = torch.randn(Lk * B, H * D, generator=g, device=dev)
+    v = torch.randn(Lk * B, H * D, generator=g, device=dev)
+    o = ops.mha_rows(q, k, v, B, H)
+    hd = lambda t, L: t.reshape(L, B, H, D).permute(1, 2, 0, 3)  # noqa: E731
+    ref = (torch.softmax(hd(q, Lq) @ hd(k, Lk).transpose(-1, -2) * D ** -0.5, -1) @ hd(v, Lk)).permute(2, 0, 1, 3)
+    torch.cuda.synchronize()
+    assert (o - ref.reshape(Lq * B, H * D)).abs().max() < 1e-4
+    print("mha ok", float(o.abs().mean()))
 if want("msda"):
     v, sh, lsi, loc, at = (t.to(dev) for t in synth.make_msda_inputs(B=1, Q=64, name="S512", P=4, seed=0))
     v.requires_grad_(True); loc.requires_grad_(True); at.requires_grad_(True)
