@@ -40,7 +40,9 @@ NUM_POINTS = 20000
 PYRAMID = "S512"
 P_POINTS = 4
 LANES = int(os.environ.get("DEMF_BENCH_LANES", "10"))   # forward graphs in flight (engine.ForwardPipeline); measured on B200: 4: 7.8 k, 6: 7.9 k, 8: 10.1 k, 10: 10.5 k, 12: 10.4 k, 16: 10.5 k scenes/s
-ROTATE = max(8, LANES)  # resident input sets (one per lane at least), rotated so that a step never finds its inputs in L2
+ROTATE = max(8, 2 * LANES)  # resident input sets = pipeline slots, two per lane (engine.ForwardPipeline(late_images=True):
+                            # a slot's buffers are long released when its next copy is queued), rotated so that a step never
+                            # finds its inputs in L2
 CPU_SAMPLE_SCENES = 2
 
 
@@ -576,7 +578,7 @@ def main():
 
     # one captured forward per resident input set, alternating between LANES streams: a step =
     # one graph launch, and consecutive (independent) batches overlap on the device
-    pipe = engine.ForwardPipeline(model, sets, lanes=LANES)
+    pipe = engine.ForwardPipeline(model, sets, lanes=LANES, late_images=True)
     graphs = pipe.slots
     for i in range(args.warmup):
         pipe.submit()

@@ -348,6 +348,7 @@ class GraphedTrainStep:
         self.mats, self.affs = mats.to(dev), affs.to(dev)
         box, label = pad_gt(example["gt_bboxes_3d"], example["gt_labels_3d"], max_gt)
         self._box_host, self._label_host = box.pin_memory(), label.pin_memory()
+        self._staged = None    # recorded behind the last copies out of the pinned staging buffers
         self.box, self.label = box.to(dev), label.to(dev)
 
         snapshot = copy.deepcopy(model.state_dict())
@@ -441,6 +442,11 @@ class GraphedTrainStep:
         for dst, src in zip(self.levels, batch["img"]):
             dst.copy_(src, non_blocking=True)
         mats, affs = self._fold(batch["img_metas"])
+        # The pinned staging buffers are rewritten by the HOST: the copies queued from them by the previous call
+        # must have run first, or a host that is a step ahead of the device would hand THAT step this batch's
+        # matrices / boxes (the host only ever waits here when it is a whole step ahead).
+        if self._staged is not None:
+            self._staged.synchronize()
         self._mats_host.copy_(mats)
         self._affs_host.copy_(affs)
         self.mats.copy_(self._mats_host, non_blocking=True)
@@ -456,6 +462,8 @@ class GraphedTrainStep:
             self._label_host.copy_(label)
             self.box.copy_(self._box_host, non_blocking=True)
             self.label.copy_(self._label_host, non_blocking=True)
+        self._staged = torch.cuda.Event()
+        self._staged.record(torch.cuda.current_stream(self.points.device))
 
     def __call__(self, batch=None, next_batch=None):
         """Run one step (on the current stream) and return the static (total loss, loss dict).
@@ -499,7 +507,7 @@ class GraphedForward:
     affs (B,4)) that `geometry.fold_projection(img_metas)` computes on the host per batch.
     """
 
-    def __init__(self, model, example, pool=None, warmup=3, stream=None):
+    def __init__(self, model, example, pool=None, warmup=3, stream=None, copy_stream=None):
         assert not model.training, "GraphedForward captures the eval-mode forward"
         dev = example["points"].device
         assert dev.type == "cuda"
@@ -512,6 +520,7 @@ class GraphedForward:
         mats, affs = geometry.fold_projection(self.metas)
         self._mats_host = mats.pin_memory()
         self._affs_host = affs.pin_memory()
+        self._staged = None    # recorded behind the last copies out of the pinned staging buffers
         self.mats = mats.to(dev)
         self.affs = affs.to(dev)
         self._fold = geometry.fold_projection
@@ -525,29 +534,84 @@ class GraphedForward:
                 self._eager()
         torch.cuda.current_stream(dev).wait_stream(self.stream)
         torch.cuda.synchronize(dev)
+        # With a `copy_stream` the forward is captured as TWO graphs, split in front of the first reader of the
+        # image features (the decoder's cross attention; heads.forward_points / forward_images): the pyramid -- 95 %
+        # of a batch's input bytes -- is copied in on `copy_stream` while the first graph (backbone, votes,
+        # aggregation: most of a forward's latency) already runs on the points; the stream waits for the copy
+        # between the two launches.
+        self.copy_stream = copy_stream
+        self.graph_b = None
+        self.pts_ready = self.img_ready = self._free = None
         self.graph = torch.cuda.CUDAGraph()
+        if copy_stream is None:
+            with torch.no_grad(), torch.cuda.graph(self.graph, pool=pool, stream=self.stream):
+                self.outputs = self._eager()
+            self.pool = self.graph.pool()
+            return
+        self.pts_ready = torch.cuda.Event()      # points + projection of the batch about to run have landed
+        self.img_ready = torch.cuda.Event()      # ... and its pyramid
+        self._free = torch.cuda.Event()          # the last replay no longer reads the static pyramid
+        with torch.cuda.stream(self.stream), torch.no_grad():
+            self._eager_split()
+        torch.cuda.synchronize(dev)
         with torch.no_grad(), torch.cuda.graph(self.graph, pool=pool, stream=self.stream):
-            self.outputs = self._eager()
+            self._state = self.model.simple_test_points(self.points, self.metas, projection=(self.mats, self.affs))
         self.pool = self.graph.pool()
+        self.graph_b = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph_b, pool=self.pool, stream=self.stream):
+            self.outputs = self.model.simple_test_images(self._state, self.levels, self.metas)
 
     def _eager(self):
         return self.model.simple_test(points=self.points, img=self.levels, img_metas=self.metas,
                                       projection=(self.mats, self.affs), nms=False)
 
+    def _eager_split(self):
+        state = self.model.simple_test_points(self.points, self.metas, projection=(self.mats, self.affs))
+        return self.model.simple_test_images(state, self.levels, self.metas)
+
     def load(self, points, levels, img_metas=None):
         """Copy a new batch (host-pinned or device tensors, same shapes) into the static buffers."""
+        if self.copy_stream is None:
+            self._copy_points(points, img_metas)
+            for dst, src in zip(self.levels, levels):
+                dst.copy_(src, non_blocking=True)
+            return
+        # every input copy of this batch on the copy stream, small ones first: points (+ projection), then the
+        # pyramid. (The points must not be copied on the lane's stream: while the copy stream keeps the host link
+        # busy with queued pyramids, a small copy issued on another stream waits until that queue has drained --
+        # measured: the first kernel of every lane then starts after ALL pyramid copies, 31 ms for 20 steps.)
+        self.copy_stream.wait_event(self._free)
+        with torch.cuda.stream(self.copy_stream):
+            self._copy_points(points, img_metas)
+            self.pts_ready.record(self.copy_stream)
+            for dst, src in zip(self.levels, levels):
+                dst.copy_(src, non_blocking=True)
+            self.img_ready.record(self.copy_stream)
+
+    def _copy_points(self, points, img_metas):
         self.points.copy_(points, non_blocking=True)
-        for dst, src in zip(self.levels, levels):
-            dst.copy_(src, non_blocking=True)
         if img_metas is not None:
             mats, affs = self._fold(img_metas)
+            # the host rewrites the pinned staging buffers: the copies queued from them by the previous load must
+            # have run (else a host several submissions ahead would give THAT batch this batch's projection)
+            if self._staged is not None:
+                self._staged.synchronize()
             self._mats_host.copy_(mats)
             self._affs_host.copy_(affs)
             self.mats.copy_(self._mats_host, non_blocking=True)
             self.affs.copy_(self._affs_host, non_blocking=True)
+            self._staged = torch.cuda.Event()
+            self._staged.record(torch.cuda.current_stream(self.device))
 
     def replay(self):
+        cur = torch.cuda.current_stream(self.device)
+        if self.graph_b is not None:
+            cur.wait_event(self.pts_ready)
         self.graph.replay()
+        if self.graph_b is not None:
+            cur.wait_event(self.img_ready)
+            self.graph_b.replay()
+            self._free.record(cur)
         return self.outputs
 
     def __call__(self, points, levels, img_metas=None):
@@ -566,20 +630,40 @@ class ForwardPipeline:
     copies. `submit` returns the lane's static output tensors; they are valid after
     `lane_done(slot).synchronize()` (or any later stream sync) and until that lane is submitted to
     again.
+
+    `late_images=True`: every slot is captured as two graphs (point branch | decoder) and all input copies go
+    through one copy stream in submission order, each batch's points first, then its pyramid: a lane starts on
+    the points while the pyramid -- 95 % of the input bytes -- is still crossing the host link. Same results;
+    a single batch end to end 3.6 -> 2.9 ms, 20 steps from an idle pipeline 20.4 -> 19.8 ms, steady state
+    unchanged (the link is the bound). Wants at least two slots per lane (see __init__).
     """
 
-    def __init__(self, model, examples, lanes=2):
+    def __init__(self, model, examples, lanes=2, late_images=False):
         if isinstance(examples, dict):
             examples = [examples] * lanes
         dev = examples[0]["points"].device
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(lanes)]
+        # late_images: split graphs (see GraphedForward) and ONE stream for every slot's pyramid copies, so that
+        # they cross the host link one after the other. (Copies issued on a stream per lane share the link instead:
+        # all pyramids then land at about the same time, the lanes fall into step and the link idles while they all
+        # compute -- measured 1.44 ms per step against 0.89.) A copy has to wait until its slot's previous replay
+        # has released the static buffers; with at least twice as many slots as lanes that replay is long over and
+        # the wait never holds up the copies queued behind it.
+        self.copy_streams = [torch.cuda.Stream(device=dev)] * lanes if late_images else None
         self.slots = []          # one captured forward (own static buffers) per example
         pools = [None] * lanes   # slots of one lane never overlap in time: they share a pool
         for j, ex in enumerate(examples):
             lane = j % lanes
-            g = GraphedForward(model, ex, pool=pools[lane], stream=self.streams[lane])
+            g = GraphedForward(model, ex, pool=pools[lane], stream=self.streams[lane],
+                               copy_stream=self.copy_streams[lane] if late_images else None)
             pools[lane] = g.pool
             self.slots.append(g)
+        # the first launch of an instantiated graph also uploads it to the device: do that here, not inside the
+        # caller's first (possibly timed) round over the slots
+        for g in self.slots:
+            with torch.cuda.stream(g.stream):
+                g.replay()
+        torch.cuda.synchronize(dev)
         self._events = [torch.cuda.Event() for _ in self.slots]
         self._next = 0
 
@@ -610,3 +694,5 @@ class ForwardPipeline:
         cur = torch.cuda.current_stream(self.slots[0].device)
         for stream in self.streams:
             cur.wait_stream(stream)
+        if self.copy_streams:
+            cur.wait_stream(self.copy_streams[0])

@@ -196,5 +196,25 @@ class DeMFVoteNet(BaseModule):
         bbox_list = head.get_bboxes(pts, bbox_preds, img_metas, rescale=rescale)
         return [bbox3d2result(b, s, l) for b, s, l in bbox_list]
 
+    # simple_test(nms=False) in two parts, for callers that overlap the image features' arrival with the first
+    # (engine.GraphedForward(split=True)): `state` = what the point branch produced, then the decoder + decoding.
+    def simple_test_points(self, points, img_metas, projection=None):
+        points = torch.stack(list(points)) if not torch.is_tensor(points) else points
+        sample_mod = self.test_cfg['pts']['sample_mod']
+        seeds_3d, seed_3d_features, seed_indices = self.extract_pts_feat(points, sample_mod, None)
+        feat_dict = dict(seed_points=seeds_3d, seed_features=seed_3d_features, seed_indices=seed_indices)
+        if self._seed_fps_indices is not None:
+            feat_dict['seed_sample_indices'] = self._seed_fps_indices
+        img_dict = dict(img_metas=img_metas)
+        if projection is not None:
+            img_dict['projection'] = projection
+        return self.pts_bbox_head.forward_points(feat_dict, sample_mod, img_dict), img_dict
+
+    def simple_test_images(self, state, img, img_metas):
+        results, img_dict = state
+        self._batch_input_shape(img, img_metas)
+        img_dict = dict(img_dict, img_features=self.extract_img_feat(img, img_metas))
+        return self.pts_bbox_head.decode_ensemble(self.pts_bbox_head.forward_images(results, img_dict))
+
     def forward(self, return_loss=True, **kwargs):
         return self.forward_train(**kwargs) if return_loss else self.simple_test(**kwargs)

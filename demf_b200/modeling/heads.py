@@ -106,9 +106,15 @@ class DeMFVoteHead(BaseModule):
 
     # ------------------------------------------------------------------ forward ---
     def forward(self, feat_dict, sample_mod, img_dict):
+        """= forward_images(forward_points(...)): the part that only needs the point cloud (vote module, proposal
+        sampling, vote aggregation; with ground truth also the early target assignment), then the decoder, which is
+        the first reader of the image features. engine.GraphedForward captures the two parts as two graphs so that
+        the image features can still be on their way to the device while the first runs."""
+        return self.forward_images(self.forward_points(feat_dict, sample_mod, img_dict), img_dict)
+
+    def forward_points(self, feat_dict, sample_mod, img_dict):
         assert sample_mod in ['vote', 'seed', 'random', 'spec']
         seed_points, seed_features, seed_indices = self._extract_input(feat_dict)
-        img_features, img_metas = img_dict['img_features'], img_dict['img_metas']
 
         vote_points, vote_features, vote_offset = self.vote_module(seed_points, seed_features)
         results = dict(seed_points=seed_points, seed_indices=seed_indices, vote_points=vote_points,
@@ -157,8 +163,13 @@ class DeMFVoteHead(BaseModule):
                 done = torch.cuda.Event()
                 done.record(side)
             results['_targets'] = (targets, done)
+        results['_aggregated_features'] = features
+        return results
+
+    def forward_images(self, results, img_dict):
+        features = results.pop('_aggregated_features')
         results['decode_res_all'] = self.transformer_decoder(
-            features, aggregated_points, img_features, img_metas,
+            features, results['aggregated_points'], img_dict['img_features'], img_dict['img_metas'],
             projection=img_dict.get('projection'))
         return results
 

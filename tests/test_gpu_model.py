@@ -682,3 +682,39 @@ def test_resnet_fused_inference_matches_plain_path(dev):
         assert a.shape == b.shape
         assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item()
     assert not torch.allclose(fused[0], fused2[0])
+
+
+@pytest.mark.gpu
+def test_forward_pipeline_late_images_identical(dev):
+    """engine.ForwardPipeline(late_images=True) -- two graphs per slot, every input copy on one copy stream, the
+    pyramid landing while the point branch already runs -- returns exactly what the single-graph pipeline returns and, in the
+    strict-fp32 mode, the eager forward's results, for host batches submitted back to back over twice as many slots as lanes."""
+    engine.set_gemm_precision("fp32")
+    torch.manual_seed(21)
+    model = engine.build_demf_votenet(num_points=4).to(dev).eval()
+    lanes, slots, B = 2, 4, 2
+    sets = [engine.synthetic_batch(B, 20000, "S512", seed=10 + i, device=dev, with_gt=False) for i in range(slots)]
+    host = [engine.synthetic_batch(B, 20000, "S512", seed=50 + i, device="cpu", with_gt=False, pin=True)
+            for i in range(6)]
+    with torch.no_grad():
+        want = []
+        for hb in host:
+            out = model.simple_test(points=hb["points"].to(dev), img=[lv.to(dev) for lv in hb["img"]],
+                                    img_metas=hb["img_metas"], nms=False)
+            want.append([t.clone() for t in out])
+    results = {}
+    for late in (False, True):
+        pipe = engine.ForwardPipeline(model, sets, lanes=lanes, late_images=late)
+        outs = [[torch.empty(tuple(t.shape), dtype=t.dtype).pin_memory() for t in pipe.slots[0].outputs]
+                for _ in host]
+        for rep in range(2):                      # the second round reuses every slot
+            for i, hb in enumerate(host):
+                pipe.submit(hb["points"], hb["img"], hb["img_metas"], outputs_to=outs[i])
+        pipe.join()
+        torch.cuda.synchronize()
+        results[late] = [[t.clone() for t in o] for o in outs]
+        del pipe
+    for one, two, ref in zip(results[False], results[True], want):
+        for a, b, r in zip(one, two, ref):
+            assert torch.equal(a, b)                                   # the two pipelines: the same graphs' arithmetic
+            torch.testing.assert_close(a, r.cpu(), atol=1e-5, rtol=1e-5)   # strict-fp32 mode: as the eager forward
