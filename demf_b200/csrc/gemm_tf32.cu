@@ -645,7 +645,15 @@ int launch_rows_gemm(const float* a, long lda, const float* w, long ldw, const f
                      long ldy, long R, int K, int N, int relu, cudaStream_t st, const BnMask* bn = nullptr) {
   // output columns per CTA: balanced blocks of at most 256, multiples of 16
   // (several blocks: multiples of 32 so that a block's last 32-column output slab never reaches into the next one)
-  const int nb = (N + 255) / 256;
+  int nb = (N + 255) / 256;
+  // Few row tiles (the small layers of the step: 1 024 - 16 384 rows): a CTA per 128 rows x 256 columns leaves most
+  // SMs idle and walks its K chunks and its eight 32-column output slabs one after the other (15 us for one
+  // 128 x 256 x 256 tile). Narrower column blocks (>= 64 columns) on more CTAs: shorter stages -> deeper ring,
+  // two slabs per epilogue, the A tile re-read from L2.
+  {
+    const long tiles_ = (R + kTileRows - 1) / kTileRows;
+    while (tiles_ * nb * 2 <= kNumSMs && (N + 2 * nb - 1) / (2 * nb) >= 64) nb *= 2;
+  }
   // (MN-major B operand: whole 32-column swizzle atoms)
   const int n_block = (nb == 1 && !kBMN) ? ((N + 15) & ~15) : ((((N + nb - 1) / nb) + 31) & ~31);
   RowsGemmParams p;
