@@ -73,6 +73,13 @@ out.append("| total us | launches | avg us | kernel |")
 out.append("|---|---|---|---|")
 for n, v in sorted(tot.items(), key=lambda kv: -kv[1])[:45]:
     out.append(f"| {v:.1f} | {cnt[n]} | {v / cnt[n]:.2f} | `{n[:110]}` |")
+out.append("")
+out.append("duration histogram of our GEMM kernels in this replay (us): launches, total")
+for key in ("rows_gemm_kernel<true>", "rows_gemm_kernel<false>", "wgrad_kernel"):
+    ds = sorted(e - s for s, e, n, st in mid if key in n)
+    for lo, hi in ((0, 8), (8, 12), (12, 20), (20, 40), (40, 1e9)):
+        sel = [d for d in ds if lo <= d < hi]
+        out.append(f"  {key:26s} [{lo:>3.0f}, {hi if hi < 1e9 else float('inf'):>4.0f}): {len(sel):3d} launches, {sum(sel):7.1f} us")
 text = "\n".join(out)
 print(text)
 if len(sys.argv) > 1:
